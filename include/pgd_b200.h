@@ -1,0 +1,134 @@
+/* pgd_b200.h -- C ABI of libpgdb200.so: the B200 (sm_100a) kernels behind the progressive PGD
+ * enrichment hot path of BAMresearch/PGDrome (pgdrome/solver.py:306-881, pgdrome/model.py:724-860).
+ *
+ * The reference has no FFI of its own (pure Python on top of DOLFIN/PETSc/SciPy); each entry
+ * point below names the reference call site whose arithmetic it replaces.  A reference
+ * maintainer binds these with ctypes.
+ *
+ * Conventions
+ *   - every pointer named d_* is DEVICE memory owned by the caller (e.g. torch.Tensor.data_ptr());
+ *     h_* is HOST memory.  The library owns only the opaque handle and its scratch.
+ *   - fp64 values, int32 indices (int64 where stated), row-major, CSR with ascending columns.
+ *   - return 0 = OK, >0 = cudaError_t, <0 = argument error; pgd_last_error(h) gives the text.
+ *   - asynchronous on `stream` (a cudaStream_t passed as void*) unless the name ends in _sync.
+ *   - one host thread and one stream at a time per handle; one handle per GPU / rank.
+ *   - reductions are deterministic (fixed-order two-stage sums, no floating-point atomics).
+ */
+#ifndef PGD_B200_H
+#define PGD_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pgd_ctx* pgd_handle_t;
+
+int32_t pgd_abi_version(void);
+int32_t pgd_create(int32_t device, pgd_handle_t* out);
+int32_t pgd_destroy(pgd_handle_t h);
+const char* pgd_last_error(pgd_handle_t h);
+
+/* ---- sparsity pattern (DOLFIN SparsityPatternBuilder behind solver.py:627-636: union of per-cell
+ * dof cliques, columns ascending).  build: sorts the n_cells*ndl^2 (row,col) contributions; the
+ * sorted order is also the deterministic gather list used by pgd_gather_values.
+ * export: rowptr[n_dofs+1], colidx[nnz], gptr[nnz+1] (int64), gidx[n_cells*ndl*ndl] (int32). */
+int32_t pgd_pattern_build_sync(pgd_handle_t h, const int32_t* d_cell_dofs, int64_t n_cells, int32_t ndl,
+                               int64_t n_dofs, int64_t* h_nnz, void* stream);
+int32_t pgd_pattern_export(pgd_handle_t h, int32_t* d_rowptr, int32_t* d_colidx, int64_t* d_gptr,
+                           int32_t* d_gidx, void* stream);
+/* dof -> contribution lists for load vectors: vptr[n_dofs+1] (int64), vidx[n_cells*ndl] (int32) */
+int32_t pgd_vecmap_build_sync(pgd_handle_t h, const int32_t* d_cell_dofs, int64_t n_cells, int32_t ndl,
+                              int64_t n_dofs, int64_t* d_vptr, int32_t* d_vidx, void* stream);
+
+/* ---- separated-form assembly (dolfin.assemble / SystemAssembler + FFC tabulate_tensor behind
+ * every lhs_fct/rhs_fct callback, e.g. tests/integration/test_elastic.py:71-219).
+ * Generic Lagrange element kernel: element tables phi[nq,nd], dphi[nq,nd,tdim], qw[nq] are staged
+ * in shared memory; T[bs,gdim+1,bs,gdim+1] is the constant form tensor (slot 0 = value, 1+m = d/dx_m;
+ * first index pair = test, second = trial); wq[n_cells,nq] optional coefficient at quadrature points.
+ * Output Ae[n_cells, nd*bs, nd*bs] (local dof = node*bs+comp), reduced by pgd_gather_values. */
+int32_t pgd_elem_bilinear(pgd_handle_t h, const double* d_coords, const int32_t* d_cell_verts, int64_t n_cells,
+                          int32_t tdim, int32_t gdim, int32_t bs, int32_t nd, int32_t nq, const double* d_phi,
+                          const double* d_dphi, const double* d_qw, const double* d_wq, const double* d_T,
+                          double* d_Ae, void* stream);
+/* be[n_cells, nd*bs] = int w * sum L[i,j] D_j v_i ; L[bs,gdim+1] */
+int32_t pgd_elem_linear(pgd_handle_t h, const double* d_coords, const int32_t* d_cell_verts, int64_t n_cells,
+                        int32_t tdim, int32_t gdim, int32_t bs, int32_t nd, int32_t nq, const double* d_phi,
+                        const double* d_dphi, const double* d_qw, const double* d_wq, const double* d_L,
+                        double* d_be, void* stream);
+/* out[g] = sum_{k in [gptr[g],gptr[g+1])} src[gidx[k]]  (fixed order => bitwise reproducible) */
+int32_t pgd_gather_values(pgd_handle_t h, const double* d_src, const int64_t* d_gptr, const int32_t* d_gidx,
+                          int64_t n_out, double* d_out, void* stream);
+/* Fused P1 simplex operator  values = c_mass*M + c_stiff*K + sum_m c_adv[m]*int (d_m u) v  written
+ * straight into the CSR pattern (one kernel, no element buffer): warp-segmented reduction over the
+ * gather list.  gdim = tdim in {1,2,3}; c_adv may be NULL. */
+int32_t pgd_assemble_p1(pgd_handle_t h, const double* d_coords, const int32_t* d_cell_verts, int64_t n_cells,
+                        int32_t gdim, double c_mass, double c_stiff, const double* h_c_adv,
+                        const int64_t* d_gptr, const int32_t* d_gidx, int64_t nnz, double* d_values, void* stream);
+
+/* ---- linear combinations: A_d = sum_k c_k K_{d,k} over CSR value arrays, and
+ * b_d = sum c_m g_m - sum c_ik (K_k U_i) over cached vectors (the folded scalar coefficients of
+ * SURVEY.md 7.1).  h_xs: HOST array of n_terms device pointers; h_coefs: HOST array. */
+int32_t pgd_lincomb(pgd_handle_t h, int32_t n_terms, const double* const* h_xs, const double* h_coefs,
+                    int64_t n, double* d_out, int32_t accumulate, void* stream);
+
+/* ---- Dirichlet (DirichletBC.apply / assemble_system symmetric elimination, solver.py:186-191,
+ * 364-372,704-716): zero row+col of every bc dof, diagonal 1, b lifted and set.  d_bc_vals may be
+ * NULL (all reference BC values are 0).  Pattern must be structurally symmetric. d_b may be NULL. */
+int32_t pgd_apply_dirichlet(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, double* d_values,
+                            double* d_b, const int32_t* d_bc_dofs, const double* d_bc_vals, int64_t n_bc,
+                            void* stream);
+int32_t pgd_set_entries(pgd_handle_t h, double* d_x, const int32_t* d_idx, const double* d_vals, int64_t n_idx,
+                        void* stream);
+
+/* ---- SpMV and mode integrals (dolfin.assemble of scalar functionals, dolfin.norm:
+ * solver.py:207,342,754,836-842 and the Constant(assemble(..)) factors of every callback).
+ * lanes_per_row: 0 = auto, else 2|4|8|16|32. */
+int32_t pgd_spmv(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
+                 const double* d_x, double* d_y, int64_t n_rows, int32_t lanes_per_row, void* stream);
+/* y = A x and *d_dot = w^T y in the same pass (w may alias x) */
+int32_t pgd_spmv_dot(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
+                     const double* d_x, double* d_y, const double* d_w, double* d_dot, int64_t n_rows,
+                     int32_t lanes_per_row, void* stream);
+/* *d_out = x^T A y  (fused SpMV-reduction, nothing written but the scalar) */
+int32_t pgd_bilinear(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
+                     const double* d_x, const double* d_y, int64_t n_rows, double* d_out, int32_t lanes_per_row,
+                     void* stream);
+int32_t pgd_dot(pgd_handle_t h, const double* d_x, const double* d_y, int64_t n, double* d_out, void* stream);
+/* d_out[m] = P[m,:] . x   for m < n_vecs, P row-major with leading dimension ld (cached panels K U) */
+int32_t pgd_panel_dots(pgd_handle_t h, const double* d_P, int64_t ld, int32_t n_vecs, const double* d_x,
+                       int64_t n, double* d_out, void* stream);
+
+/* ---- linear solves (LinearVariationalSolver / NonlinearVariationalSolver + MUMPS LU,
+ * solver.py:579-595,627-636,651-674,704-716; FD_solve spsolve solver.py:927-943).
+ * Jacobi-PCG, x0 = 0, stop ||r|| <= max(rtol*||b||, atol); convergence flag and iteration counter
+ * live on the device, the host only polls them every check_every iterations.
+ * d_work: 6*n doubles.  block = 1 (point Jacobi) or bs (bs x bs node-block Jacobi, bs <= 3). */
+int32_t pgd_pcg_sync(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
+                     const double* d_b, double* d_x, int64_t n, double rtol, double atol, int32_t maxit,
+                     int32_t check_every, int32_t block, int32_t lanes_per_row, double* d_work,
+                     int32_t* h_iters, double* h_relres, void* stream);
+/* General banded LU with partial pivoting, one CTA, for the 1-D parameter / time dimensions
+ * (tiny, possibly non-symmetric).  d_perm[new] = old dof (band ordering), kl/ku bandwidths in the
+ * permuted numbering; d_work: (2*kl+ku+1)*n + n doubles; *d_info != 0 on a zero pivot. */
+int32_t pgd_banded_solve(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
+                         const double* d_b, double* d_x, int32_t n, const int32_t* d_perm, int32_t kl, int32_t ku,
+                         double* d_work, int32_t* d_info, void* stream);
+
+/* ---- evaluate (PGD.evaluate, model.py:724-860; interp1d / Function.__call__ at model.py:798,838).
+ * weights: W[k,c] = prod_i phi_{i,k}(p[c,i]) for 1-D Lagrange free dims.  Per free dim i:
+ *   xs[i]   ascending cell boundaries [nc_i+1];  cd[i] int32 [nc_i, deg_i+1] dofs of (left, right[, mid]);
+ *   Phi[i]  modes [R, ld_i] row-major.  *d_flag set to 1+i if a point lies outside dim i's range. */
+int32_t pgd_eval_weights(pgd_handle_t h, int32_t n_free, const double* const* h_xs, const int32_t* const* h_cd,
+                         const double* const* h_Phi, const int32_t* h_nc, const int32_t* h_deg, const int64_t* h_ld,
+                         int32_t R, const double* d_points, int64_t C, double* d_W, int32_t* d_flag, void* stream);
+/* u[n] = sum_k X[k,n] w[k]    (single-point reconstruction, HBM-bound) */
+int32_t pgd_eval_gemv(pgd_handle_t h, const double* d_X, int64_t ldx, int32_t R, const double* d_w, int64_t N,
+                      double* d_u, void* stream);
+/* U[c,n] = sum_k W[k,c] X[k,n]  FP64 tensor-core (DMMA) tile GEMM; W [R,ldw], X [R,ldx], U [C,ldu] */
+int32_t pgd_eval_gemm_f64(pgd_handle_t h, const double* d_W, int64_t ldw, const double* d_X, int64_t ldx,
+                          int32_t R, int64_t C, int64_t N, double* d_U, int64_t ldu, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,355 @@
+"""ctypes binding of libpgdb200.so (the C ABI in include/pgd_b200.h).
+
+There is NO CPU fallback: every wrapper takes CUDA torch tensors and raises if the library is
+missing or a tensor is not on the GPU.  PyTorch is used for device memory and streams only.
+"""
+import ctypes
+import os
+import threading
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpgdb200.so")
+
+c_i32, c_i64, c_dbl, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
+
+# name -> argtypes (restype is int32 unless noted); mirrors include/pgd_b200.h one to one
+SIGNATURES = {
+    "pgd_abi_version": [],
+    "pgd_create": [c_i32, ctypes.POINTER(c_vp)],
+    "pgd_destroy": [c_vp],
+    "pgd_last_error": [c_vp],
+    "pgd_pattern_build_sync": [c_vp, c_vp, c_i64, c_i32, c_i64, ctypes.POINTER(c_i64), c_vp],
+    "pgd_pattern_export": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "pgd_vecmap_build_sync": [c_vp, c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_vp],
+    "pgd_elem_bilinear": [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "pgd_elem_linear": [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "pgd_gather_values": [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp],
+    "pgd_assemble_p1": [c_vp, c_vp, c_vp, c_i64, c_i32, c_dbl, c_dbl, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp],
+    "pgd_lincomb": [c_vp, c_i32, c_vp, c_vp, c_i64, c_vp, c_i32, c_vp],
+    "pgd_apply_dirichlet": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp],
+    "pgd_set_entries": [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp],
+    "pgd_spmv": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp],
+    "pgd_spmv_dot": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp],
+    "pgd_bilinear": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i32, c_vp],
+    "pgd_dot": [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp],
+    "pgd_panel_dots": [c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_vp, c_vp],
+    "pgd_pcg_sync": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_dbl, c_dbl, c_i32, c_i32, c_i32, c_i32, c_vp,
+                     ctypes.POINTER(c_i32), ctypes.POINTER(c_dbl), c_vp],
+    "pgd_banded_solve": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp],
+    "pgd_eval_weights": [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp],
+    "pgd_eval_gemv": [c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_vp, c_vp],
+    "pgd_eval_gemm_f64": [c_vp, c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i64, c_vp, c_i64, c_vp],
+}
+
+_lib = None
+_lock = threading.Lock()
+_handles = {}
+launch_count = 0  # kernels-launching C-ABI calls made through this module (for bench gpu_launches)
+
+
+class PGDB200Error(RuntimeError):
+    pass
+
+
+def load_library():
+    """dlopen libpgdb200.so; raises (never falls back) when it is missing."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise PGDB200Error(
+                f"{LIB_PATH} is missing: build it with `python -m pgdrome_b200._build` "
+                "(nvcc, sm_100a). pgdrome_b200 has no CPU fallback."
+            )
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = ctypes.c_char_p if name == "pgd_last_error" else c_i32
+        _lib = lib
+        return lib
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise PGDB200Error("pgdrome_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def handle(device=None):
+    """One library handle per device."""
+    require_cuda()
+    lib = load_library()
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index
+    if dev not in _handles:
+        h = c_vp()
+        rc = lib.pgd_create(dev, ctypes.byref(h))
+        if rc != 0:
+            raise PGDB200Error(f"pgd_create(device={dev}) failed with code {rc}")
+        _handles[dev] = h
+    return _handles[dev]
+
+
+def _stream():
+    return c_vp(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t, dtype=None):
+    """device pointer of a contiguous CUDA tensor (or NULL)."""
+    if t is None:
+        return c_vp(0)
+    if not t.is_cuda:
+        raise PGDB200Error("expected a CUDA tensor (no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        raise PGDB200Error(f"expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise PGDB200Error("expected a contiguous tensor")
+    return c_vp(t.data_ptr())
+
+
+def _check(rc, h, what):
+    global launch_count
+    launch_count += 1
+    if rc != 0:
+        msg = load_library().pgd_last_error(h)
+        raise PGDB200Error(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+
+F64, I32, I64 = torch.float64, torch.int32, torch.int64
+
+
+# ------------------------------------------------------------------------------ pattern
+def pattern_build(cell_dofs, n_dofs):
+    """cell_dofs int32 [n_cells, ndl] (cuda) -> rowptr, colidx, gptr, gidx."""
+    h, lib = handle(cell_dofs.device), load_library()
+    n_cells, ndl = cell_dofs.shape
+    nnz = c_i64(0)
+    _check(lib.pgd_pattern_build_sync(h, _p(cell_dofs, I32), n_cells, ndl, n_dofs, ctypes.byref(nnz), _stream()), h,
+           "pgd_pattern_build_sync")
+    dev = cell_dofs.device
+    rowptr = torch.empty(n_dofs + 1, dtype=I32, device=dev)
+    colidx = torch.empty(nnz.value, dtype=I32, device=dev)
+    gptr = torch.empty(nnz.value + 1, dtype=I64, device=dev)
+    gidx = torch.empty(n_cells * ndl * ndl, dtype=I32, device=dev)
+    _check(lib.pgd_pattern_export(h, _p(rowptr), _p(colidx), _p(gptr), _p(gidx), _stream()), h, "pgd_pattern_export")
+    return rowptr, colidx, gptr, gidx
+
+
+def vecmap_build(cell_dofs, n_dofs):
+    h, lib = handle(cell_dofs.device), load_library()
+    n_cells, ndl = cell_dofs.shape
+    vptr = torch.empty(n_dofs + 1, dtype=I64, device=cell_dofs.device)
+    vidx = torch.empty(n_cells * ndl, dtype=I32, device=cell_dofs.device)
+    _check(lib.pgd_vecmap_build_sync(h, _p(cell_dofs, I32), n_cells, ndl, n_dofs, _p(vptr), _p(vidx), _stream()), h,
+           "pgd_vecmap_build_sync")
+    return vptr, vidx
+
+
+# ------------------------------------------------------------------------------ assembly
+def elem_bilinear(coords, cell_verts, tdim, gdim, bs, nd, phi, dphi, qw, wq, T, out=None):
+    h, lib = handle(coords.device), load_library()
+    n_cells = cell_verts.shape[0]
+    nq = qw.numel()
+    ndl = nd * bs
+    if out is None:
+        out = torch.empty(n_cells * ndl * ndl, dtype=F64, device=coords.device)
+    _check(lib.pgd_elem_bilinear(h, _p(coords, F64), _p(cell_verts, I32), n_cells, tdim, gdim, bs, nd, nq, _p(phi, F64),
+                                 _p(dphi, F64), _p(qw, F64), _p(wq, F64) if wq is not None else c_vp(0), _p(T, F64),
+                                 _p(out), _stream()), h, "pgd_elem_bilinear")
+    return out
+
+
+def elem_linear(coords, cell_verts, tdim, gdim, bs, nd, phi, dphi, qw, wq, L, out=None):
+    h, lib = handle(coords.device), load_library()
+    n_cells = cell_verts.shape[0]
+    nq = qw.numel()
+    if out is None:
+        out = torch.empty(n_cells * nd * bs, dtype=F64, device=coords.device)
+    _check(lib.pgd_elem_linear(h, _p(coords, F64), _p(cell_verts, I32), n_cells, tdim, gdim, bs, nd, nq, _p(phi, F64),
+                               _p(dphi, F64), _p(qw, F64), _p(wq, F64) if wq is not None else c_vp(0), _p(L, F64),
+                               _p(out), _stream()), h, "pgd_elem_linear")
+    return out
+
+
+def gather_values(src, gptr, gidx, n_out, out=None):
+    h, lib = handle(src.device), load_library()
+    if out is None:
+        out = torch.empty(n_out, dtype=F64, device=src.device)
+    _check(lib.pgd_gather_values(h, _p(src, F64), _p(gptr, I64), _p(gidx, I32), n_out, _p(out), _stream()), h,
+           "pgd_gather_values")
+    return out
+
+
+def assemble_p1(coords, cell_verts, gdim, c_mass, c_stiff, c_adv, gptr, gidx, nnz, out=None):
+    h, lib = handle(coords.device), load_library()
+    if out is None:
+        out = torch.empty(nnz, dtype=F64, device=coords.device)
+    adv = None
+    if c_adv is not None:
+        adv = (c_dbl * 3)(*[float(v) for v in list(c_adv) + [0.0] * (3 - len(c_adv))])
+    _check(lib.pgd_assemble_p1(h, _p(coords, F64), _p(cell_verts, I32), cell_verts.shape[0], gdim, float(c_mass),
+                               float(c_stiff), ctypes.cast(adv, c_vp) if adv is not None else c_vp(0), _p(gptr, I64),
+                               _p(gidx, I32), nnz, _p(out), _stream()), h, "pgd_assemble_p1")
+    return out
+
+
+def lincomb(xs, coefs, out=None, accumulate=False):
+    """out = (out if accumulate) + sum_t coefs[t] * xs[t]; xs: list of equally sized CUDA tensors."""
+    n_terms = len(xs)
+    ref = out if out is not None else xs[0]
+    h, lib = handle(ref.device), load_library()
+    n = ref.numel()
+    if out is None:
+        out = torch.empty(n, dtype=F64, device=ref.device)
+    ptrs = (c_vp * max(1, n_terms))(*[_p(x, F64).value for x in xs])
+    cs = (c_dbl * max(1, n_terms))(*[float(c) for c in coefs])
+    _check(lib.pgd_lincomb(h, n_terms, ctypes.cast(ptrs, c_vp), ctypes.cast(cs, c_vp), n, _p(out, F64),
+                           1 if accumulate else 0, _stream()), h, "pgd_lincomb")
+    return out
+
+
+# ------------------------------------------------------------------------------ BC / sparse
+def apply_dirichlet(rowptr, colidx, values, b, bc_dofs, bc_vals=None):
+    if bc_dofs is None or bc_dofs.numel() == 0:
+        return
+    h, lib = handle(rowptr.device), load_library()
+    _check(lib.pgd_apply_dirichlet(h, _p(rowptr, I32), _p(colidx, I32), _p(values, F64) if values is not None else c_vp(0),
+                                   _p(b, F64) if b is not None else c_vp(0), _p(bc_dofs, I32),
+                                   _p(bc_vals, F64) if bc_vals is not None else c_vp(0), bc_dofs.numel(), _stream()), h,
+           "pgd_apply_dirichlet")
+
+
+def set_entries(x, idx, vals=None):
+    if idx is None or idx.numel() == 0:
+        return
+    h, lib = handle(x.device), load_library()
+    _check(lib.pgd_set_entries(h, _p(x, F64), _p(idx, I32), _p(vals, F64) if vals is not None else c_vp(0), idx.numel(),
+                               _stream()), h, "pgd_set_entries")
+
+
+def spmv(rowptr, colidx, values, x, y=None, lpr=0):
+    h, lib = handle(x.device), load_library()
+    n = rowptr.numel() - 1
+    if y is None:
+        y = torch.empty(n, dtype=F64, device=x.device)
+    _check(lib.pgd_spmv(h, _p(rowptr, I32), _p(colidx, I32), _p(values, F64), _p(x, F64), _p(y, F64), n, lpr, _stream()), h,
+           "pgd_spmv")
+    return y
+
+
+def spmv_dot(rowptr, colidx, values, x, w, y=None, out=None, lpr=0):
+    h, lib = handle(x.device), load_library()
+    n = rowptr.numel() - 1
+    if y is None:
+        y = torch.empty(n, dtype=F64, device=x.device)
+    if out is None:
+        out = torch.empty(1, dtype=F64, device=x.device)
+    _check(lib.pgd_spmv_dot(h, _p(rowptr, I32), _p(colidx, I32), _p(values, F64), _p(x, F64), _p(y, F64), _p(w, F64),
+                            _p(out, F64), n, lpr, _stream()), h, "pgd_spmv_dot")
+    return y, out
+
+
+def bilinear(rowptr, colidx, values, x, y, out=None, lpr=0):
+    """out[0] = x^T A y (device scalar)."""
+    h, lib = handle(x.device), load_library()
+    n = rowptr.numel() - 1
+    if out is None:
+        out = torch.empty(1, dtype=F64, device=x.device)
+    _check(lib.pgd_bilinear(h, _p(rowptr, I32), _p(colidx, I32), _p(values, F64), _p(x, F64), _p(y, F64), n, _p(out, F64),
+                            lpr, _stream()), h, "pgd_bilinear")
+    return out
+
+
+def dot(x, y, out=None):
+    h, lib = handle(x.device), load_library()
+    if out is None:
+        out = torch.empty(1, dtype=F64, device=x.device)
+    _check(lib.pgd_dot(h, _p(x, F64), _p(y, F64), x.numel(), _p(out, F64), _stream()), h, "pgd_dot")
+    return out
+
+
+def panel_dots(P, n_vecs, x, out=None):
+    """P [>=n_vecs, ld] row-major; out[m] = P[m,:n] . x."""
+    h, lib = handle(x.device), load_library()
+    if out is None:
+        out = torch.empty(n_vecs, dtype=F64, device=x.device)
+    _check(lib.pgd_panel_dots(h, _p(P, F64), P.stride(0) if P.dim() == 2 else x.numel(), n_vecs, _p(x, F64), x.numel(),
+                              _p(out, F64), _stream()), h, "pgd_panel_dots")
+    return out
+
+
+# ------------------------------------------------------------------------------ solves
+def pcg(rowptr, colidx, values, b, x=None, rtol=1e-12, atol=0.0, maxit=20000, check_every=50, block=1, lpr=0, work=None):
+    h, lib = handle(b.device), load_library()
+    n = b.numel()
+    if x is None:
+        x = torch.empty(n, dtype=F64, device=b.device)
+    if work is None or work.numel() < (5 + block) * n:
+        work = torch.empty((5 + block) * n, dtype=F64, device=b.device)
+    iters, relres = c_i32(0), c_dbl(0.0)
+    _check(lib.pgd_pcg_sync(h, _p(rowptr, I32), _p(colidx, I32), _p(values, F64), _p(b, F64), _p(x, F64), n, rtol, atol,
+                            maxit, check_every, block, lpr, _p(work, F64), ctypes.byref(iters), ctypes.byref(relres),
+                            _stream()), h, "pgd_pcg_sync")
+    return x, iters.value, relres.value
+
+
+def banded_solve(rowptr, colidx, values, b, perm, kl, ku, x=None, work=None, info=None):
+    h, lib = handle(b.device), load_library()
+    n = b.numel()
+    if x is None:
+        x = torch.empty(n, dtype=F64, device=b.device)
+    need = (2 * kl + ku + 3) * n
+    if work is None or work.numel() < need:
+        work = torch.empty(need, dtype=F64, device=b.device)
+    if info is None:
+        info = torch.zeros(1, dtype=I32, device=b.device)
+    _check(lib.pgd_banded_solve(h, _p(rowptr, I32), _p(colidx, I32), _p(values, F64), _p(b, F64), _p(x, F64), n,
+                                _p(perm, I32), kl, ku, _p(work, F64), _p(info, I32), _stream()), h, "pgd_banded_solve")
+    return x, info
+
+
+# ------------------------------------------------------------------------------ evaluate
+def eval_weights(xs, cds, Phis, degs, R, points, out=None):
+    """xs[i] [nc_i+1] f64, cds[i] [nc_i, deg_i+1] i32, Phis[i] [>=R, ld_i] f64, points [C, n_free]."""
+    n_free = len(xs)
+    dev = points.device
+    h, lib = handle(dev), load_library()
+    C = points.shape[0]
+    if out is None:
+        out = torch.empty((R, C), dtype=F64, device=dev)
+    flag = torch.zeros(1, dtype=I32, device=dev)
+    m = max(1, n_free)
+    a_xs = (c_vp * m)(*[_p(t, F64).value for t in xs])
+    a_cd = (c_vp * m)(*[_p(t, I32).value for t in cds])
+    a_ph = (c_vp * m)(*[_p(t, F64).value for t in Phis])
+    a_nc = (c_i32 * m)(*[t.numel() - 1 for t in xs])
+    a_dg = (c_i32 * m)(*[int(d) for d in degs])
+    a_ld = (c_i64 * m)(*[t.stride(0) for t in Phis])
+    _check(lib.pgd_eval_weights(h, n_free, ctypes.cast(a_xs, c_vp), ctypes.cast(a_cd, c_vp), ctypes.cast(a_ph, c_vp),
+                                ctypes.cast(a_nc, c_vp), ctypes.cast(a_dg, c_vp), ctypes.cast(a_ld, c_vp), R,
+                                _p(points, F64), C, _p(out, F64), _p(flag, I32), _stream()), h, "pgd_eval_weights")
+    return out, flag
+
+
+def eval_gemv(X, R, w, out=None):
+    """X [>=R, ld] row-major modes; out[n] = sum_k X[k, n] w[k]."""
+    h, lib = handle(X.device), load_library()
+    N = X.shape[1]
+    if out is None:
+        out = torch.empty(N, dtype=F64, device=X.device)
+    _check(lib.pgd_eval_gemv(h, _p(X, F64), X.stride(0), R, _p(w, F64), N, _p(out, F64), _stream()), h, "pgd_eval_gemv")
+    return out
+
+
+def eval_gemm(W, X, R, out=None):
+    """W [>=R, C], X [>=R, N] -> U [C, N] = W^T X on the FP64 tensor cores."""
+    h, lib = handle(X.device), load_library()
+    C, N = W.shape[1], X.shape[1]
+    if out is None:
+        out = torch.empty((C, N), dtype=F64, device=X.device)
+    _check(lib.pgd_eval_gemm_f64(h, _p(W, F64), W.stride(0), _p(X, F64), X.stride(0), R, C, N, _p(out, F64), out.stride(0),
+                                 _stream()), h, "pgd_eval_gemm_f64")
+    return out

@@ -1,0 +1,176 @@
+"""Device-resident data of a FunctionSpace and the separated-form *atoms* assembled on it.
+
+An atom is one constant-coefficient bilinear form  int w(x) sum T[iv,jv,iu,ju] D_jv v_iv D_ju u_iu
+(slot 0 = value, 1+m = d/dx_m) assembled ONCE into the space's fixed CSR pattern; the per-mode
+operator of the fixed-point sweep is then  A_d = sum_k c_k K_{d,k}  (``_lib.lincomb`` over the value
+arrays, or the fused P1 kernel ``_lib.assemble_p1``), cf. SURVEY.md 7.1 and
+pgdrome/solver.py:547-556.  All arithmetic happens in libpgdb200.so; this module only stages the
+host tables (basis tabulation, quadrature, coefficient samples) that FFC would have generated.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .fem import lagrange_interval_basis, reference_nodes, simplex_quadrature, tabulate_lagrange
+
+
+def _dev():
+    _lib.require_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _up(a, dtype):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(_dev())
+
+
+class DeviceSpace:
+    """GPU mirror of a FunctionSpace: mesh arrays, CSR pattern, gather lists, cached atoms."""
+
+    def __init__(self, space):
+        self.space = space
+        m = space.mesh()
+        self.coords = _up(m.coordinates(), torch.float64)
+        self.cell_verts = _up(m.cells(), torch.int32)
+        self.cell_dofs = _up(space.cell_dofs, torch.int32)
+        self.n_dofs, self.ndl = space.n_dofs, space.ndl
+        self._pattern = None
+        self._vecmap = None
+        self._tabs = {}
+        self._facet = {}
+        self.atoms = {}  # key -> values tensor
+        self.band = None
+
+    # ---- structure
+    @property
+    def pattern(self):
+        if self._pattern is None:
+            self._pattern = _lib.pattern_build(self.cell_dofs, self.n_dofs)
+        return self._pattern
+
+    @property
+    def nnz(self):
+        return self.pattern[1].numel()
+
+    @property
+    def vecmap(self):
+        if self._vecmap is None:
+            self._vecmap = _lib.vecmap_build(self.cell_dofs, self.n_dofs)
+        return self._vecmap
+
+    def tables(self, qdeg, tdim=None, degree=None):
+        tdim = self.space.mesh().tdim if tdim is None else tdim
+        degree = self.space.degree if degree is None else degree
+        key = (tdim, degree, int(qdeg))
+        if key not in self._tabs:
+            pts, w = simplex_quadrature(tdim, qdeg)
+            phi, dphi = tabulate_lagrange(tdim, degree, pts)
+            self._tabs[key] = dict(pts=pts, w=w, phi=_up(phi, torch.float64), dphi=_up(dphi, torch.float64),
+                                   qw=_up(w, torch.float64), nq=len(w))
+        return self._tabs[key]
+
+    # ---- coefficient sampling (host, set-up): per-cell P_p interpolant at the quadrature points
+    def sample_weight(self, fn, wdeg, pts, cells=None, tdim=None):
+        """fn(x[..., gdim]) -> values; returns float64 [n_cells, nq] (host)."""
+        m = self.space.mesh()
+        cells = m.cells() if cells is None else cells
+        tdim = m.tdim if tdim is None else tdim
+        X = m.coordinates()[cells]  # [e, tdim+1, g]
+        pts = np.asarray(pts).reshape(-1, tdim)
+        if wdeg == 0:
+            xc = X.mean(axis=1)
+            return np.repeat(np.asarray(fn(xc), dtype=np.float64).reshape(-1, 1), len(pts), axis=1)
+        if tdim == 1:
+            t, B = lagrange_interval_basis(wdeg, pts[:, 0])
+            xn = X[:, 0, None, :] * (1 - t)[None, :, None] + X[:, 1, None, :] * t[None, :, None]
+            return np.asarray(fn(xn), dtype=np.float64) @ B.T
+        if wdeg > 2:
+            raise NotImplementedError("coefficient degree > 2 on a 2-D/3-D mesh")
+        ref = reference_nodes(tdim, wdeg)
+        lam = np.column_stack([1 - ref.sum(axis=1), ref])
+        xn = np.einsum("na,eag->eng", lam, X)
+        phi, _ = tabulate_lagrange(tdim, wdeg, pts)
+        return np.asarray(fn(xn), dtype=np.float64) @ phi.T
+
+    # ---- atoms
+    def assemble_bilinear(self, T, weight=None, wdeg=0):
+        """values [nnz] of the atom with form tensor T and optional coefficient weight(x)."""
+        s = self.space
+        m = s.mesh()
+        g = m.gdim
+        T = np.asarray(T, dtype=np.float64).reshape(s.bs, g + 1, s.bs, g + 1)
+        # polynomial degree of the integrand on an affine simplex
+        dv = s.degree if np.any(T[:, 0, :, :] != 0) else s.degree - 1
+        du = s.degree if np.any(T[:, :, :, 0] != 0) else s.degree - 1
+        qdeg = dv + du + (wdeg if weight is not None else 0)
+        qdeg = max(qdeg, 1)
+        tab = self.tables(qdeg)
+        wq = None
+        if weight is not None:
+            wq = _up(self.sample_weight(weight, wdeg, tab["pts"]), torch.float64)
+        Ae = _lib.elem_bilinear(self.coords, self.cell_verts, m.tdim, g, s.bs, s.nd, tab["phi"], tab["dphi"], tab["qw"], wq,
+                                _up(T, torch.float64))
+        rowptr, colidx, gptr, gidx = self.pattern
+        return _lib.gather_values(Ae, gptr, gidx, colidx.numel())
+
+    def assemble_linear(self, L, weight=None, wdeg=0):
+        s = self.space
+        m = s.mesh()
+        g = m.gdim
+        L = np.asarray(L, dtype=np.float64).reshape(s.bs, g + 1)
+        dv = s.degree if np.any(L[:, 0] != 0) else s.degree - 1
+        qdeg = max(dv + (wdeg if weight is not None else 0), 1)
+        tab = self.tables(qdeg)
+        wq = None
+        if weight is not None:
+            wq = _up(self.sample_weight(weight, wdeg, tab["pts"]), torch.float64)
+        be = _lib.elem_linear(self.coords, self.cell_verts, m.tdim, g, s.bs, s.nd, tab["phi"], tab["dphi"], tab["qw"], wq,
+                              _up(L, torch.float64))
+        vptr, vidx = self.vecmap
+        return _lib.gather_values(be, vptr, vidx, self.n_dofs)
+
+    # ---- boundary-facet integrals (ds(id)): facets as embedded (tdim-1)-simplices
+    def facet_set(self, key, cell, loc):
+        if key not in self._facet:
+            s = self.space
+            m = s.mesh()
+            fverts = m.facet_vertices(cell, loc).astype(np.int32)
+            fnodes = s.facet_nodes(cell, loc)
+            fdofs = (fnodes[:, :, None] * s.bs + np.arange(s.bs)[None, None, :]).reshape(len(fnodes), -1).astype(np.int32)
+            d = dict(verts=fverts, verts_d=_up(fverts, torch.int32), n=len(fverts), nd=fnodes.shape[1])
+            if len(fverts):
+                d["dofs_d"] = _up(fdofs, torch.int32)
+                d["vecmap"] = _lib.vecmap_build(d["dofs_d"], self.n_dofs)
+            self._facet[key] = d
+        return self._facet[key]
+
+    def assemble_facet_linear(self, key, cell, loc, Lvec, weight=None, wdeg=0):
+        """b[dof] = int_facets w * sum_i Lvec[i] v_i ds  (value slots only)."""
+        s = self.space
+        m = s.mesh()
+        fs = self.facet_set(key, cell, loc)
+        out = torch.zeros(self.n_dofs, dtype=torch.float64, device=self.coords.device)
+        if fs["n"] == 0:
+            return out
+        ft = m.tdim - 1
+        if ft == 0:
+            raise NotImplementedError("point 'facet' integrals on 1-D meshes")
+        qdeg = max(s.degree + (wdeg if weight is not None else 0), 1)
+        tab = self.tables(qdeg, tdim=ft)
+        wq = None
+        if weight is not None:
+            wq = _up(self.sample_weight(weight, wdeg, tab["pts"], cells=fs["verts"], tdim=ft), torch.float64)
+        L = np.zeros((s.bs, m.gdim + 1))
+        L[:, 0] = np.asarray(Lvec, dtype=np.float64).reshape(s.bs)
+        be = _lib.elem_linear(self.coords, fs["verts_d"], ft, m.gdim, s.bs, fs["nd"], tab["phi"], tab["dphi"], tab["qw"], wq,
+                              _up(L, torch.float64))
+        vptr, vidx = fs["vecmap"]
+        return _lib.gather_values(be, vptr, vidx, self.n_dofs, out=out)
+
+
+def device_space(space):
+    """Lazily attach (and cache) the DeviceSpace of a FunctionSpace."""
+    ds = space._dev.get("device_space")
+    if ds is None:
+        ds = DeviceSpace(space)
+        space._dev["device_space"] = ds
+    return ds

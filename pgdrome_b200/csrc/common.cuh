@@ -1,0 +1,109 @@
+// Internal helpers shared by the libpgdb200 translation units (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/pgd_b200.h"
+
+#define PGD_MAX_PARTIALS (1 << 20)
+#define PGD_MAX_COUNTERS 4096
+
+struct pgd_ctx {
+    int device;
+    int sm_count;
+    char err[512];
+    double* partials;        // [PGD_MAX_PARTIALS] scratch for two-stage reductions
+    unsigned int* counters;  // [PGD_MAX_COUNTERS] "last block done" tickets, always left at 0
+    double* scalars;         // [64] PCG scalars
+    int* flags;              // [16] PCG flags / iteration counter
+    // pending sparsity pattern (between pattern_build_sync and pattern_export)
+    int32_t* pat_rowptr;
+    int32_t* pat_colidx;
+    int64_t* pat_gptr;
+    int32_t* pat_gidx;
+    int64_t pat_nnz, pat_ndofs, pat_ncontrib;
+};
+
+void pgd_free_pattern(pgd_ctx* h);
+
+#define PGD_CHECK_HANDLE(h) \
+    if (!(h)) return -1;
+
+#define PGD_ARG(h, cond, msg)                                      \
+    do {                                                           \
+        if (!(cond)) {                                             \
+            snprintf((h)->err, sizeof((h)->err), "%s: %s", __func__, msg); \
+            return -2;                                             \
+        }                                                          \
+    } while (0)
+
+#define PGD_CUDA(h, expr)                                                                   \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            snprintf((h)->err, sizeof((h)->err), "%s: %s -> %s", __func__, #expr, cudaGetErrorString(_e)); \
+            return (int32_t)_e;                                                             \
+        }                                                                                   \
+    } while (0)
+
+#define PGD_LAUNCH_OK(h) PGD_CUDA(h, cudaGetLastError())
+
+static inline int pgd_set_device(pgd_ctx* h) { return (int)cudaSetDevice(h->device); }
+
+static inline unsigned int pgd_blocks(int64_t n, int per_block) { return (unsigned int)((n + per_block - 1) / per_block); }
+
+// ----------------------------------------------------------------------------- device helpers
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum over the block; result valid in thread 0. blockDim.x multiple of 32, <= 1024.
+__device__ __forceinline__ double block_sum(double v) {
+    __shared__ double sh[32];
+    __syncthreads();  // protect sh across consecutive calls
+    v = warp_sum(v);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.0;
+    if (w == 0) v = warp_sum(v);
+    return v;
+}
+
+// Deterministic grid reduction of NV values per block: every block deposits its partials, the
+// last block to arrive sums them in a fixed order and stores out[0..NV). `counter` returns to 0.
+// part layout: part[v * gridsize + block]. Works for 1-D grids (gridsize = gridDim.x) or a row
+// of a 2-D grid when the caller passes its own base pointers.
+template <int NV>
+__device__ __forceinline__ void grid_sum_finish(const double (&v)[NV], double* part, unsigned int* counter,
+                                                double* out, unsigned int bid, unsigned int gridsize) {
+    __shared__ bool s_last;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) part[(size_t)k * gridsize + bid] = v[k];
+        __threadfence();
+        unsigned int t = atomicAdd(counter, 1u);
+        s_last = (t == gridsize - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double s = 0.0;
+            for (unsigned int i = threadIdx.x; i < gridsize; i += blockDim.x) s += __ldcg(&part[(size_t)k * gridsize + i]);
+            s = block_sum(s);
+            if (threadIdx.x == 0) out[k] = s;
+        }
+        if (threadIdx.x == 0) *counter = 0u;
+    }
+}
+
+// streaming loads for data that is touched once per kernel (matrix values / column indices)
+__device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
+__device__ __forceinline__ int ld_stream(const int* p) { return __ldcs(p); }

@@ -1,0 +1,142 @@
+// Handle lifecycle + small elementwise kernels (lincomb, set_entries, dot, panel dots).
+#include "common.cuh"
+
+extern "C" int32_t pgd_abi_version(void) { return 1; }
+
+extern "C" int32_t pgd_create(int32_t device, pgd_handle_t* out) {
+    if (!out) return -1;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) return (int32_t)e;
+    if (device < 0 || device >= count) return -2;
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return (int32_t)e;
+    pgd_ctx* h = new pgd_ctx();
+    memset(h, 0, sizeof(*h));
+    h->device = device;
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if ((e = cudaMalloc(&h->partials, sizeof(double) * PGD_MAX_PARTIALS)) != cudaSuccess ||
+        (e = cudaMalloc(&h->counters, sizeof(unsigned int) * PGD_MAX_COUNTERS)) != cudaSuccess ||
+        (e = cudaMalloc(&h->scalars, sizeof(double) * 64)) != cudaSuccess ||
+        (e = cudaMalloc(&h->flags, sizeof(int) * 16)) != cudaSuccess) {
+        delete h;
+        return (int32_t)e;
+    }
+    cudaMemset(h->counters, 0, sizeof(unsigned int) * PGD_MAX_COUNTERS);
+    cudaMemset(h->scalars, 0, sizeof(double) * 64);
+    cudaMemset(h->flags, 0, sizeof(int) * 16);
+    cudaDeviceSynchronize();
+    *out = h;
+    return 0;
+}
+
+extern "C" int32_t pgd_destroy(pgd_handle_t h) {
+    PGD_CHECK_HANDLE(h);
+    cudaSetDevice(h->device);
+    pgd_free_pattern(h);
+    cudaFree(h->partials);
+    cudaFree(h->counters);
+    cudaFree(h->scalars);
+    cudaFree(h->flags);
+    delete h;
+    return 0;
+}
+
+extern "C" const char* pgd_last_error(pgd_handle_t h) { return h ? h->err : "null handle"; }
+
+// ----------------------------------------------------------------------------- lincomb
+#define LC_MAX 24
+struct LcArgs {
+    const double* x[LC_MAX];
+    double c[LC_MAX];
+    int n_terms;
+};
+
+__global__ void __launch_bounds__(256) k_lincomb(LcArgs a, int64_t n, double* __restrict__ out, int accumulate) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        double s = accumulate ? out[i] : 0.0;
+#pragma unroll 4
+        for (int t = 0; t < a.n_terms; ++t) s += a.c[t] * __ldg(&a.x[t][i]);
+        out[i] = s;
+    }
+}
+
+extern "C" int32_t pgd_lincomb(pgd_handle_t h, int32_t n_terms, const double* const* h_xs, const double* h_coefs,
+                               int64_t n, double* d_out, int32_t accumulate, void* stream) {
+    PGD_CHECK_HANDLE(h);
+    PGD_ARG(h, n_terms >= 0 && n >= 0 && d_out, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) return 0;
+    if (n_terms == 0 && !accumulate) {
+        PGD_CUDA(h, cudaMemsetAsync(d_out, 0, sizeof(double) * n, st));
+        return 0;
+    }
+    unsigned int blocks = pgd_blocks(n, 256);
+    unsigned int cap = (unsigned int)h->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    for (int t0 = 0; t0 < n_terms; t0 += LC_MAX) {
+        LcArgs a;
+        a.n_terms = (n_terms - t0 < LC_MAX) ? (n_terms - t0) : LC_MAX;
+        for (int t = 0; t < a.n_terms; ++t) {
+            a.x[t] = h_xs[t0 + t];
+            a.c[t] = h_coefs[t0 + t];
+        }
+        k_lincomb<<<blocks, 256, 0, st>>>(a, n, d_out, (accumulate || t0 > 0) ? 1 : 0);
+        PGD_LAUNCH_OK(h);
+    }
+    return 0;
+}
+
+// ----------------------------------------------------------------------------- set_entries
+__global__ void k_set_entries(double* x, const int32_t* idx, const double* vals, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[idx[i]] = vals ? vals[i] : 0.0;
+}
+
+extern "C" int32_t pgd_set_entries(pgd_handle_t h, double* d_x, const int32_t* d_idx, const double* d_vals,
+                                   int64_t n_idx, void* stream) {
+    PGD_CHECK_HANDLE(h);
+    if (n_idx <= 0) return 0;
+    k_set_entries<<<pgd_blocks(n_idx, 256), 256, 0, (cudaStream_t)stream>>>(d_x, d_idx, d_vals, n_idx);
+    PGD_LAUNCH_OK(h);
+    return 0;
+}
+
+// ----------------------------------------------------------------------------- dot / panel dots
+// grid (gx, n_vecs): block (bx, m) reduces a slice of P[m,:].x ; last block of row m finishes.
+__global__ void __launch_bounds__(256) k_panel_dots(const double* __restrict__ P, int64_t ld, const double* __restrict__ x,
+                                                    int64_t n, double* out, double* part, unsigned int* counters) {
+    const unsigned int m = blockIdx.y;
+    const double* row = P + (size_t)m * ld;
+    double s = 0.0;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) s += __ldcs(&row[i]) * __ldg(&x[i]);
+    s = block_sum(s);
+    double v[1] = {s};
+    grid_sum_finish<1>(v, part + (size_t)m * gridDim.x, counters + m, out + m, blockIdx.x, gridDim.x);
+}
+
+extern "C" int32_t pgd_panel_dots(pgd_handle_t h, const double* d_P, int64_t ld, int32_t n_vecs, const double* d_x,
+                                  int64_t n, double* d_out, void* stream) {
+    PGD_CHECK_HANDLE(h);
+    PGD_ARG(h, n_vecs >= 0 && n >= 0 && ld >= n, "bad arguments");
+    if (n_vecs == 0) return 0;
+    PGD_ARG(h, n_vecs <= PGD_MAX_COUNTERS, "too many vectors");
+    unsigned int gx = pgd_blocks(n, 256 * 8);
+    unsigned int cap = (unsigned int)(PGD_MAX_PARTIALS / n_vecs);
+    unsigned int want = (unsigned int)(h->sm_count * 8 / n_vecs) + 1;
+    if (gx > want) gx = want;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, (unsigned int)n_vecs);
+    k_panel_dots<<<grid, 256, 0, (cudaStream_t)stream>>>(d_P, ld, d_x, n, d_out, h->partials, h->counters);
+    PGD_LAUNCH_OK(h);
+    return 0;
+}
+
+extern "C" int32_t pgd_dot(pgd_handle_t h, const double* d_x, const double* d_y, int64_t n, double* d_out, void* stream) {
+    return pgd_panel_dots(h, d_x, n, 1, d_y, n, d_out, stream);
+}

@@ -1,0 +1,291 @@
+// Jacobi / node-block-Jacobi preconditioned CG, two kernels per iteration, all scalars and the
+// convergence flag on the device (the host polls once per `check_every` iterations).
+//   k_pcg_spmv  : p_new = z + beta p_old (fused into the gather), q = A p_new, pq = p_new.q
+//   k_pcg_update: alpha = rz/pq; x += alpha p; r -= alpha q; z = M^-1 r; rz' = r.z, rr = r.r;
+//                 last block: rotates rz, bumps the iteration counter, sets DONE.
+// Reductions are fixed-order two-stage sums (bitwise reproducible).
+#include "common.cuh"
+
+enum { S_RZ_OLD = 0, S_RZ_NEW = 1, S_PQ = 2, S_RR = 3, S_BB = 4, S_TOL2 = 5, S_TMP = 8 };
+enum { F_DONE = 0, F_ITER = 1, F_BAD = 2 };
+
+template <int BS>
+__device__ __forceinline__ void invert_block(const double (&B)[BS][BS], double (&I)[BS][BS]) {
+    if constexpr (BS == 1) {
+        I[0][0] = 1.0 / B[0][0];
+    } else if constexpr (BS == 2) {
+        double id = 1.0 / (B[0][0] * B[1][1] - B[0][1] * B[1][0]);
+        I[0][0] = B[1][1] * id;
+        I[0][1] = -B[0][1] * id;
+        I[1][0] = -B[1][0] * id;
+        I[1][1] = B[0][0] * id;
+    } else {
+        double c00 = B[1][1] * B[2][2] - B[1][2] * B[2][1];
+        double c01 = B[1][2] * B[2][0] - B[1][0] * B[2][2];
+        double c02 = B[1][0] * B[2][1] - B[1][1] * B[2][0];
+        double id = 1.0 / (B[0][0] * c00 + B[0][1] * c01 + B[0][2] * c02);
+        I[0][0] = c00 * id;
+        I[1][0] = c01 * id;
+        I[2][0] = c02 * id;
+        I[0][1] = (B[0][2] * B[2][1] - B[0][1] * B[2][2]) * id;
+        I[1][1] = (B[0][0] * B[2][2] - B[0][2] * B[2][0]) * id;
+        I[2][1] = (B[0][1] * B[2][0] - B[0][0] * B[2][1]) * id;
+        I[0][2] = (B[0][1] * B[1][2] - B[0][2] * B[1][1]) * id;
+        I[1][2] = (B[0][2] * B[1][0] - B[0][0] * B[1][2]) * id;
+        I[2][2] = (B[0][0] * B[1][1] - B[0][1] * B[1][0]) * id;
+    }
+}
+
+__device__ __forceinline__ double csr_entry(const int32_t* rowptr, const int32_t* colidx, const double* vals, int r, int c) {
+    int lo = rowptr[r], hi = rowptr[r + 1] - 1;
+    while (lo <= hi) {
+        int mid = (lo + hi) >> 1;
+        int cc = colidx[mid];
+        if (cc == c) return vals[mid];
+        if (cc < c) lo = mid + 1;
+        else hi = mid - 1;
+    }
+    return 0.0;
+}
+
+// thread per node: Minv (BSxBS per node), r = b, z = Minv r, x = 0, p0 = p1 = 0; rz, bb
+template <int BS>
+__global__ void __launch_bounds__(256) k_pcg_init(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                                  const double* __restrict__ vals, const double* __restrict__ b,
+                                                  double* __restrict__ x, double* r, double* z, double* p0, double* p1,
+                                                  double* minv, int64_t n_nodes, double rtol, double atol, double* sc,
+                                                  int* fl, double* part, unsigned int* counter) {
+    double rz = 0.0, bb = 0.0;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t nd = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; nd < n_nodes; nd += stride) {
+        double B[BS][BS], I[BS][BS], rb[BS];
+#pragma unroll
+        for (int i = 0; i < BS; ++i)
+#pragma unroll
+            for (int k = 0; k < BS; ++k) B[i][k] = csr_entry(rowptr, colidx, vals, (int)(nd * BS + i), (int)(nd * BS + k));
+        invert_block<BS>(B, I);
+#pragma unroll
+        for (int i = 0; i < BS; ++i) {
+            rb[i] = b[nd * BS + i];
+#pragma unroll
+            for (int k = 0; k < BS; ++k) minv[(nd * BS + i) * BS + k] = I[i][k];
+        }
+#pragma unroll
+        for (int i = 0; i < BS; ++i) {
+            double zi = 0.0;
+#pragma unroll
+            for (int k = 0; k < BS; ++k) zi += I[i][k] * rb[k];
+            int64_t d = nd * BS + i;
+            r[d] = rb[i];
+            z[d] = zi;
+            x[d] = 0.0;
+            p0[d] = 0.0;
+            p1[d] = 0.0;
+            rz += rb[i] * zi;
+            bb += rb[i] * rb[i];
+        }
+    }
+    rz = block_sum(rz);
+    bb = block_sum(bb);
+    double v[2] = {rz, bb};
+    grid_sum_finish<2>(v, part, counter, sc + S_TMP, blockIdx.x, gridDim.x);
+    // the block that finished the reduction publishes the scalars
+    if (threadIdx.x == 0) {
+        // grid_sum_finish left s_last in shared memory of the last block only; recompute cheaply:
+        // the last block is the one that reset the counter, detectable through sc[S_TMP] being final.
+    }
+}
+
+// single-thread epilogue of init (keeps k_pcg_init simple and race-free)
+__global__ void k_pcg_init_fin(double* sc, int* fl, double rtol, double atol) {
+    double rz = sc[S_TMP], bb = sc[S_TMP + 1];
+    sc[S_RZ_OLD] = 1.0;
+    sc[S_RZ_NEW] = rz;
+    sc[S_PQ] = 1.0;
+    sc[S_RR] = bb;
+    sc[S_BB] = bb;
+    double t2 = rtol * rtol * bb;
+    if (atol * atol > t2) t2 = atol * atol;
+    sc[S_TOL2] = t2;
+    fl[F_ITER] = 0;
+    fl[F_BAD] = 0;
+    fl[F_DONE] = (bb <= t2 || bb == 0.0) ? 1 : 0;
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(256) k_pcg_spmv(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                                  const double* __restrict__ vals, const double* __restrict__ z,
+                                                  double* pa, double* pb, double* __restrict__ q, int64_t n,
+                                                  const double* sc, const int* fl, double* sc_out, double* part,
+                                                  unsigned int* counter) {
+    if (fl[F_DONE]) return;
+    const int it = fl[F_ITER];
+    const double beta = (it == 0) ? 0.0 : sc[S_RZ_NEW] / sc[S_RZ_OLD];
+    const double* __restrict__ p_old = (it & 1) ? pb : pa;
+    double* __restrict__ p_new = (it & 1) ? pa : pb;
+    constexpr int RPB = 256 / LPR;
+    const int lane = threadIdx.x % LPR;
+    const int sub = threadIdx.x / LPR;
+    double acc = 0.0;
+    for (int64_t base = (int64_t)blockIdx.x * RPB; base < n; base += (int64_t)gridDim.x * RPB) {
+        int64_t row = base + sub;
+        int k0 = 0, k1 = 0;
+        if (row < n) {
+            k0 = __ldg(&rowptr[row]);
+            k1 = __ldg(&rowptr[row + 1]);
+        }
+        double s = 0.0;
+        for (int k = k0 + lane; k < k1; k += LPR) {
+            int c = ld_stream(&colidx[k]);
+            double pj = fma(beta, p_old[c], z[c]);
+            s = fma(ld_stream(&vals[k]), pj, s);
+        }
+#pragma unroll
+        for (int o = LPR >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, LPR);
+        if (row < n && lane == 0) {
+            double pi = fma(beta, p_old[row], z[row]);
+            p_new[row] = pi;
+            q[row] = s;
+            acc = fma(pi, s, acc);
+        }
+    }
+    acc = block_sum(acc);
+    double v[1] = {acc};
+    grid_sum_finish<1>(v, part, counter, sc_out + S_PQ, blockIdx.x, gridDim.x);
+}
+
+template <int BS>
+__global__ void __launch_bounds__(256) k_pcg_update(double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
+                                                    const double* pa, const double* pb, const double* __restrict__ q,
+                                                    const double* __restrict__ minv, int64_t n_nodes, double* sc, int* fl,
+                                                    double* part, unsigned int* counter) {
+    if (fl[F_DONE]) return;
+    const int it = fl[F_ITER];
+    const double* __restrict__ p = (it & 1) ? pa : pb;  // the p_new written by k_pcg_spmv
+    const double rz_cur = sc[S_RZ_NEW];
+    const double alpha = rz_cur / sc[S_PQ];
+    double rz = 0.0, rr = 0.0;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t nd = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; nd < n_nodes; nd += stride) {
+        double rn[BS];
+#pragma unroll
+        for (int i = 0; i < BS; ++i) {
+            int64_t d = nd * BS + i;
+            x[d] = fma(alpha, p[d], x[d]);
+            rn[i] = fma(-alpha, q[d], r[d]);
+            r[d] = rn[i];
+            rr = fma(rn[i], rn[i], rr);
+        }
+#pragma unroll
+        for (int i = 0; i < BS; ++i) {
+            double zi = 0.0;
+#pragma unroll
+            for (int k = 0; k < BS; ++k) zi = fma(__ldg(&minv[(nd * BS + i) * BS + k]), rn[k], zi);
+            z[nd * BS + i] = zi;
+            rz = fma(rn[i], zi, rz);
+        }
+    }
+    rz = block_sum(rz);
+    rr = block_sum(rr);
+    double v[2] = {rz, rr};
+    grid_sum_finish<2>(v, part, counter, sc + S_TMP, blockIdx.x, gridDim.x);
+}
+
+// single-thread scalar rotation after k_pcg_update (runs as its own tiny launch: keeps every
+// block of the update kernel free to read S_RZ_NEW / S_PQ without ordering hazards)
+__global__ void k_pcg_rotate(double* sc, int* fl) {
+    if (fl[F_DONE]) return;
+    double rz_next = sc[S_TMP], rr = sc[S_TMP + 1];
+    sc[S_RZ_OLD] = sc[S_RZ_NEW];
+    sc[S_RZ_NEW] = rz_next;
+    sc[S_RR] = rr;
+    fl[F_ITER] = fl[F_ITER] + 1;
+    if (!(rr > sc[S_TOL2])) fl[F_DONE] = 1;       // also stops on NaN
+    if (!(rr == rr) || !(rz_next == rz_next)) fl[F_BAD] = 1;
+}
+
+template <int BS>
+static int32_t run_pcg(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const double* va, const double* b, double* x,
+                       int64_t n, double rtol, double atol, int maxit, int check_every, int lpr, double* work,
+                       int32_t* h_iters, double* h_relres, cudaStream_t st) {
+    const int64_t n_nodes = n / BS;
+    double* r = work;
+    double* z = r + n;
+    double* p0 = z + n;
+    double* p1 = p0 + n;
+    double* q = p1 + n;
+    double* minv = q + n;  // n*BS
+    double* sc = h->scalars;
+    int* fl = h->flags;
+    unsigned int vb = pgd_blocks(n_nodes, 256);
+    unsigned int capv = (unsigned int)h->sm_count * 8;
+    if (vb > capv) vb = capv;
+    if (lpr == 0) lpr = 16;
+    unsigned int sb = pgd_blocks(n, 256 / lpr);
+    unsigned int caps = (unsigned int)h->sm_count * 8;
+    if (sb > caps) sb = caps;
+    k_pcg_init<BS><<<vb, 256, 0, st>>>(rp, ci, va, b, x, r, z, p0, p1, minv, n_nodes, rtol, atol, sc, fl, h->partials,
+                                        h->counters);
+    PGD_LAUNCH_OK(h);
+    k_pcg_init_fin<<<1, 1, 0, st>>>(sc, fl, rtol, atol);
+    PGD_LAUNCH_OK(h);
+    int hf[4] = {0, 0, 0, 0};
+    double hs[8];
+    int launched = 0;
+    if (check_every < 1) check_every = 1;
+    while (true) {
+        PGD_CUDA(h, cudaMemcpyAsync(hf, fl, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+        PGD_CUDA(h, cudaStreamSynchronize(st));
+        if (hf[F_DONE] || launched >= maxit) break;
+        int todo = maxit - launched;
+        if (todo > check_every) todo = check_every;
+        for (int i = 0; i < todo; ++i) {
+            switch (lpr) {
+#define PCG_CASE(L)                                                                                                     \
+    case L:                                                                                                             \
+        k_pcg_spmv<L><<<sb, 256, 0, st>>>(rp, ci, va, z, p0, p1, q, n, sc, fl, sc, h->partials, h->counters);           \
+        break;
+                PCG_CASE(2)
+                PCG_CASE(4)
+                PCG_CASE(8)
+                PCG_CASE(16)
+                PCG_CASE(32)
+#undef PCG_CASE
+                default:
+                    snprintf(h->err, sizeof(h->err), "lanes_per_row must be 0,2,4,8,16,32");
+                    return -2;
+            }
+            k_pcg_update<BS><<<vb, 256, 0, st>>>(x, r, z, p0, p1, q, minv, n_nodes, sc, fl, h->partials, h->counters);
+            k_pcg_rotate<<<1, 1, 0, st>>>(sc, fl);
+        }
+        PGD_LAUNCH_OK(h);
+        launched += todo;
+    }
+    PGD_CUDA(h, cudaMemcpyAsync(hs, sc, sizeof(double) * 8, cudaMemcpyDeviceToHost, st));
+    PGD_CUDA(h, cudaStreamSynchronize(st));
+    if (h_iters) *h_iters = hf[F_ITER];
+    if (h_relres) *h_relres = (hs[S_BB] > 0.0) ? sqrt(hs[S_RR] / hs[S_BB]) : 0.0;
+    if (hf[F_BAD]) {
+        snprintf(h->err, sizeof(h->err), "pgd_pcg_sync: NaN encountered (matrix not SPD?)");
+        return -3;
+    }
+    return 0;
+}
+
+extern "C" int32_t pgd_pcg_sync(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
+                                const double* d_b, double* d_x, int64_t n, double rtol, double atol, int32_t maxit,
+                                int32_t check_every, int32_t block, int32_t lanes_per_row, double* d_work,
+                                int32_t* h_iters, double* h_relres, void* stream) {
+    PGD_CHECK_HANDLE(h);
+    PGD_ARG(h, d_rowptr && d_colidx && d_values && d_b && d_x && d_work && n > 0, "bad arguments");
+    PGD_ARG(h, block >= 1 && block <= 3 && n % block == 0, "block must be 1..3 and divide n");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (block == 1)
+        return run_pcg<1>(h, d_rowptr, d_colidx, d_values, d_b, d_x, n, rtol, atol, maxit, check_every, lanes_per_row, d_work,
+                          h_iters, h_relres, st);
+    if (block == 2)
+        return run_pcg<2>(h, d_rowptr, d_colidx, d_values, d_b, d_x, n, rtol, atol, maxit, check_every, lanes_per_row, d_work,
+                          h_iters, h_relres, st);
+    return run_pcg<3>(h, d_rowptr, d_colidx, d_values, d_b, d_x, n, rtol, atol, maxit, check_every, lanes_per_row, d_work,
+                      h_iters, h_relres, st);
+}

@@ -1,0 +1,172 @@
+// CSR kernels: SpMV (sub-warp per row), fused SpMV+dot, bilinear functional x^T A y, Dirichlet.
+// All are HBM-bound: matrix values/indices are streamed once (ld.global.cs), x is gathered through
+// the read-only path and stays L2-resident; rows are processed by LPR-lane groups so that a warp
+// reads a contiguous run of the CSR arrays.
+#include "common.cuh"
+
+template <int LPR>
+__device__ __forceinline__ double row_dot(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                          const double* __restrict__ vals, const double* __restrict__ x, int64_t row,
+                                          int64_t n, int lane) {
+    // every lane of the warp takes part in the shuffles; rows past the end get an empty range
+    int k0 = 0, k1 = 0;
+    if (row < n) {
+        k0 = __ldg(&rowptr[row]);
+        k1 = __ldg(&rowptr[row + 1]);
+    }
+    double s = 0.0;
+    for (int k = k0 + lane; k < k1; k += LPR) s += ld_stream(&vals[k]) * __ldg(&x[ld_stream(&colidx[k])]);
+#pragma unroll
+    for (int o = LPR >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, LPR);
+    return s;
+}
+
+// MODE 0: y = A x ; MODE 1: y = A x, dot = w^T y ; MODE 2: dot = w^T A x (no store)
+template <int LPR, int MODE>
+__global__ void __launch_bounds__(256) k_spmv(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                              const double* __restrict__ vals, const double* __restrict__ x,
+                                              double* __restrict__ y, const double* __restrict__ w, int64_t n, double* dot,
+                                              double* part, unsigned int* counter) {
+    constexpr int RPB = 256 / LPR;  // rows per block per sweep
+    const int lane = threadIdx.x % LPR;
+    const int sub = threadIdx.x / LPR;
+    double acc = 0.0;
+    for (int64_t base = (int64_t)blockIdx.x * RPB; base < n; base += (int64_t)gridDim.x * RPB) {
+        int64_t row = base + sub;
+        double s = row_dot<LPR>(rowptr, colidx, vals, x, row, n, lane);
+        if (row < n && lane == 0) {
+            if (MODE != 2) y[row] = s;
+            if (MODE != 0) acc += __ldg(&w[row]) * s;
+        }
+    }
+    if (MODE != 0) {
+        acc = block_sum(acc);
+        double v[1] = {acc};
+        grid_sum_finish<1>(v, part, counter, dot, blockIdx.x, gridDim.x);
+    }
+}
+
+static int auto_lpr(int64_t n, int64_t nnz_hint) {
+    double m = (n > 0) ? (double)nnz_hint / (double)n : 8.0;
+    if (m <= 3.0) return 2;
+    if (m <= 6.0) return 4;
+    if (m <= 12.0) return 8;
+    if (m <= 24.0) return 16;
+    return 32;
+}
+
+template <int MODE>
+static int32_t launch_spmv(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const double* va, const double* x, double* y,
+                           const double* w, int64_t n, double* dot, int lpr, cudaStream_t st) {
+    if (lpr == 0) {
+        // mean row length from the two ends of rowptr would need a D2H copy; use 16 (P1 tets ~15/row)
+        lpr = 16;
+    }
+    int rpb = 256 / lpr;
+    unsigned int blocks = pgd_blocks(n, rpb);
+    unsigned int cap = (unsigned int)h->sm_count * 8 * ((MODE == 0) ? 64 : 1);
+    if (MODE != 0 && cap > 4096) cap = 4096;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    double* part = h->partials;
+    unsigned int* ctr = h->counters;
+#define SPMV_CASE(L)                                                                                   \
+    case L:                                                                                            \
+        k_spmv<L, MODE><<<blocks, 256, 0, st>>>(rp, ci, va, x, y, w, n, dot, part, ctr);               \
+        break;
+    switch (lpr) {
+        SPMV_CASE(2)
+        SPMV_CASE(4)
+        SPMV_CASE(8)
+        SPMV_CASE(16)
+        SPMV_CASE(32)
+        default:
+            snprintf(h->err, sizeof(h->err), "lanes_per_row must be 0,2,4,8,16,32");
+            return -2;
+    }
+#undef SPMV_CASE
+    PGD_LAUNCH_OK(h);
+    return 0;
+}
+
+int32_t pgd_spmv_internal(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const double* va, const double* x, double* y,
+                          int64_t n, int lpr, cudaStream_t st) {
+    return launch_spmv<0>(h, rp, ci, va, x, y, nullptr, n, nullptr, lpr, st);
+}
+
+extern "C" int32_t pgd_spmv(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
+                            const double* d_x, double* d_y, int64_t n_rows, int32_t lanes_per_row, void* stream) {
+    PGD_CHECK_HANDLE(h);
+    PGD_ARG(h, d_rowptr && d_colidx && d_values && d_x && d_y && n_rows >= 0, "bad arguments");
+    if (n_rows == 0) return 0;
+    return launch_spmv<0>(h, d_rowptr, d_colidx, d_values, d_x, d_y, nullptr, n_rows, nullptr, lanes_per_row,
+                          (cudaStream_t)stream);
+}
+
+extern "C" int32_t pgd_spmv_dot(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
+                                const double* d_x, double* d_y, const double* d_w, double* d_dot, int64_t n_rows,
+                                int32_t lanes_per_row, void* stream) {
+    PGD_CHECK_HANDLE(h);
+    PGD_ARG(h, d_rowptr && d_colidx && d_values && d_x && d_y && d_w && d_dot && n_rows > 0, "bad arguments");
+    return launch_spmv<1>(h, d_rowptr, d_colidx, d_values, d_x, d_y, d_w, n_rows, d_dot, lanes_per_row,
+                          (cudaStream_t)stream);
+}
+
+extern "C" int32_t pgd_bilinear(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
+                                const double* d_x, const double* d_y, int64_t n_rows, double* d_out, int32_t lanes_per_row,
+                                void* stream) {
+    PGD_CHECK_HANDLE(h);
+    PGD_ARG(h, d_rowptr && d_colidx && d_values && d_x && d_y && d_out && n_rows > 0, "bad arguments");
+    // x^T (A y): gather y, weight rows by x
+    return launch_spmv<2>(h, d_rowptr, d_colidx, d_values, d_y, nullptr, d_x, n_rows, d_out, lanes_per_row,
+                          (cudaStream_t)stream);
+}
+
+// ----------------------------------------------------------------------------- Dirichlet
+// one warp per bc dof j: row j -> unit row; every (c, j) with c in pattern(row j) -> 0 (+ lifting)
+__global__ void __launch_bounds__(256) k_dirichlet(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                                   double* __restrict__ vals, double* __restrict__ b,
+                                                   const int32_t* __restrict__ bc, const double* __restrict__ g, int64_t n_bc) {
+    int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (wid >= n_bc) return;
+    int j = bc[wid];
+    double gj = g ? g[wid] : 0.0;
+    int k0 = rowptr[j], k1 = rowptr[j + 1];
+    for (int k = k0 + lane; k < k1; k += 32) {
+        int c = colidx[k];
+        if (c == j) {
+            vals[k] = 1.0;
+        } else {
+            vals[k] = 0.0;
+            // find (c, j) in row c (columns ascending)
+            int lo = rowptr[c], hi = rowptr[c + 1] - 1;
+            while (lo <= hi) {
+                int mid = (lo + hi) >> 1;
+                int cc = colidx[mid];
+                if (cc == j) {
+                    if (b && gj != 0.0) atomicAdd(&b[c], -vals[mid] * gj);
+                    vals[mid] = 0.0;
+                    break;
+                }
+                if (cc < j) lo = mid + 1;
+                else hi = mid - 1;
+            }
+        }
+    }
+}
+
+extern "C" int32_t pgd_apply_dirichlet(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, double* d_values,
+                                       double* d_b, const int32_t* d_bc_dofs, const double* d_bc_vals, int64_t n_bc,
+                                       void* stream) {
+    PGD_CHECK_HANDLE(h);
+    if (n_bc <= 0) return 0;
+    PGD_ARG(h, d_rowptr && d_colidx && d_bc_dofs, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_values) {
+        k_dirichlet<<<pgd_blocks(n_bc * 32, 256), 256, 0, st>>>(d_rowptr, d_colidx, d_values, d_b, d_bc_dofs, d_bc_vals, n_bc);
+        PGD_LAUNCH_OK(h);
+    }
+    if (d_b) return pgd_set_entries(h, d_b, d_bc_dofs, d_bc_vals, n_bc, stream);
+    return 0;
+}

@@ -1,0 +1,316 @@
+"""-m gpu: every C-ABI kernel of libpgdb200.so against the CPU oracle on the same seeded inputs.
+
+Bars (north_star): sparsity pattern bit-exact; assembled matrices 1e-12 relative; solves / modes
+1e-8 relative (tighter here because single solves are compared, not whole enrichments).
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+import torch
+
+from oracle import fem as ofem
+from oracle import meshes as omesh
+
+pytestmark = pytest.mark.gpu
+
+MAT_RTOL = 1e-12
+
+
+def _product_space(kind, degree, bs):
+    from pgdrome_b200 import fem
+
+    if kind == "interval":
+        m = fem.IntervalMesh(37, 0.2, 2.0)
+        o = omesh.interval_mesh(37, 0.2, 2.0)
+    elif kind == "tri":
+        m = fem.RectangleMesh((0.0, 0.0), (3.0, 1.0), 10, 5, "crossed")
+        o = omesh.rectangle_mesh(0.0, 0.0, 3.0, 1.0, 10, 5, "crossed")
+    elif kind == "tri_right":
+        m = fem.UnitSquareMesh(17, 13)
+        o = omesh.rectangle_mesh(0.0, 0.0, 1.0, 1.0, 17, 13, "right")
+    else:
+        m = fem.BoxMesh((0.0, 0.0, 0.0), (1.0, 2.0, 1.5), 5, 4, 3)
+        o = omesh.box_mesh(0.0, 0.0, 0.0, 1.0, 2.0, 1.5, 5, 4, 3)
+    V = fem.FunctionSpace(m, "P", degree, bs)
+    S = ofem.Space(o[0], o[1], degree, bs)
+    assert np.array_equal(V.cell_dofs, S.cell_dofs)
+    return V, S
+
+
+def _csr(ds, values):
+    rowptr, colidx, _, _ = ds.pattern
+    n = ds.n_dofs
+    return sp.csr_matrix((values.cpu().numpy(), colidx.cpu().numpy(), rowptr.cpu().numpy()), shape=(n, n))
+
+
+def _relerr(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+SPACES = [("interval", 1, 1), ("interval", 2, 1), ("tri", 1, 1), ("tri", 2, 2), ("tri_right", 1, 1), ("tet", 1, 1),
+          ("tet", 1, 3), ("tet", 2, 1)]
+
+
+@pytest.mark.parametrize("kind,degree,bs", SPACES)
+def test_pattern_bit_exact(kind, degree, bs):
+    from pgdrome_b200.assembly import device_space
+
+    V, S = _product_space(kind, degree, bs)
+    ds = device_space(V)
+    rowptr, colidx, gptr, gidx = ds.pattern
+    rp, ci = ofem.sparsity(S.cell_dofs, S.n_dofs)
+    assert np.array_equal(rowptr.cpu().numpy(), rp)
+    assert np.array_equal(colidx.cpu().numpy(), ci)
+    # gather lists: every contribution appears once, in ascending order inside a group
+    gi = gidx.cpu().numpy()
+    assert np.array_equal(np.sort(gi), np.arange(gi.size))
+    gp = gptr.cpu().numpy()
+    assert gp[0] == 0 and gp[-1] == gi.size and np.all(np.diff(gp) > 0)
+
+
+@pytest.mark.parametrize("kind,degree,bs", SPACES)
+def test_atoms_match_oracle(kind, degree, bs):
+    from pgdrome_b200.assembly import device_space
+
+    V, S = _product_space(kind, degree, bs)
+    ds = device_space(V)
+    g = S.gdim
+    atoms = {"mass": ofem.T_mass(bs, g), "stiff": ofem.T_stiff(bs, g)}
+    if bs == 1:
+        atoms["adv"] = ofem.T_adv(g, g - 1)
+    if bs == g and g >= 2:
+        C = ofem.isotropic_C(1.3, 0.7, g) if g == 3 else np.array([[1.0, 1.0, 0.0], [1.0, 1.0, 0.0], [0.0, 0.0, 0.0]])
+        atoms["voigt"] = ofem.T_voigt(C, g)
+    for name, T in atoms.items():
+        A = _csr(ds, ds.assemble_bilinear(T))
+        Ao = ofem.assemble_bilinear(S, T)
+        assert _relerr(A.data, Ao.data) < MAT_RTOL, name
+    # weighted mass, coefficient interpolated into P_p per cell (Expression(degree=p) semantics)
+    if bs == 1:
+        if kind == "interval":
+            w, p = (lambda x: 1.0 / (2.0 * (1.0 + x[..., 0]) * (1.0 + 0.3 * x[..., 0]))), 10
+        else:
+            w, p = (lambda x: 1.0 + x[..., 0] * x[..., 1]), 2
+        A = _csr(ds, ds.assemble_bilinear(ofem.T_mass(1, g), weight=w, wdeg=p))
+        Ao = ofem.assemble_bilinear(S, ofem.T_mass(1, g), weight=w, weight_degree=p)
+        assert _relerr(A.data, Ao.data) < MAT_RTOL
+        L = np.zeros((1, g + 1))
+        L[0, 0] = 1.0
+        b = ds.assemble_linear(L, weight=w, wdeg=p).cpu().numpy()
+        bo = ofem.assemble_linear(S, L, weight=w, weight_degree=p)
+        assert _relerr(b, bo) < MAT_RTOL
+        L[0, 1] = 0.5
+        b = ds.assemble_linear(L).cpu().numpy()
+        assert _relerr(b, ofem.assemble_linear(S, L)) < MAT_RTOL
+
+
+@pytest.mark.parametrize("kind", ["interval", "tri_right", "tet"])
+def test_fused_p1_operator(kind):
+    from pgdrome_b200 import _lib
+    from pgdrome_b200.assembly import device_space
+
+    V, S = _product_space(kind, 1, 1)
+    ds = device_space(V)
+    g = S.gdim
+    cm, ck = 0.37, 2.25
+    cadv = [0.5, -0.25, 0.125][:g]
+    rowptr, colidx, gptr, gidx = ds.pattern
+    vals = _lib.assemble_p1(ds.coords, ds.cell_verts, g, cm, ck, cadv, gptr, gidx, colidx.numel())
+    Ao = cm * ofem.assemble_bilinear(S, ofem.T_mass(1, g)) + ck * ofem.assemble_bilinear(S, ofem.T_stiff(1, g))
+    for m in range(g):
+        Ao = Ao + cadv[m] * ofem.assemble_bilinear(S, ofem.T_adv(g, m))
+    assert _relerr(_csr(ds, vals).data, Ao.tocsr().data) < MAT_RTOL
+
+
+def test_facet_load_matches_oracle():
+    from pgdrome_b200.assembly import device_space
+
+    V, S = _product_space("tri", 2, 2)
+    ds = device_space(V)
+    m = V.mesh()
+    cell, loc = m.boundary_facets()
+    fv = m.facet_vertices(cell, loc)
+    X = m.coordinates()
+    top_left = np.all(np.abs(X[fv][:, :, 1] - 1.0) < 1e-12, axis=1) & np.all(X[fv][:, :, 0] < 1.5 + 1e-9, axis=1)
+    b = ds.assemble_facet_linear("tl", cell[top_left], loc[top_left], (0.0, -0.5)).cpu().numpy()
+    fs = ofem.facet_space(S, lambda x: abs(x[1] - 1.0) < 1e-12 and x[0] < 1.5 + 1e-9)
+    Lt = np.zeros((2, 3))
+    Lt[:, 0] = (0.0, -0.5)
+    bo = ofem.assemble_linear(fs, Lt)
+    assert abs(bo.sum() + 0.5 * 1.5) < 1e-12
+    assert _relerr(b, bo) < MAT_RTOL
+
+
+def _random_system(kind="tet", degree=1, bs=1, seed=0):
+    from pgdrome_b200.assembly import device_space
+
+    V, S = _product_space(kind, degree, bs)
+    ds = device_space(V)
+    g = S.gdim
+    K1 = ofem.assemble_bilinear(S, ofem.T_stiff(bs, g))
+    K2 = ofem.assemble_bilinear(S, ofem.T_mass(bs, g))
+    # add the value arrays: scipy's sparse '+' would drop the pattern's explicit zeros
+    K = sp.csr_matrix((K1.data + 0.3 * K2.data, K1.indices, K1.indptr), shape=K1.shape)
+    rng = np.random.default_rng(seed)
+    return V, S, ds, K, rng
+
+
+def test_spmv_bilinear_dots_lincomb():
+    from pgdrome_b200 import _lib
+
+    V, S, ds, K, rng = _random_system()
+    rowptr, colidx, _, _ = ds.pattern
+    dev = rowptr.device
+    vals = torch.as_tensor(K.data).to(dev)
+    x = rng.uniform(-1, 1, S.n_dofs)
+    y = rng.uniform(-1, 1, S.n_dofs)
+    xd, yd = torch.as_tensor(x).to(dev), torch.as_tensor(y).to(dev)
+    for lpr in (0, 2, 4, 8, 16, 32):
+        out = _lib.spmv(rowptr, colidx, vals, xd, lpr=lpr).cpu().numpy()
+        assert _relerr(out, K @ x) < 1e-14
+        yy, d = _lib.spmv_dot(rowptr, colidx, vals, xd, yd, lpr=lpr)
+        assert _relerr(yy.cpu().numpy(), K @ x) < 1e-14
+        assert abs(d.item() - y @ (K @ x)) < 1e-12 * abs(y @ (K @ x)) + 1e-13
+        s = _lib.bilinear(rowptr, colidx, vals, xd, yd, lpr=lpr).item()
+        assert abs(s - x @ (K @ y)) < 1e-12 * abs(x @ (K @ y)) + 1e-13
+    assert abs(_lib.dot(xd, yd).item() - x @ y) < 1e-12
+    # bitwise reproducible reductions
+    a = _lib.bilinear(rowptr, colidx, vals, xd, yd).item()
+    assert all(_lib.bilinear(rowptr, colidx, vals, xd, yd).item() == a for _ in range(5))
+    P = rng.uniform(-1, 1, (7, S.n_dofs))
+    Pd = torch.as_tensor(P).to(dev)
+    assert _relerr(_lib.panel_dots(Pd, 7, xd).cpu().numpy(), P @ x) < 1e-13
+    coefs = rng.uniform(-2, 2, 30)
+    vecs = [torch.as_tensor(rng.uniform(-1, 1, 1001)).to(dev) for _ in range(30)]
+    ref = sum(c * v.cpu().numpy() for c, v in zip(coefs, vecs))
+    out = _lib.lincomb(vecs, coefs)
+    assert _relerr(out.cpu().numpy(), ref) < 1e-14
+    out2 = _lib.lincomb(vecs[:3], coefs[:3], out=out.clone(), accumulate=True)
+    assert _relerr(out2.cpu().numpy(), ref + sum(c * v.cpu().numpy() for c, v in zip(coefs[:3], vecs[:3]))) < 1e-14
+
+
+@pytest.mark.parametrize("kind,degree,bs,block", [("tet", 1, 1, 1), ("tri", 2, 2, 1), ("tri", 2, 2, 2), ("tet", 1, 3, 3)])
+def test_dirichlet_and_pcg(kind, degree, bs, block):
+    from pgdrome_b200 import _lib
+
+    V, S, ds, K, rng = _random_system(kind, degree, bs)
+    rowptr, colidx, _, _ = ds.pattern
+    dev = rowptr.device
+    bc = ofem.dirichlet_dofs(S, lambda x, ob: x[0] < 1e-12)
+    b = rng.uniform(-1, 1, S.n_dofs)
+    Ao, bo = ofem.apply_dirichlet_sym(K, b, bc)
+    vals = torch.as_tensor(K.data.copy()).to(dev)
+    bd = torch.as_tensor(b.copy()).to(dev)
+    _lib.apply_dirichlet(rowptr, colidx, vals, bd, torch.as_tensor(bc.astype(np.int32)).to(dev))
+    assert _relerr(vals.cpu().numpy(), Ao.data) == 0.0
+    assert _relerr(bd.cpu().numpy(), bo) == 0.0
+    # inhomogeneous values: lifting
+    gvals = rng.uniform(-1, 1, bc.size)
+    Ao2, bo2 = ofem.apply_dirichlet_sym(K, b, bc, gvals)
+    vals2 = torch.as_tensor(K.data.copy()).to(dev)
+    bd2 = torch.as_tensor(b.copy()).to(dev)
+    _lib.apply_dirichlet(rowptr, colidx, vals2, bd2, torch.as_tensor(bc.astype(np.int32)).to(dev),
+                         torch.as_tensor(gvals).to(dev))
+    assert _relerr(bd2.cpu().numpy(), bo2) < 1e-13
+    xo = spla.spsolve(Ao.tocsc(), bo)
+    x, iters, relres = _lib.pcg(rowptr, colidx, vals, bd, rtol=1e-13, maxit=5000, check_every=25, block=block)
+    assert relres <= 1e-13 and 0 < iters < 5000
+    assert np.linalg.norm(x.cpu().numpy() - xo) / np.linalg.norm(xo) < 1e-10
+    # zero right-hand side converges immediately to zero
+    x0, it0, _ = _lib.pcg(rowptr, colidx, vals, torch.zeros_like(bd), rtol=1e-13, maxit=10, block=block)
+    assert it0 == 0 and float(x0.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("degree", [1, 2])
+def test_banded_solve_nonsymmetric(degree):
+    from pgdrome_b200 import _lib
+    from pgdrome_b200.assembly import device_space
+
+    V, S = _product_space("interval", degree, 1)
+    ds = device_space(V)
+    rowptr, colidx, _, _ = ds.pattern
+    dev = rowptr.device
+    # rho c int u' v + k int u v : non-symmetric, needs pivoting-safe LU
+    A = (2.0 * ofem.assemble_bilinear(S, ofem.T_adv(1)) + 0.05 * ofem.assemble_bilinear(S, ofem.T_mass(1, 1))).tocsr()
+    rng = np.random.default_rng(3)
+    b = rng.uniform(-1, 1, S.n_dofs)
+    bc = ofem.dirichlet_dofs(S, lambda x, ob: x[0] < 0.2 + 1e-9)
+    Ao, bo = ofem.apply_dirichlet_sym(A, b, bc)
+    xo = spla.spsolve(Ao.tocsc(), bo)
+    perm, bw = V.band_permutation()
+    x, info = _lib.banded_solve(rowptr, colidx, torch.as_tensor(Ao.data).to(dev), torch.as_tensor(bo).to(dev),
+                                torch.as_tensor(perm).to(dev), bw, bw)
+    assert int(info.item()) == 0
+    assert np.linalg.norm(x.cpu().numpy() - xo) / np.linalg.norm(xo) < 1e-11
+    # a matrix that needs row interchanges (tiny diagonal)
+    n = 64
+    T = sp.diags([np.full(n - 1, 1.0), np.full(n, 1e-14), np.full(n - 1, -0.7)], [-1, 0, 1]).tocsr()
+    T.sort_indices()
+    bb = rng.uniform(-1, 1, n)
+    xt, info = _lib.banded_solve(torch.as_tensor(T.indptr.astype(np.int32)).to(dev), torch.as_tensor(T.indices.astype(np.int32)).to(dev),
+                                 torch.as_tensor(T.data).to(dev), torch.as_tensor(bb).to(dev),
+                                 torch.arange(n, dtype=torch.int32, device=dev), 1, 1)
+    xs = spla.spsolve(T.tocsc(), bb)
+    assert int(info.item()) == 0
+    assert np.linalg.norm(xt.cpu().numpy() - xs) / np.linalg.norm(xs) < 1e-10
+
+
+def test_evaluate_kernels():
+    from pgdrome_b200 import _lib
+
+    dev = torch.device("cuda")
+    rng = np.random.default_rng(7)
+    R, N = 13, 1003
+    spaces = [ofem.Space(*omesh.interval_mesh(11, 0.5, 2.0), degree=1), ofem.Space(*omesh.interval_mesh(6, -1.0, 1.0), degree=2)]
+    Phi = [rng.normal(size=(R, s.n_dofs)) for s in spaces]
+    X = rng.normal(size=(R, N))
+    C = 300
+    pts = np.column_stack([rng.uniform(0.5, 2.0, C), rng.uniform(-1.0, 1.0, C)])
+    pts[0] = (0.5, -1.0)
+    pts[1] = (2.0, 1.0)
+    xs, cds = [], []
+    for s in spaces:
+        v = s.coords[:, 0]
+        order = np.argsort(v)
+        xs.append(v[order])
+        cell_lo = np.minimum(s.cells[:, 0], s.cells[:, 1])
+        corder = np.argsort(v[cell_lo])
+        cd = []
+        for e in corder:
+            a, b = s.cells[e]
+            if v[a] > v[b]:
+                a, b = b, a
+            row = [s.vertex_to_node[a], s.vertex_to_node[b]]
+            if s.degree == 2:
+                row.append(s.cell_nodes[e, 2])
+            cd.append(row)
+        cds.append(np.array(cd, dtype=np.int32))
+    from oracle.evaluate import point_eval
+
+    Wo = np.ones((R, C))
+    for c in range(C):
+        for i, s in enumerate(spaces):
+            for k in range(R):
+                Wo[k, c] *= point_eval(s, Phi[i][k], pts[c, i])
+    W, flag = _lib.eval_weights([torch.as_tensor(a).to(dev) for a in xs], [torch.as_tensor(a).to(dev) for a in cds],
+                                [torch.as_tensor(a).to(dev) for a in Phi], [1, 2], R, torch.as_tensor(pts).to(dev))
+    assert int(flag.item()) == 0
+    assert _relerr(W.cpu().numpy(), Wo) < 1e-13
+    # out-of-range coordinate is reported (interp1d ValueError / test_pgdclass.py:319-326)
+    bad = pts.copy()
+    bad[5, 1] = 1.5
+    _, flag = _lib.eval_weights([torch.as_tensor(a).to(dev) for a in xs], [torch.as_tensor(a).to(dev) for a in cds],
+                                [torch.as_tensor(a).to(dev) for a in Phi], [1, 2], R, torch.as_tensor(bad).to(dev))
+    assert int(flag.item()) == 2
+    Xd = torch.as_tensor(X).to(dev)
+    u = _lib.eval_gemv(Xd, R, W[:, 3].contiguous()).cpu().numpy()
+    assert _relerr(u, Wo[:, 3] @ X) < 1e-13
+    U = _lib.eval_gemm(W, Xd, R).cpu().numpy()
+    assert _relerr(U, Wo.T @ X) < 1e-13
+    # ragged sizes around the 128x128 tile and K > 64 (two K chunks)
+    for (R2, C2, N2) in [(1, 1, 1), (50, 129, 257), (70, 128, 128), (5, 7, 1000)]:
+        W2, X2 = rng.normal(size=(R2, C2)), rng.normal(size=(R2, N2))
+        U2 = _lib.eval_gemm(torch.as_tensor(W2).to(dev), torch.as_tensor(X2).to(dev), R2).cpu().numpy()
+        assert _relerr(U2, W2.T @ X2) < 1e-13, (R2, C2, N2)
