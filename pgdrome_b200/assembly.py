@@ -52,6 +52,15 @@ class DeviceSpace:
         return self.pattern[1].numel()
 
     @property
+    def lpr(self):
+        """lanes per CSR row for the SpMV-type kernels, from the mean row length."""
+        m = self.nnz / max(1, self.n_dofs)
+        for l in (2, 4, 8, 16):
+            if m <= 1.5 * l:
+                return l
+        return 32
+
+    @property
     def vecmap(self):
         if self._vecmap is None:
             self._vecmap = _lib.vecmap_build(self.cell_dofs, self.n_dofs)
@@ -91,9 +100,40 @@ class DeviceSpace:
         phi, _ = tabulate_lagrange(tdim, wdeg, pts)
         return np.asarray(fn(xn), dtype=np.float64) @ phi.T
 
+    # ---- weights: product of per-cell P_p interpolants at the quadrature points (host, set-up)
+    def _weights_at(self, weights, weight, wdeg, pts, cells=None, tdim=None):
+        """weights: list of specs ("expr"|"fn"|"callable", obj, comp, degree, key); returns
+        (float64 [n_cells, nq] on the device or None, total polynomial degree)."""
+        specs = list(weights or [])
+        if weight is not None:
+            specs.append(("callable", weight, None, wdeg, None))
+        if not specs:
+            return None, 0
+        wq, deg = None, 0
+        for kind, obj, comp, d, _ in specs:
+            if kind == "fn":
+                if cells is not None:
+                    raise NotImplementedError("coefficient Function inside a boundary integral")
+                w = self._sample_function(obj, comp, pts)
+            else:
+                fn = obj if kind == "callable" else (lambda X, o=obj, c=comp: o.eval_np(X, c))
+                w = self.sample_weight(fn, d, pts, cells=cells, tdim=tdim)
+            wq = w if wq is None else wq * w
+            deg += d
+        return _up(wq, torch.float64), deg
+
+    def _sample_function(self, f, comp, pts):
+        V = f.V
+        phi, _ = tabulate_lagrange(V.mesh().tdim, V.degree, pts)
+        vals = f.values_host().reshape(V.n_nodes, V.bs)[:, comp or 0]
+        return vals[V.cell_nodes] @ phi.T
+
+    def _wdeg(self, weights, weight, wdeg):
+        return sum(s[3] for s in (weights or [])) + (wdeg if weight is not None else 0)
+
     # ---- atoms
-    def assemble_bilinear(self, T, weight=None, wdeg=0):
-        """values [nnz] of the atom with form tensor T and optional coefficient weight(x)."""
+    def assemble_bilinear(self, T, weight=None, wdeg=0, weights=None):
+        """values [nnz] of the atom with form tensor T and optional coefficient weight(s)."""
         s = self.space
         m = s.mesh()
         g = m.gdim
@@ -101,28 +141,23 @@ class DeviceSpace:
         # polynomial degree of the integrand on an affine simplex
         dv = s.degree if np.any(T[:, 0, :, :] != 0) else s.degree - 1
         du = s.degree if np.any(T[:, :, :, 0] != 0) else s.degree - 1
-        qdeg = dv + du + (wdeg if weight is not None else 0)
-        qdeg = max(qdeg, 1)
+        qdeg = max(dv + du + self._wdeg(weights, weight, wdeg), 1)
         tab = self.tables(qdeg)
-        wq = None
-        if weight is not None:
-            wq = _up(self.sample_weight(weight, wdeg, tab["pts"]), torch.float64)
+        wq, _ = self._weights_at(weights, weight, wdeg, tab["pts"])
         Ae = _lib.elem_bilinear(self.coords, self.cell_verts, m.tdim, g, s.bs, s.nd, tab["phi"], tab["dphi"], tab["qw"], wq,
                                 _up(T, torch.float64))
         rowptr, colidx, gptr, gidx = self.pattern
         return _lib.gather_values(Ae, gptr, gidx, colidx.numel())
 
-    def assemble_linear(self, L, weight=None, wdeg=0):
+    def assemble_linear(self, L, weight=None, wdeg=0, weights=None):
         s = self.space
         m = s.mesh()
         g = m.gdim
         L = np.asarray(L, dtype=np.float64).reshape(s.bs, g + 1)
         dv = s.degree if np.any(L[:, 0] != 0) else s.degree - 1
-        qdeg = max(dv + (wdeg if weight is not None else 0), 1)
+        qdeg = max(dv + self._wdeg(weights, weight, wdeg), 1)
         tab = self.tables(qdeg)
-        wq = None
-        if weight is not None:
-            wq = _up(self.sample_weight(weight, wdeg, tab["pts"]), torch.float64)
+        wq, _ = self._weights_at(weights, weight, wdeg, tab["pts"])
         be = _lib.elem_linear(self.coords, self.cell_verts, m.tdim, g, s.bs, s.nd, tab["phi"], tab["dphi"], tab["qw"], wq,
                               _up(L, torch.float64))
         vptr, vidx = self.vecmap
@@ -143,7 +178,7 @@ class DeviceSpace:
             self._facet[key] = d
         return self._facet[key]
 
-    def assemble_facet_linear(self, key, cell, loc, Lvec, weight=None, wdeg=0):
+    def assemble_facet_linear(self, key, cell, loc, Lvec, weight=None, wdeg=0, weights=None):
         """b[dof] = int_facets w * sum_i Lvec[i] v_i ds  (value slots only)."""
         s = self.space
         m = s.mesh()
@@ -154,11 +189,9 @@ class DeviceSpace:
         ft = m.tdim - 1
         if ft == 0:
             raise NotImplementedError("point 'facet' integrals on 1-D meshes")
-        qdeg = max(s.degree + (wdeg if weight is not None else 0), 1)
+        qdeg = max(s.degree + self._wdeg(weights, weight, wdeg), 1)
         tab = self.tables(qdeg, tdim=ft)
-        wq = None
-        if weight is not None:
-            wq = _up(self.sample_weight(weight, wdeg, tab["pts"], cells=fs["verts"], tdim=ft), torch.float64)
+        wq, _ = self._weights_at(weights, weight, wdeg, tab["pts"], cells=fs["verts"], tdim=ft)
         L = np.zeros((s.bs, m.gdim + 1))
         L[:, 0] = np.asarray(Lvec, dtype=np.float64).reshape(s.bs)
         be = _lib.elem_linear(self.coords, fs["verts_d"], ft, m.gdim, s.bs, fs["nd"], tab["phi"], tab["dphi"], tab["qw"], wq,

@@ -1,0 +1,458 @@
+"""Form compiler + device evaluator: turns the expanded mini-UFL forms produced by the user's
+callbacks into calls of the libpgdb200 kernels.
+
+Classification of every group of monomials (same scalar coefficients, weights, operands, measure):
+
+  rank 2  test x trial [x weights]        -> operator atom  K[T, w]   (assembled once, cached)
+  rank 1  test x Function [x weights]     -> K[T, w] @ f              (SpMV, cached for stable f)
+          test [x weights]                -> load vector              (assembled once, cached)
+  rank 0  Function x Function [x weights] -> f1^T K[T, w] f2          (mode integral: fused
+                                             SpMV-reduction, or a panel dot with the cached K @ f)
+          Function [x weights]            -> load . f
+          [weights]                       -> sum(load)
+
+T[iv, jv, iu, ju] is the constant form tensor (slot 0 = value, 1+m = d/dx_m; first pair = test /
+first operand, second pair = trial / second operand).  This is the separated-form registry of
+SURVEY.md 2.4: mass, weighted mass, stiffness, first-derivative (advection/time), Voigt elasticity,
+volume / lifting / boundary-traction loads.  Anything else raises NotImplementedError.
+
+The per-dimension system of the fixed-point sweep (pgdrome/solver.py:547-720) is then
+    A = sum_g coef_g * K_g          (pgd_lincomb over CSR value arrays)
+    b = sum_g coef_g * vec_g        (pgd_lincomb over cached vectors)
+with coef_g = float constants x the mode integrals of the other dimensions (LazyScalars, evaluated
+in one batch per system, one device->host copy).
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, lazy
+from .assembly import device_space
+from .functions import Constant, DeviceVector, Expression, Function, _DofOwner, _device
+from .lazy import LazyScalar
+from .ufl import Form
+
+MAX_PANEL_ROWS = 8
+
+
+# ------------------------------------------------------------------------------- compile (host)
+class Group:
+    """Monomials of one integral that share scalar leaves, weights, operands and measure."""
+
+    __slots__ = ("scalars", "weights", "operands", "measure", "entries", "space", "has_test", "has_trial")
+
+    def __init__(self, scalars, weights, operands, measure, space, has_test, has_trial):
+        self.scalars, self.weights, self.operands, self.measure = scalars, weights, operands, measure
+        self.space, self.has_test, self.has_trial = space, has_test, has_trial
+        self.entries = {}  # (iv, jv, iu, ju) | (iv, jv) | () -> float
+
+    @property
+    def rank(self):
+        return int(self.has_test) + int(self.has_trial)
+
+    def tensor(self):
+        """Dense form tensor: T [bs,g+1,bs,g+1] (two slots), L [bs,g+1] (one slot) or a float."""
+        bs, g = self.space.bs, self.space.mesh().gdim
+        nslots = int(self.has_test) + int(self.has_trial) + len(self.operands)
+        if nslots == 2:
+            T = np.zeros((bs, g + 1, bs, g + 1))
+        elif nslots == 1:
+            T = np.zeros((bs, g + 1))
+        else:
+            return float(sum(self.entries.values()))
+        for k, v in self.entries.items():
+            T[k] += v
+        return T
+
+    def coefficient(self):
+        """float constant part is folded into the tensor; this is the product of the scalar leaves."""
+        c = 1.0
+        for s in self.scalars:
+            c = c * _scalar_value(s)
+        return c
+
+
+def _scalar_value(leaf):
+    if leaf.kind == "lazy":
+        return leaf.lazy
+    return leaf.value  # scalar Constant: float or LazyScalar
+
+
+def _slot(deriv):
+    return 0 if deriv is None else 1 + int(deriv)
+
+
+def _same_space(A, B):
+    return A is B or (A.mesh() is B.mesh() and A.degree == B.degree and A.bs == B.bs)
+
+
+def compile_form(form):
+    """Form -> list of Groups (pure host work, no device access)."""
+    groups = {}
+    order = []
+    for it in form.integrals:
+        meas = it.measure
+        mkey = (meas.kind, id(meas.subdomain_data) if meas.subdomain_data is not None else None, meas.subdomain_id)
+        for m in it.monos:
+            if m.coef == 0.0:
+                continue
+            coef = m.coef
+            test = trial = None
+            scalars, weights, fns = [], [], []
+            for f in m.factors:
+                k = f.leaf.kind
+                if k == "constant":
+                    v = f.leaf.value
+                    if isinstance(v, tuple):
+                        coef *= v[f.comp or 0]
+                    elif isinstance(v, LazyScalar):
+                        scalars.append(f.leaf)
+                    else:
+                        coef *= v
+                elif k == "lazy":
+                    scalars.append(f.leaf)
+                elif k == "expression":
+                    if f.deriv is not None:
+                        raise NotImplementedError("derivative of an Expression inside a form")
+                    weights.append((f.leaf, f.comp))
+                elif k == "argument":
+                    if f.leaf.number == 0:
+                        if test is not None:
+                            raise NotImplementedError("form that is not linear in the test function")
+                        test = f
+                    else:
+                        if trial is not None:
+                            raise NotImplementedError("form that is not linear in the trial function")
+                        trial = f
+                elif k == "function":
+                    fns.append(f)
+                else:
+                    raise NotImplementedError("leaf kind '%s' inside a form" % k)
+            if coef == 0.0:
+                continue
+            # the space the integral lives on
+            if test is not None:
+                space = test.leaf.V
+            elif trial is not None:
+                space = trial.leaf.V
+            elif fns:
+                space = fns[0].leaf.V
+            else:
+                raise NotImplementedError("integral without any function or argument (pure coefficient integral)")
+            if meas.domain is not None and meas.domain is not space.mesh():
+                raise ValueError("integration domain does not match the mesh of the integrand")
+            free = 2 - (test is not None) - (trial is not None)
+            operands = []
+            for f in fns:
+                if len(operands) < free and _same_space(f.leaf.V, space):
+                    operands.append(f)
+                else:
+                    if f.deriv is not None:
+                        raise NotImplementedError("derivative of a coefficient Function used as a weight")
+                    if f.leaf.V.mesh() is not space.mesh():
+                        raise NotImplementedError("coefficient Function living on a different mesh")
+                    weights.append((f.leaf, f.comp))
+            if test is None and trial is not None:
+                raise NotImplementedError("form with a trial but no test function")
+            gkey = (id(space), tuple(sorted(id(s) for s in scalars)),
+                    tuple(sorted((id(w), c) for w, c in weights)), tuple(id(o.leaf) for o in operands), mkey,
+                    test is not None, trial is not None)
+            g = groups.get(gkey)
+            if g is None:
+                g = Group(tuple(scalars), tuple(sorted(weights, key=lambda wc: (id(wc[0]), wc[1] or 0))),
+                          tuple(o.leaf for o in operands), meas, space, test is not None, trial is not None)
+                groups[gkey] = g
+                order.append(gkey)
+            idx = ()
+            for f in ([test] if test is not None else []) + ([trial] if trial is not None else []) + operands:
+                idx += (f.comp or 0, _slot(f.deriv))
+            g.entries[idx] = g.entries.get(idx, 0.0) + coef
+    return [groups[k] for k in order]
+
+
+# ------------------------------------------------------------------------------- device resources
+def _weight_specs(weights):
+    """[(Expression|Function, comp)] -> list of (sampler, degree, key) for DeviceSpace."""
+    specs = []
+    for w, comp in weights:
+        if isinstance(w, Expression):
+            specs.append(("expr", w, comp, w.degree, (id(w), comp, w._version)))
+        else:
+            specs.append(("fn", w, comp, w.V.degree, (id(w), comp, w._version)))
+    return specs
+
+
+def _measure_key(meas):
+    if meas.kind == "dx":
+        if meas.subdomain_id is not None and meas.subdomain_data is not None:
+            return ("dx", id(meas.subdomain_data), meas.subdomain_data._version, meas.subdomain_id)
+        return ("dx",)
+    if meas.kind == "ds":
+        if meas.subdomain_data is None or meas.subdomain_id is None:
+            return ("ds", None, None, None)
+        return ("ds", id(meas.subdomain_data), meas.subdomain_data._version, meas.subdomain_id)
+    raise NotImplementedError("measure '%s'" % meas.kind)
+
+
+class Atom:
+    """One assembled operator K[T, weights] on a space + the panel of cached products K @ f."""
+
+    def __init__(self, ds, values, symmetric):
+        self.ds, self.values, self.symmetric = ds, values, symmetric
+        self.panel = None  # [cap, n_dofs]
+        self.rows = {}  # id(fn) -> (row, version, fn)  (keeps fn alive)
+        self.n_rows = 0
+
+    def product(self, fn):
+        """Cached K @ fn (a row of the panel); recomputed if fn changed."""
+        ent = self.rows.get(id(fn))
+        if ent is not None and ent[1] == fn._version:
+            return ent[0]
+        if ent is None:
+            if self.panel is None or self.n_rows == self.panel.shape[0]:
+                cap = MAX_PANEL_ROWS if self.panel is None else 2 * self.panel.shape[0]
+                new = torch.empty((cap, self.ds.n_dofs), dtype=torch.float64, device=self.values.device)
+                if self.panel is not None:
+                    new[: self.n_rows].copy_(self.panel[: self.n_rows])
+                self.panel = new
+            row = self.n_rows
+            self.n_rows += 1
+        else:
+            row = ent[0]
+        rowptr, colidx, _, _ = self.ds.pattern
+        _lib.spmv(rowptr, colidx, self.values, fn.tensor(), self.panel[row], lpr=self.ds.lpr)
+        self.rows[id(fn)] = (row, fn._version, fn)
+        return row
+
+    def has_fresh(self, fn):
+        ent = self.rows.get(id(fn))
+        return ent is not None and ent[1] == fn._version
+
+
+def get_atom(space, T, weights, meas):
+    ds = device_space(space)
+    if meas.kind != "dx":
+        raise NotImplementedError("bilinear forms over '%s' (only dx)" % meas.kind)
+    mk = _measure_key(meas)
+    if mk != ("dx",):
+        raise NotImplementedError("bilinear forms restricted to a cell sub-domain")
+    specs = _weight_specs(weights)
+    key = ("atom", T.tobytes(), tuple(s[4] for s in specs))
+    a = ds.atoms.get(key)
+    if a is None:
+        vals = ds.assemble_bilinear(T, weights=specs)
+        sym = bool(np.array_equal(T, T.transpose(2, 3, 0, 1)))
+        a = Atom(ds, vals, sym)
+        ds.atoms[key] = a
+    return a
+
+
+def get_load(space, L, weights, meas):
+    """Cached load vector  int w sum L[i,j] D_j v_i  over dx or ds(id)."""
+    ds = device_space(space)
+    specs = _weight_specs(weights)
+    mk = _measure_key(meas)
+    key = ("load", L.tobytes(), tuple(s[4] for s in specs), mk)
+    v = ds.atoms.get(key)
+    if v is None:
+        if meas.kind == "dx":
+            if mk != ("dx",):
+                raise NotImplementedError("linear forms restricted to a cell sub-domain")
+            v = ds.assemble_linear(L, weights=specs)
+        else:
+            if np.any(L[:, 1:] != 0):
+                raise NotImplementedError("derivatives of the test function in a boundary integral")
+            if meas.subdomain_data is None:
+                cell, loc = space.mesh().boundary_facets()
+            else:
+                cell, loc = meas.subdomain_data.facets(meas.subdomain_id)
+            v = ds.assemble_facet_linear(mk, cell, loc, L[:, 0], weights=specs)
+        ds.atoms[key] = v
+    return v
+
+
+# ------------------------------------------------------------------------------- functionals (rank 0)
+class _Functional:
+    """Payload of a LazyScalar leaf: one mode integral, evaluated in the next flush."""
+
+    __slots__ = ("kind", "space", "T", "weights", "measure", "f1", "f2", "v1", "v2")
+
+    def __init__(self, kind, space, T, weights, measure, f1=None, f2=None):
+        self.kind, self.space, self.T, self.weights, self.measure, self.f1, self.f2 = kind, space, T, weights, measure, f1, f2
+        self.v1 = f1._version if f1 is not None else None
+        self.v2 = f2._version if f2 is not None else None
+
+
+def _functional_value(g):
+    """Group of rank 0 -> LazyScalar (leaf) for  sum_entries  operand integrals."""
+    n = len(g.operands)
+    T = g.tensor()
+    if n == 2:
+        p = _Functional("bil", g.space, T, g.weights, g.measure, g.operands[0], g.operands[1])
+    elif n == 1:
+        p = _Functional("lin", g.space, T, g.weights, g.measure, g.operands[0])
+    else:
+        raise NotImplementedError("functional without a Function operand")
+    return LazyScalar("leaf", (p,))
+
+
+def _flush(leaves):
+    """Evaluate all pending functionals: batched device launches, ONE device->host copy."""
+    dev = _device()
+    plan = []  # (leaf, slot)
+    n_slots = 0
+    panel_jobs = {}  # (id(atom), id(x)) -> [atom, x, base_slot]
+    direct = []  # (slot, kind, args)
+    for leaf in leaves:
+        p = leaf.args[0]
+        if p.f1 is not None and p.f1._version != p.v1 or p.f2 is not None and p.f2._version != p.v2:
+            raise RuntimeError("a Function was modified between assemble(<functional>) and its evaluation")
+        if p.kind == "lin":
+            vec = get_load(p.space, p.T, p.weights, p.measure)
+            direct.append((n_slots, "dot", (vec, p.f1.tensor())))
+            plan.append((leaf, n_slots))
+            n_slots += 1
+            continue
+        if p.measure.kind != "dx":
+            raise NotImplementedError("bilinear functionals over '%s'" % p.measure.kind)
+        atom = get_atom(p.space, p.T, p.weights, p.measure)
+        x = stable = None
+        at = atom
+        if p.f2.stable or atom.has_fresh(p.f2):
+            stable, x = p.f2, p.f1
+        elif p.f1.stable:
+            stable, x = p.f1, p.f2
+            at = atom if atom.symmetric else get_atom(p.space, np.ascontiguousarray(p.T.transpose(2, 3, 0, 1)), p.weights, p.measure)
+        if stable is None or stable is x:
+            direct.append((n_slots, "bil", (atom, p.f1.tensor(), p.f2.tensor())))
+            plan.append((leaf, n_slots))
+            n_slots += 1
+            continue
+        row = at.product(stable)
+        job = panel_jobs.get((id(at), id(x)))
+        if job is None:
+            job = [at, x, None, []]
+            panel_jobs[(id(at), id(x))] = job
+        job[3].append((leaf, row))
+    for job in panel_jobs.values():
+        at = job[0]
+        job[2] = n_slots
+        for leaf, row in job[3]:
+            plan.append((leaf, n_slots + row))
+        n_slots += at.n_rows
+    res = torch.empty(max(n_slots, 1), dtype=torch.float64, device=dev)
+    for slot, kind, args in direct:
+        if kind == "dot":
+            _lib.dot(args[0], args[1], out=res[slot:slot + 1])
+        else:
+            atom = args[0]
+            rowptr, colidx, _, _ = atom.ds.pattern
+            _lib.bilinear(rowptr, colidx, atom.values, args[1], args[2], out=res[slot:slot + 1], lpr=atom.ds.lpr)
+    for at, x, base, _ in panel_jobs.values():
+        _lib.panel_dots(at.panel, at.n_rows, x.tensor(), out=res[base:base + at.n_rows])
+    host = res.cpu().numpy()
+    for leaf, slot in plan:
+        leaf._value = float(host[slot])
+
+
+lazy._flush_hook[0] = _flush
+
+
+# ------------------------------------------------------------------------------- public assemble
+def assemble(form):
+    """dolfin.assemble: rank 0 -> LazyScalar, rank 1 -> DeviceVector, rank 2 -> AssembledMatrix."""
+    if not isinstance(form, Form):
+        raise TypeError("assemble expects a Form, got %r" % type(form))
+    groups = compile_form(form)
+    if not groups:
+        return lazy.constant(0.0)
+    rank = groups[0].rank
+    if any(g.rank != rank for g in groups):
+        raise ValueError("all integrals of a form must have the same arity")
+    if rank == 0:
+        total = None
+        for g in groups:
+            v = _functional_value(g)
+            c = g.coefficient()
+            term = v if (isinstance(c, float) and c == 1.0) else c * v
+            total = term if total is None else total + term
+        return total
+    if rank == 1:
+        return DeviceVector(assemble_vector(groups))
+    return assemble_matrix(groups)
+
+
+def _coefs(groups):
+    lazy.flush()
+    return [float(g.coefficient()) for g in groups]
+
+
+def assemble_vector(groups, out=None):
+    """b = sum_g coef_g * (load_g | K_g @ f_g)  on the device."""
+    space = groups[0].space
+    vecs = []
+    for g in groups:
+        if not _same_space(g.space, space):
+            raise ValueError("linear form mixes test spaces")
+        if len(g.operands) == 0:
+            vecs.append(get_load(g.space, g.tensor(), g.weights, g.measure))
+        elif len(g.operands) == 1:
+            atom = get_atom(g.space, g.tensor(), g.weights, g.measure)
+            f = g.operands[0]
+            if f.stable or atom.has_fresh(f):
+                vecs.append(atom.panel[atom.product(f)])
+            else:
+                rowptr, colidx, _, _ = atom.ds.pattern
+                vecs.append(_lib.spmv(rowptr, colidx, atom.values, f.tensor(), lpr=atom.ds.lpr))
+        else:
+            raise NotImplementedError("linear form with two Function operands in one term")
+    coefs = _coefs(groups)
+    return _lib.lincomb(vecs, coefs, out=out)
+
+
+class AssembledMatrix:
+    def __init__(self, ds, values):
+        self.ds, self.values = ds, values
+
+    def scipy(self):
+        import scipy.sparse as sp
+
+        rowptr, colidx, _, _ = self.ds.pattern
+        n = self.ds.n_dofs
+        return sp.csr_matrix((self.values.cpu().numpy(), colidx.cpu().numpy(), rowptr.cpu().numpy()), shape=(n, n))
+
+    def array(self):
+        return self.scipy().toarray()
+
+
+def assemble_matrix(groups, out=None):
+    space = groups[0].space
+    ds = device_space(space)
+    atoms = []
+    for g in groups:
+        if not _same_space(g.space, space) or g.operands:
+            raise NotImplementedError("bilinear form with Function operands (non-linear form?)")
+        atoms.append(get_atom(g.space, g.tensor(), g.weights, g.measure))
+    coefs = _coefs(groups)
+    vals = _lib.lincomb([a.values for a in atoms], coefs, out=out)
+    m = AssembledMatrix(ds, vals)
+    m.symmetric = all(a.symmetric for a in atoms)
+    return m
+
+
+def norm(f, norm_type="L2", mesh=None):
+    """dolfin.norm(Function): sqrt(int f.f dx)  (fused SpMV-reduction with the mass atom)."""
+    if isinstance(f, _DofOwner) and not isinstance(f, Function):
+        t = f.tensor()
+        return math.sqrt(float(_lib.dot(t, t).item()))
+    if norm_type.lower() != "l2":
+        raise NotImplementedError("norm type '%s'" % norm_type)
+    return mass_product(f, f).sqrt()
+
+
+def mass_product(f, g):
+    """LazyScalar  int f.g dx  for two Functions of the same space."""
+    from .ufl import dx, inner
+
+    return assemble(inner(f, g) * dx(f.V.mesh()))
