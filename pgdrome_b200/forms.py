@@ -40,11 +40,11 @@ MAX_PANEL_ROWS = 8
 class Group:
     """Monomials of one integral that share scalar leaves, weights, operands and measure."""
 
-    __slots__ = ("scalars", "weights", "operands", "measure", "entries", "space", "has_test", "has_trial")
+    __slots__ = ("scalars", "weights", "operands", "measure", "entries", "space", "has_test", "has_trial", "op")
 
-    def __init__(self, scalars, weights, operands, measure, space, has_test, has_trial):
+    def __init__(self, scalars, weights, operands, measure, space, has_test, has_trial, op=None):
         self.scalars, self.weights, self.operands, self.measure = scalars, weights, operands, measure
-        self.space, self.has_test, self.has_trial = space, has_test, has_trial
+        self.space, self.has_test, self.has_trial, self.op = space, has_test, has_trial, op
         self.entries = {}  # (iv, jv, iu, ju) | (iv, jv) | () -> float
 
     @property
@@ -98,7 +98,7 @@ def compile_form(form):
             if m.coef == 0.0:
                 continue
             coef = m.coef
-            test = trial = None
+            test = trial = op = None
             scalars, weights, fns = [], [], []
             for f in m.factors:
                 k = f.leaf.kind
@@ -127,6 +127,10 @@ def compile_form(form):
                         trial = f
                 elif k == "function":
                     fns.append(f)
+                elif k == "operator":
+                    if op is not None:
+                        raise NotImplementedError("product of two MatrixOperators in one term")
+                    op = f.leaf
                 else:
                     raise NotImplementedError("leaf kind '%s' inside a form" % k)
             if coef == 0.0:
@@ -155,13 +159,19 @@ def compile_form(form):
                     weights.append((f.leaf, f.comp))
             if test is None and trial is not None:
                 raise NotImplementedError("form with a trial but no test function")
+            if op is not None:
+                slots = ([test] if test is not None else []) + ([trial] if trial is not None else []) + operands
+                if len(slots) != 2 or weights or any(f.deriv is not None for f in slots) or meas.kind != "dx":
+                    raise NotImplementedError("MatrixOperator terms must be op(u, v)*dx with two plain operands")
+                if not _same_space(op.V, space):
+                    raise ValueError("MatrixOperator lives on a different space than its operands")
             gkey = (id(space), tuple(sorted(id(s) for s in scalars)),
                     tuple(sorted((id(w), c) for w, c in weights)), tuple(id(o.leaf) for o in operands), mkey,
-                    test is not None, trial is not None)
+                    test is not None, trial is not None, id(op) if op is not None else None)
             g = groups.get(gkey)
             if g is None:
                 g = Group(tuple(scalars), tuple(sorted(weights, key=lambda wc: (id(wc[0]), wc[1] or 0))),
-                          tuple(o.leaf for o in operands), meas, space, test is not None, trial is not None)
+                          tuple(o.leaf for o in operands), meas, space, test is not None, trial is not None, op)
                 groups[gkey] = g
                 order.append(gkey)
             idx = ()
@@ -230,8 +240,43 @@ class Atom:
         return ent is not None and ent[1] == fn._version
 
 
-def get_atom(space, T, weights, meas):
+def _embed_operator(ds, op, scale, transpose):
+    """Values of the user matrix (times the scalar form-tensor entry) inside the space's CSR pattern."""
+    import scipy.sparse as sp
+
+    rowptr, colidx, _, _ = ds.pattern
+    rp, ci = rowptr.cpu().numpy().astype(np.int64), colidx.cpu().numpy().astype(np.int64)
+    n = ds.n_dofs
+    A = (op.A.T if transpose else op.A).tocoo()
+    key_pat = np.repeat(np.arange(n, dtype=np.int64), np.diff(rp)) * n + ci  # ascending
+    key_a = A.row.astype(np.int64) * n + A.col.astype(np.int64)
+    pos = np.searchsorted(key_pat, key_a)
+    ok = (pos < len(key_pat))
+    ok[ok] &= key_pat[pos[ok]] == key_a[ok]
+    if np.any(~ok & (A.data != 0.0)):
+        raise NotImplementedError("MatrixOperator has nonzeros outside the Lagrange sparsity pattern of its space")
+    vals = np.zeros(len(key_pat))
+    np.add.at(vals, pos[ok], scale * A.data[ok])
+    sym = (abs(op.A - op.A.T)).max() == 0.0 if op.A.nnz else True
+    return torch.as_tensor(vals).to(ds.coords.device), bool(sym)
+
+
+def get_atom(space, T, weights, meas, op=None, transpose=False):
     ds = device_space(space)
+    if transpose and op is None:
+        T = np.ascontiguousarray(T.transpose(2, 3, 0, 1))
+    if op is not None:
+        key = ("op", id(op), op._version, T.tobytes(), bool(transpose))
+        a = ds.atoms.get(key)
+        if a is None:
+            nz = np.argwhere(T != 0.0)
+            if len(nz) != 1 or tuple(nz[0]) != (0, 0, 0, 0):
+                raise NotImplementedError("MatrixOperator applied to derivatives / vector components")
+            vals, sym = _embed_operator(ds, op, float(T[0, 0, 0, 0]), bool(transpose))
+            a = Atom(ds, vals, sym)
+            a.keepalive = op
+            ds.atoms[key] = a
+        return a
     if meas.kind != "dx":
         raise NotImplementedError("bilinear forms over '%s' (only dx)" % meas.kind)
     mk = _measure_key(meas)
@@ -276,10 +321,11 @@ def get_load(space, L, weights, meas):
 class _Functional:
     """Payload of a LazyScalar leaf: one mode integral, evaluated in the next flush."""
 
-    __slots__ = ("kind", "space", "T", "weights", "measure", "f1", "f2", "v1", "v2")
+    __slots__ = ("kind", "space", "T", "weights", "measure", "f1", "f2", "v1", "v2", "op")
 
-    def __init__(self, kind, space, T, weights, measure, f1=None, f2=None):
+    def __init__(self, kind, space, T, weights, measure, f1=None, f2=None, op=None):
         self.kind, self.space, self.T, self.weights, self.measure, self.f1, self.f2 = kind, space, T, weights, measure, f1, f2
+        self.op = op
         self.v1 = f1._version if f1 is not None else None
         self.v2 = f2._version if f2 is not None else None
 
@@ -289,7 +335,7 @@ def _functional_value(g):
     n = len(g.operands)
     T = g.tensor()
     if n == 2:
-        p = _Functional("bil", g.space, T, g.weights, g.measure, g.operands[0], g.operands[1])
+        p = _Functional("bil", g.space, T, g.weights, g.measure, g.operands[0], g.operands[1], g.op)
     elif n == 1:
         p = _Functional("lin", g.space, T, g.weights, g.measure, g.operands[0])
     else:
@@ -316,14 +362,14 @@ def _flush(leaves):
             continue
         if p.measure.kind != "dx":
             raise NotImplementedError("bilinear functionals over '%s'" % p.measure.kind)
-        atom = get_atom(p.space, p.T, p.weights, p.measure)
+        atom = get_atom(p.space, p.T, p.weights, p.measure, p.op)
         x = stable = None
         at = atom
         if p.f2.stable or atom.has_fresh(p.f2):
             stable, x = p.f2, p.f1
         elif p.f1.stable:
             stable, x = p.f1, p.f2
-            at = atom if atom.symmetric else get_atom(p.space, np.ascontiguousarray(p.T.transpose(2, 3, 0, 1)), p.weights, p.measure)
+            at = atom if atom.symmetric else get_atom(p.space, p.T, p.weights, p.measure, p.op, transpose=True)
         if stable is None or stable is x:
             direct.append((n_slots, "bil", (atom, p.f1.tensor(), p.f2.tensor())))
             plan.append((leaf, n_slots))
@@ -398,10 +444,11 @@ def assemble_vector(groups, out=None):
         if len(g.operands) == 0:
             vecs.append(get_load(g.space, g.tensor(), g.weights, g.measure))
         elif len(g.operands) == 1:
-            atom = get_atom(g.space, g.tensor(), g.weights, g.measure)
+            atom = get_atom(g.space, g.tensor(), g.weights, g.measure, g.op)
             f = g.operands[0]
             if f.stable or atom.has_fresh(f):
-                vecs.append(atom.panel[atom.product(f)])
+                row = atom.product(f)
+                vecs.append(atom.panel[row])
             else:
                 rowptr, colidx, _, _ = atom.ds.pattern
                 vecs.append(_lib.spmv(rowptr, colidx, atom.values, f.tensor(), lpr=atom.ds.lpr))
@@ -433,7 +480,7 @@ def assemble_matrix(groups, out=None):
     for g in groups:
         if not _same_space(g.space, space) or g.operands:
             raise NotImplementedError("bilinear form with Function operands (non-linear form?)")
-        atoms.append(get_atom(g.space, g.tensor(), g.weights, g.measure))
+        atoms.append(get_atom(g.space, g.tensor(), g.weights, g.measure, g.op))
     coefs = _coefs(groups)
     vals = _lib.lincomb([a.values for a in atoms], coefs, out=out)
     m = AssembledMatrix(ds, vals)

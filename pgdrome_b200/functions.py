@@ -233,6 +233,42 @@ class UserExpression(Expression):
         return out[..., 0] if self._n == 1 else out
 
 
+# ------------------------------------------------------------------------------- MatrixOperator
+class MatrixOperator(Leaf):
+    """A user-assembled sparse operator on the dofs of a space (the reference's FD matrices
+    ``M``, ``D2``, ``D1_up`` of pgdrome/solver.py:947-988, which its callbacks apply with host
+    SciPy products: tests/integration/test_heat1D.py:291-306) lifted into the form language so that
+    the whole sweep stays on the device::
+
+        D1 = MatrixOperator(D1_up_t, V_t)
+        a  = Constant(c) * D1(u, v) * dx(mesh_t)          # operator atom (row = v, col = u)
+        s  = assemble(D1(G, F) * dx(mesh_t))              # mode integral  F^T D1 G
+
+    The nonzeros must lie inside the Lagrange sparsity pattern of ``V`` (true for the tridiagonal FD
+    operators on a 1-D P1 space); they are embedded once, at set-up."""
+
+    kind = "operator"
+
+    def __init__(self, A, V):
+        import scipy.sparse as sp
+
+        self.V = V
+        self.A = sp.csr_matrix(A).astype(np.float64)
+        if self.A.shape != (V.n_dofs, V.n_dofs):
+            raise ValueError("operator shape %s does not match the space (%d dofs)" % (self.A.shape, V.n_dofs))
+        self._version = 0
+        self._init_leaf(1)
+
+    def __call__(self, u, v):
+        """Form integrand with u in the trial (column) role and v in the test (row) role."""
+        from .ufl import Expr
+
+        u, v = Expr.wrap(u), Expr.wrap(v)
+        if u is None or v is None or not (u.is_scalar and v.is_scalar):
+            raise NotImplementedError("MatrixOperator needs scalar operands")
+        return self * v * u
+
+
 # ------------------------------------------------------------------------------- Function / Vector
 class Vector:
     """Host-facing proxy of a Function's device dof vector (``f.vector()``)."""

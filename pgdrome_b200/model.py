@@ -1,0 +1,493 @@
+"""PGD model container and ``evaluate`` on the B200 (pgdrome/model.py:25-160, 589-860, 955-1086,
+1456-1825).
+
+Same classes and call signatures as the reference (``PGD``/``PGDModel``, ``PGDMesh``,
+``PGDAttribute``, ``PGDErrorComputation``); the rank-R reconstruction
+
+    u(fixed dofs; coord) = sum_k X[k, :] * prod_i phi_{i,k}(coord_i)          model.py:780-860
+
+runs as two libpgdb200 kernels: ``pgd_eval_weights`` (1-D Lagrange / piecewise-linear interpolation
+of every free-dimension mode at every parameter point, replaces interp1d / Function.__call__ at
+model.py:798,838) and ``pgd_eval_gemv`` (one point) or the FP64 tensor-core GEMM
+``pgd_eval_gemm_f64`` (a batch of points: ``evaluate_batch`` -- the vademecum sweep the reference
+performs as a Python loop of single evaluations, model.py:1785-1803).
+
+Out of scope (C13-C15): PXDMF/XDMF/HDF5 I/O, sensor/derivative evaluation -- the
+methods exist and raise NotImplementedError naming themselves.
+"""
+import logging
+
+import numpy as np
+import torch
+from scipy.stats import qmc
+
+from . import _lib
+from .functions import Function, _device
+
+LOGGER = logging.getLogger(__name__)
+
+
+class _LazyData:
+    """``PGDAttribute.data`` for modes that live on the device: the vertex-order host arrays
+    (model.py:1510-1556) are only materialised when somebody indexes them."""
+
+    def __init__(self, attr, num_modes, mesh, pgd_modes):
+        self._attr, self._n, self._mesh, self._modes = attr, num_modes, mesh, pgd_modes
+        self._cache = {}
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self[i] for i in range(*k.indices(self._n))]
+        if k < 0:
+            k += self._n
+        if not 0 <= k < self._n:
+            raise IndexError(k)
+        if k not in self._cache:
+            self._cache[k] = self._attr._vertex_data(self._mesh, self._modes[k])
+        return self._cache[k]
+
+    def __iter__(self):
+        return (self[k] for k in range(self._n))
+
+
+class PGDAttribute(object):
+    def __init__(self, num_modes=0, mesh=None, pgd_modes=None, modes_info=None):
+        """modes_info: [name, type (Node|Cell), field (Scalar|Vector)]  (model.py:1456-1494)."""
+        self.logger = logging.getLogger(__name__ + "." + self.__class__.__name__)
+        if modes_info is not None:
+            self.name = modes_info[0]
+            self._type = modes_info[1]
+            self.field = modes_info[2]
+        self.data = list()
+        self.interpolationInfo = {"name": 1}
+        self.interpolationfct = list()
+        self.derivationfct = list()
+        for ctr in range(num_modes):
+            self.interpolationfct.append(pgd_modes[ctr])
+        self.fill_data(num_modes, mesh, pgd_modes)
+
+    def _vertex_data(self, mesh, mode):
+        t = self._type.lower()
+        if t == "node":
+            out = np.zeros((mesh.numNodes, mesh.meshdim))
+        elif t == "cell":
+            out = np.zeros((mesh.numElements, mesh.meshdim))
+        else:
+            raise ValueError(" Error in filling attribute data: self._type not known")
+        # the reference only fills scalar nodal fields (the vector branch is dead code because of
+        # the missing call in ``self.field.lower == "vector"``, model.py:1529)
+        if self.field.lower() == "scalar" and t == "node":
+            out[:, 0] = mode.compute_vertex_values()[:]
+        return out
+
+    def fill_data(self, num_modes, mesh, pgd_modes):
+        if num_modes and pgd_modes is not None:
+            self.data = _LazyData(self, num_modes, mesh, pgd_modes)
+        else:
+            self.data = list()
+        return self
+
+    def print_info(self):
+        print("\n")
+        print("summary of PGDAttribute class")
+        print("----------------------------")
+        print("name:                        ", self.name)
+        print("type:                        ", self._type)
+        print("field type:                  ", self.field)
+        print("len of data:                 ", len(self.data))
+        print("interpolationInfo:           ", self.interpolationInfo)
+        print("len of interpolation fct     ", len(self.interpolationfct))
+        print("\n")
+
+
+class PGDMesh(object):
+    """Mesh wrapper of one PGD coordinate (model.py:1573-1663)."""
+
+    def __init__(self, name=None, mesh=None, name_coord=None, pgd_modes=None, num_modes=0, modes_info=None):
+        self.logger = logging.getLogger(__name__ + "." + self.__class__.__name__)
+        self.name = name
+        self.meshdim = mesh.topology().dim() if mesh is not None else 0
+        self.info = [self.meshdim, name_coord, "-?-"]
+        self.numElements = mesh.num_cells() if mesh is not None else None
+        self.numNodes = mesh.num_vertices() if mesh is not None else 0
+        self.topology = mesh.cells() if mesh is not None else None
+        self.typGeometry = "XYZ"
+        self.dataX = np.zeros(self.numNodes)
+        self.dataY = np.zeros(self.numNodes)
+        self.dataZ = np.zeros(self.numNodes)
+        self.fenics_mesh = mesh
+        if self.meshdim == 1:
+            self.dataX = mesh.coordinates()[:, 0]
+            self.typElements = "Polyline"
+        elif self.meshdim == 2:
+            xy = mesh.coordinates()[:]
+            self.dataX, self.dataY = xy[:, 0], xy[:, 1]
+            self.typElements = "Triangle"
+        elif self.meshdim == 3:
+            xyz = mesh.coordinates()
+            self.dataX, self.dataY, self.dataZ = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+            self.typElements = "Tetrahedron"
+        self.attributes = list()
+        if mesh is not None or modes_info is not None:
+            self.attributes.append(PGDAttribute(num_modes, self, pgd_modes, modes_info=modes_info))
+
+    def print_info(self):
+        print("\n")
+        print("summary of PGDMesh class")
+        print("----------------------------")
+        print("name:                            ", self.name)
+        print("info:                            ", self.info)
+        print("number of Elements:              ", self.numElements)
+        print("number of Nodes:                 ", self.numNodes)
+        print("number of saved attributes:      ", len(self.attributes))
+        print("\n")
+
+
+def _as_f64(a):
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(_device())
+
+
+def _as_i32(a):
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(_device())
+
+
+class _FreeDim:
+    """Device description of one free dimension for pgd_eval_weights: ascending cell boundaries xs,
+    per-cell dof triples cd, degree, and the modes Phi [R, n]."""
+
+    __slots__ = ("xs", "cd", "deg", "Phi", "lo", "hi")
+
+
+class PGD:
+    """Stores the PGD solution (meshes + modes) and evaluates it (model.py:25-160, 724-1086)."""
+
+    def __init__(self, name=None, n_modes=None, fmeshes=[], pgd_modes=None, name_coord=None, modes_info=None,
+                 verbose=False, problem=None, *args, **kwargs):
+        self.logger = logging.getLogger(__name__)
+        self.name = name
+        self.folder = ""
+        self.numModes = n_modes
+        self.used_numModes = n_modes
+        self.mesh = list()
+        self.name_coord = name_coord
+        self.modes_info = modes_info
+        for ctr, mesh in enumerate(fmeshes):
+            grid = PGDMesh("PGD" + str(ctr + 1), mesh, self.name_coord[ctr], pgd_modes[ctr], self.numModes,
+                           modes_info=self.modes_info)
+            self.mesh.append(grid)
+            if verbose:
+                for att in grid.attributes:
+                    att.print_info()
+                grid.print_info()
+        self.problem = None
+        self.pos = 0
+        self._eval_fixed_modes = {}
+        self._dev_cache = {}
+
+    def __str__(self):
+        return "PGD(name: %s)(meshes: %s)(modes: %s)" % (self.name, len(self.mesh), self.numModes)
+
+    def __repr__(self):
+        return f"{str(self)}"
+
+    @property
+    def num_pgd_var(self):
+        return len(self.mesh)
+
+    @property
+    def fenics_meshes(self):
+        return [m.fenics_mesh for m in self.mesh]
+
+    def _info_str(self):
+        info = "summary of PGDModel class\n"
+        info += "-------------------------------\n"
+        info += "name:                          %s\n" % self.name
+        info += "number of PGD variables:       %s\n" % self.num_pgd_var
+        info += "number of modes for each mesh -- max: %s -- used: %s\n" % (self.numModes, self.used_numModes)
+        info += "number of saved meshes:        %s\n" % len(self.mesh)
+        info += "number of elements per mesh:    "
+        for i in range(0, len(self.mesh)):
+            info += " %s, " % self.mesh[i].numElements
+        info += "\nfolder:                        %s" % self.folder
+        return info
+
+    def print_info(self):
+        print("\n" + self._info_str() + "\n")
+
+    def create_from_problem(self, problem=None):
+        self.problem = problem
+        self.name = problem.name
+        return self
+
+    # ------------------------------------------------------------------ out of scope (I/O, sensors)
+    def _out_of_scope(self, what):
+        raise NotImplementedError("PGD.%s is outside the B200 hot path (SURVEY.md 2.1 C13-C15)" % what)
+
+    def write_hdf5(self, *a, **k):
+        self._out_of_scope("write_hdf5")
+
+    def write_pxdmf(self, *a, **k):
+        self._out_of_scope("write_pxdmf")
+
+    def load_pxdmf(self, *a, **k):
+        self._out_of_scope("load_pxdmf")
+
+    def evaluate_sensor_response(self, *a, **k):
+        self._out_of_scope("evaluate_sensor_response")
+
+    def evaluate_derivative(self, *a, **k):
+        self._out_of_scope("evaluate_derivative")
+
+    # ------------------------------------------------------------------ interpolation set-up
+    def create_interpolation_fcts(self, free_dim, attri, verbose=True):
+        """Prepare the free dimensions for evaluation (model.py:589-722).  name == 0: piecewise-linear
+        interpolation of the vertex data (scipy interp1d semantics, only kind='linear' exists on the
+        device); name == 1: the modes' own Lagrange spaces.  Builds the device tables once."""
+        if len(free_dim) > self.num_pgd_var:
+            raise ValueError("given number of Dimensions larger then existing Meshes in PGD solution")
+        if attri > len(self.mesh[free_dim[0]].attributes):
+            raise ValueError("attribute number not possible")
+        for d in free_dim:
+            att = self.mesh[d].attributes[attri]
+            name = att.interpolationInfo["name"]
+            if name == 0:
+                if sum(self.mesh[d].dataY) != 0 and sum(self.mesh[d].dataZ) != 0:
+                    raise ValueError("free Dimensions are not 1D, interpolation with INTERP1D not possible")
+                kind = att.interpolationInfo.get("kind", "linear")
+                if kind != "linear":
+                    raise NotImplementedError("interp1d kind '%s' (the device kernel interpolates linearly)" % kind)
+                att.interpolationfct = [("interp1d", d, k) for k in range(self.numModes)]
+            elif name == 1:
+                if not att.interpolationfct:
+                    self._out_of_scope("create_interpolation_fcts from *_data.h5 files")
+            else:
+                self.logger.error("interpolation name not defined: %s", name)
+            self._dev_cache.pop(("free", d, attri), None)
+        self.logger.info("Attribute interpolation functions saved")
+
+    def _free_dev(self, d, attri):
+        key = ("free", d, attri)
+        att = self.mesh[d].attributes[attri]
+        name = att.interpolationInfo["name"]
+        R = self.numModes
+        ent = self._dev_cache.get(key)
+        if ent is not None and ent[0] == (name, R):
+            return ent[1]
+        f = _FreeDim()
+        if name == 0:
+            x = np.asarray(self.mesh[d].dataX, dtype=np.float64)
+            order = np.argsort(x, kind="stable")
+            nc = len(x) - 1
+            f.xs = _as_f64(x[order])
+            f.cd = _as_i32(np.column_stack([order[:-1], order[1:]]))
+            f.deg = 1
+            f.Phi = _as_f64(np.stack([np.asarray(att.data[k])[:, 0] for k in range(R)]))
+            f.lo, f.hi = float(x.min()), float(x.max())
+        else:
+            modes = att.interpolationfct[:R]
+            V = modes[0].function_space()
+            m = V.mesh()
+            if m.tdim != 1 or V.bs != 1:
+                raise NotImplementedError("free dimensions must be scalar 1-D Lagrange spaces")
+            X = m.coordinates()[:, 0]
+            cells = m.cells()
+            left = np.where(X[cells[:, 0]] <= X[cells[:, 1]], 0, 1)
+            lo_v = cells[np.arange(len(cells)), left]
+            corder = np.argsort(X[lo_v], kind="stable")
+            cn = V.cell_nodes[corder]
+            lf = left[corder]
+            cols = [np.where(lf == 0, cn[:, 0], cn[:, 1]), np.where(lf == 0, cn[:, 1], cn[:, 0])]
+            if V.degree == 2:
+                cols.append(cn[:, 2])
+            xs = np.concatenate([X[lo_v][corder], [X.max()]])
+            f.xs, f.cd, f.deg = _as_f64(xs), _as_i32(np.column_stack(cols)), V.degree
+            f.Phi = torch.stack([mo.tensor() for mo in modes]).contiguous()
+            f.lo, f.hi = float(X.min()), float(X.max())
+        self._dev_cache[key] = ((name, R), f)
+        return f
+
+    def _fixed_dev(self, d, attri, name):
+        """X [R, N]: the fixed dimension's modes, vertex data (name 0) or dof vectors (name 1)."""
+        key = ("fixed", d, attri, name)
+        R = self.numModes
+        ent = self._dev_cache.get(key)
+        if ent is not None and ent[0] == R:
+            return ent[1]
+        att = self.mesh[d].attributes[attri]
+        if name == 0:
+            X = _as_f64(np.stack([np.asarray(att.data[k]).reshape(-1) for k in range(R)]))
+        else:
+            X = torch.stack([mo.tensor() for mo in att.interpolationfct[:R]]).contiguous()
+        self._dev_cache[key] = (R, X)
+        return X
+
+    def invalidate_device_cache(self):
+        self._dev_cache = {}
+
+    def _weights(self, free_dim, coords, attri):
+        """W [R_used, C] on the device for coords [C, n_free]; raises ValueError outside the range."""
+        fr = [self._free_dev(d, attri) for d in free_dim]
+        R = self.used_numModes
+        pts = _as_f64(np.asarray(coords, dtype=np.float64).reshape(-1, len(free_dim)))
+        W, flag = _lib.eval_weights([f.xs for f in fr], [f.cd for f in fr], [f.Phi for f in fr], [f.deg for f in fr], R, pts)
+        bad = int(flag.item())
+        if bad:
+            f = fr[bad - 1]
+            raise ValueError("A value in the coordinate of free dimension %d is outside the interpolation range [%s, %s]"
+                             % (free_dim[bad - 1], f.lo, f.hi))
+        return W
+
+    def _check_args(self, fixed_dim, free_dim, coord, attri):
+        if len(free_dim) != self.num_pgd_var - 1:
+            raise ValueError("given variables are missing or to much, free_dim=%s <-> num_pgd_var=%s", free_dim,
+                             self.num_pgd_var - 1)
+        if len(coord) != self.num_pgd_var - 1:
+            raise ValueError("given variables are missing or to much, coord=%s <-> num_pgd_var=%s", coord,
+                             self.num_pgd_var - 1)
+        if len(free_dim) != len(coord):
+            raise ValueError("Number of free Dimensions and given coordinates are not the same, free_dim=%s <-> coord=%s",
+                             free_dim, coord)
+        if attri >= len(self.mesh[fixed_dim].attributes):
+            raise ValueError("attribute number not possible")
+        for idx in free_dim:
+            if len(self.mesh[idx].attributes[attri].interpolationfct) == 0:
+                self.create_interpolation_fcts(free_dim, attri)
+                break
+
+    # ------------------------------------------------------------------ evaluate
+    def evaluate(self, fixed_dim, free_dim, coord, attri):
+        """Reconstruct the PGD solution on the fixed variable at one parameter point
+        (model.py:724-860).  name == 0 -> ndarray shaped like the vertex data; else a Function."""
+        self._check_args(fixed_dim, free_dim, coord, attri)
+        name = self.mesh[free_dim[0]].attributes[attri].interpolationInfo["name"]
+        W = self._weights(free_dim, [coord], attri)
+        X = self._fixed_dev(fixed_dim, attri, 0 if name == 0 else 1)
+        u = _lib.eval_gemv(X, self.used_numModes, W[:, 0].contiguous())
+        if name == 0:
+            shape = np.asarray(self.mesh[fixed_dim].attributes[attri].data[0]).shape
+            return u.cpu().numpy().reshape(shape)
+        V = self.mesh[fixed_dim].attributes[attri].interpolationfct[0].function_space()
+        return Function(V, u)
+
+    def evaluate_batch(self, fixed_dim, free_dim, coords, attri, out=None, rows=None):
+        """Vademecum sweep: coords [C, D-1] -> device tensor U [C, N] (one FP64 tensor-core GEMM).
+        ``rows=(n0, n1)`` restricts the fixed dimension to a dof range (sharded evaluation: each
+        rank reconstructs its own slice of the spatial points, no communication)."""
+        coords = np.asarray(coords, dtype=np.float64)
+        if coords.ndim != 2:
+            raise ValueError("coords must be [n_points, n_free_dims]")
+        self._check_args(fixed_dim, free_dim, coords[0] if len(coords) else [0.0] * len(free_dim), attri)
+        name = self.mesh[free_dim[0]].attributes[attri].interpolationInfo["name"]
+        W = self._weights(free_dim, coords, attri)
+        X = self._fixed_dev(fixed_dim, attri, 0 if name == 0 else 1)
+        if rows is not None:
+            X = X[:, rows[0]:rows[1]]
+        return _lib.eval_gemm(W, X, self.used_numModes, out=out)
+
+    def _values(self, fixed_dim, free_dim, coord, attri):
+        r = self.evaluate(fixed_dim, free_dim, coord, attri)
+        return r if isinstance(r, np.ndarray) else r.vector()[:]
+
+    def evaluate_min(self, fixed_dim, free_dim, coord, attri, *args, **kwargs):
+        return self._values(fixed_dim, free_dim, coord, attri).min()
+
+    def evaluate_min_abs(self, fixed_dim, free_dim, coord, attri, *args, **kwargs):
+        return abs(self._values(fixed_dim, free_dim, coord, attri)).min()
+
+    def evaluate_max(self, fixed_dim, free_dim, coord, attri, *args, **kwargs):
+        return self._values(fixed_dim, free_dim, coord, attri).max()
+
+    def evaluate_max_abs(self, fixed_dim, free_dim, coord, attri, *args, **kwargs):
+        return abs(self._values(fixed_dim, free_dim, coord, attri)).max()
+
+    def evaluate_max_norm(self, fixed_dim, free_dim, coord, attri, *args, **kwargs):
+        new = self.evaluate(fixed_dim, free_dim, coord, attri)
+        if isinstance(new, np.ndarray):
+            return max(np.linalg.norm(new, axis=1))
+        V = new.function_space()
+        if V.mesh().geometry().dim() == 1:
+            raise ValueError("Function is 1D use evaluate_max instead!!")
+        return float(np.linalg.norm(new.vector()[:].reshape(V.n_nodes, V.bs), axis=1).max())
+
+    def evaluate_abs_value(self, fixed_dim, free_dim, coord, attri, *args, **kwargs):
+        new = self.evaluate(fixed_dim, free_dim, coord, attri)
+        return np.abs(new(self.pos)).max()
+
+
+PGDModel = PGD
+
+
+class PGDErrorComputation(object):
+    """LHS sampling + relative L2 error of the PGD against a full-order model (model.py:1666-1825)."""
+
+    def __init__(self, fixed_dim=0, n_samples=1, data_test=[], FOM_model=[], PGD_model=[], lim_samples=[], fixed_var=[],
+                 *args, **kwargs):
+        self.fixed_dim = fixed_dim
+        self.n_smp = n_samples
+        self.data_test = data_test
+        self.FOM_sol = FOM_model
+        self.PGD_sol = PGD_model
+        self.lim_smp = lim_samples
+        self.fixed_var = fixed_var
+        self.free_dim = [item for item in list(range(0, self.PGD_sol.num_pgd_var)) if item not in fixed_dim]
+
+    def sampling_LHS(self):
+        sampler = qmc.LatinHypercube(d=len(self.free_dim), seed=3452)
+        sample = sampler.random(n=self.n_smp)
+        min_bnd = [None] * len(self.free_dim)
+        max_bnd = [None] * len(self.free_dim)
+        ind = 0
+        if not self.lim_smp:
+            for i in self.free_dim:
+                c = self.PGD_sol.problem.meshes[i].coordinates()
+                if len(c[0]) == 1:
+                    min_bnd[ind] = float(c.min())
+                    max_bnd[ind] = float(c.max())
+                    ind = ind + 1
+                else:
+                    print("Not implemented")
+        else:
+            for i in self.free_dim:
+                if len(self.lim_smp[i]) == 2:
+                    min_bnd[ind] = float(min(self.lim_smp[i]))
+                    max_bnd[ind] = float(max(self.lim_smp[i]))
+                    ind = ind + 1
+                else:
+                    print("Not implemented")
+        return qmc.scale(sample, min_bnd, max_bnd).tolist()
+
+    def compute_SampleError(self, u_FOM, u_PGD):
+        if isinstance(u_FOM, np.ndarray) and isinstance(u_PGD, np.ndarray):
+            residual = u_PGD.reshape(-1) - u_FOM.reshape(-1)
+            return np.linalg.norm(residual, 2) / np.linalg.norm(u_FOM.reshape(-1), 2)
+        if isinstance(u_FOM, np.ndarray):
+            residual = u_PGD.compute_vertex_values()[:] - u_FOM.reshape(-1)
+            return np.linalg.norm(residual, 2) / np.linalg.norm(u_FOM.reshape(-1), 2)
+        a, b = u_FOM.tensor(), u_PGD.tensor()
+        d = a - b
+        return float(np.sqrt(_lib.dot(d, d).item()) / np.sqrt(_lib.dot(a, a).item()))
+
+    def evaluate_error(self):
+        if not self.data_test:
+            self.data_test = self.sampling_LHS()
+        errorL2 = np.zeros(len(self.data_test))
+        for i in range(len(self.data_test)):
+            if self.FOM_sol:
+                u_fem = self.FOM_sol(self.data_test[i])
+                if isinstance(u_fem, float):
+                    u_fem = np.array(u_fem)
+            else:
+                raise ValueError("FEM not defined")
+            if self.PGD_sol:
+                u_pgd = self.PGD_sol.evaluate(int(self.fixed_dim[0]), self.free_dim, self.data_test[i], 0)
+            else:
+                raise ValueError("PGD model not defined")
+            if not self.fixed_var:
+                errorL2[i] = self.compute_SampleError(u_fem, u_pgd)
+            else:
+                u_pgdPoint = np.array([u_pgd(item) for item in self.fixed_var])
+                errorL2[i] = self.compute_SampleError(u_fem, u_pgdPoint)
+        return errorL2, np.mean(errorL2), np.max(errorL2)

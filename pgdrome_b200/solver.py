@@ -26,9 +26,11 @@ import torch
 
 from . import _lib, forms, lazy
 from .assembly import device_space
-from .functions import Constant, DeviceVector, Expression, Function, bc_list, interpolate, merged_bc_dofs
+from .functions import (Constant, DeviceVector, Expression, Function, MatrixOperator, bc_list, interpolate,
+                        merged_bc_dofs)
 from .lazy import LazyScalar
 from .ufl import Form, TestFunction, TrialFunction, derivative
+from .ufl import dx as forms_dx
 
 F64, I32 = torch.float64, torch.int32
 
@@ -149,12 +151,26 @@ class PGDProblem:
     def _is_fd(self, solve_modes, dim):
         return solve_modes is not None and solve_modes[dim] == self.solve_mode["FD"]
 
-    def _norm(self, f, dim, solve_modes):
-        """LazyScalar / float  ||f||: dolfin.norm, or sqrt(f^T MM f) for FD dims (solver.py:198-207)."""
+    def _mm_operator(self, dim):
+        """MM[dim] given as a device MatrixOperator (extension: keeps FD-type norms on the device)."""
+        if len(self.MM) > dim and isinstance(self.MM[dim], MatrixOperator):
+            return self.MM[dim]
+        return None
+
+    def _mass_product(self, f, g, dim, solve_modes):
+        """<f, g> in the norm of dimension dim: MM[dim] for FD dims (solver.py:198-207, 814-835),
+        the consistent L2 mass otherwise.  LazyScalar or float."""
+        op = self._mm_operator(dim)
+        if op is not None:
+            return forms.assemble(op(g, f) * forms_dx(self.meshes[dim]))
         if self._is_fd(solve_modes, dim):
-            t = f.tensor()
-            return float(self._mm(dim).product(t, t).item()) ** 0.5
-        return forms.norm(f)
+            return float(self._mm(dim).product(f.tensor(), g.tensor()).item())
+        return forms.mass_product(f, g)
+
+    def _norm(self, f, dim, solve_modes):
+        """LazyScalar / float  ||f||: dolfin.norm, or sqrt(f^T MM f) for FD dims."""
+        r = self._mass_product(f, f, dim, solve_modes)
+        return r.sqrt() if isinstance(r, LazyScalar) else float(r) ** 0.5
 
     # ------------------------------------------------------------------ initial modes
     def get_Fsinit(self, V, bc=None, solve_modes=None):
@@ -331,14 +347,14 @@ class PGDProblem:
             newnew, newold, oldold = 1, 1, 1
             terms = []
             for d in range(D):
-                if self._is_fd(solve_modes, d):
+                if self._is_fd(solve_modes, d) and self._mm_operator(d) is None:
                     M = self._mm(d)
                     tn, to = Fs[d].tensor(), Fs_init[d].tensor()
                     trip = torch.cat([M.product(tn, tn), M.product(tn, to), M.product(to, to)]).cpu().numpy()
                     terms.append((float(trip[0]), float(trip[1]), float(trip[2])))
                 else:
-                    terms.append((forms.norm(Fs[d]) ** 2, forms.mass_product(Fs[d], Fs_init[d]),
-                                  forms.norm(Fs_init[d]) ** 2))
+                    terms.append((self._norm(Fs[d], d, solve_modes) ** 2, self._mass_product(Fs[d], Fs_init[d], d, solve_modes),
+                                  self._norm(Fs_init[d], d, solve_modes) ** 2))
             for nn, no, oo in terms:
                 newnew *= _f(nn)
                 newold *= _f(no)

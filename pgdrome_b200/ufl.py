@@ -160,6 +160,8 @@ class Expr:
                     kind = f.leaf.kind
                     if kind in ("constant", "lazy"):
                         continue
+                    if kind == "operator":
+                        raise NotImplementedError("derivative of a MatrixOperator term")
                     if kind == "expression":
                         raise NotImplementedError("derivative of an Expression (interpolate it into a Function first)")
                     if f.deriv is not None:

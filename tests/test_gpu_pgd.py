@@ -1,0 +1,85 @@
+"""-m gpu: the public API (PGDProblem.solve_PGD, PGD.evaluate) on the B200 against the CPU oracle.
+
+Bar (north_star): each normalised mode and the reconstruction agree to 1e-8 relative L2 (up to
+sign), at matching fixed-point iteration counts."""
+import numpy as np
+import pytest
+
+from oracle import fem as ofem
+from oracle import pgd as opgd
+from oracle import problems as oprob
+from oracle.evaluate import evaluate_dofs
+
+pytestmark = pytest.mark.gpu
+
+MODE_RTOL = 1e-8
+
+
+def _ospaces(p):
+    return [ofem.Space(v.mesh().coordinates(), v.mesh().cells(), v.degree, v.bs) for v in p.V]
+
+
+def _mode_err(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return min(np.linalg.norm(a - b), np.linalg.norm(a + b)) / np.linalg.norm(b)
+
+
+def _compare(p, o, tol=MODE_RTOL):
+    assert p.PGD_modes == o.PGD_modes
+    assert p.num_fp_it == o.num_fp_it
+    for d in range(len(p.V)):
+        for k in range(p.PGD_modes):
+            assert _mode_err(p.PGD_func[d][k].vector()[:], o.PGD_func[d][k]) < tol, (d, k)
+    assert np.allclose(p.amplitude, o.amplitude, rtol=1e-8, atol=0)
+
+
+def test_config1_poisson1d_k_full_size():
+    """BASELINE configs[0] at full size: 1000 nodes x 101 k-nodes, PGD_nmax = 10."""
+    from pgdrome_b200 import configs
+
+    p = configs.poisson1d_k()
+    p.solve_PGD(_problem="linear")
+    o, _ = oprob.poisson1d_k(spaces=_ospaces(p))
+    opgd.solve_pgd(o)
+    _compare(p, o)
+    # analytic solution u = x(1-x)/(2k)
+    pgd = p.return_PGD()
+    x = p.V[0].tabulate_dof_coordinates()[:, 0]
+    for k in (0.5, 1.234, 2.0):
+        u = pgd.evaluate(0, [1], [k], 0).vector()[:]
+        assert np.abs(u - x * (1 - x) / (2 * k)).max() < 1e-5
+    # reconstruction parity with the oracle's evaluate loop, single point and batched
+    sk = _ospaces(p)[1]
+    uo = evaluate_dofs(o.PGD_func[0], [sk], [o.PGD_func[1]], [1.234])
+    u = pgd.evaluate(0, [1], [1.234], 0).vector()[:]
+    assert np.linalg.norm(u - uo) / np.linalg.norm(uo) < MODE_RTOL
+    ks = np.linspace(0.5, 2.0, 37)[:, None]
+    U = pgd.evaluate_batch(0, [1], ks, 0).cpu().numpy()
+    for c in (0, 11, 36):
+        uo = evaluate_dofs(o.PGD_func[0], [sk], [o.PGD_func[1]], ks[c])
+        assert np.linalg.norm(U[c] - uo) / np.linalg.norm(uo) < MODE_RTOL
+    with pytest.raises(ValueError):
+        pgd.evaluate(0, [1], [2.5], 0)
+
+
+def test_config1_newton_equals_linear():
+    from pgdrome_b200 import configs
+
+    a = configs.poisson1d_k(nx=120, nk=20, PGD_nmax=5)
+    a.solve_PGD(_problem="linear")
+    b = configs.poisson1d_k(nx=120, nk=20, PGD_nmax=5)
+    b.solve_PGD()  # default "nonlinear"
+    assert np.allclose(a.amplitude, b.amplitude, rtol=1e-8, atol=0)
+
+
+@pytest.mark.parametrize("n,nt,nk,nmax", [(16, 20, 6, 3), (48, 40, 10, 4)])
+def test_config2_heat2d_tk_reduced(n, nt, nk, nmax):
+    """BASELINE configs[1] at sizes the oracle's SuperLU finishes in seconds."""
+    from pgdrome_b200 import configs
+
+    p = configs.heat2d_tk(n=n, nt=nt, nk=nk, PGD_nmax=nmax)
+    p.solve_PGD(_problem="linear")
+    o, _ = oprob.heat2d_tk(n=n, nt=nt, nk=nk, PGD_nmax=nmax, spaces=_ospaces(p))
+    opgd.solve_pgd(o)
+    _compare(p, o)
+    assert p.solver_stats["pcg_solves"] > 0 and p.solver_stats["banded_solves"] > 0
