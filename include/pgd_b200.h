@@ -27,6 +27,10 @@ int32_t pgd_abi_version(void);
 int32_t pgd_create(int32_t device, pgd_handle_t* out);
 int32_t pgd_destroy(pgd_handle_t h);
 const char* pgd_last_error(pgd_handle_t h);
+/* library-side counters since the last reset: h_counts[0] kernels launched, [1] PCG solves,
+ * [2] PCG iterations; *h_pcg_ms device time (CUDA events on the solve's stream) spent in the PCG
+ * iteration kernels.  Used by bench.py for gpu_launches and the live roofline. */
+int32_t pgd_get_stats(pgd_handle_t h, int64_t* h_counts, double* h_pcg_ms, int32_t reset);
 
 /* ---- sparsity pattern (DOLFIN SparsityPatternBuilder behind solver.py:627-636: union of per-cell
  * dof cliques, columns ascending).  build: sorts the n_cells*ndl^2 (row,col) contributions; the

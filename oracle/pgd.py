@@ -153,8 +153,9 @@ def FP_solve(p, Fs_init, norm_Fs, n_enr):
     return Fs, norm_Fs
 
 
-def solve_pgd(p, rng=None):
-    """solver.py:306-506."""
+def solve_pgd(p, rng=None, step_hook=None):
+    """solver.py:306-506.  step_hook(n_enr) is called after every completed enrichment step
+    (bench.py's CPU legs time the steps with it)."""
     D = p.D
     p.PGD_func = [[] for _ in range(D)]
     p.alpha, p.num_fp_it, p.err_fp_it, p.res_errors = [], [], [], []
@@ -201,6 +202,8 @@ def solve_pgd(p, rng=None):
                 p.PGD_func[d].append((norm_all / norm_Fs[d]) * Fs[d])
         normConv.append(normU)
         relConv.append(normU / normConv[0])
+        if step_hook is not None:
+            step_hook(n_enr)
         if relConv[n_enr] < p.PGD_tol:
             break
     p.amplitude = relConv

@@ -21,6 +21,7 @@ SIGNATURES = {
     "pgd_create": [c_i32, ctypes.POINTER(c_vp)],
     "pgd_destroy": [c_vp],
     "pgd_last_error": [c_vp],
+    "pgd_get_stats": [c_vp, c_vp, c_vp, c_i32],
     "pgd_pattern_build_sync": [c_vp, c_vp, c_i64, c_i32, c_i64, ctypes.POINTER(c_i64), c_vp],
     "pgd_pattern_export": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "pgd_vecmap_build_sync": [c_vp, c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_vp],
@@ -119,6 +120,32 @@ def _check(rc, h, what):
 
 
 F64, I32, I64 = torch.float64, torch.int32, torch.int64
+
+# host <-> device traffic made by the package (bytes), for bench.py's e2e accounting
+traffic = {"h2d": 0, "d2h": 0}
+
+
+def to_device(a, dtype=None):
+    """NumPy array / tensor -> contiguous CUDA tensor (counted as host->device traffic)."""
+    require_cuda()
+    t = torch.as_tensor(a if isinstance(a, torch.Tensor) else np.ascontiguousarray(a), dtype=dtype)
+    traffic["h2d"] += t.numel() * t.element_size()
+    return t.to(torch.device("cuda", torch.cuda.current_device()))
+
+
+def to_host(t):
+    """CUDA tensor -> NumPy array (counted as device->host traffic; synchronises)."""
+    traffic["d2h"] += t.numel() * t.element_size()
+    return t.cpu().numpy()
+
+
+def stats(device=None, reset=False):
+    """dict(launches, pcg_solves, pcg_iters, pcg_ms) from the library handle."""
+    h, lib = handle(device), load_library()
+    counts = (c_i64 * 3)()
+    ms = c_dbl(0.0)
+    lib.pgd_get_stats(h, ctypes.cast(counts, c_vp), ctypes.cast(ctypes.pointer(ms), c_vp), 1 if reset else 0)
+    return {"launches": int(counts[0]), "pcg_solves": int(counts[1]), "pcg_iters": int(counts[2]), "pcg_ms": float(ms.value)}
 
 
 # ------------------------------------------------------------------------------ pattern

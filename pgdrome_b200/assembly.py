@@ -20,7 +20,7 @@ def _dev():
 
 
 def _up(a, dtype):
-    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(_dev())
+    return _lib.to_device(a, dtype)
 
 
 class DeviceSpace:

@@ -24,6 +24,10 @@ struct pgd_ctx {
     int64_t* pat_gptr;
     int32_t* pat_gidx;
     int64_t pat_nnz, pat_ndofs, pat_ncontrib;
+    // statistics (pgd_get_stats): kernel launches, PCG solves / iterations / device time
+    int64_t n_launches, pcg_solves, pcg_iters;
+    double pcg_ms;
+    cudaEvent_t ev0, ev1;
 };
 
 void pgd_free_pattern(pgd_ctx* h);
@@ -48,7 +52,11 @@ void pgd_free_pattern(pgd_ctx* h);
         }                                                                                   \
     } while (0)
 
-#define PGD_LAUNCH_OK(h) PGD_CUDA(h, cudaGetLastError())
+#define PGD_LAUNCH_OK(h)                 \
+    do {                                 \
+        (h)->n_launches += 1;            \
+        PGD_CUDA(h, cudaGetLastError()); \
+    } while (0)
 
 static inline int pgd_set_device(pgd_ctx* h) { return (int)cudaSetDevice(h->device); }
 

@@ -23,6 +23,8 @@ extern "C" int32_t pgd_create(int32_t device, pgd_handle_t* out) {
         delete h;
         return (int32_t)e;
     }
+    cudaEventCreate(&h->ev0);
+    cudaEventCreate(&h->ev1);
     cudaMemset(h->counters, 0, sizeof(unsigned int) * PGD_MAX_COUNTERS);
     cudaMemset(h->scalars, 0, sizeof(double) * 64);
     cudaMemset(h->flags, 0, sizeof(int) * 16);
@@ -39,7 +41,24 @@ extern "C" int32_t pgd_destroy(pgd_handle_t h) {
     cudaFree(h->counters);
     cudaFree(h->scalars);
     cudaFree(h->flags);
+    cudaEventDestroy(h->ev0);
+    cudaEventDestroy(h->ev1);
     delete h;
+    return 0;
+}
+
+extern "C" int32_t pgd_get_stats(pgd_handle_t h, int64_t* h_counts, double* h_pcg_ms, int32_t reset) {
+    PGD_CHECK_HANDLE(h);
+    if (h_counts) {
+        h_counts[0] = h->n_launches;
+        h_counts[1] = h->pcg_solves;
+        h_counts[2] = h->pcg_iters;
+    }
+    if (h_pcg_ms) *h_pcg_ms = h->pcg_ms;
+    if (reset) {
+        h->n_launches = h->pcg_solves = h->pcg_iters = 0;
+        h->pcg_ms = 0.0;
+    }
     return 0;
 }
 

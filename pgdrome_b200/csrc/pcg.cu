@@ -233,6 +233,7 @@ static int32_t run_pcg(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const d
     double hs[8];
     int launched = 0;
     if (check_every < 1) check_every = 1;
+    PGD_CUDA(h, cudaEventRecord(h->ev0, st));
     while (true) {
         PGD_CUDA(h, cudaMemcpyAsync(hf, fl, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
         PGD_CUDA(h, cudaStreamSynchronize(st));
@@ -259,10 +260,18 @@ static int32_t run_pcg(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const d
             k_pcg_rotate<<<1, 1, 0, st>>>(sc, fl);
         }
         PGD_LAUNCH_OK(h);
+        h->n_launches += 3 * (int64_t)todo - 1;
         launched += todo;
     }
+    PGD_CUDA(h, cudaEventRecord(h->ev1, st));
     PGD_CUDA(h, cudaMemcpyAsync(hs, sc, sizeof(double) * 8, cudaMemcpyDeviceToHost, st));
     PGD_CUDA(h, cudaStreamSynchronize(st));
+    {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->pcg_ms += ms;
+        h->pcg_solves += 1;
+        h->pcg_iters += hf[F_ITER];
+    }
     if (h_iters) *h_iters = hf[F_ITER];
     if (h_relres) *h_relres = (hs[S_BB] > 0.0) ? sqrt(hs[S_RR] / hs[S_BB]) : 0.0;
     if (hf[F_BAD]) {

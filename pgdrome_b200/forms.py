@@ -245,7 +245,7 @@ def _embed_operator(ds, op, scale, transpose):
     import scipy.sparse as sp
 
     rowptr, colidx, _, _ = ds.pattern
-    rp, ci = rowptr.cpu().numpy().astype(np.int64), colidx.cpu().numpy().astype(np.int64)
+    rp, ci = _lib.to_host(rowptr).astype(np.int64), _lib.to_host(colidx).astype(np.int64)
     n = ds.n_dofs
     A = (op.A.T if transpose else op.A).tocoo()
     key_pat = np.repeat(np.arange(n, dtype=np.int64), np.diff(rp)) * n + ci  # ascending
@@ -258,7 +258,7 @@ def _embed_operator(ds, op, scale, transpose):
     vals = np.zeros(len(key_pat))
     np.add.at(vals, pos[ok], scale * A.data[ok])
     sym = (abs(op.A - op.A.T)).max() == 0.0 if op.A.nnz else True
-    return torch.as_tensor(vals).to(ds.coords.device), bool(sym)
+    return _lib.to_device(vals), bool(sym)
 
 
 def get_atom(space, T, weights, meas, op=None, transpose=False):
@@ -397,7 +397,7 @@ def _flush(leaves):
             _lib.bilinear(rowptr, colidx, atom.values, args[1], args[2], out=res[slot:slot + 1], lpr=atom.ds.lpr)
     for at, x, base, _ in panel_jobs.values():
         _lib.panel_dots(at.panel, at.n_rows, x.tensor(), out=res[base:base + at.n_rows])
-    host = res.cpu().numpy()
+    host = _lib.to_host(res)
     for leaf, slot in plan:
         leaf._value = float(host[slot])
 
@@ -467,7 +467,7 @@ class AssembledMatrix:
 
         rowptr, colidx, _, _ = self.ds.pattern
         n = self.ds.n_dofs
-        return sp.csr_matrix((self.values.cpu().numpy(), colidx.cpu().numpy(), rowptr.cpu().numpy()), shape=(n, n))
+        return sp.csr_matrix((_lib.to_host(self.values), _lib.to_host(colidx), _lib.to_host(rowptr)), shape=(n, n))
 
     def array(self):
         return self.scipy().toarray()

@@ -358,7 +358,7 @@ class Vector:
         return self
 
     def axpy(self, a, other):
-        o = other._o.tensor() if isinstance(other, Vector) else torch.as_tensor(np.asarray(other, dtype=np.float64)).to(_device())
+        o = other._o.tensor() if isinstance(other, Vector) else _lib.to_device(np.asarray(other, dtype=np.float64))
         t = self._o.tensor()
         self._o.before_write()
         _lib.lincomb([t, o], [1.0, float(a)], out=t)
@@ -416,7 +416,7 @@ class _DofOwner:
 
     def values_host(self):
         if self._host_version != self._version or self._host is None:
-            self._host = self.tensor().cpu().numpy()
+            self._host = _lib.to_host(self.tensor())
             self._host_version = self._version
         return self._host
 
@@ -425,7 +425,7 @@ class _DofOwner:
         if a.size != self.n_dofs:
             raise ValueError("size mismatch: %d values for %d dofs" % (a.size, self.n_dofs))
         self.before_write()
-        self.tensor().copy_(torch.from_numpy(a))
+        self.tensor().copy_(_lib.to_device(a))
         self.touch()
 
     def set_tensor(self, t):
@@ -740,7 +740,7 @@ class DirichletBC:
     def device(self):
         if self._dev is None:
             dev = _device()
-            self._dev = (torch.as_tensor(self.dofs).to(dev), torch.as_tensor(self.vals).to(dev))
+            self._dev = (_lib.to_device(self.dofs), _lib.to_device(self.vals))
         return self._dev
 
     def apply(self, *objs):

@@ -147,11 +147,11 @@ class PGDMesh(object):
 
 
 def _as_f64(a):
-    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(_device())
+    return _lib.to_device(np.ascontiguousarray(a, dtype=np.float64))
 
 
 def _as_i32(a):
-    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(_device())
+    return _lib.to_device(np.ascontiguousarray(a, dtype=np.int32))
 
 
 class _FreeDim:
@@ -368,7 +368,7 @@ class PGD:
         u = _lib.eval_gemv(X, self.used_numModes, W[:, 0].contiguous())
         if name == 0:
             shape = np.asarray(self.mesh[fixed_dim].attributes[attri].data[0]).shape
-            return u.cpu().numpy().reshape(shape)
+            return _lib.to_host(u).reshape(shape)
         V = self.mesh[fixed_dim].attributes[attri].interpolationfct[0].function_space()
         return Function(V, u)
 

@@ -47,9 +47,9 @@ class _CsrOnDevice:
         A.sort_indices()
         dev = forms._device()
         self.n = A.shape[0]
-        self.rowptr = torch.as_tensor(A.indptr.astype(np.int32)).to(dev)
-        self.colidx = torch.as_tensor(A.indices.astype(np.int32)).to(dev)
-        self.values = torch.as_tensor(A.data.astype(np.float64)).to(dev)
+        self.rowptr = _lib.to_device(A.indptr.astype(np.int32))
+        self.colidx = _lib.to_device(A.indices.astype(np.int32))
+        self.values = _lib.to_device(A.data.astype(np.float64))
         coo = A.tocoo()
         nz = coo.data != 0
         d = (coo.row[nz] - coo.col[nz]) if nz.any() else np.zeros(1, dtype=np.int64)
@@ -140,7 +140,7 @@ class PGDProblem:
             else:
                 dofs, vals = merged_bc_dofs(bcs, self.V[dim])
                 dev = forms._device()
-                self._bcd[dim] = (torch.as_tensor(dofs).to(dev), torch.as_tensor(vals).to(dev) if np.any(vals) else None)
+                self._bcd[dim] = (_lib.to_device(dofs), _lib.to_device(vals) if np.any(vals) else None)
         return self._bcd[dim]
 
     def _mm(self, dim):
@@ -219,6 +219,21 @@ class PGDProblem:
         self.PGD_modes = len(self.PGD_func[0])
         return self
 
+    def begin_PGD(self, _problem="nonlinear", solve_modes=None, settings={"linear_solver": "mumps"}):
+        """Stepping form of solve_PGD (bench.py times single enrichment steps): returns the loop state."""
+        _lib.require_cuda()
+        self.invalidate_caches()
+        self.PGD_func = [[] for _ in range(self.num_pgd_var)]
+        return {"n_enr": -1, "normConv": [], "relConv": [], "args": (_problem, solve_modes, settings), "done": False}
+
+    def step_PGD(self, state):
+        """One enrichment step; returns True when the enrichment has stopped."""
+        state["n_enr"] += 1
+        state["done"] = self.enrichment_step(state["n_enr"], state["normConv"], state["relConv"], *state["args"])
+        self.amplitude = state["relConv"]
+        self.PGD_modes = len(self.PGD_func[0])
+        return state["done"]
+
     def enrichment_step(self, n_enr, normConv, relConv, _problem="nonlinear", solve_modes=None,
                         settings={"linear_solver": "mumps"}):
         """One pass of the enrichment loop body (one new mode per dimension). True = stop."""
@@ -244,9 +259,9 @@ class PGDProblem:
             else:
                 v = self.rhs_fct(Fs_init, Fs_init, Fs_init, self.meshes, self.dom, self.param, self.load, self.PGD_func,
                                  self.prob[dim], n_enr, dim)
-                ll = torch.as_tensor(np.atleast_1d(np.asarray(v, dtype=np.float64)).ravel()).to(res_dev.device)
+                ll = _lib.to_device(np.atleast_1d(np.asarray(v, dtype=np.float64)).ravel())
             _lib.dot(ll, ll, out=res_dev[dim:dim + 1])
-        res = res_dev.cpu().numpy()
+        res = _lib.to_host(res_dev)
         res_error = np.sqrt(np.sum(res))
         self.simulation_info += f"-- residuum norm: {res_error} --\n"
         if res_error < 1e-10:
@@ -350,7 +365,7 @@ class PGDProblem:
                 if self._is_fd(solve_modes, d) and self._mm_operator(d) is None:
                     M = self._mm(d)
                     tn, to = Fs[d].tensor(), Fs_init[d].tensor()
-                    trip = torch.cat([M.product(tn, tn), M.product(tn, to), M.product(to, to)]).cpu().numpy()
+                    trip = _lib.to_host(torch.cat([M.product(tn, tn), M.product(tn, to), M.product(to, to)]))
                     terms.append((float(trip[0]), float(trip[1]), float(trip[2])))
                 else:
                     terms.append((self._norm(Fs[d], d, solve_modes) ** 2, self._mass_product(Fs[d], Fs_init[d], d, solve_modes),
@@ -440,7 +455,7 @@ class PGDProblem:
         if V.mesh().tdim == 1:
             perm, bw = V.band_permutation()
             if ds.band is None:
-                ds.band = torch.as_tensor(perm).to(b.device)
+                ds.band = _lib.to_device(perm)
             x, info = _lib.banded_solve(rowptr, colidx, values, b, ds.band, bw, bw)
             self.solver_stats["banded_solves"] += 1
             self._last_info = info
@@ -473,13 +488,13 @@ class PGDProblem:
         """spsolve(A, B) of a user-assembled finite-difference system (solver.py:927-943) as a
         banded LU on the device (dense LU through torch.linalg for bandwidth > 64)."""
         M = _CsrOnDevice(A)
-        b = torch.as_tensor(np.ascontiguousarray(np.asarray(B, dtype=np.float64).ravel())).to(M.values.device)
+        b = _lib.to_device(np.ascontiguousarray(np.asarray(B, dtype=np.float64).ravel()))
         if max(M.kl, M.ku) <= 64:
             perm = torch.arange(M.n, dtype=I32, device=b.device)
             x, info = _lib.banded_solve(M.rowptr, M.colidx, M.values, b, perm, M.kl, M.ku)
             self._last_info = info
         else:
-            dense = torch.as_tensor(sp.csr_matrix(A).toarray()).to(b.device)
+            dense = _lib.to_device(sp.csr_matrix(A).toarray())
             x = torch.linalg.solve(dense, b)
         self.solver_stats["banded_solves"] += 1
         return Function(self.V[dim], x)
