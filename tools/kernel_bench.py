@@ -13,7 +13,12 @@ import numpy as np
 import torch
 
 
+PROFILE = False  # --profile: one warm-up + one timed launch per kernel (for ncu captures)
+
+
 def _time(fn, reps=10, warm=3):
+    if PROFILE:
+        reps, warm = 1, 1
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -120,5 +125,7 @@ if __name__ == "__main__":
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     ap = argparse.ArgumentParser()
     ap.add_argument("--mesh", type=int, default=128)
+    ap.add_argument("--profile", action="store_true")
     a = ap.parse_args()
+    PROFILE = a.profile
     print(json.dumps(run(a.mesh)))
