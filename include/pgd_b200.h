@@ -27,8 +27,11 @@ int32_t pgd_abi_version(void);
 int32_t pgd_create(int32_t device, pgd_handle_t* out);
 int32_t pgd_destroy(pgd_handle_t h);
 const char* pgd_last_error(pgd_handle_t h);
+/* options: "pcg_resident" (default 1) = solve with the single-kernel SM-resident PCG whenever the
+ * matrix slice of every SM fits in its shared memory (else, and with 0, the multi-kernel PCG). */
+int32_t pgd_set_option(pgd_handle_t h, const char* name, int64_t value);
 /* library-side counters since the last reset: h_counts[0] kernels launched, [1] PCG solves,
- * [2] PCG iterations; *h_pcg_ms device time (CUDA events on the solve's stream) spent in the PCG
+ * [2] PCG iterations, [3] solves done by the SM-resident kernel; *h_pcg_ms device time (CUDA events on the solve's stream) spent in the PCG
  * iteration kernels.  Used by bench.py for gpu_launches and the live roofline. */
 int32_t pgd_get_stats(pgd_handle_t h, int64_t* h_counts, double* h_pcg_ms, int32_t reset);
 

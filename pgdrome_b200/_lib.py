@@ -22,6 +22,7 @@ SIGNATURES = {
     "pgd_destroy": [c_vp],
     "pgd_last_error": [c_vp],
     "pgd_get_stats": [c_vp, c_vp, c_vp, c_i32],
+    "pgd_set_option": [c_vp, ctypes.c_char_p, c_i64],
     "pgd_pattern_build_sync": [c_vp, c_vp, c_i64, c_i32, c_i64, ctypes.POINTER(c_i64), c_vp],
     "pgd_pattern_export": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "pgd_vecmap_build_sync": [c_vp, c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_vp],
@@ -142,10 +143,18 @@ def to_host(t):
 def stats(device=None, reset=False):
     """dict(launches, pcg_solves, pcg_iters, pcg_ms) from the library handle."""
     h, lib = handle(device), load_library()
-    counts = (c_i64 * 3)()
+    counts = (c_i64 * 4)()
     ms = c_dbl(0.0)
     lib.pgd_get_stats(h, ctypes.cast(counts, c_vp), ctypes.cast(ctypes.pointer(ms), c_vp), 1 if reset else 0)
-    return {"launches": int(counts[0]), "pcg_solves": int(counts[1]), "pcg_iters": int(counts[2]), "pcg_ms": float(ms.value)}
+    return {"launches": int(counts[0]), "pcg_solves": int(counts[1]), "pcg_iters": int(counts[2]),
+            "pcg_resident_solves": int(counts[3]), "pcg_ms": float(ms.value)}
+
+
+def set_option(name, value, device=None):
+    h, lib = handle(device), load_library()
+    rc = lib.pgd_set_option(h, name.encode(), int(value))
+    if rc != 0:
+        raise PGDB200Error("pgd_set_option(%s) failed: %s" % (name, lib.pgd_last_error(h).decode()))
 
 
 # ------------------------------------------------------------------------------ pattern

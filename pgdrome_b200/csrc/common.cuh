@@ -25,8 +25,11 @@ struct pgd_ctx {
     int32_t* pat_gidx;
     int64_t pat_nnz, pat_ndofs, pat_ncontrib;
     // statistics (pgd_get_stats): kernel launches, PCG solves / iterations / device time
-    int64_t n_launches, pcg_solves, pcg_iters;
+    int64_t n_launches, pcg_solves, pcg_iters, pcg_resident_solves;
     double pcg_ms;
+    int opt_resident;        // pgd_set_option("pcg_resident"): 1 = use the SM-resident PCG when the system fits
+    const void* nnz_key;     // cache of rowptr[n] (one 4-byte D2H per new matrix)
+    int64_t nnz_key_n, nnz_val;
     cudaEvent_t ev0, ev1;
 };
 

@@ -15,6 +15,7 @@ extern "C" int32_t pgd_create(int32_t device, pgd_handle_t* out) {
     pgd_ctx* h = new pgd_ctx();
     memset(h, 0, sizeof(*h));
     h->device = device;
+    h->opt_resident = 1;
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     if ((e = cudaMalloc(&h->partials, sizeof(double) * PGD_MAX_PARTIALS)) != cudaSuccess ||
         (e = cudaMalloc(&h->counters, sizeof(unsigned int) * PGD_MAX_COUNTERS)) != cudaSuccess ||
@@ -53,16 +54,28 @@ extern "C" int32_t pgd_get_stats(pgd_handle_t h, int64_t* h_counts, double* h_pc
         h_counts[0] = h->n_launches;
         h_counts[1] = h->pcg_solves;
         h_counts[2] = h->pcg_iters;
+        h_counts[3] = h->pcg_resident_solves;
     }
     if (h_pcg_ms) *h_pcg_ms = h->pcg_ms;
     if (reset) {
-        h->n_launches = h->pcg_solves = h->pcg_iters = 0;
+        h->n_launches = h->pcg_solves = h->pcg_iters = h->pcg_resident_solves = 0;
         h->pcg_ms = 0.0;
     }
     return 0;
 }
 
 extern "C" const char* pgd_last_error(pgd_handle_t h) { return h ? h->err : "null handle"; }
+
+extern "C" int32_t pgd_set_option(pgd_handle_t h, const char* name, int64_t value) {
+    PGD_CHECK_HANDLE(h);
+    PGD_ARG(h, name != nullptr, "null option name");
+    if (strcmp(name, "pcg_resident") == 0) {
+        h->opt_resident = value ? 1 : 0;
+        return 0;
+    }
+    snprintf(h->err, sizeof(h->err), "pgd_set_option: unknown option '%s'", name);
+    return -2;
+}
 
 // ----------------------------------------------------------------------------- lincomb
 #define LC_MAX 24

@@ -281,6 +281,10 @@ static int32_t run_pcg(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const d
     return 0;
 }
 
+int32_t pgd_pcg_resident(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const double* va, const double* b, double* x,
+                         int64_t n, int64_t nnz_hint, double rtol, double atol, int maxit, int block, double* work,
+                         int32_t* h_iters, double* h_relres, cudaStream_t st);
+
 extern "C" int32_t pgd_pcg_sync(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
                                 const double* d_b, double* d_x, int64_t n, double rtol, double atol, int32_t maxit,
                                 int32_t check_every, int32_t block, int32_t lanes_per_row, double* d_work,
@@ -289,6 +293,19 @@ extern "C" int32_t pgd_pcg_sync(pgd_handle_t h, const int32_t* d_rowptr, const i
     PGD_ARG(h, d_rowptr && d_colidx && d_values && d_b && d_x && d_work && n > 0, "bad arguments");
     PGD_ARG(h, block >= 1 && block <= 3 && n % block == 0, "block must be 1..3 and divide n");
     cudaStream_t st = (cudaStream_t)stream;
+    if (h->opt_resident && n <= ((int64_t)1 << 22)) {
+        if (h->nnz_key != (const void*)d_rowptr || h->nnz_key_n != n) {
+            int32_t last = 0;
+            PGD_CUDA(h, cudaMemcpyAsync(&last, d_rowptr + n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            PGD_CUDA(h, cudaStreamSynchronize(st));
+            h->nnz_key = (const void*)d_rowptr;
+            h->nnz_key_n = n;
+            h->nnz_val = last;
+        }
+        int32_t rc = pgd_pcg_resident(h, d_rowptr, d_colidx, d_values, d_b, d_x, n, h->nnz_val, rtol, atol, maxit, block,
+                                      d_work, h_iters, h_relres, st);
+        if (rc != 1) return rc;
+    }
     if (block == 1)
         return run_pcg<1>(h, d_rowptr, d_colidx, d_values, d_b, d_x, n, rtol, atol, maxit, check_every, lanes_per_row, d_work,
                           h_iters, h_relres, st);

@@ -215,12 +215,26 @@ def test_dirichlet_and_pcg(kind, degree, bs, block):
                          torch.as_tensor(gvals).to(dev))
     assert _relerr(bd2.cpu().numpy(), bo2) < 1e-13
     xo = spla.spsolve(Ao.tocsc(), bo)
-    x, iters, relres = _lib.pcg(rowptr, colidx, vals, bd, rtol=1e-13, maxit=5000, check_every=25, block=block)
-    assert relres <= 1e-13 and 0 < iters < 5000
-    assert np.linalg.norm(x.cpu().numpy() - xo) / np.linalg.norm(xo) < 1e-10
-    # zero right-hand side converges immediately to zero
-    x0, it0, _ = _lib.pcg(rowptr, colidx, vals, torch.zeros_like(bd), rtol=1e-13, maxit=10, block=block)
-    assert it0 == 0 and float(x0.abs().max()) == 0.0
+    its = {}
+    for resident in (1, 0):  # single-kernel SM-resident PCG and the multi-kernel (HBM-streaming) PCG
+        _lib.set_option("pcg_resident", resident)
+        _lib.stats(reset=True)
+        x, iters, relres = _lib.pcg(rowptr, colidx, vals, bd, rtol=1e-13, maxit=5000, check_every=25, block=block)
+        assert _lib.stats()["pcg_resident_solves"] == resident
+        assert relres <= 1e-13 and 0 < iters < 5000
+        assert np.linalg.norm(x.cpu().numpy() - xo) / np.linalg.norm(xo) < 1e-10
+        its[resident] = iters
+        # bitwise reproducible
+        x2, iters2, _ = _lib.pcg(rowptr, colidx, vals, bd, rtol=1e-13, maxit=5000, check_every=25, block=block)
+        assert iters2 == iters and torch.equal(x, x2)
+        # iteration cap is honoured
+        _, itc, rc = _lib.pcg(rowptr, colidx, vals, bd, rtol=1e-13, maxit=7, check_every=3, block=block)
+        assert itc == 7 and rc > 1e-13
+        # zero right-hand side converges immediately to zero
+        x0, it0, _ = _lib.pcg(rowptr, colidx, vals, torch.zeros_like(bd), rtol=1e-13, maxit=10, block=block)
+        assert it0 == 0 and float(x0.abs().max()) == 0.0
+    _lib.set_option("pcg_resident", 1)
+    assert abs(its[0] - its[1]) <= max(3, its[0] // 20)
 
 
 @pytest.mark.parametrize("degree", [1, 2])
