@@ -63,3 +63,29 @@ def test_heat2d_tk_matches_oracle(cpu):
     o, _ = oprob.heat2d_tk(n=8, nt=12, nk=5, PGD_nmax=3, spaces=_ospaces(p))
     opgd.solve_pgd(o)
     _compare(p, o)
+
+
+# ---- host logic against the reference-generated golden vectors (same bodies as tests/test_gpu_golden.py,
+# with the NumPy ABI stand-in): FD-mode enrichment loop, normalisations, stopping criteria, evaluate
+def test_golden_laplace_fd_host_logic(cpu):
+    from tests import test_gpu_golden as tg
+
+    tg.test_laplace_fd_reference_test_on_device()
+
+
+@pytest.mark.parametrize("key,opts", [
+    ("v_stiff", dict(norm_modes="stiff", PGD_nmax=6)),
+    ("v_l2", dict(norm_modes="l2", PGD_nmax=6)),
+    ("v_no", dict(norm_modes="no", PGD_nmax=4)),
+    ("v_delta", dict(stop_fp="delta", PGD_nmax=4, tol_fp_it=1e-6)),
+])
+def test_golden_laplace_fd_variants_host_logic(cpu, key, opts):
+    from tests import test_gpu_golden as tg
+
+    tg.test_laplace_fd_variants_on_device(key, opts)
+
+
+def test_golden_pgdclass_host_logic(cpu):
+    from tests import test_gpu_golden as tg
+
+    tg.test_pgdclass_evaluate_on_device()
