@@ -17,13 +17,18 @@ FEniCS/DOLFIN 2019.1 + PETSc/MUMPS + SciPy:
 * ``oracle.problems`` matrix-form restatements of the reference's own callback sets
                       (tests/integration/*.py) and of the BASELINE.json configs.
 
-PARITY STATUS: **parity unpinned** at the north-star tolerances (sparsity bit-exact,
-matrices 1e-12, modes/reconstruction 1e-8).  The arithmetic of the reference lives in
-un-vendored third-party code (fenics=2019.1.0, environment.yml:8) that cannot be
-imported in this image (Python 3.12, no dolfin/ufl/ffc/petsc4py), and the reference
-ships no golden vectors.  What pins this oracle are the reference's own
-tolerance-vs-analytic tests, restated in ``tests/test_oracle_kat.py``:
-tests/unit/test_FD.py:166-169, tests/unit/test_pgdclass.py:298-326,
-tests/integration/test_elastic.py:353,380, test_laplace.py:970-971,1091-1092,
-test_heat1D.py:804-807,903-904.
+PARITY STATUS: **partly pinned**.
+  * PINNED to round-off by golden vectors generated from the UNMODIFIED reference code
+    (tests/golden/make_golden.py runs pgdrome/solver.py + pgdrome/model.py + the reference's own
+    test callbacks in this container through a NumPy stand-in for the few DOLFIN containers the
+    finite-difference paths touch): ``FD_matrices``; the enrichment loop in FD mode (get_Fsinit,
+    residual check, FP_solve with both stopping criteria, the three normalisations, the stopping
+    test); ``PGD.evaluate`` interp1d path and mode point-evaluation loop; evaluate_min/max; LHS
+    sampling; the error loop.  Checked in tests/test_oracle_golden.py.
+  * **parity unpinned** for everything that goes through DOLFIN's finite-element assembly
+    (sparsity bit-exact, matrices 1e-12): fenics=2019.1.0 (environment.yml:8) cannot be imported
+    here (Python 3.12, no dolfin/ufl/ffc/petsc4py) and the reference ships no stored matrices.
+    That part is pinned only to the tolerances of the reference's own tests, restated in
+    tests/test_oracle_kat.py: tests/unit/test_FD.py:166-169, tests/integration/test_elastic.py:353,380,
+    test_laplace.py:970-971,1091-1092, test_heat1D.py:804-807,903-904, test_solver_problem.py:748-752.
 """
