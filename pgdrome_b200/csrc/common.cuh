@@ -9,6 +9,8 @@
 
 #define PGD_MAX_PARTIALS (1 << 20)
 #define PGD_MAX_COUNTERS 4096
+#define PGD_STREAM_MIN_ROWS 8192
+#define PGD_BULK_MIN_ROWS 32768
 
 struct pgd_ctx {
     int device;
@@ -28,6 +30,9 @@ struct pgd_ctx {
     int64_t n_launches, pcg_solves, pcg_iters, pcg_resident_solves;
     double pcg_ms;
     int opt_resident;        // pgd_set_option("pcg_resident"): 1 = use the SM-resident PCG when the system fits
+    int opt_stream;          // pgd_set_option("spmv_stream"): 0 = sub-warp-per-row kernels only; 1 = register-staged row-block
+                             // streaming for n >= PGD_STREAM_MIN_ROWS; 2 (default) = additionally the TMA-pipelined kernel
+                             // for n >= PGD_BULK_MIN_ROWS
     const void* nnz_key;     // cache of rowptr[n] (one 4-byte D2H per new matrix)
     int64_t nnz_key_n, nnz_val;
     cudaEvent_t ev0, ev1;
@@ -90,8 +95,9 @@ __device__ __forceinline__ double block_sum(double v) {
 // last block to arrive sums them in a fixed order and stores out[0..NV). `counter` returns to 0.
 // part layout: part[v * gridsize + block]. Works for 1-D grids (gridsize = gridDim.x) or a row
 // of a 2-D grid when the caller passes its own base pointers.
+// Returns true (to every thread) in the block that performed the final sum.
 template <int NV>
-__device__ __forceinline__ void grid_sum_finish(const double (&v)[NV], double* part, unsigned int* counter,
+__device__ __forceinline__ bool grid_sum_finish(const double (&v)[NV], double* part, unsigned int* counter,
                                                 double* out, unsigned int bid, unsigned int gridsize) {
     __shared__ bool s_last;
     if (threadIdx.x == 0) {
@@ -113,6 +119,7 @@ __device__ __forceinline__ void grid_sum_finish(const double (&v)[NV], double* p
         }
         if (threadIdx.x == 0) *counter = 0u;
     }
+    return s_last;
 }
 
 // streaming loads for data that is touched once per kernel (matrix values / column indices)

@@ -16,6 +16,7 @@ extern "C" int32_t pgd_create(int32_t device, pgd_handle_t* out) {
     memset(h, 0, sizeof(*h));
     h->device = device;
     h->opt_resident = 1;
+    h->opt_stream = 2;
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     if ((e = cudaMalloc(&h->partials, sizeof(double) * PGD_MAX_PARTIALS)) != cudaSuccess ||
         (e = cudaMalloc(&h->counters, sizeof(unsigned int) * PGD_MAX_COUNTERS)) != cudaSuccess ||
@@ -71,6 +72,10 @@ extern "C" int32_t pgd_set_option(pgd_handle_t h, const char* name, int64_t valu
     PGD_ARG(h, name != nullptr, "null option name");
     if (strcmp(name, "pcg_resident") == 0) {
         h->opt_resident = value ? 1 : 0;
+        return 0;
+    }
+    if (strcmp(name, "spmv_stream") == 0) {
+        h->opt_stream = (value < 0 || value > 2) ? 2 : (int)value;
         return 0;
     }
     snprintf(h->err, sizeof(h->err), "pgd_set_option: unknown option '%s'", name);

@@ -1,10 +1,14 @@
 // Jacobi / node-block-Jacobi preconditioned CG, two kernels per iteration, all scalars and the
 // convergence flag on the device (the host polls once per `check_every` iterations).
-//   k_pcg_spmv  : p_new = z + beta p_old (fused into the gather), q = A p_new, pq = p_new.q
-//   k_pcg_update: alpha = rz/pq; x += alpha p; r -= alpha q; z = M^-1 r; rz' = r.z, rr = r.r;
-//                 last block: rotates rz, bumps the iteration counter, sets DONE.
+//   k_pcg_spmv[_stream]: p_new = z + beta p_old (fused into the gather), q = A p_new, pq = p_new.q
+//   k_pcg_update       : alpha = rz/pq; x += alpha p; r -= alpha q; z = M^-1 r; rz' = r.z, rr = r.r;
+//                        the block that finishes the reduction rotates rz, bumps the iteration
+//                        counter and sets DONE (every other block has consumed the old scalars
+//                        before it deposited its partials, so there is no ordering hazard).
 // Reductions are fixed-order two-stage sums (bitwise reproducible).
 #include "common.cuh"
+#include "spmv_bulk.cuh"
+#include "spmv_stream.cuh"
 
 enum { S_RZ_OLD = 0, S_RZ_NEW = 1, S_PQ = 2, S_RR = 3, S_BB = 4, S_TOL2 = 5, S_TMP = 8 };
 enum { F_DONE = 0, F_ITER = 1, F_BAD = 2 };
@@ -188,20 +192,79 @@ __global__ void __launch_bounds__(256) k_pcg_update(double* __restrict__ x, doub
     rz = block_sum(rz);
     rr = block_sum(rr);
     double v[2] = {rz, rr};
-    grid_sum_finish<2>(v, part, counter, sc + S_TMP, blockIdx.x, gridDim.x);
+    const bool last = grid_sum_finish<2>(v, part, counter, sc + S_TMP, blockIdx.x, gridDim.x);
+    if (last && threadIdx.x == 0) {  // scalar rotation
+        const double rz_next = sc[S_TMP], rr_new = sc[S_TMP + 1];
+        sc[S_RZ_OLD] = rz_cur;
+        sc[S_RZ_NEW] = rz_next;
+        sc[S_RR] = rr_new;
+        fl[F_ITER] = it + 1;
+        if (!(rr_new > sc[S_TOL2])) fl[F_DONE] = 1;  // also stops on NaN
+        if (!(rr_new == rr_new) || !(rz_next == rz_next)) fl[F_BAD] = 1;
+    }
 }
 
-// single-thread scalar rotation after k_pcg_update (runs as its own tiny launch: keeps every
-// block of the update kernel free to read S_RZ_NEW / S_PQ without ordering hazards)
-__global__ void k_pcg_rotate(double* sc, int* fl) {
+// TMA-pipelined variant of k_pcg_spmv (spmv_bulk.cuh)
+__global__ void __launch_bounds__(BK_THREADS, 2) k_pcg_spmv_bulk(const int32_t* __restrict__ rowptr,
+                                                                 const int32_t* __restrict__ colidx,
+                                                                 const double* __restrict__ vals,
+                                                                 const double* __restrict__ z, double* pa, double* pb,
+                                                                 double* __restrict__ q, int64_t n, const double* sc,
+                                                                 const int* fl, double* sc_out, double* part,
+                                                                 unsigned int* counter) {
+    extern __shared__ __align__(128) unsigned char bk_smem[];
     if (fl[F_DONE]) return;
-    double rz_next = sc[S_TMP], rr = sc[S_TMP + 1];
-    sc[S_RZ_OLD] = sc[S_RZ_NEW];
-    sc[S_RZ_NEW] = rz_next;
-    sc[S_RR] = rr;
-    fl[F_ITER] = fl[F_ITER] + 1;
-    if (!(rr > sc[S_TOL2])) fl[F_DONE] = 1;       // also stops on NaN
-    if (!(rr == rr) || !(rz_next == rz_next)) fl[F_BAD] = 1;
+    const int it = fl[F_ITER];
+    const double beta = (it == 0) ? 0.0 : sc[S_RZ_NEW] / sc[S_RZ_OLD];
+    const double* __restrict__ p_old = (it & 1) ? pb : pa;
+    double* __restrict__ p_new = (it & 1) ? pa : pb;
+    double acc = 0.0;
+    bk_spmv_rows(rowptr, colidx, vals, n, BkGatherZP{z, p_old, beta},
+                 [&](int64_t row, double s) {
+                     const double pi = fma(beta, p_old[row], z[row]);
+                     p_new[row] = pi;
+                     q[row] = s;
+                     acc = fma(pi, s, acc);
+                 },
+                 bk_smem);
+    acc = block_sum(acc);
+    double v[1] = {acc};
+    grid_sum_finish<1>(v, part, counter, sc_out + S_PQ, blockIdx.x, gridDim.x);
+}
+
+// streaming variant of k_pcg_spmv for systems that do not fit on chip (spmv_stream.cuh)
+__global__ void __launch_bounds__(ST_THREADS) k_pcg_spmv_stream(const int32_t* __restrict__ rowptr,
+                                                                 const int32_t* __restrict__ colidx,
+                                                                 const double* __restrict__ vals,
+                                                                 const double* __restrict__ z, double* pa, double* pb,
+                                                                 double* __restrict__ q, int64_t n, const double* sc,
+                                                                 const int* fl, double* sc_out, double* part,
+                                                                 unsigned int* counter) {
+    __shared__ double s_prod[ST_TILE];
+    __shared__ int s_rp[ST_ROWS + 1];
+    if (fl[F_DONE]) return;
+    const int it = fl[F_ITER];
+    const double beta = (it == 0) ? 0.0 : sc[S_RZ_NEW] / sc[S_RZ_OLD];
+    const double* __restrict__ p_old = (it & 1) ? pb : pa;
+    double* __restrict__ p_new = (it & 1) ? pa : pb;
+    const GatherZP g{z, p_old, beta};
+    const int64_t nblk = (n + ST_ROWS - 1) / ST_ROWS;
+    double acc = 0.0;
+    for (int64_t rb = blockIdx.x; rb < nblk; rb += gridDim.x) {
+        const int64_t r0 = rb * ST_ROWS;
+        const int nr = (int)min((int64_t)ST_ROWS, n - r0);
+        const double s = stream_rowblock(rowptr, colidx, vals, g, r0, nr, s_prod, s_rp);
+        if ((int)threadIdx.x < nr) {
+            const int64_t row = r0 + threadIdx.x;
+            const double pi = fma(beta, p_old[row], z[row]);
+            p_new[row] = pi;
+            q[row] = s;
+            acc = fma(pi, s, acc);
+        }
+    }
+    acc = block_sum(acc);
+    double v[1] = {acc};
+    grid_sum_finish<1>(v, part, counter, sc_out + S_PQ, blockIdx.x, gridDim.x);
 }
 
 template <int BS>
@@ -240,7 +303,19 @@ static int32_t run_pcg(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const d
         if (hf[F_DONE] || launched >= maxit) break;
         int todo = maxit - launched;
         if (todo > check_every) todo = check_every;
+        const bool stream = h->opt_stream && n >= PGD_STREAM_MIN_ROWS;
+        const unsigned int stb = (unsigned int)min((n + ST_ROWS - 1) / ST_ROWS, (int64_t)h->sm_count * 6);
+        const bool bulk = h->opt_stream >= 2 && n >= PGD_BULK_MIN_ROWS && (((uintptr_t)ci | (uintptr_t)va) & 15) == 0;
+        if (bulk)
+            PGD_CUDA(h, cudaFuncSetAttribute(k_pcg_spmv_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM_BYTES));
         for (int i = 0; i < todo; ++i) {
+            if (bulk) {
+                k_pcg_spmv_bulk<<<2 * h->sm_count, BK_THREADS, BK_SMEM_BYTES, st>>>(rp, ci, va, z, p0, p1, q, n, sc, fl, sc,
+                                                                                    h->partials, h->counters);
+            } else if (stream) {
+                k_pcg_spmv_stream<<<stb, ST_THREADS, 0, st>>>(rp, ci, va, z, p0, p1, q, n, sc, fl, sc, h->partials,
+                                                               h->counters);
+            } else
             switch (lpr) {
 #define PCG_CASE(L)                                                                                                     \
     case L:                                                                                                             \
@@ -257,10 +332,9 @@ static int32_t run_pcg(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const d
                     return -2;
             }
             k_pcg_update<BS><<<vb, 256, 0, st>>>(x, r, z, p0, p1, q, minv, n_nodes, sc, fl, h->partials, h->counters);
-            k_pcg_rotate<<<1, 1, 0, st>>>(sc, fl);
         }
         PGD_LAUNCH_OK(h);
-        h->n_launches += 3 * (int64_t)todo - 1;
+        h->n_launches += 2 * (int64_t)todo - 1;
         launched += todo;
     }
     PGD_CUDA(h, cudaEventRecord(h->ev1, st));

@@ -3,6 +3,58 @@
 // the read-only path and stays L2-resident; rows are processed by LPR-lane groups so that a warp
 // reads a contiguous run of the CSR arrays.
 #include "common.cuh"
+#include "spmv_bulk.cuh"
+#include "spmv_stream.cuh"
+
+// TMA-pipelined SpMV (spmv_bulk.cuh).  MODE as in k_spmv below.
+template <int MODE>
+__global__ void __launch_bounds__(BK_THREADS, 2) k_spmv_bulk(const int32_t* __restrict__ rowptr,
+                                                             const int32_t* __restrict__ colidx,
+                                                             const double* __restrict__ vals, const double* __restrict__ x,
+                                                             double* __restrict__ y, const double* __restrict__ w, int64_t n,
+                                                             double* dot, double* part, unsigned int* counter) {
+    extern __shared__ __align__(128) unsigned char bk_smem[];
+    double acc = 0.0;
+    bk_spmv_rows(rowptr, colidx, vals, n, BkGatherX{x},
+                 [&](int64_t row, double s) {
+                     if (MODE != 2) y[row] = s;
+                     if (MODE != 0) acc = fma(__ldg(&w[row]), s, acc);
+                 },
+                 bk_smem);
+    if (MODE != 0) {
+        acc = block_sum(acc);
+        double v[1] = {acc};
+        grid_sum_finish<1>(v, part, counter, dot, blockIdx.x, gridDim.x);
+    }
+}
+
+// MODE as in k_spmv below.  Persistent grid, one ST_ROWS row block per CTA pass.
+template <int MODE>
+__global__ void __launch_bounds__(ST_THREADS) k_spmv_stream(const int32_t* __restrict__ rowptr,
+                                                             const int32_t* __restrict__ colidx,
+                                                             const double* __restrict__ vals, const double* __restrict__ x,
+                                                             double* __restrict__ y, const double* __restrict__ w, int64_t n,
+                                                             double* dot, double* part, unsigned int* counter) {
+    __shared__ double s_prod[ST_TILE];
+    __shared__ int s_rp[ST_ROWS + 1];
+    const GatherX g{x};
+    const int64_t nblk = (n + ST_ROWS - 1) / ST_ROWS;
+    double acc = 0.0;
+    for (int64_t rb = blockIdx.x; rb < nblk; rb += gridDim.x) {
+        const int64_t r0 = rb * ST_ROWS;
+        const int nr = (int)min((int64_t)ST_ROWS, n - r0);
+        const double s = stream_rowblock(rowptr, colidx, vals, g, r0, nr, s_prod, s_rp);
+        if ((int)threadIdx.x < nr) {
+            if (MODE != 2) y[r0 + threadIdx.x] = s;
+            if (MODE != 0) acc = fma(__ldg(&w[r0 + threadIdx.x]), s, acc);
+        }
+    }
+    if (MODE != 0) {
+        acc = block_sum(acc);
+        double v[1] = {acc};
+        grid_sum_finish<1>(v, part, counter, dot, blockIdx.x, gridDim.x);
+    }
+}
 
 template <int LPR>
 __device__ __forceinline__ double row_dot(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
@@ -58,6 +110,24 @@ static int auto_lpr(int64_t n, int64_t nnz_hint) {
 template <int MODE>
 static int32_t launch_spmv(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const double* va, const double* x, double* y,
                            const double* w, int64_t n, double* dot, int lpr, cudaStream_t st) {
+    if (h->opt_stream >= 2 && n >= PGD_BULK_MIN_ROWS && (((uintptr_t)ci | (uintptr_t)va) & 15) == 0) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            PGD_CUDA(h, cudaFuncSetAttribute(k_spmv_bulk<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM_BYTES));
+            attr_set = true;
+        }
+        k_spmv_bulk<MODE><<<2 * h->sm_count, BK_THREADS, BK_SMEM_BYTES, st>>>(rp, ci, va, x, y, w, n, dot, h->partials,
+                                                                              h->counters);
+        PGD_LAUNCH_OK(h);
+        return 0;
+    }
+    if (h->opt_stream && n >= PGD_STREAM_MIN_ROWS) {
+        const int64_t nblk = (n + ST_ROWS - 1) / ST_ROWS;
+        unsigned int blocks = (unsigned int)min(nblk, (int64_t)h->sm_count * 6);
+        k_spmv_stream<MODE><<<blocks, ST_THREADS, 0, st>>>(rp, ci, va, x, y, w, n, dot, h->partials, h->counters);
+        PGD_LAUNCH_OK(h);
+        return 0;
+    }
     if (lpr == 0) {
         // mean row length from the two ends of rowptr would need a D2H copy; use 16 (P1 tets ~15/row)
         lpr = 16;

@@ -328,3 +328,62 @@ def test_evaluate_kernels():
         W2, X2 = rng.normal(size=(R2, C2)), rng.normal(size=(R2, N2))
         U2 = _lib.eval_gemm(torch.as_tensor(W2).to(dev), torch.as_tensor(X2).to(dev), R2).cpu().numpy()
         assert _relerr(U2, W2.T @ X2) < 1e-13, (R2, C2, N2)
+
+
+def _spd_random_csr(n, rng, long_row=None):
+    """Random sparse SPD matrix with ascending columns; `long_row` makes row 0 / column 0 dense over
+    the first `long_row` entries so that one row spans several ST_TILE buffers of the stream kernel."""
+    m = 9
+    rows = np.repeat(np.arange(n), m)
+    cols = (rows + rng.integers(-60, 61, size=rows.size)) % n
+    A = sp.coo_matrix((rng.uniform(-1, 1, rows.size), (rows, cols)), shape=(n, n)).tocsr()
+    if long_row:
+        A = A.tolil()
+        A[0, :long_row] = rng.uniform(-1, 1, long_row)
+        A = A.tocsr()
+    A = A + A.T
+    A = A + sp.diags(np.abs(A).sum(axis=1).A1 + 1.0)
+    A = A.tocsr()
+    A.sort_indices()
+    return A
+
+
+@pytest.mark.parametrize("n,long_row", [(8192, None), (20011, 9500), (70001, None), (40003, 21000), (131075, None)])
+def test_stream_spmv_and_pcg(n, long_row):
+    """Row-block streaming SpMV / PCG (n >= 8192 rows) against SciPy and against the sub-warp kernels."""
+    from pgdrome_b200 import _lib
+
+    rng = np.random.default_rng(n)
+    A = _spd_random_csr(n, rng, long_row)
+    dev = torch.device("cuda")
+    rowptr = torch.as_tensor(A.indptr.astype(np.int32)).to(dev)
+    colidx = torch.as_tensor(A.indices.astype(np.int32)).to(dev)
+    vals = torch.as_tensor(A.data).to(dev)
+    x, y = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    xd, yd = torch.as_tensor(x).to(dev), torch.as_tensor(y).to(dev)
+    ref = A @ x
+    scale = np.abs(A).dot(np.abs(x)).max()
+    res = {}
+    try:
+        for stream in (2, 1, 0):  # TMA-pipelined (n >= 32768) / register-staged row blocks / sub-warp per row
+            _lib.set_option("spmv_stream", stream)
+            out = _lib.spmv(rowptr, colidx, vals, xd, lpr=8).cpu().numpy()
+            assert np.abs(out - ref).max() < 1e-14 * scale
+            yy, d = _lib.spmv_dot(rowptr, colidx, vals, xd, yd, lpr=8)
+            assert np.abs(yy.cpu().numpy() - ref).max() < 1e-14 * scale
+            assert abs(d.item() - y @ ref) < 1e-12 * np.abs(y) @ np.abs(ref)
+            s = _lib.bilinear(rowptr, colidx, vals, xd, yd, lpr=8).item()
+            assert abs(s - x @ (A @ y)) < 1e-12 * np.abs(x) @ np.abs(A @ y)
+            assert all(_lib.bilinear(rowptr, colidx, vals, xd, yd, lpr=8).item() == s for _ in range(3))
+            _lib.set_option("pcg_resident", 0)
+            b = torch.as_tensor(ref).to(dev)
+            xs, iters, relres = _lib.pcg(rowptr, colidx, vals, b, rtol=1e-13, maxit=2000, check_every=20, lpr=8)
+            assert relres <= 1e-13 and 0 < iters < 2000
+            assert np.linalg.norm(xs.cpu().numpy() - x) / np.linalg.norm(x) < 1e-10
+            xs2, iters2, _ = _lib.pcg(rowptr, colidx, vals, b, rtol=1e-13, maxit=2000, check_every=20, lpr=8)
+            assert iters2 == iters and torch.equal(xs, xs2)
+            res[stream] = iters
+    finally:
+        _lib.set_option("spmv_stream", 2)
+        _lib.set_option("pcg_resident", 1)
+    assert max(res.values()) - min(res.values()) <= max(2, res[0] // 20)

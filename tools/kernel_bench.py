@@ -79,8 +79,10 @@ def run(mesh_n=128, hbm_peak=6451.2, evaluate=True, fp64_peak=None):
     lpr = ds.lpr
     yv = torch.empty(n, dtype=torch.float64, device=dev)
     spmv_bytes = 12 * nnz + 4 * (n + 1) + 16 * n
-    ms = _time(lambda: _lib.spmv(rowptr, colidx, vals, x, y=yv, lpr=lpr))
-    entry("spmv", ms, spmv_bytes, lanes_per_row=lpr)
+    for opt, name in ((0, "spmv_subwarp_per_row"), (1, "spmv_regstaged_rowblocks"), (2, "spmv")):
+        _lib.set_option("spmv_stream", opt)
+        ms = _time(lambda: _lib.spmv(rowptr, colidx, vals, x, y=yv, lpr=lpr))
+        entry(name, ms, spmv_bytes, lanes_per_row=lpr, kernel=["k_spmv", "k_spmv_stream", "k_spmv_bulk (TMA ring)"][opt])
     sc = torch.empty(1, dtype=torch.float64, device=dev)
     ms = _time(lambda: _lib.bilinear(rowptr, colidx, vals, x, y, out=sc, lpr=lpr))
     entry("bilinear_functional", ms, spmv_bytes, lanes_per_row=lpr)
