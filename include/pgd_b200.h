@@ -72,6 +72,20 @@ int32_t pgd_assemble_p1(pgd_handle_t h, const double* d_coords, const int32_t* d
                         int32_t gdim, double c_mass, double c_stiff, const double* h_c_adv,
                         const int64_t* d_gptr, const int32_t* d_gidx, int64_t nnz, double* d_values, void* stream);
 
+/* Row-owner variant of the fused P1 operator (same arithmetic, ~20x faster on 3-D meshes): a thread
+ * owns one row / mesh node and walks the cells around it in vecmap order.  The plan d_vent
+ * (int32 [2 * n_cells * nv]: pairs {vidx entry, nv packed byte positions inside the CSR row}) is built
+ * once per mesh from the pattern, the cell -> dof table (local dof a = local vertex a; the dof numbering
+ * need not equal the vertex numbering) and the vecmap of the scalar P1 space;
+ * returns -4 if a row has more than 255 entries (use pgd_assemble_p1 then). */
+int32_t pgd_p1_rowplan_build_sync(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx,
+                                  const int32_t* d_cell_dofs, int64_t n_cells, int32_t nv, const int64_t* d_vptr,
+                                  const int32_t* d_vidx, int64_t n_nodes, int32_t* d_vent, void* stream);
+int32_t pgd_assemble_p1_rows(pgd_handle_t h, const double* d_coords, const int32_t* d_cell_verts, int64_t n_cells,
+                             int32_t gdim, double c_mass, double c_stiff, const double* h_c_adv,
+                             const int32_t* d_rowptr, const int64_t* d_vptr, const int32_t* d_vent, int64_t n_nodes,
+                             double* d_values, void* stream);
+
 /* ---- linear combinations: A_d = sum_k c_k K_{d,k} over CSR value arrays, and
  * b_d = sum c_m g_m - sum c_ik (K_k U_i) over cached vectors (the folded scalar coefficients of
  * SURVEY.md 7.1).  h_xs: HOST array of n_terms device pointers; h_coefs: HOST array. */

@@ -26,6 +26,8 @@ SIGNATURES = {
     "pgd_pattern_build_sync": [c_vp, c_vp, c_i64, c_i32, c_i64, ctypes.POINTER(c_i64), c_vp],
     "pgd_pattern_export": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "pgd_vecmap_build_sync": [c_vp, c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_vp],
+    "pgd_p1_rowplan_build_sync": [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_i64, c_vp, c_vp],
+    "pgd_assemble_p1_rows": [c_vp, c_vp, c_vp, c_i64, c_i32, c_dbl, c_dbl, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp],
     "pgd_elem_bilinear": [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "pgd_elem_linear": [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "pgd_gather_values": [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp],
@@ -230,6 +232,39 @@ def assemble_p1(coords, cell_verts, gdim, c_mass, c_stiff, c_adv, gptr, gidx, nn
                                float(c_stiff), ctypes.cast(adv, c_vp) if adv is not None else c_vp(0), _p(gptr, I64),
                                _p(gidx, I32), nnz, _p(out), _stream()), h, "pgd_assemble_p1")
     return out
+
+
+def p1_rowplan_build(rowptr, colidx, cell_dofs, vptr, vidx, n_nodes):
+    """Plan of the row-owner fused P1 kernel: int32 [n_cells * nv * 2] (pairs {vidx entry, packed positions})."""
+    h, lib = handle(rowptr.device), load_library()
+    n_cells, nv = cell_dofs.shape
+    vent = torch.empty(n_cells * nv * 2, dtype=I32, device=rowptr.device)
+    _check(lib.pgd_p1_rowplan_build_sync(h, _p(rowptr, I32), _p(colidx, I32), _p(cell_dofs, I32), n_cells, nv, _p(vptr, I64),
+                                         _p(vidx, I32), n_nodes, _p(vent), _stream()), h, "pgd_p1_rowplan_build_sync")
+    return vent
+
+
+def assemble_p1_rows(coords, cell_verts, gdim, c_mass, c_stiff, c_adv, rowptr, vptr, vent, n_nodes, out=None):
+    h, lib = handle(coords.device), load_library()
+    if out is None:
+        out = torch.empty(_nnz_of(rowptr), dtype=F64, device=coords.device)
+    adv = None
+    if c_adv is not None:
+        adv = (c_dbl * 3)(*[float(v) for v in list(c_adv) + [0.0] * (3 - len(c_adv))])
+    _check(lib.pgd_assemble_p1_rows(h, _p(coords, F64), _p(cell_verts, I32), cell_verts.shape[0], gdim, float(c_mass),
+                                    float(c_stiff), ctypes.cast(adv, c_vp) if adv is not None else c_vp(0), _p(rowptr, I32),
+                                    _p(vptr, I64), _p(vent, I32), n_nodes, _p(out), _stream()), h, "pgd_assemble_p1_rows")
+    return out
+
+
+_NNZ_CACHE = {}
+
+
+def _nnz_of(rowptr):
+    key = (rowptr.data_ptr(), rowptr.numel())
+    if key not in _NNZ_CACHE:
+        _NNZ_CACHE[key] = int(rowptr[-1].item())
+    return _NNZ_CACHE[key]
 
 
 def lincomb(xs, coefs, out=None, accumulate=False):

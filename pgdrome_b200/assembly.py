@@ -35,6 +35,7 @@ class DeviceSpace:
         self.n_dofs, self.ndl = space.n_dofs, space.ndl
         self._pattern = None
         self._vecmap = None
+        self._rowplan = None
         self._tabs = {}
         self._facet = {}
         self.atoms = {}  # key -> values tensor
@@ -65,6 +66,32 @@ class DeviceSpace:
         if self._vecmap is None:
             self._vecmap = _lib.vecmap_build(self.cell_dofs, self.n_dofs)
         return self._vecmap
+
+    @property
+    def rowplan(self):
+        """Plan of the row-owner fused P1 kernel (scalar P1 spaces only; False if a row is too long)."""
+        if self._rowplan is None:
+            rowptr, colidx, _, _ = self.pattern
+            vptr, vidx = self.vecmap
+            try:
+                self._rowplan = _lib.p1_rowplan_build(rowptr, colidx, self.cell_dofs, vptr, vidx, self.n_dofs)
+            except _lib.PGDB200Error:
+                self._rowplan = False
+        return self._rowplan
+
+    def _p1_closed_form(self, T):
+        """(c_mass, c_stiff, c_adv) if T is  c_m u v + c_k grad u.grad v + sum_m c_adv[m] (d_m u) v, else None."""
+        s = self.space
+        g = s.mesh().gdim
+        if s.bs != 1 or s.degree != 1 or s.mesh().tdim != g:
+            return None
+        t = T[0, :, 0, :]
+        if np.any(t[1:, 0] != 0):  # (d_m v) u terms are not in the closed form
+            return None
+        ck = t[1, 1]
+        if np.any(t[1:, 1:] != ck * np.eye(g)):
+            return None
+        return float(t[0, 0]), float(ck), [float(v) for v in t[0, 1:]]
 
     def tables(self, qdeg, tdim=None, degree=None):
         tdim = self.space.mesh().tdim if tdim is None else tdim
@@ -138,6 +165,13 @@ class DeviceSpace:
         m = s.mesh()
         g = m.gdim
         T = np.asarray(T, dtype=np.float64).reshape(s.bs, g + 1, s.bs, g + 1)
+        if weight is None and not weights:
+            cf = self._p1_closed_form(T)
+            if cf is not None and self.rowplan is not False:
+                # constant-coefficient P1 operator: one fused kernel straight into the CSR pattern
+                rowptr = self.pattern[0]
+                return _lib.assemble_p1_rows(self.coords, self.cell_verts, g, cf[0], cf[1], cf[2] if any(cf[2]) else None,
+                                             rowptr, self.vecmap[0], self.rowplan, self.n_dofs)
         # polynomial degree of the integrand on an affine simplex
         dv = s.degree if np.any(T[:, 0, :, :] != 0) else s.degree - 1
         du = s.degree if np.any(T[:, :, :, 0] != 0) else s.degree - 1

@@ -1,0 +1,224 @@
+// Row-owner fused P1 assembly: values = c_mass*M + c_stiff*K + sum_m c_adv[m] * int (d_m u) v written
+// straight into the CSR pattern, one kernel, no element buffer, no atomics.
+//
+// The first fused kernel (k_assemble_p1, assemble.cu) owns one NONZERO per 4 lanes and re-derives
+// the element geometry for every one of the (nv*nv) local entries of every cell: ncu showed it
+// FP64/latency-bound at 1.3 % of the HBM roofline (profiles/README.md).  Here a thread owns one ROW
+// (= mesh node): it walks the cells around its node in the fixed order of the vecmap, computes the
+// geometry of each cell once, forms the nv entries of the local row and adds them at precomputed
+// positions (one byte per entry, packed next to the cell id in the plan) into the CTA's slice of the
+// value array held in shared memory; the slice is then written out fully coalesced.  The geometry is
+// evaluated nv times per cell instead of nv*nv times, each thread has 3*nv independent coordinate
+// loads in flight per cell, and the summation order is fixed => bitwise reproducible.
+#include "common.cuh"
+
+#define AR_ROWS 128       // rows (threads) per CTA
+#define AR_CAP 3072       // doubles of shared memory for the CTA's value slice (24 KB => 9 CTAs per SM)
+
+// ------------------------------------------------------------------------------------ plan
+template <int NV>
+__global__ void __launch_bounds__(256) k_p1_rowplan(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                                    const int32_t* __restrict__ cd, const int64_t* __restrict__ vptr,
+                                                    const int32_t* __restrict__ vidx, int64_t n_nodes, int2* __restrict__ vent,
+                                                    int* flag) {
+    int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_nodes) return;
+    const int k0 = rowptr[row], k1 = rowptr[row + 1];
+    if (k1 - k0 > 255) {
+        *flag = 1;
+        return;
+    }
+    for (int64_t e = vptr[row]; e < vptr[row + 1]; ++e) {
+        const int ent = vidx[e];
+        const int cell = ent / NV;
+        unsigned int packed = 0;
+#pragma unroll
+        for (int b = 0; b < NV; ++b) {
+            const int c = cd[(int64_t)cell * NV + b];
+            int lo = k0, hi = k1 - 1, pos = 0;
+            while (lo <= hi) {
+                const int mid = (lo + hi) >> 1;
+                const int cc = colidx[mid];
+                if (cc == c) {
+                    pos = mid - k0;
+                    break;
+                }
+                if (cc < c) lo = mid + 1;
+                else hi = mid - 1;
+            }
+            packed |= (unsigned int)pos << (8 * b);
+        }
+        vent[e] = make_int2(ent, (int)packed);
+    }
+}
+
+extern "C" int32_t pgd_p1_rowplan_build_sync(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx,
+                                             const int32_t* d_cell_dofs, int64_t n_cells, int32_t nv, const int64_t* d_vptr,
+                                             const int32_t* d_vidx, int64_t n_nodes, int32_t* d_vent, void* stream) {
+    PGD_CHECK_HANDLE(h);
+    PGD_ARG(h, d_rowptr && d_colidx && d_cell_dofs && d_vptr && d_vidx && d_vent && n_nodes > 0 && n_cells > 0, "bad arguments");
+    PGD_ARG(h, nv >= 2 && nv <= 4, "nv must be 2, 3 or 4 (P1 interval / triangle / tetrahedron)");
+    cudaStream_t st = (cudaStream_t)stream;
+    int* flag = h->flags + 12;
+    PGD_CUDA(h, cudaMemsetAsync(flag, 0, sizeof(int), st));
+    unsigned int blocks = pgd_blocks(n_nodes, 256);
+    int2* vent = reinterpret_cast<int2*>(d_vent);
+    if (nv == 2) k_p1_rowplan<2><<<blocks, 256, 0, st>>>(d_rowptr, d_colidx, d_cell_dofs, d_vptr, d_vidx, n_nodes, vent, flag);
+    else if (nv == 3) k_p1_rowplan<3><<<blocks, 256, 0, st>>>(d_rowptr, d_colidx, d_cell_dofs, d_vptr, d_vidx, n_nodes, vent, flag);
+    else k_p1_rowplan<4><<<blocks, 256, 0, st>>>(d_rowptr, d_colidx, d_cell_dofs, d_vptr, d_vidx, n_nodes, vent, flag);
+    PGD_LAUNCH_OK(h);
+    int hf = 0;
+    PGD_CUDA(h, cudaMemcpyAsync(&hf, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PGD_CUDA(h, cudaStreamSynchronize(st));
+    if (hf) {
+        snprintf(h->err, sizeof(h->err), "pgd_p1_rowplan_build_sync: a row has more than 255 entries");
+        return -4;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ kernel
+struct ArCoef {
+    double cm, ck, cadv[3];
+};
+
+template <int G>
+__global__ void __launch_bounds__(AR_ROWS) k_assemble_p1_rows(const double* __restrict__ coords, const int32_t* __restrict__ cv,
+                                                              const int32_t* __restrict__ rowptr,
+                                                              const int64_t* __restrict__ vptr, const int2* __restrict__ vent,
+                                                              int64_t n_nodes, ArCoef cf, double* __restrict__ values) {
+    constexpr int NV = G + 1;
+    __shared__ double s_val[AR_CAP];
+    const int tid = threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.x * AR_ROWS;
+    const int nr = (int)min((int64_t)AR_ROWS, n_nodes - r0);
+    const int kbase = __ldg(&rowptr[r0]);
+    const int kcnt = __ldg(&rowptr[r0 + nr]) - kbase;
+    const bool in_smem = kcnt <= AR_CAP;  // uniform; otherwise accumulate in global memory (thread-private rows)
+    double* acc = in_smem ? s_val : (values + kbase);
+    for (int j = tid; j < kcnt; j += AR_ROWS) acc[j] = 0.0;
+    __syncthreads();
+    if (tid < nr) {
+        const int64_t row = r0 + tid;
+        double* arow = acc + (__ldg(&rowptr[row]) - kbase);
+        const int64_t e1 = __ldg(&vptr[row + 1]);
+        constexpr double fact = (G == 1) ? 1.0 : (G == 2 ? 2.0 : 6.0);
+        for (int64_t e = __ldg(&vptr[row]); e < e1; ++e) {
+            const int2 en = __ldg(&vent[e]);
+            const int cell = en.x / NV;
+            const int a = en.x - cell * NV;
+            const unsigned int packed = (unsigned int)en.y;
+            int vi[NV];
+            if constexpr (NV == 4) {
+                const int4 q = __ldg(reinterpret_cast<const int4*>(cv) + cell);
+                vi[0] = q.x, vi[1] = q.y, vi[2] = q.z, vi[3] = q.w;
+            } else if constexpr (NV == 2) {
+                const int2 q = __ldg(reinterpret_cast<const int2*>(cv) + cell);
+                vi[0] = q.x, vi[1] = q.y;
+            } else {
+#pragma unroll
+                for (int v = 0; v < NV; ++v) vi[v] = __ldg(&cv[(int64_t)cell * NV + v]);
+            }
+            double X[NV][G];
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+#pragma unroll
+                for (int g = 0; g < G; ++g) X[v][g] = __ldg(&coords[(int64_t)vi[v] * G + g]);
+            // J[g][t] = X[t+1][g] - X[0][g];  grad phi_{t+1} = row t of J^-1, grad phi_0 = -sum_t
+            double Jinv[G][G], det;
+            if constexpr (G == 1) {
+                const double j00 = X[1][0] - X[0][0];
+                det = j00;
+                Jinv[0][0] = 1.0 / j00;
+            } else if constexpr (G == 2) {
+                const double j00 = X[1][0] - X[0][0], j01 = X[2][0] - X[0][0];
+                const double j10 = X[1][1] - X[0][1], j11 = X[2][1] - X[0][1];
+                det = j00 * j11 - j01 * j10;
+                const double id = 1.0 / det;
+                Jinv[0][0] = j11 * id;
+                Jinv[0][1] = -j01 * id;
+                Jinv[1][0] = -j10 * id;
+                Jinv[1][1] = j00 * id;
+            } else {
+                double J[3][3];
+#pragma unroll
+                for (int g = 0; g < 3; ++g)
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) J[g][t] = X[t + 1][g] - X[0][g];
+                const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+                const double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+                const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+                det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+                const double id = 1.0 / det;
+                Jinv[0][0] = c00 * id;
+                Jinv[1][0] = c01 * id;
+                Jinv[2][0] = c02 * id;
+                Jinv[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * id;
+                Jinv[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * id;
+                Jinv[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * id;
+                Jinv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * id;
+                Jinv[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * id;
+                Jinv[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id;
+            }
+            const double vol = fabs(det) / fact;
+            double grad[NV][G];
+#pragma unroll
+            for (int m = 0; m < G; ++m) {
+                double s0 = 0.0;
+#pragma unroll
+                for (int t = 0; t < G; ++t) {
+                    s0 -= Jinv[t][m];
+                    grad[t + 1][m] = Jinv[t][m];
+                }
+                grad[0][m] = s0;
+            }
+            double ga[G];
+#pragma unroll
+            for (int m = 0; m < G; ++m) {
+                double v = grad[0][m];
+#pragma unroll
+                for (int t = 1; t < NV; ++t) v = (a == t) ? grad[t][m] : v;
+                ga[m] = v;
+            }
+#pragma unroll
+            for (int b = 0; b < NV; ++b) {
+                double dotg = 0.0, adv = 0.0;
+#pragma unroll
+                for (int m = 0; m < G; ++m) {
+                    dotg += ga[m] * grad[b][m];
+                    adv += cf.cadv[m] * grad[b][m];
+                }
+                const double mass = vol * ((a == b) ? 2.0 : 1.0) / (double)((G + 1) * (G + 2));
+                const double val = cf.cm * mass + cf.ck * vol * dotg + adv * vol / (double)(G + 1);
+                arow[(packed >> (8 * b)) & 255u] += val;
+            }
+        }
+    }
+    if (in_smem) {
+        __syncthreads();
+        for (int j = tid; j < kcnt; j += AR_ROWS) values[kbase + j] = s_val[j];
+    }
+}
+
+extern "C" int32_t pgd_assemble_p1_rows(pgd_handle_t h, const double* d_coords, const int32_t* d_cell_verts, int64_t n_cells,
+                                        int32_t gdim, double c_mass, double c_stiff, const double* h_c_adv,
+                                        const int32_t* d_rowptr, const int64_t* d_vptr, const int32_t* d_vent, int64_t n_nodes,
+                                        double* d_values, void* stream) {
+    PGD_CHECK_HANDLE(h);
+    PGD_ARG(h, d_coords && d_cell_verts && d_rowptr && d_vptr && d_vent && d_values, "null pointer");
+    PGD_ARG(h, gdim >= 1 && gdim <= 3, "gdim must be 1, 2 or 3");
+    (void)n_cells;
+    if (n_nodes <= 0) return 0;
+    ArCoef cf;
+    cf.cm = c_mass;
+    cf.ck = c_stiff;
+    for (int m = 0; m < 3; ++m) cf.cadv[m] = (h_c_adv && m < gdim) ? h_c_adv[m] : 0.0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned int blocks = pgd_blocks(n_nodes, AR_ROWS);
+    const int2* vent = reinterpret_cast<const int2*>(d_vent);
+    if (gdim == 1) k_assemble_p1_rows<1><<<blocks, AR_ROWS, 0, st>>>(d_coords, d_cell_verts, d_rowptr, d_vptr, vent, n_nodes, cf, d_values);
+    else if (gdim == 2) k_assemble_p1_rows<2><<<blocks, AR_ROWS, 0, st>>>(d_coords, d_cell_verts, d_rowptr, d_vptr, vent, n_nodes, cf, d_values);
+    else k_assemble_p1_rows<3><<<blocks, AR_ROWS, 0, st>>>(d_coords, d_cell_verts, d_rowptr, d_vptr, vent, n_nodes, cf, d_values);
+    PGD_LAUNCH_OK(h);
+    return 0;
+}

@@ -197,11 +197,128 @@ __global__ void __launch_bounds__(256, 1) k_eval_gemm(const double* __restrict__
     }
 }
 
+
+// ---- v2: 2 CTAs per SM, A tile resident, B tiles double-buffered with cp.async -----------------
+// CTA = one 128-row c-tile x a run of GM2_RUN consecutive 64-column n-tiles.  W's tile (A) is staged
+// once; X's tiles (B) stream through a 2-deep cp.async ring so that the loads of tile t+1 overlap the
+// DMMAs and the streaming stores of tile t, and the second resident CTA fills the remaining bubbles
+// (warp tile 32 x 32 = 64 accumulator registers => 2 CTAs of 256 threads per SM).  Leading dimensions
+// 132 / 68 make every fragment load bank-conflict free (4 k-rows x 4 m-columns per half-warp hit 16
+// distinct bank pairs).  Requires 16-byte aligned W/X/U and even ldw/ldx/ldu (launcher checks).
+#define GM2_TM 128
+#define GM2_TN 64
+#define GM2_KMAX 64
+#define GM2_LDA 132
+#define GM2_LDB 68
+#define GM2_RUN 16
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+    unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 2) k_eval_gemm2(const double* __restrict__ W, int64_t ldw, const double* __restrict__ X,
+                                                       int64_t ldx, int R, int64_t C, int64_t N, double* __restrict__ U,
+                                                       int64_t ldu, int64_t n_tiles, int64_t n_groups) {
+    extern __shared__ __align__(16) double sm2[];
+    const int kc4 = (R + 3) & ~3;
+    double* As = sm2;                       // [kc4][GM2_LDA]
+    double* Bs = sm2 + kc4 * GM2_LDA;       // [2][kc4][GM2_LDB]
+    const int64_t ct = blockIdx.x / n_groups, ng = blockIdx.x % n_groups;
+    const int64_t c0 = ct * GM2_TM;
+    const int64_t t0 = ng * GM2_RUN;
+    const int nt = (int)min((int64_t)GM2_RUN, n_tiles - t0);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
+    const int fr = lane >> 2, fk = lane & 3;
+    // zero the K padding rows once (never touched by cp.async)
+    for (int idx = tid; idx < (kc4 - R) * GM2_LDA; idx += 256) As[R * GM2_LDA + idx] = 0.0;
+    for (int b = 0; b < 2; ++b)
+        for (int idx = tid; idx < (kc4 - R) * GM2_LDB; idx += 256) Bs[(b * kc4 + R) * GM2_LDB + idx] = 0.0;
+    // A tile: R rows x 64 chunks of 16 B
+    for (int idx = tid; idx < R * (GM2_TM / 2); idx += 256) {
+        const int k = idx / (GM2_TM / 2), ch = idx - k * (GM2_TM / 2);
+        const int64_t c = c0 + 2 * ch;
+        const int64_t left = (C - c) * 8;
+        const int bytes = left >= 16 ? 16 : (left > 0 ? (int)left : 0);
+        cp_async16(&As[k * GM2_LDA + 2 * ch], &W[(size_t)k * ldw + (bytes ? c : 0)], bytes);
+    }
+    auto load_B = [&](int t, int buf) {
+        const int64_t n0 = (t0 + t) * GM2_TN;
+        double* dst = Bs + (size_t)buf * kc4 * GM2_LDB;
+        for (int idx = tid; idx < R * (GM2_TN / 2); idx += 256) {
+            const int k = idx / (GM2_TN / 2), ch = idx - k * (GM2_TN / 2);
+            const int64_t n = n0 + 2 * ch;
+            const int64_t left = (N - n) * 8;
+            const int bytes = left >= 16 ? 16 : (left > 0 ? (int)left : 0);
+            cp_async16(&dst[k * GM2_LDB + 2 * ch], &X[(size_t)k * ldx + (bytes ? n : 0)], bytes);
+        }
+    };
+    load_B(0, 0);
+    cp_async_commit();
+    for (int t = 0; t < nt; ++t) {
+        if (t + 1 < nt) load_B(t + 1, (t + 1) & 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const double* Bt = Bs + (size_t)(t & 1) * kc4 * GM2_LDB;
+        double acc[4][4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int kk = 0; kk < kc4; kk += 4) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) af[i] = As[(kk + fk) * GM2_LDA + wm + i * 8 + fr];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = Bt[(kk + fk) * GM2_LDB + wn + j * 8 + fr];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        const int64_t n0 = (t0 + t) * GM2_TN;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t c = c0 + wm + i * 8 + fr;
+            if (c >= C) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t n = n0 + wn + j * 8 + 2 * fk;
+                double* dst = U + (size_t)c * ldu + n;
+                if (n + 1 < N) __stcs(reinterpret_cast<double2*>(dst), make_double2(acc[i][j][0], acc[i][j][1]));
+                else if (n < N) __stcs(dst, acc[i][j][0]);
+            }
+        }
+        __syncthreads();  // every warp is done with Bs[t & 1] before iteration t + 1 prefetches into it
+    }
+}
+
 extern "C" int32_t pgd_eval_gemm_f64(pgd_handle_t h, const double* d_W, int64_t ldw, const double* d_X, int64_t ldx,
                                      int32_t R, int64_t C, int64_t N, double* d_U, int64_t ldu, void* stream) {
     PGD_CHECK_HANDLE(h);
     PGD_ARG(h, d_W && d_X && d_U && R > 0 && C >= 0 && N >= 0 && ldw >= C && ldx >= N && ldu >= N, "bad arguments");
     if (C == 0 || N == 0) return 0;
+    const bool aligned = ((ldu | ldx | ldw) % 2 == 0) &&
+                         (((reinterpret_cast<uintptr_t>(d_U) | reinterpret_cast<uintptr_t>(d_X) | reinterpret_cast<uintptr_t>(d_W)) % 16) == 0);
+    if (aligned && R <= GM2_KMAX) {
+        const int kc4 = (R + 3) & ~3;
+        const int64_t n_tiles = (N + GM2_TN - 1) / GM2_TN, c_tiles = (C + GM2_TM - 1) / GM2_TM;
+        const int64_t n_groups = (n_tiles + GM2_RUN - 1) / GM2_RUN;
+        PGD_ARG(h, c_tiles * n_groups < ((int64_t)1 << 31), "too many tiles");
+        const size_t smem2 = sizeof(double) * (size_t)kc4 * (GM2_LDA + 2 * GM2_LDB);
+        PGD_CUDA(h, cudaFuncSetAttribute(k_eval_gemm2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        k_eval_gemm2<<<(unsigned int)(c_tiles * n_groups), 256, smem2, (cudaStream_t)stream>>>(d_W, ldw, d_X, ldx, R, C, N, d_U,
+                                                                                            ldu, n_tiles, n_groups);
+        PGD_LAUNCH_OK(h);
+        return 0;
+    }
     int64_t tiles = ((C + GM_TM - 1) / GM_TM) * ((N + GM_TN - 1) / GM_TN);
     PGD_ARG(h, tiles < ((int64_t)1 << 31), "too many tiles");
     size_t smem = sizeof(double) * 2 * GM_KC * GM_LD;

@@ -102,6 +102,40 @@ def assemble_p1(coords, cell_verts, gdim, c_mass, c_stiff, c_adv, gptr, gidx, nn
     raise NotImplementedError("cpu_abi: fused P1 kernel is covered by the gpu tests only")
 
 
+def p1_rowplan_build(rowptr, colidx, cell_dofs, vptr, vidx, n_nodes):
+    return cell_dofs  # the stand-in below only needs the cell -> dof table
+
+
+def assemble_p1_rows(coords, cell_verts, gdim, c_mass, c_stiff, c_adv, rowptr, vptr, vent, n_nodes, out=None):
+    """closed-form P1 simplex matrices (mass, stiffness, advection) summed into CSR order."""
+    import scipy.sparse as sp
+
+    g = gdim
+    X = _n(coords).reshape(-1, g)[_n(cell_verts).astype(np.int64)]
+    J = np.swapaxes(X[:, 1:, :] - X[:, :1, :], 1, 2)
+    det = np.linalg.det(J)
+    Jinv = np.linalg.inv(J)  # [e, t, g]
+    grad = np.concatenate([-Jinv.sum(axis=1, keepdims=True), Jinv], axis=1)  # [e, nv, g]
+    vol = np.abs(det) / {1: 1.0, 2: 2.0, 3: 6.0}[g]
+    nv = g + 1
+    mass = vol[:, None, None] * (np.ones((nv, nv)) + np.eye(nv))[None] / ((g + 1) * (g + 2))
+    stiff = vol[:, None, None] * np.einsum("eam,ebm->eab", grad, grad)
+    cadv = np.zeros(g) if c_adv is None else np.asarray(list(c_adv)[:g], dtype=np.float64)
+    adv = (vol / (g + 1))[:, None, None] * np.einsum("m,ebm->eb", cadv, grad)[:, None, :] * np.ones((1, nv, 1))
+    Ae = c_mass * mass + c_stiff * stiff + adv
+    cv = _n(vent).astype(np.int64)  # the stand-in "plan" is the cell -> dof table
+    rows = np.repeat(cv[:, :, None], nv, axis=2).ravel()
+    cols = np.repeat(cv[:, None, :], nv, axis=1).ravel()
+    A = sp.coo_matrix((Ae.ravel(), (rows, cols)), shape=(n_nodes, n_nodes)).tocsr()
+    A.sort_indices()
+    assert np.array_equal(A.indptr, _n(rowptr))
+    r = _t(A.data, F64)
+    if out is not None:
+        out.copy_(r)
+        return out
+    return r
+
+
 def lincomb(xs, coefs, out=None, accumulate=False):
     n = (out if out is not None else xs[0]).numel()
     acc = out.clone() if (accumulate and out is not None) else torch.zeros(n, dtype=F64)
@@ -237,7 +271,8 @@ def eval_gemm(W, X, R, out=None):
     return r
 
 
-NAMES = ["pattern_build", "vecmap_build", "elem_bilinear", "elem_linear", "gather_values", "assemble_p1", "lincomb",
+NAMES = ["pattern_build", "vecmap_build", "elem_bilinear", "elem_linear", "gather_values", "assemble_p1",
+         "p1_rowplan_build", "assemble_p1_rows", "lincomb",
          "apply_dirichlet", "set_entries", "spmv", "spmv_dot", "bilinear", "dot", "panel_dots", "pcg", "banded_solve",
          "eval_weights", "eval_gemv", "eval_gemm"]
 

@@ -122,6 +122,34 @@ def test_fused_p1_operator(kind):
     for m in range(g):
         Ao = Ao + cadv[m] * ofem.assemble_bilinear(S, ofem.T_adv(g, m))
     assert _relerr(_csr(ds, vals).data, Ao.tocsr().data) < MAT_RTOL
+    # row-owner kernel (one thread per mesh node): same operator, bitwise reproducible
+    assert ds.rowplan is not False
+    v2 = _lib.assemble_p1_rows(ds.coords, ds.cell_verts, g, cm, ck, cadv, rowptr, ds.vecmap[0], ds.rowplan, ds.n_dofs)
+    assert _relerr(_csr(ds, v2).data, Ao.tocsr().data) < MAT_RTOL
+    v3 = _lib.assemble_p1_rows(ds.coords, ds.cell_verts, g, cm, ck, cadv, rowptr, ds.vecmap[0], ds.rowplan, ds.n_dofs)
+    assert torch.equal(v2, v3)
+    # and it is what the atom assembly of a scalar P1 space uses
+    K = ds.assemble_bilinear(ofem.T_stiff(1, g))
+    assert _relerr(_csr(ds, K).data, ofem.assemble_bilinear(S, ofem.T_stiff(1, g)).tocsr().data) < MAT_RTOL
+
+
+def test_fused_p1_rows_large_mesh():
+    """Row blocks whose value slice exceeds the shared-memory buffer fall back to global accumulation;
+    a 20^3 box exercises full interior rows (15 entries) over many CTAs."""
+    from pgdrome_b200 import _lib, fem
+    from pgdrome_b200.assembly import device_space
+
+    m = fem.UnitCubeMesh(20, 20, 20)
+    V = fem.FunctionSpace(m, "P", 1)
+    o = omesh.box_mesh(0.0, 0.0, 0.0, 1.0, 1.0, 1.0, 20, 20, 20)
+    S = ofem.Space(o[0], o[1], 1, 1)
+    ds = device_space(V)
+    rowptr, colidx, gptr, gidx = ds.pattern
+    v_old = _lib.assemble_p1(ds.coords, ds.cell_verts, 3, 0.3, 1.7, None, gptr, gidx, colidx.numel())
+    v_new = _lib.assemble_p1_rows(ds.coords, ds.cell_verts, 3, 0.3, 1.7, None, rowptr, ds.vecmap[0], ds.rowplan, ds.n_dofs)
+    Ao = 0.3 * ofem.assemble_bilinear(S, ofem.T_mass(1, 3)) + 1.7 * ofem.assemble_bilinear(S, ofem.T_stiff(1, 3))
+    assert _relerr(_csr(ds, v_new).data, Ao.tocsr().data) < MAT_RTOL
+    assert _relerr(v_new.cpu().numpy(), v_old.cpu().numpy()) < MAT_RTOL
 
 
 def test_facet_load_matches_oracle():
@@ -324,7 +352,9 @@ def test_evaluate_kernels():
     U = _lib.eval_gemm(W, Xd, R).cpu().numpy()
     assert _relerr(U, Wo.T @ X) < 1e-13
     # ragged sizes around the 128x128 tile and K > 64 (two K chunks)
-    for (R2, C2, N2) in [(1, 1, 1), (50, 129, 257), (70, 128, 128), (5, 7, 1000)]:
+    # (even leading dimensions take the cp.async double-buffered kernel, odd ones / K > 64 the general one)
+    for (R2, C2, N2) in [(1, 1, 1), (50, 129, 257), (70, 128, 128), (5, 7, 1000), (50, 130, 2050), (13, 300, 1004),
+                         (64, 128, 64), (3, 2, 1026), (52, 258, 1090)]:
         W2, X2 = rng.normal(size=(R2, C2)), rng.normal(size=(R2, N2))
         U2 = _lib.eval_gemm(torch.as_tensor(W2).to(dev), torch.as_tensor(X2).to(dev), R2).cpu().numpy()
         assert _relerr(U2, W2.T @ X2) < 1e-13, (R2, C2, N2)

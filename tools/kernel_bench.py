@@ -63,11 +63,22 @@ def run(mesh_n=128, hbm_peak=6451.2, evaluate=True, fp64_peak=None):
     ms = _time(lambda: _lib.assemble_p1(ds.coords, ds.cell_verts, 3, 0.3, 1.7, None, gptr, gidx, nnz, out=vals))
     entry("assemble_p1_fused", ms, 4 * 4 * nc + 8 * 3 * m.num_vertices() + 8 * nnz,
           note="algorithmic bytes exclude the 8 B/nnz + 4 B/contribution gather list the kernel also reads")
+    t0 = time.perf_counter()
+    plan = ds.rowplan
+    torch.cuda.synchronize()
+    out["rowplan_build_s"] = time.perf_counter() - t0
+    vptr = ds.vecmap[0]
+    ms = _time(lambda: _lib.assemble_p1_rows(ds.coords, ds.cell_verts, 3, 0.3, 1.7, None, rowptr, vptr, plan, n, out=vals))
+    entry("assemble_p1_rows", ms, 4 * 4 * nc + 8 * 3 * m.num_vertices() + 8 * nnz,
+          note="row-owner kernel; also reads the 8 B/(cell,vertex) plan (%d MB) and re-reads cell vertices 4x through L1/L2"
+               % (8 * 4 * nc // 1000000))
     # generic element kernel + gather (used once per atom at set-up)
     T = np.zeros((1, 4, 1, 4))
     for k in range(1, 4):
         T[0, k, 0, k] = 1.0
-    ms = _time(lambda: ds.assemble_bilinear(T), reps=5, warm=2)
+    Tg = T.copy()
+    Tg[0, 1, 0, 0] = 1e-300  # a (d_x v) u term is outside the closed form => generic element kernel + gather
+    ms = _time(lambda: ds.assemble_bilinear(Tg), reps=5, warm=2)
     entry("assemble_atom_generic", ms, 4 * 4 * nc + 8 * 3 * m.num_vertices() + 8 * nnz)
     K = ds.assemble_bilinear(T)
     Tm = np.zeros((1, 4, 1, 4))
