@@ -128,6 +128,47 @@ int32_t pgd_pcg_sync(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_c
                      const double* d_b, double* d_x, int64_t n, double rtol, double atol, int32_t maxit,
                      int32_t check_every, int32_t block, int32_t lanes_per_row, double* d_work,
                      int32_t* h_iters, double* h_relres, void* stream);
+/* ---- sharded PCG building blocks (spatial mesh partitioned by rows over the GPUs of one box; no
+ * counterpart in the serial reference).  Local vectors are laid out [owned | ghost], the local CSR
+ * (n_owned rows) uses that numbering.  One iteration on every rank:
+ *   pgd_spcg_direction -> [halo exchange of p] -> pgd_spcg_matvec -> [allreduce d_sc[2]] ->
+ *   pgd_spcg_update -> [allreduce d_sc[8..9]] -> pgd_spcg_rotate
+ * with the collectives issued by the host (NCCL) on the same stream.  No call synchronises or
+ * allocates, so an iteration can be captured in a CUDA graph.  Caller-owned device state:
+ *   d_sc (>= 16 doubles): [0] r.z old, [1] r.z, [2] p.q, [3] r.r, [4] b.b, [5] tol^2, [8..9] partial sums
+ *   d_fl (>= 4 int32):    [0] done, [1] iterations, [2] NaN seen
+ *   d_work: n_owned*(3+block) + n_local doubles; p (with its ghost tail) starts at
+ *           d_work + n_owned*(3+block); d_x [n_owned] is the solution (x0 = 0).
+ * pgd_spcg_init leaves the local (r.z, b.b) in d_sc[8..9]: all-reduce them, then pgd_spcg_init_fin. */
+int32_t pgd_spcg_init(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
+                      const double* d_b, double* d_x, int64_t n_owned, int64_t n_local, int32_t block, double* d_work,
+                      double* d_sc, int32_t* d_fl, void* stream);
+int32_t pgd_spcg_init_fin(pgd_handle_t h, double* d_sc, int32_t* d_fl, double rtol, double atol, void* stream);
+int32_t pgd_spcg_direction(pgd_handle_t h, double* d_work, int64_t n_owned, int32_t block, const double* d_sc,
+                           const int32_t* d_fl, void* stream);
+int32_t pgd_spcg_matvec(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
+                        double* d_work, int64_t n_owned, int32_t block, double* d_sc, void* stream);
+int32_t pgd_spcg_update(pgd_handle_t h, double* d_x, double* d_work, int64_t n_owned, int32_t block, double* d_sc,
+                        const int32_t* d_fl, void* stream);
+int32_t pgd_spcg_rotate(pgd_handle_t h, double* d_sc, int32_t* d_fl, void* stream);
+
+/* The whole sharded solve in one call: the loop above with NCCL send/recv for the halo of p (ghosts land in
+ * p's tail, grouped by source rank) and ncclAllReduce for the three dot products, all enqueued on
+ * `stream`; the host polls the convergence flag every check_every iterations.  Communicator: rank 0 calls
+ * pgd_comm_unique_id (128 bytes, NCCL is dlopen'ed at run time), the host distributes it (e.g.
+ * torch.distributed.broadcast) and every rank calls pgd_comm_init on its handle.  Without a communicator
+ * the call is the single-rank solve.  d_send_idx: int64 local owned indices grouped by destination
+ * rank; h_send_counts / h_recv_counts: [world] host arrays.
+ * d_work: n_owned*(3+block) + n_local + sum(send_counts) doubles. */
+int32_t pgd_comm_unique_id(void* h_id128);
+int32_t pgd_comm_init(pgd_handle_t h, const void* h_id128, int32_t rank, int32_t world);
+int32_t pgd_comm_destroy(pgd_handle_t h);
+int32_t pgd_spcg_solve_sync(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
+                            const double* d_b, double* d_x, int64_t n_owned, int64_t n_local, int32_t block,
+                            const int64_t* d_send_idx, const int64_t* h_send_counts, const int64_t* h_recv_counts,
+                            double rtol, double atol, int32_t maxit, int32_t check_every, double* d_work,
+                            int32_t* h_iters, double* h_relres, void* stream);
+
 /* General banded LU with partial pivoting, one CTA, for the 1-D parameter / time dimensions
  * (tiny, possibly non-symmetric).  d_perm[new] = old dof (band ordering), kl/ku bandwidths in the
  * permuted numbering; d_work: (2*kl+ku+1)*n + n doubles; *d_info != 0 on a zero pivot. */

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpgdb200.so")
-SOURCES = ["core.cu", "pattern.cu", "assemble.cu", "assemble_rows.cu", "sparse.cu", "pcg.cu", "pcg_resident.cu", "banded.cu", "evaluate.cu"]
+SOURCES = ["core.cu", "pattern.cu", "assemble.cu", "assemble_rows.cu", "sparse.cu", "pcg.cu", "pcg_resident.cu", "sharded.cu", "banded.cu", "evaluate.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -56,7 +56,7 @@ def build_library(force=False, verbose=False):
             print(f"--- {src}\n{out}")
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-ldl"]
     subprocess.run(cmd, check=True)
     return LIB
 

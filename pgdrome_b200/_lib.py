@@ -42,6 +42,17 @@ SIGNATURES = {
     "pgd_panel_dots": [c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_vp, c_vp],
     "pgd_pcg_sync": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_dbl, c_dbl, c_i32, c_i32, c_i32, c_i32, c_vp,
                      ctypes.POINTER(c_i32), ctypes.POINTER(c_dbl), c_vp],
+    "pgd_spcg_init": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp],
+    "pgd_spcg_init_fin": [c_vp, c_vp, c_vp, c_dbl, c_dbl, c_vp],
+    "pgd_spcg_direction": [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp],
+    "pgd_spcg_matvec": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp],
+    "pgd_spcg_update": [c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp],
+    "pgd_spcg_rotate": [c_vp, c_vp, c_vp, c_vp],
+    "pgd_comm_unique_id": [c_vp],
+    "pgd_comm_init": [c_vp, c_vp, c_i32, c_i32],
+    "pgd_comm_destroy": [c_vp],
+    "pgd_spcg_solve_sync": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_dbl, c_dbl, c_i32,
+                            c_i32, c_vp, c_vp, c_vp, c_vp],
     "pgd_banded_solve": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp],
     "pgd_eval_weights": [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp],
     "pgd_eval_gemv": [c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_vp, c_vp],
@@ -157,6 +168,56 @@ def set_option(name, value, device=None):
     rc = lib.pgd_set_option(h, name.encode(), int(value))
     if rc != 0:
         raise PGDB200Error("pgd_set_option(%s) failed: %s" % (name, lib.pgd_last_error(h).decode()))
+
+
+# ------------------------------------------------------------------------------ multi-GPU
+_COMM = {}
+
+
+def comm_init(group=None):
+    """Create the library's own NCCL communicator over the ranks of `group` (default: the world):
+    rank 0 draws the unique id, torch.distributed carries it to the others.  Idempotent per device."""
+    import torch.distributed as dist
+
+    h, lib = handle(None), load_library()
+    key = (torch.cuda.current_device(), id(group))
+    if key in _COMM:
+        return _COMM[key]
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    buf = (ctypes.c_ubyte * 128)()
+    if rank == 0:
+        rc = lib.pgd_comm_unique_id(ctypes.cast(buf, c_vp))
+        if rc != 0:
+            raise PGDB200Error("pgd_comm_unique_id failed (%d): NCCL not loadable" % rc)
+    t = torch.tensor(list(buf), dtype=torch.uint8, device="cuda")
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+    dist.broadcast(t, src=src, group=group)
+    raw = (ctypes.c_ubyte * 128)(*t.cpu().tolist())
+    _check(lib.pgd_comm_init(h, ctypes.cast(raw, c_vp), rank, world), h, "pgd_comm_init")
+    _COMM[key] = (rank, world)
+    return _COMM[key]
+
+
+def spcg_solve(A, b, rtol=1e-13, atol=0.0, maxit=10000, check_every=50, block=1, work=None):
+    """Sharded PCG solve (pgd_spcg_solve_sync): A is a partition.ShardedMatrix, b the owned slice.
+    Needs comm_init() when more than one rank takes part."""
+    h, lib = handle(b.device), load_library()
+    halo = A.halo
+    world = len(halo.send_counts)
+    n_send = int(sum(halo.send_counts))
+    need = A.n_owned * (3 + block) + A.n_local + n_send
+    if work is None or work.numel() < need:
+        work = torch.empty(need, dtype=F64, device=b.device)
+    x = torch.empty(A.n_owned, dtype=F64, device=b.device)
+    sc = (c_i64 * world)(*[int(v) for v in halo.send_counts])
+    rc_ = (c_i64 * world)(*[int(v) for v in halo.recv_counts])
+    iters, relres = c_i32(0), c_dbl(0.0)
+    _check(lib.pgd_spcg_solve_sync(h, _p(A.rowptr, I32), _p(A.colidx, I32), _p(A.values, F64), _p(b, F64), _p(x), A.n_owned,
+                                   A.n_local, block, _p(halo.send_idx, I64) if n_send else c_vp(0), ctypes.cast(sc, c_vp),
+                                   ctypes.cast(rc_, c_vp), float(rtol), float(atol), int(maxit), int(check_every), _p(work),
+                                   ctypes.cast(ctypes.pointer(iters), c_vp), ctypes.cast(ctypes.pointer(relres), c_vp),
+                                   _stream()), h, "pgd_spcg_solve_sync")
+    return x, int(iters.value), float(relres.value)
 
 
 # ------------------------------------------------------------------------------ pattern

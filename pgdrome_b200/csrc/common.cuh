@@ -36,6 +36,8 @@ struct pgd_ctx {
     const void* nnz_key;     // cache of rowptr[n] (one 4-byte D2H per new matrix)
     int64_t nnz_key_n, nnz_val;
     cudaEvent_t ev0, ev1;
+    void* comm;              // ncclComm_t of the sharded solves (pgd_comm_init), NULL = single rank
+    int comm_rank, comm_world;
 };
 
 void pgd_free_pattern(pgd_ctx* h);

@@ -389,3 +389,170 @@ extern "C" int32_t pgd_pcg_sync(pgd_handle_t h, const int32_t* d_rowptr, const i
     return run_pcg<3>(h, d_rowptr, d_colidx, d_values, d_b, d_x, n, rtol, atol, maxit, check_every, lanes_per_row, d_work,
                       h_iters, h_relres, st);
 }
+
+// ================================================================================================
+// Sharded PCG building blocks (spatial mesh partitioned by rows over the GPUs of one box).
+//
+// Each rank owns a contiguous block of rows; its local vectors are laid out [owned | ghost] and the
+// local CSR uses that numbering.  One iteration on every rank is
+//     pgd_spcg_direction   p = z + beta p                         (owned entries; beta from device scalars)
+//     <halo exchange of p  -- NCCL, issued by the host on the same stream>
+//     pgd_spcg_matvec      q = A_loc p,  local p.q   -> sc[S_PQ]  (the TMA-pipelined SpMV+dot kernel)
+//     <allreduce sc[S_PQ]>
+//     pgd_spcg_update      x += a p; r -= a q; z = M^-1 r; local r.z, r.r -> sc[S_TMP], sc[S_TMP+1]
+//     <allreduce sc[S_TMP..S_TMP+1]>
+//     pgd_spcg_rotate      scalar rotation, iteration counter, DONE flag (identical on every rank)
+// All calls are asynchronous launches without host synchronisation or allocation, so the host can
+// capture an iteration (kernels + NCCL collectives) in a CUDA graph.  d_sc: >= 16 doubles, d_fl: >= 4
+// ints, both caller-owned (the collectives operate on slices of d_sc).
+// work layout: r[no] z[no] q[no] minv[no*block] p[nl]   (no = owned rows, nl = owned + ghost)
+// ================================================================================================
+__global__ void __launch_bounds__(256) k_spcg_direction(const double* __restrict__ z, double* __restrict__ p, int64_t n,
+                                                        const double* sc, const int* fl) {
+    if (fl[F_DONE]) return;
+    const double beta = (fl[F_ITER] == 0) ? 0.0 : sc[S_RZ_NEW] / sc[S_RZ_OLD];
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = fma(beta, p[i], z[i]);
+}
+
+// x += alpha p ; r -= alpha q ; z = M^-1 r ; local sums (no rotation: the host all-reduces first)
+template <int BS>
+__global__ void __launch_bounds__(256) k_spcg_update(double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
+                                                     const double* __restrict__ p, const double* __restrict__ q,
+                                                     const double* __restrict__ minv, int64_t n_nodes, double* sc,
+                                                     const int* fl, double* part, unsigned int* counter) {
+    if (fl[F_DONE]) return;
+    const double alpha = sc[S_RZ_NEW] / sc[S_PQ];
+    double rz = 0.0, rr = 0.0;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t nd = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; nd < n_nodes; nd += stride) {
+        double rn[BS];
+#pragma unroll
+        for (int i = 0; i < BS; ++i) {
+            int64_t d = nd * BS + i;
+            x[d] = fma(alpha, p[d], x[d]);
+            rn[i] = fma(-alpha, q[d], r[d]);
+            r[d] = rn[i];
+            rr = fma(rn[i], rn[i], rr);
+        }
+#pragma unroll
+        for (int i = 0; i < BS; ++i) {
+            double zi = 0.0;
+#pragma unroll
+            for (int k = 0; k < BS; ++k) zi = fma(__ldg(&minv[(nd * BS + i) * BS + k]), rn[k], zi);
+            z[nd * BS + i] = zi;
+            rz = fma(rn[i], zi, rz);
+        }
+    }
+    rz = block_sum(rz);
+    rr = block_sum(rr);
+    double v[2] = {rz, rr};
+    grid_sum_finish<2>(v, part, counter, sc + S_TMP, blockIdx.x, gridDim.x);
+}
+
+__global__ void k_spcg_rotate(double* sc, int* fl) {
+    if (fl[F_DONE]) return;
+    const double rz_next = sc[S_TMP], rr = sc[S_TMP + 1];
+    sc[S_RZ_OLD] = sc[S_RZ_NEW];
+    sc[S_RZ_NEW] = rz_next;
+    sc[S_RR] = rr;
+    fl[F_ITER] = fl[F_ITER] + 1;
+    if (!(rr > sc[S_TOL2])) fl[F_DONE] = 1;
+    if (!(rr == rr) || !(rz_next == rz_next)) fl[F_BAD] = 1;
+}
+
+struct SpcgWork {
+    double *r, *z, *q, *minv, *p;
+};
+static SpcgWork spcg_work(double* work, int64_t no, int block) {
+    SpcgWork w;
+    w.r = work;
+    w.z = w.r + no;
+    w.q = w.z + no;
+    w.minv = w.q + no;
+    w.p = w.minv + no * block;
+    return w;
+}
+
+extern "C" int32_t pgd_spcg_init(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
+                                 const double* d_b, double* d_x, int64_t n_owned, int64_t n_local, int32_t block,
+                                 double* d_work, double* d_sc, int32_t* d_fl, void* stream) {
+    PGD_CHECK_HANDLE(h);
+    PGD_ARG(h, d_rowptr && d_colidx && d_values && d_b && d_x && d_work && d_sc && d_fl, "null pointer");
+    PGD_ARG(h, n_owned >= 0 && n_local >= n_owned && block >= 1 && block <= 3 && n_owned % block == 0, "bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    SpcgWork w = spcg_work(d_work, n_owned, block);
+    PGD_CUDA(h, cudaMemsetAsync(w.p, 0, sizeof(double) * n_local, st));
+    PGD_CUDA(h, cudaMemsetAsync(d_sc, 0, sizeof(double) * 16, st));
+    PGD_CUDA(h, cudaMemsetAsync(d_fl, 0, sizeof(int32_t) * 4, st));
+    const int64_t n_nodes = n_owned / block;
+    if (n_nodes == 0) return 0;
+    unsigned int vb = pgd_blocks(n_nodes, 256);
+    unsigned int capv = (unsigned int)h->sm_count * 8;
+    if (vb > capv) vb = capv;
+    // k_pcg_init writes p0/p1 = 0 for owned entries (here both alias w.p) and the local (rz, bb) to sc[S_TMP..]
+    if (block == 1) k_pcg_init<1><<<vb, 256, 0, st>>>(d_rowptr, d_colidx, d_values, d_b, d_x, w.r, w.z, w.p, w.p, w.minv, n_nodes, 0.0, 0.0, d_sc, d_fl, h->partials, h->counters);
+    else if (block == 2) k_pcg_init<2><<<vb, 256, 0, st>>>(d_rowptr, d_colidx, d_values, d_b, d_x, w.r, w.z, w.p, w.p, w.minv, n_nodes, 0.0, 0.0, d_sc, d_fl, h->partials, h->counters);
+    else k_pcg_init<3><<<vb, 256, 0, st>>>(d_rowptr, d_colidx, d_values, d_b, d_x, w.r, w.z, w.p, w.p, w.minv, n_nodes, 0.0, 0.0, d_sc, d_fl, h->partials, h->counters);
+    PGD_LAUNCH_OK(h);
+    return 0;
+}
+
+/* after the all-reduce of d_sc[S_TMP..S_TMP+1] = (r.z, b.b) */
+extern "C" int32_t pgd_spcg_init_fin(pgd_handle_t h, double* d_sc, int32_t* d_fl, double rtol, double atol, void* stream) {
+    PGD_CHECK_HANDLE(h);
+    PGD_ARG(h, d_sc && d_fl, "null pointer");
+    k_pcg_init_fin<<<1, 1, 0, (cudaStream_t)stream>>>(d_sc, d_fl, rtol, atol);
+    PGD_LAUNCH_OK(h);
+    return 0;
+}
+
+extern "C" int32_t pgd_spcg_direction(pgd_handle_t h, double* d_work, int64_t n_owned, int32_t block, const double* d_sc,
+                                      const int32_t* d_fl, void* stream) {
+    PGD_CHECK_HANDLE(h);
+    PGD_ARG(h, d_work && d_sc && d_fl && n_owned >= 0, "bad arguments");
+    if (n_owned == 0) return 0;
+    SpcgWork w = spcg_work(d_work, n_owned, block);
+    unsigned int vb = pgd_blocks(n_owned, 256);
+    unsigned int capv = (unsigned int)h->sm_count * 16;
+    if (vb > capv) vb = capv;
+    k_spcg_direction<<<vb, 256, 0, (cudaStream_t)stream>>>(w.z, w.p, n_owned, d_sc, d_fl);
+    PGD_LAUNCH_OK(h);
+    return 0;
+}
+
+extern "C" int32_t pgd_spcg_matvec(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
+                                   double* d_work, int64_t n_owned, int32_t block, double* d_sc, void* stream) {
+    PGD_CHECK_HANDLE(h);
+    PGD_ARG(h, d_rowptr && d_colidx && d_values && d_work && d_sc && n_owned >= 0, "bad arguments");
+    SpcgWork w = spcg_work(d_work, n_owned, block);
+    if (n_owned == 0) return (int32_t)cudaMemsetAsync(d_sc + S_PQ, 0, sizeof(double), (cudaStream_t)stream);
+    // q = A_loc p (p includes the ghost entries), sc[S_PQ] = local p.q     [not skipped when DONE: harmless]
+    return pgd_spmv_dot(h, d_rowptr, d_colidx, d_values, w.p, w.q, w.p, d_sc + S_PQ, n_owned, 0, stream);
+}
+
+extern "C" int32_t pgd_spcg_update(pgd_handle_t h, double* d_x, double* d_work, int64_t n_owned, int32_t block, double* d_sc,
+                                   const int32_t* d_fl, void* stream) {
+    PGD_CHECK_HANDLE(h);
+    PGD_ARG(h, d_x && d_work && d_sc && d_fl && n_owned >= 0 && block >= 1 && block <= 3, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    SpcgWork w = spcg_work(d_work, n_owned, block);
+    const int64_t n_nodes = n_owned / block;
+    if (n_nodes == 0) return (int32_t)cudaMemsetAsync(d_sc + S_TMP, 0, 2 * sizeof(double), st);
+    unsigned int vb = pgd_blocks(n_nodes, 256);
+    unsigned int capv = (unsigned int)h->sm_count * 8;
+    if (vb > capv) vb = capv;
+    if (block == 1) k_spcg_update<1><<<vb, 256, 0, st>>>(d_x, w.r, w.z, w.p, w.q, w.minv, n_nodes, d_sc, d_fl, h->partials, h->counters);
+    else if (block == 2) k_spcg_update<2><<<vb, 256, 0, st>>>(d_x, w.r, w.z, w.p, w.q, w.minv, n_nodes, d_sc, d_fl, h->partials, h->counters);
+    else k_spcg_update<3><<<vb, 256, 0, st>>>(d_x, w.r, w.z, w.p, w.q, w.minv, n_nodes, d_sc, d_fl, h->partials, h->counters);
+    PGD_LAUNCH_OK(h);
+    return 0;
+}
+
+extern "C" int32_t pgd_spcg_rotate(pgd_handle_t h, double* d_sc, int32_t* d_fl, void* stream) {
+    PGD_CHECK_HANDLE(h);
+    PGD_ARG(h, d_sc && d_fl, "null pointer");
+    k_spcg_rotate<<<1, 1, 0, (cudaStream_t)stream>>>(d_sc, d_fl);
+    PGD_LAUNCH_OK(h);
+    return 0;
+}

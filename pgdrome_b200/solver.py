@@ -469,6 +469,8 @@ class PGDProblem:
         maxit = int(settings.get("maximum_iterations", max(10000, 4 * V.n_dofs // max(1, V.bs))))
         prec = str(settings.get("preconditioner", "default")).lower()
         block = V.bs if (V.bs <= 3 and prec not in ("jacobi", "none_block")) else 1
+        if self._use_sharded(V, settings):
+            return self._sharded_solve(ds, values, b, block, rtol, atol, maxit, settings)
         x, iters, relres = _lib.pcg(rowptr, colidx, values, b, rtol=rtol, atol=atol, maxit=maxit,
                                     check_every=int(settings.get("check_every", 50)), block=block, lpr=ds.lpr)
         self.solver_stats["pcg_solves"] += 1
@@ -476,6 +478,40 @@ class PGDProblem:
         if relres > max(rtol, 1e-15) * 10 and iters >= maxit:
             self.logger.warning("PCG stopped at relative residual %.3e after %d iterations", relres, iters)
         return x
+
+    # ---- multi-GPU: the spatial solve sharded by rows over the ranks of torch.distributed
+    @staticmethod
+    def _use_sharded(V, settings):
+        """settings["sharded"]: True / False / "auto" (default: more than one rank and >= 200 000 dofs)."""
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return False
+        mode = settings.get("sharded", "auto")
+        return bool(mode) if mode != "auto" else V.n_dofs >= 200000
+
+    def _sharded_solve(self, ds, values, b, block, rtol, atol, maxit, settings):
+        """Every rank holds the (replicated) operator and right-hand side of the sub-problem, keeps its
+        slab of rows, takes part in the sharded PCG (halo exchange + dot-product all-reduces over NCCL)
+        and receives the full solution back; 1-D dimensions and mode integrals stay replicated."""
+        import torch.distributed as dist
+
+        from . import partition as pt
+
+        rank, world = dist.get_rank(), dist.get_world_size()
+        if getattr(ds, "shard", None) is None:
+            rowptr, colidx, _, _ = ds.pattern
+            part = pt.RowPartition(ds.n_dofs, world, block)
+            ds.shard = (part, pt.shard_csr(rowptr, colidx, None, part, rank))
+        part, S = ds.shard
+        S.values = S.take_values(values)
+        r0, r1 = part.range(rank)
+        x_owned, iters, relres = pt.sharded_pcg(S, b[r0:r1].contiguous(), rtol=rtol, atol=atol, maxit=maxit,
+                                                check_every=int(settings.get("check_every", 50)), block=block)
+        self.solver_stats["pcg_solves"] += 1
+        self.solver_stats["pcg_iterations"] += iters
+        self.solver_stats["sharded_solves"] = self.solver_stats.get("sharded_solves", 0) + 1
+        return pt.gather_owned(x_owned, part)
 
     def direct_solve(self, a, b, dim):
         """scalar problem: every dof = b / a (solver.py:909-925)."""

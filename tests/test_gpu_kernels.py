@@ -417,3 +417,30 @@ def test_stream_spmv_and_pcg(n, long_row):
         _lib.set_option("spmv_stream", 2)
         _lib.set_option("pcg_resident", 1)
     assert max(res.values()) - min(res.values()) <= max(2, res[0] // 20)
+
+
+def test_sharded_pcg_single_rank_matches_pcg():
+    """The sharded-PCG kernel set (pgd_spcg_*) on one rank (no ghosts, no collectives) against pgd_pcg_sync."""
+    from pgdrome_b200 import _lib, partition as pt
+
+    for block, n in ((1, 50000), (3, 30003)):
+        rng = np.random.default_rng(n)
+        A = _spd_random_csr(n, rng)
+        dev = torch.device("cuda")
+        rowptr = torch.as_tensor(A.indptr.astype(np.int32)).to(dev)
+        colidx = torch.as_tensor(A.indices.astype(np.int32)).to(dev)
+        vals = torch.as_tensor(A.data).to(dev)
+        x = rng.uniform(-1, 1, n)
+        b = torch.as_tensor(A @ x).to(dev)
+        S = pt.shard_csr(rowptr, colidx, vals, pt.RowPartition(n, 1, block), 0)
+        for graph in (False, True):
+            xs, it, rr = pt.sharded_pcg(S, b, rtol=1e-13, maxit=2000, check_every=10, block=block, use_graph=graph)
+            assert rr <= 1e-13 and 0 < it < 2000
+            assert np.linalg.norm(xs.cpu().numpy() - x) / np.linalg.norm(x) < 1e-10
+        _lib.set_option("pcg_resident", 0)
+        try:
+            x1, it1, _ = _lib.pcg(rowptr, colidx, vals, b, rtol=1e-13, maxit=2000, check_every=10, block=block, lpr=8)
+        finally:
+            _lib.set_option("pcg_resident", 1)
+        assert abs(it - it1) <= max(2, it1 // 20)
+        assert np.linalg.norm(xs.cpu().numpy() - x1.cpu().numpy()) / np.linalg.norm(x) < 1e-10

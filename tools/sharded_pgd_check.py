@@ -1,0 +1,55 @@
+"""2-GPU check of the sharded spatial solve inside the enrichment loop:
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port P -m tools.sharded_pgd_check
+
+Every rank runs configs[1] (heat2d_tk, reduced) twice -- spatial sub-problems solved by the single-GPU
+PCG, then by the sharded PCG over all ranks -- and compares modes, amplitudes and iteration counts."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def main(n=96, nmax=3):
+    import torch.distributed as dist
+
+    from pgdrome_b200 import configs
+
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank = dist.get_rank()
+    a = configs.heat2d_tk(n=n, nt=40, nk=10, PGD_nmax=nmax)
+    a.solve_PGD(_problem="linear", settings={"sharded": False})
+    b = configs.heat2d_tk(n=n, nt=40, nk=10, PGD_nmax=nmax)
+    b.solve_PGD(_problem="linear", settings={"sharded": True})
+    assert b.solver_stats.get("sharded_solves", 0) > 0 and a.solver_stats.get("sharded_solves", 0) == 0
+    assert a.PGD_modes == b.PGD_modes and a.num_fp_it == b.num_fp_it, (a.num_fp_it, b.num_fp_it)
+    worst = 0.0
+    for d in range(3):
+        for k in range(a.PGD_modes):
+            u, v = a.PGD_func[d][k].vector()[:], b.PGD_func[d][k].vector()[:]
+            worst = max(worst, min(np.linalg.norm(u - v), np.linalg.norm(u + v)) / np.linalg.norm(u))
+    assert worst < 1e-8, worst
+    assert np.allclose(a.amplitude, b.amplitude, rtol=1e-8, atol=0)
+    # every rank must hold bitwise the same modes (the replicated dimensions rely on it)
+    chk = torch.tensor([float(np.sum(b.PGD_func[0][-1].vector()[:]))], dtype=torch.float64, device="cuda")
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    assert float(lo) == float(hi)
+    if rank == 0:
+        print(json.dumps({"ok": True, "world": dist.get_world_size(), "spatial_dofs": (n + 1) ** 2, "modes": a.PGD_modes,
+                          "fp_iterations": a.num_fp_it, "worst_mode_diff": worst, "sharded_solves": b.solver_stats["sharded_solves"],
+                          "pcg_iterations": [a.solver_stats["pcg_iterations"], b.solver_stats["pcg_iterations"]]}))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
