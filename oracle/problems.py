@@ -10,6 +10,8 @@ the product generated (the dofmap is an *input*, like DOLFIN's would be).
   elasticity2d   tests/integration/test_solver_problem.py:127-627 (plane strain, vector P2)
   poisson1d_k    BASELINE.json configs[0]  (no reference callback set: parity unpinned)
   heat2d_tk      BASELINE.json configs[1]  (no reference callback set: parity unpinned)
+  elasticity3d   BASELINE.json configs[2]  (no reference callback set: parity unpinned)
+  thermal3d      BASELINE.json configs[3]  (no reference callback set: parity unpinned)
 """
 import numpy as np
 import scipy.sparse as sp
@@ -224,3 +226,71 @@ def heat2d_tk(n=256, nt=199, nk=49, krange=(0.5, 2.0), rho_cp=1.0, a=0.2, xc=(0.
                          bc_dofs=[bcx, bct, np.zeros(0, dtype=np.int64)], lhs_terms=lhs, rhs_terms=rhs,
                          seq_fp=[0, 1, 2], **opts)
     return p, {"spaces": S, "src": src}
+
+
+def elasticity3d(n=68, nE=49, nF=2, nu=0.3, Erange=(0.5, 1.5), Frange=(0.0, 2.0), spaces=None, **kw):
+    """configs[2] (pgdrome_b200/configs.py:elasticity3d) in matrix form: two-material cube, clamped at
+    x=0, traction on x=1.  No reference callback set exists for it: parity unpinned (oracle only)."""
+    from .meshes import box_mesh
+
+    if spaces is None:
+        S = [fem.Space(*box_mesh(0.0, 0.0, 0.0, 1.0, 1.0, 1.0, n, n, n), degree=1, bs=3)] + _interval_spaces(
+            (nE, nF), (1, 1), (Erange, Frange))
+    else:
+        S = spaces
+    lam, mu = nu / ((1 + nu) * (1 - 2 * nu)), 1.0 / (2 * (1 + nu))
+    T = fem.T_voigt(fem.isotropic_C(lam, mu, 3), 3)
+    chi1 = lambda x: np.where(x[..., 0] < 0.5, 1.0, 0.0)
+    chi2 = lambda x: np.where(x[..., 0] < 0.5, 0.0, 1.0)
+    K1 = fem.assemble_bilinear(S[0], T, weight=chi1, weight_degree=0)
+    K2 = fem.assemble_bilinear(S[0], T, weight=chi2, weight_degree=0)
+    ME, MEw, MF = _mass(S[1]), _mass(S[1], _x, 1), _mass(S[2])
+    near = lambda a, b: abs(a - b) < 3e-16 * max(1.0, abs(a), abs(b)) + 3e-16
+    face = fem.facet_space(S[0], lambda x: near(x[0], 1.0))
+    Lt = np.zeros((3, 4))
+    Lt[:, 0] = (0.0, 0.0, -1.0)
+    gx = fem.assemble_linear(face, Lt)
+    rhs = [(1.0, [gx, _load(S[1], _one, 1), _load(S[2], _x, 1)])]
+    bcx = fem.dirichlet_dofs(S[0], lambda x, ob: near(x[0], 0.0))
+    none = np.zeros(0, dtype=np.int64)
+    opts = dict(PGD_nmax=30, tol_fp_it=1e-5, max_fp_it=50)
+    opts.update(kw)
+    p = SeparatedProblem(n_dofs=[s.n_dofs for s in S], mass=[_mass(s) for s in S], bc_dofs=[bcx, none, none],
+                         lhs_terms=[(1.0, [K1, ME, MF]), (1.0, [K2, MEw, MF])], rhs_terms=rhs, seq_fp=[0, 1, 2], **opts)
+    return p, {"spaces": S}
+
+
+def thermal3d(n=158, nt=199, nP=19, nv=19, kappa=0.05, rho_cp=1.0, a=0.12, n_src=6, spaces=None, **kw):
+    """configs[3] (pgdrome_b200/configs.py:thermal3d) in matrix form: moving source pre-separated into
+    n_src terms g_m(x) h_m(t) P w_m(v); FD in time.  Parity unpinned (oracle only)."""
+    from .meshes import box_mesh
+
+    if spaces is None:
+        S = [fem.Space(*box_mesh(0.0, 0.0, 0.0, 1.0, 1.0, 1.0, n, n, n))] + _interval_spaces(
+            (nt, nP, nv), (1, 1, 1), ((0.0, 1.0), (0.5, 1.5), (0.5, 1.5)))
+    else:
+        S = spaces
+    t_dofs = S[1].dof_coordinates().ravel()
+    srt = np.argsort(t_dofs)
+    M_t, _, D1 = FD_matrices(t_dofs[srt])
+    Mt, At = M_t[srt, :][:, srt].tocsr(), D1[srt, :][:, srt].tocsr()
+    Mx, Kx = _mass(S[0]), _stiff(S[0])
+    MP, Mv = _mass(S[2]), _mass(S[3])
+    lhs = [(rho_cp, [Mx, At, MP, Mv]), (kappa, [Kx, Mt, MP, Mv])]
+    rhs = []
+    for m in range(n_src):
+        xm = 0.2 + 0.6 * m / max(n_src - 1, 1)
+        tm = 0.1 + 0.8 * m / max(n_src - 1, 1)
+        vm = 0.5 + m / max(n_src - 1, 1)
+        g = _interp(S[0], lambda x: np.exp(-3.0 * ((x[..., 0] - xm) ** 2 + (x[..., 1] - 0.5) ** 2 + (x[..., 2] - 1.0) ** 2) / (a * a)))
+        h = _interp(S[1], lambda x: np.exp(-(((x[..., 0] - tm) / 0.08) ** 2)))
+        w = lambda x, vm=vm: np.exp(-(((x[..., 0] - vm) / 0.6) ** 2))
+        rhs.append((1.0, [Mx @ g, Mt @ h, _load(S[2], _x, 1), _load(S[3], w, 2)]))
+    bcx = fem.dirichlet_dofs(S[0], lambda x, ob: abs(x[2]) < 1e-14)
+    bct = np.where(t_dofs < 1e-12)[0]
+    none = np.zeros(0, dtype=np.int64)
+    opts = dict(PGD_nmax=50, tol_fp_it=1e-5, max_fp_it=50)
+    opts.update(kw)
+    p = SeparatedProblem(n_dofs=[s.n_dofs for s in S], mass=[Mx, Mt, MP, Mv], bc_dofs=[bcx, bct, none, none],
+                         lhs_terms=lhs, rhs_terms=rhs, seq_fp=[0, 1, 2, 3], **opts)
+    return p, {"spaces": S}

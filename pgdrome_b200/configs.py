@@ -138,3 +138,146 @@ def heat2d_tk(n=256, nt=199, nk=49, krange=(0.5, 2.0), rho_cp=1.0, a=0.2, xc=(0.
     for k, v in attrs.items():
         setattr(p, k, v)
     return p
+
+
+# ------------------------------------------------------------------------------- configs[2] / configs[3]
+def _separated_problem(name, name_coord, Vs, ops, coefs, loads, bc_fct, probs, PGD_nmax, MM=None, **attrs):
+    """PGDProblem whose callbacks have the separated shape of every reference example:
+    ops[k][d](u, v) -> bilinear form of term k on dimension d, loads[m][d](w) -> linear form.  The
+    callbacks below are what a PGDrome user writes by hand (cf. test_elastic.py:71-219)."""
+    D = len(Vs)
+    which = {p: i for i, p in enumerate(probs)}
+
+    def lhs_fct(fct_F, var_F, Fs, meshes, dom, param, typ, dim):
+        d = which[typ]
+        a = 0
+        for k, op in enumerate(ops):
+            c = coefs[k]
+            for j in range(D):
+                if j != d:
+                    c = c * df.assemble(op[j](Fs[j], Fs[j]))
+            a = a + df.Constant(c) * op[d](fct_F, var_F)
+        return a
+
+    def rhs_fct(fct_F, var_F, Fs, meshes, dom, param, G, PGD_func, typ, nE, dim):
+        d = which[typ]
+        l = 0
+        for ld in loads:
+            c = 1.0
+            for j in range(D):
+                if j != d:
+                    c = c * df.assemble(ld[j](Fs[j]))
+            l = l + df.Constant(c) * ld[d](var_F)
+        for old in range(nE):
+            for k, op in enumerate(ops):
+                c = coefs[k]
+                for j in range(D):
+                    if j != d:
+                        c = c * df.assemble(op[j](PGD_func[j][old], Fs[j]))
+                l = l + (-df.Constant(c)) * op[d](PGD_func[d][old], var_F)
+        return l
+
+    p = PGDProblem(name=name, name_coord=name_coord, modes_info=["U", "Node", "Vector" if Vs[0].bs > 1 else "Scalar"], Vs=Vs,
+                   dom_fct=None, bc_fct=bc_fct, load=[], param={}, rhs_fct=rhs_fct, lhs_fct=lhs_fct, probs=probs,
+                   seq_fp=list(range(D)), PGD_nmax=PGD_nmax)
+    if MM is not None:
+        p.MM = MM
+    p.tol_fp_it, p.max_fp_it, p.stop_fp, p.norm_modes = 1e-5, 50, "norm", "stiff"
+    for k, v in attrs.items():
+        setattr(p, k, v)
+    return p
+
+
+def elasticity3d(n=68, nE=49, nF=2, nu=0.3, Erange=(0.5, 1.5), Frange=(0.0, 2.0), PGD_nmax=30, **attrs):
+    """configs[2]: 3-D linear elasticity u(x, E, F) on a unit cube of vector P1 tetrahedra (n=68:
+    985 527 dofs), clamped at x=0, traction F*(0,0,-1) on the face x=1.  The stiff half x < 1/2 keeps
+    Young's modulus 1, the half x >= 1/2 has the parametric modulus E, which makes the solution
+    non-separable in (x, E); the load amplitude F enters linearly."""
+    mx = df.UnitCubeMesh(n, n, n)
+    mE, mF = df.IntervalMesh(nE, Erange[0], Erange[1]), df.IntervalMesh(nF, Frange[0], Frange[1])
+    Vs = [df.VectorFunctionSpace(mx, "P", 1), df.FunctionSpace(mE, "P", 1), df.FunctionSpace(mF, "P", 1)]
+    lam, mu = nu / ((1 + nu) * (1 - 2 * nu)), 1.0 / (2 * (1 + nu))
+    C = np.zeros((6, 6))
+    C[:3, :3] = lam
+    C[np.arange(3), np.arange(3)] += 2 * mu
+    C[np.arange(3, 6), np.arange(3, 6)] = mu
+    Cm = df.as_matrix(C)
+    chi1 = df.Expression("x[0] < 0.5 ? 1.0 : 0.0", degree=0)
+    chi2 = df.Expression("x[0] < 0.5 ? 0.0 : 1.0", degree=0)
+    Ew = df.Expression("x[0]", degree=1)
+    trac = df.Constant((0.0, 0.0, -1.0))
+    facets = df.MeshFunction("size_t", mx, 2, 0)
+
+    class Right(df.SubDomain):
+        def inside(self, x, on_boundary):
+            return on_boundary and df.near(x[0], 1.0)
+
+    Right().mark(facets, 2)
+    ds = df.Measure("ds", domain=mx, subdomain_data=facets)
+
+    def eps(v):  # Voigt strain (xx, yy, zz, yz, xz, xy)
+        return df.as_vector([v[0].dx(0), v[1].dx(1), v[2].dx(2), v[1].dx(2) + v[2].dx(1), v[0].dx(2) + v[2].dx(0),
+                             v[0].dx(1) + v[1].dx(0)])
+
+    def kx(chi):
+        return lambda u, v: chi * df.inner(Cm * eps(u), eps(v)) * df.dx(mx)
+
+    mass = lambda mesh: (lambda u, v: u * v * df.dx(mesh))
+    ops = [[kx(chi1), mass(mE), mass(mF)],
+           [kx(chi2), lambda u, v: u * Ew * v * df.dx(mE), mass(mF)]]
+    Fw = df.Expression("x[0]", degree=1)
+    one = df.Expression("1.0", degree=1)
+    loads = [[lambda w: df.dot(trac, w) * ds(2), lambda w: one * w * df.dx(mE), lambda w: Fw * w * df.dx(mF)]]
+
+    def bc_fct(Vs, dom, param):
+        def left(x, on_boundary):
+            return on_boundary and df.near(x[0], 0.0)
+
+        return [df.DirichletBC(Vs[0], df.Constant((0.0, 0.0, 0.0)), left), 0, 0]
+
+    return _separated_problem("elasticity3d", ["X", "E", "F"], Vs, ops, [1.0, 1.0], loads, bc_fct, ["r", "s", "t"],
+                              PGD_nmax, **attrs)
+
+
+def thermal3d(n=158, nt=199, nP=19, nv=19, kappa=0.05, rho_cp=1.0, a=0.12, n_src=6, PGD_nmax=50, **attrs):
+    """configs[3]: 3-D moving-heat-source thermal problem u(x, t, P, v) on a unit cube of P1
+    tetrahedra (n=158: 4 019 679 dofs) x 200 time nodes (FD: M_t, D1_up as in
+    tests/integration/test_heat1D.py:507-519) x power P x travel speed v.  The source moving along
+    the x axis, Q = P exp(-3|x - x_s(t, v)|^2 / a^2), is pre-separated into n_src terms
+    g_m(x) h_m(t) P w_m(v) (Gaussians at way-points x_m reached at t_m)."""
+    mx = df.UnitCubeMesh(n, n, n)
+    mt = df.IntervalMesh(nt, 0.0, 1.0)
+    mP, mv = df.IntervalMesh(nP, 0.5, 1.5), df.IntervalMesh(nv, 0.5, 1.5)
+    Vs = [df.FunctionSpace(mx, "P", 1), df.FunctionSpace(mt, "P", 1), df.FunctionSpace(mP, "P", 1), df.FunctionSpace(mv, "P", 1)]
+    t_dofs = Vs[1].tabulate_dof_coordinates()[:].flatten()
+    srt = np.argsort(t_dofs)
+    M_t, _, D1 = FD_matrices(t_dofs[srt])
+    M_t, D1 = M_t.tocsr()[srt, :][:, srt], D1.tocsr()[srt, :][:, srt]
+    Mt, Dt = df.MatrixOperator(M_t, Vs[1]), df.MatrixOperator(D1, Vs[1])
+    mass = lambda mesh: (lambda u, v: u * v * df.dx(mesh))
+    ops = [[mass(mx), lambda u, v: Dt(u, v) * df.dx(mt), mass(mP), mass(mv)],
+           [lambda u, v: df.inner(df.grad(u), df.grad(v)) * df.dx(mx), lambda u, v: Mt(u, v) * df.dx(mt), mass(mP), mass(mv)]]
+    coefs = [rho_cp, kappa]
+    Pw = df.Expression("x[0]", degree=1)
+    loads = []
+    for m in range(n_src):
+        xm = 0.2 + 0.6 * m / max(n_src - 1, 1)
+        tm = 0.1 + 0.8 * m / max(n_src - 1, 1)
+        g = df.interpolate(df.Expression("exp(-3.0*(pow(x[0]-xm,2)+pow(x[1]-0.5,2)+pow(x[2]-1.0,2))/(a*a))", degree=2, xm=xm, a=a),
+                           Vs[0])
+        h = df.interpolate(df.Expression("exp(-pow((x[0]-tm)/0.08,2))", degree=1, tm=tm), Vs[1])
+        w = df.Expression("exp(-pow((x[0]-vm)/0.6,2))", degree=2, vm=0.5 + m / max(n_src - 1, 1))
+        loads.append([lambda q, g=g: g * q * df.dx(mx), lambda q, h=h: Mt(h, q) * df.dx(mt), lambda q: Pw * q * df.dx(mP),
+                      lambda q, w=w: w * q * df.dx(mv)])
+
+    def bc_fct(Vs, dom, param):
+        def bottom(x, on_boundary):
+            return on_boundary and df.near(x[2], 0.0)
+
+        def initial(x, on_boundary):
+            return x[0] < 1e-12
+
+        return [df.DirichletBC(Vs[0], df.Constant(0.0), bottom), df.DirichletBC(Vs[1], df.Constant(0.0), initial), 0, 0]
+
+    return _separated_problem("thermal3d", ["X", "T", "P", "V"], Vs, ops, coefs, loads, bc_fct, ["r", "s", "t", "u"],
+                              PGD_nmax, MM=[0, Mt, 0, 0], **attrs)

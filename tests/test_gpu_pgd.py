@@ -83,3 +83,34 @@ def test_config2_heat2d_tk_reduced(n, nt, nk, nmax):
     opgd.solve_pgd(o)
     _compare(p, o)
     assert p.solver_stats["pcg_solves"] > 0 and p.solver_stats["banded_solves"] > 0
+
+
+def test_config3_elasticity3d_reduced():
+    """BASELINE configs[2] reduced: vector P1 tetrahedra (node-block-Jacobi PCG), two materials, traction."""
+    from pgdrome_b200 import configs
+
+    p = configs.elasticity3d(n=6, nE=8, nF=2, PGD_nmax=4)
+    p.solve_PGD(_problem="linear")
+    o, _ = oprob.elasticity3d(n=6, nE=8, nF=2, PGD_nmax=4, spaces=_ospaces(p))
+    opgd.solve_pgd(o)
+    _compare(p, o)
+    assert p.PGD_modes == 4 and p.solver_stats["pcg_solves"] > 0
+
+
+def test_config4_thermal3d_reduced():
+    """BASELINE configs[3] reduced: P1 tetrahedra x FD time x power x speed, separated moving source."""
+    from pgdrome_b200 import configs
+
+    p = configs.thermal3d(n=8, nt=30, nP=4, nv=4, n_src=4, PGD_nmax=4)
+    p.solve_PGD(_problem="linear")
+    o, _ = oprob.thermal3d(n=8, nt=30, nP=4, nv=4, n_src=4, PGD_nmax=4, spaces=_ospaces(p))
+    opgd.solve_pgd(o)
+    _compare(p, o)
+    # reconstruction: batched evaluate on the device vs the oracle loop at a few parameter points
+    pgd = p.return_PGD()
+    S = _ospaces(p)
+    pts = np.array([[0.3, 0.7, 1.2], [0.9, 1.4, 0.6]])
+    U = pgd.evaluate_batch(0, [1, 2, 3], pts, 0).cpu().numpy()
+    for c in range(len(pts)):
+        uo = evaluate_dofs(o.PGD_func[0], S[1:], [o.PGD_func[d] for d in (1, 2, 3)], pts[c])
+        assert np.linalg.norm(U[c] - uo) / np.linalg.norm(uo) < MODE_RTOL

@@ -65,6 +65,30 @@ def test_heat2d_tk_matches_oracle(cpu):
     _compare(p, o)
 
 
+def test_elasticity3d_matches_oracle(cpu):
+    """configs[2] reduced: vector P1 tetrahedra, two-material Voigt stiffness (degree-0 indicator weights),
+    facet traction, clamped face."""
+    from pgdrome_b200 import configs
+
+    p = configs.elasticity3d(n=3, nE=6, nF=2, PGD_nmax=3)
+    p.solve_PGD(_problem="linear")
+    o, _ = oprob.elasticity3d(n=3, nE=6, nF=2, PGD_nmax=3, spaces=_ospaces(p))
+    opgd.solve_pgd(o)
+    _compare(p, o)
+    assert p.PGD_modes == 3
+
+
+def test_thermal3d_matches_oracle(cpu):
+    """configs[3] reduced: P1 tetrahedra x FD time x P x v, 3 separated source terms."""
+    from pgdrome_b200 import configs
+
+    p = configs.thermal3d(n=4, nt=12, nP=3, nv=3, n_src=3, PGD_nmax=3)
+    p.solve_PGD(_problem="linear")
+    o, _ = oprob.thermal3d(n=4, nt=12, nP=3, nv=3, n_src=3, PGD_nmax=3, spaces=_ospaces(p))
+    opgd.solve_pgd(o)
+    _compare(p, o)
+
+
 # ---- host logic against the reference-generated golden vectors (same bodies as tests/test_gpu_golden.py,
 # with the NumPy ABI stand-in): FD-mode enrichment loop, normalisations, stopping criteria, evaluate
 def test_golden_laplace_fd_host_logic(cpu):

@@ -1,0 +1,74 @@
+"""Run one BASELINE config at a chosen size on the B200 and print a timing JSON line.
+
+  python -m tools.run_config --config thermal3d --n 158 --modes 3
+
+Reports set-up (mesh, pattern, atoms), per-enrichment-step device time, PCG iterations and the
+byte-based PCG roofline of the spatial solves.  Full sizes: elasticity3d --n 68 (985 527 dofs),
+thermal3d --n 158 (4 019 679 dofs)."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="thermal3d", choices=["heat2d_tk", "elasticity3d", "thermal3d"])
+    ap.add_argument("--n", type=int, default=None)
+    ap.add_argument("--modes", type=int, default=3)
+    ap.add_argument("--rtol", type=float, default=1e-13)
+    a = ap.parse_args()
+    from pgdrome_b200 import _lib, configs
+
+    peak = 6451.2
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", peak)
+    except Exception:
+        pass
+    t0 = time.perf_counter()
+    kw = {} if a.n is None else {"n": a.n}
+    p = getattr(configs, a.config)(PGD_nmax=a.modes, PGD_tol=0.0, **kw)
+    t_build = time.perf_counter() - t0
+    st = p.begin_PGD(_problem="linear", settings={"linear_solver": "cg", "relative_tolerance": a.rtol})
+    steps = []
+    _lib.stats(reset=True)
+    for i in range(a.modes):
+        torch.cuda.synchronize()
+        s0 = _lib.stats()
+        t1 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        done = p.step_PGD(st)
+        e1.record()
+        torch.cuda.synchronize()
+        s1 = _lib.stats()
+        steps.append({"ms": e0.elapsed_time(e1), "wall_s": time.perf_counter() - t1, "fp_iterations": p.num_fp_it[-1] if p.num_fp_it else None,
+                      "pcg_solves": s1["pcg_solves"] - s0["pcg_solves"], "pcg_iters": s1["pcg_iters"] - s0["pcg_iters"],
+                      "pcg_ms": s1["pcg_ms"] - s0["pcg_ms"], "launches": s1["launches"] - s0["launches"]})
+        if done:
+            break
+    ds = p.V[0]._dev["device_space"]
+    n, nnz = ds.n_dofs, ds.nnz
+    s = _lib.stats()
+    it_bytes = 12 * nnz + 4 * (n + 1) + 56 * n
+    it_ms = s["pcg_ms"] / max(s["pcg_iters"], 1)
+    out = {"config": a.config, "spatial_dofs": n, "nnz": nnz, "dims": [v.n_dofs for v in p.V], "modes": p.PGD_modes,
+           "build_problem_s": t_build, "steps": steps, "amplitude": [float(x) for x in p.amplitude],
+           "pcg": {"iterations": s["pcg_iters"], "ms_per_iteration": it_ms, "bytes_per_iteration": it_bytes,
+                   "gbs": it_bytes / (it_ms * 1e-3) / 1e9 if s["pcg_iters"] else None,
+                   "frac_hbm": it_bytes / (it_ms * 1e-3) / 1e9 / peak if s["pcg_iters"] else None,
+                   "share_of_step_time": s["pcg_ms"] / max(sum(x["ms"] for x in steps), 1e-9)},
+           "enrichment_steps_per_s": len(steps) / (sum(x["ms"] for x in steps) * 1e-3),
+           "device_mem_gb": torch.cuda.max_memory_allocated() / 1e9}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
