@@ -133,6 +133,17 @@ def test_laplace_fd_reference_test_on_device():
         assert np.linalg.norm(u - ref) <= 1e-8 * scale
     U = pgd.evaluate_batch(0, [1, 2, 3], g["ref_eval_points"], 0).cpu().numpy()
     assert np.linalg.norm(U - g["ref_eval"]) <= 1e-8 * scale
+    # PGDErrorComputation (model.py:1666-1825) through the product classes: LHS samples over the mesh ranges
+    # (seed 3452) and the relative-L2 error loop against the reference's own numbers for the same synthetic FOM
+    from pgdrome_b200.model import PGDErrorComputation
+
+    xv = p.meshes[0].coordinates()[:, 0]
+    fom = lambda s: (1.0 + 0.01 * s[1]) * np.sin(xv) * s[2] / 10.0 + 0.1 * s[0]
+    ec = PGDErrorComputation(fixed_dim=[0], n_samples=7, FOM_model=fom, PGD_model=pgd)
+    err, mean_err, max_err = ec.evaluate_error()
+    assert np.allclose(ec.data_test, g["ref_err_samples"], rtol=1e-14, atol=0)
+    assert np.allclose(err, g["ref_err"], rtol=1e-7, atol=0)
+    assert np.allclose([mean_err, max_err], g["ref_err_mean_max"], rtol=1e-7, atol=0)
 
 
 @pytest.mark.parametrize("key,opts", [
