@@ -77,14 +77,16 @@ int32_t pgd_assemble_p1(pgd_handle_t h, const double* d_coords, const int32_t* d
  * (int32 [2 * n_cells * nv]: pairs {vidx entry, nv packed byte positions inside the CSR row}) is built
  * once per mesh from the pattern, the cell -> dof table (local dof a = local vertex a; the dof numbering
  * need not equal the vertex numbering) and the vecmap of the scalar P1 space;
- * returns -4 if a row has more than 255 entries (use pgd_assemble_p1 then). */
+ * returns -4 if a row has more than 255 entries (use pgd_assemble_p1 then).
+ * d_coords_soa (optional, else NULL): the same coordinates component-major [gdim][n_verts]; with it a
+ * warp-wide coordinate load touches 2 cache lines instead of 6-8 (d_coords may then be NULL). */
 int32_t pgd_p1_rowplan_build_sync(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx,
                                   const int32_t* d_cell_dofs, int64_t n_cells, int32_t nv, const int64_t* d_vptr,
                                   const int32_t* d_vidx, int64_t n_nodes, int32_t* d_vent, void* stream);
 int32_t pgd_assemble_p1_rows(pgd_handle_t h, const double* d_coords, const int32_t* d_cell_verts, int64_t n_cells,
                              int32_t gdim, double c_mass, double c_stiff, const double* h_c_adv,
                              const int32_t* d_rowptr, const int64_t* d_vptr, const int32_t* d_vent, int64_t n_nodes,
-                             double* d_values, void* stream);
+                             double* d_values, const double* d_coords_soa, int64_t n_verts, void* stream);
 
 /* ---- linear combinations: A_d = sum_k c_k K_{d,k} over CSR value arrays, and
  * b_d = sum c_m g_m - sum c_ik (K_k U_i) over cached vectors (the folded scalar coefficients of
@@ -139,7 +141,7 @@ int32_t pgd_pcg_sync(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_c
  *   d_fl (>= 4 int32):    [0] done, [1] iterations, [2] NaN seen
  *   d_work: n_owned*(3+block) + n_local doubles; p (with its ghost tail) starts at
  *           d_work + n_owned*(3+block); d_x [n_owned] is the solution (x0 = 0).
- * pgd_spcg_init leaves the local (r.z, b.b) in d_sc[8..9]: all-reduce them, then pgd_spcg_init_fin. */
+ * pgd_spcg_init leaves the local (r.z, b.b, r.r) in d_sc[8..10]: all-reduce them, then pgd_spcg_init_fin. */
 int32_t pgd_spcg_init(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
                       const double* d_b, double* d_x, int64_t n_owned, int64_t n_local, int32_t block, double* d_work,
                       double* d_sc, int32_t* d_fl, void* stream);
@@ -168,6 +170,14 @@ int32_t pgd_spcg_solve_sync(pgd_handle_t h, const int32_t* d_rowptr, const int32
                             const int64_t* d_send_idx, const int64_t* h_send_counts, const int64_t* h_recv_counts,
                             double rtol, double atol, int32_t maxit, int32_t check_every, double* d_work,
                             int32_t* h_iters, double* h_relres, void* stream);
+
+/* Same solve with a warm start: on entry d_x holds the initial guess x0 (r0 = b - A x0); the stopping
+ * rule stays relative to ||b||.  The fixed-point sweeps of solver.py:531-757 solve a sequence of nearby
+ * systems, so the previous sweep's mode is passed as x0 (the reference's direct LU has no such notion). */
+int32_t pgd_pcg_x0_sync(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
+                        const double* d_b, double* d_x, int64_t n, double rtol, double atol, int32_t maxit,
+                        int32_t check_every, int32_t block, int32_t lanes_per_row, double* d_work,
+                        int32_t* h_iters, double* h_relres, void* stream);
 
 /* General banded LU with partial pivoting, one CTA, for the 1-D parameter / time dimensions
  * (tiny, possibly non-symmetric).  d_perm[new] = old dof (band ordering), kl/ku bandwidths in the

@@ -27,7 +27,7 @@ SIGNATURES = {
     "pgd_pattern_export": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "pgd_vecmap_build_sync": [c_vp, c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_vp],
     "pgd_p1_rowplan_build_sync": [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_i64, c_vp, c_vp],
-    "pgd_assemble_p1_rows": [c_vp, c_vp, c_vp, c_i64, c_i32, c_dbl, c_dbl, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp],
+    "pgd_assemble_p1_rows": [c_vp, c_vp, c_vp, c_i64, c_i32, c_dbl, c_dbl, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp],
     "pgd_elem_bilinear": [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "pgd_elem_linear": [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "pgd_gather_values": [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp],
@@ -53,6 +53,8 @@ SIGNATURES = {
     "pgd_comm_destroy": [c_vp],
     "pgd_spcg_solve_sync": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_dbl, c_dbl, c_i32,
                             c_i32, c_vp, c_vp, c_vp, c_vp],
+    "pgd_pcg_x0_sync": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_dbl, c_dbl, c_i32, c_i32, c_i32, c_i32, c_vp,
+                        ctypes.POINTER(c_i32), ctypes.POINTER(c_dbl), c_vp],
     "pgd_banded_solve": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp],
     "pgd_eval_weights": [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp],
     "pgd_eval_gemv": [c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_vp, c_vp],
@@ -305,7 +307,8 @@ def p1_rowplan_build(rowptr, colidx, cell_dofs, vptr, vidx, n_nodes):
     return vent
 
 
-def assemble_p1_rows(coords, cell_verts, gdim, c_mass, c_stiff, c_adv, rowptr, vptr, vent, n_nodes, out=None):
+def assemble_p1_rows(coords, cell_verts, gdim, c_mass, c_stiff, c_adv, rowptr, vptr, vent, n_nodes, out=None, coords_soa=None):
+    """coords_soa: optional component-major copy [gdim, n_verts] of coords (faster coordinate gathers)."""
     h, lib = handle(coords.device), load_library()
     if out is None:
         out = torch.empty(_nnz_of(rowptr), dtype=F64, device=coords.device)
@@ -314,7 +317,9 @@ def assemble_p1_rows(coords, cell_verts, gdim, c_mass, c_stiff, c_adv, rowptr, v
         adv = (c_dbl * 3)(*[float(v) for v in list(c_adv) + [0.0] * (3 - len(c_adv))])
     _check(lib.pgd_assemble_p1_rows(h, _p(coords, F64), _p(cell_verts, I32), cell_verts.shape[0], gdim, float(c_mass),
                                     float(c_stiff), ctypes.cast(adv, c_vp) if adv is not None else c_vp(0), _p(rowptr, I32),
-                                    _p(vptr, I64), _p(vent, I32), n_nodes, _p(out), _stream()), h, "pgd_assemble_p1_rows")
+                                    _p(vptr, I64), _p(vent, I32), n_nodes, _p(out),
+                                    _p(coords_soa, F64) if coords_soa is not None else c_vp(0),
+                                    coords_soa.shape[1] if coords_soa is not None else 0, _stream()), h, "pgd_assemble_p1_rows")
     return out
 
 
@@ -414,17 +419,22 @@ def panel_dots(P, n_vecs, x, out=None):
 
 
 # ------------------------------------------------------------------------------ solves
-def pcg(rowptr, colidx, values, b, x=None, rtol=1e-12, atol=0.0, maxit=20000, check_every=50, block=1, lpr=0, work=None):
+def pcg(rowptr, colidx, values, b, x=None, rtol=1e-12, atol=0.0, maxit=20000, check_every=50, block=1, lpr=0, work=None,
+        x0=None):
+    """Jacobi / node-block-Jacobi PCG.  x0: optional initial guess (copied; warm start, pgd_pcg_x0_sync)."""
     h, lib = handle(b.device), load_library()
     n = b.numel()
-    if x is None:
+    if x0 is not None:
+        x = x0.detach().clone() if x is None else x.copy_(x0)
+    elif x is None:
         x = torch.empty(n, dtype=F64, device=b.device)
     if work is None or work.numel() < (5 + block) * n:
         work = torch.empty((5 + block) * n, dtype=F64, device=b.device)
     iters, relres = c_i32(0), c_dbl(0.0)
-    _check(lib.pgd_pcg_sync(h, _p(rowptr, I32), _p(colidx, I32), _p(values, F64), _p(b, F64), _p(x, F64), n, rtol, atol,
-                            maxit, check_every, block, lpr, _p(work, F64), ctypes.byref(iters), ctypes.byref(relres),
-                            _stream()), h, "pgd_pcg_sync")
+    fn = lib.pgd_pcg_x0_sync if x0 is not None else lib.pgd_pcg_sync
+    _check(fn(h, _p(rowptr, I32), _p(colidx, I32), _p(values, F64), _p(b, F64), _p(x, F64), n, rtol, atol,
+              maxit, check_every, block, lpr, _p(work, F64), ctypes.byref(iters), ctypes.byref(relres),
+              _stream()), h, "pgd_pcg_sync")
     return x, iters.value, relres.value
 
 

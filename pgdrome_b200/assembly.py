@@ -79,6 +79,13 @@ class DeviceSpace:
                 self._rowplan = False
         return self._rowplan
 
+    @property
+    def coords_soa(self):
+        """component-major copy of the vertex coordinates for the row-owner assembly kernel"""
+        if getattr(self, "_coords_soa", None) is None:
+            self._coords_soa = self.coords.reshape(-1, self.space.mesh().gdim).t().contiguous()
+        return self._coords_soa
+
     def _p1_closed_form(self, T):
         """(c_mass, c_stiff, c_adv) if T is  c_m u v + c_k grad u.grad v + sum_m c_adv[m] (d_m u) v, else None."""
         s = self.space
@@ -171,7 +178,7 @@ class DeviceSpace:
                 # constant-coefficient P1 operator: one fused kernel straight into the CSR pattern
                 rowptr = self.pattern[0]
                 return _lib.assemble_p1_rows(self.coords, self.cell_verts, g, cf[0], cf[1], cf[2] if any(cf[2]) else None,
-                                             rowptr, self.vecmap[0], self.rowplan, self.n_dofs)
+                                             rowptr, self.vecmap[0], self.rowplan, self.n_dofs, coords_soa=self.coords_soa)
         # polynomial degree of the integrand on an affine simplex
         dv = s.degree if np.any(T[:, 0, :, :] != 0) else s.degree - 1
         du = s.degree if np.any(T[:, :, :, 0] != 0) else s.degree - 1

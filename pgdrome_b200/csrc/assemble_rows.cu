@@ -82,8 +82,12 @@ struct ArCoef {
     double cm, ck, cadv[3];
 };
 
-template <int G>
-__global__ void __launch_bounds__(AR_ROWS) k_assemble_p1_rows(const double* __restrict__ coords, const int32_t* __restrict__ cv,
+// SOA: coords is [G][n_verts] (component-major).  A warp = 32 consecutive rows whose k-th cells are
+// neighbouring cells on a mesh-ordered numbering, so a warp-wide load of one coordinate component touches
+// 2 cache lines instead of the 6-8 of the interleaved [n_verts][G] layout (ncu: L1TEX was the top unit).
+template <int G, bool SOA, bool ADV>
+__global__ void __launch_bounds__(AR_ROWS) k_assemble_p1_rows(const double* __restrict__ coords, int64_t n_verts,
+                                                              const int32_t* __restrict__ cv,
                                                               const int32_t* __restrict__ rowptr,
                                                               const int64_t* __restrict__ vptr, const int2* __restrict__ vent,
                                                               int64_t n_nodes, ArCoef cf, double* __restrict__ values) {
@@ -101,29 +105,58 @@ __global__ void __launch_bounds__(AR_ROWS) k_assemble_p1_rows(const double* __re
     if (tid < nr) {
         const int64_t row = r0 + tid;
         double* arow = acc + (__ldg(&rowptr[row]) - kbase);
-        const int64_t e1 = __ldg(&vptr[row + 1]);
+        const int64_t e0 = __ldg(&vptr[row]), e1 = __ldg(&vptr[row + 1]);
         constexpr double fact = (G == 1) ? 1.0 : (G == 2 ? 2.0 : 6.0);
-        for (int64_t e = __ldg(&vptr[row]); e < e1; ++e) {
-            const int2 en = __ldg(&vent[e]);
+        auto coord = [&](int vid, int g) -> double {
+            return SOA ? __ldg(&coords[(int64_t)g * n_verts + vid]) : __ldg(&coords[(int64_t)vid * G + g]);
+        };
+        // the row's own vertex is a vertex of every cell in its list: fetch its coordinates once
+        double own[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) own[g] = 0.0;
+        if (e0 < e1) {
+            const int ent0 = __ldg(&vent[e0]).x;
+            const int vid = __ldg(&cv[ent0]);  // cv[cell * NV + a]
+#pragma unroll
+            for (int g = 0; g < G; ++g) own[g] = coord(vid, g);
+        }
+        // software pipeline over the cells of the row: the plan entry is fetched two cells ahead and the
+        // cell's vertex ids one cell ahead, so that only the coordinate loads of the current cell are
+        // on the critical path (ncu: the vent -> cell_verts -> coords chain was the top stall).
+        auto load_verts = [&](int cell, int (&vv)[NV]) {
+            if constexpr (NV == 4) {
+                const int4 q = __ldg(reinterpret_cast<const int4*>(cv) + cell);
+                vv[0] = q.x, vv[1] = q.y, vv[2] = q.z, vv[3] = q.w;
+            } else if constexpr (NV == 2) {
+                const int2 q = __ldg(reinterpret_cast<const int2*>(cv) + cell);
+                vv[0] = q.x, vv[1] = q.y;
+            } else {
+#pragma unroll
+                for (int v = 0; v < NV; ++v) vv[v] = __ldg(&cv[(int64_t)cell * NV + v]);
+            }
+        };
+        int2 en1 = (e0 < e1) ? __ldg(&vent[e0]) : make_int2(0, 0);
+        int2 en2 = (e0 + 1 < e1) ? __ldg(&vent[e0 + 1]) : make_int2(0, 0);
+        int vi1[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) vi1[v] = 0;
+        if (e0 < e1) load_verts(en1.x / NV, vi1);
+        for (int64_t e = e0; e < e1; ++e) {
+            const int2 en = en1;
+            int vi[NV];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) vi[v] = vi1[v];
+            en1 = en2;
+            if (e + 2 < e1) en2 = __ldg(&vent[e + 2]);
+            if (e + 1 < e1) load_verts(en1.x / NV, vi1);
             const int cell = en.x / NV;
             const int a = en.x - cell * NV;
             const unsigned int packed = (unsigned int)en.y;
-            int vi[NV];
-            if constexpr (NV == 4) {
-                const int4 q = __ldg(reinterpret_cast<const int4*>(cv) + cell);
-                vi[0] = q.x, vi[1] = q.y, vi[2] = q.z, vi[3] = q.w;
-            } else if constexpr (NV == 2) {
-                const int2 q = __ldg(reinterpret_cast<const int2*>(cv) + cell);
-                vi[0] = q.x, vi[1] = q.y;
-            } else {
-#pragma unroll
-                for (int v = 0; v < NV; ++v) vi[v] = __ldg(&cv[(int64_t)cell * NV + v]);
-            }
             double X[NV][G];
 #pragma unroll
             for (int v = 0; v < NV; ++v)
 #pragma unroll
-                for (int g = 0; g < G; ++g) X[v][g] = __ldg(&coords[(int64_t)vi[v] * G + g]);
+                for (int g = 0; g < G; ++g) X[v][g] = (v == a) ? own[g] : coord(vi[v], g);
             // J[g][t] = X[t+1][g] - X[0][g];  grad phi_{t+1} = row t of J^-1, grad phi_0 = -sum_t
             double Jinv[G][G], det;
             if constexpr (G == 1) {
@@ -186,10 +219,11 @@ __global__ void __launch_bounds__(AR_ROWS) k_assemble_p1_rows(const double* __re
 #pragma unroll
                 for (int m = 0; m < G; ++m) {
                     dotg += ga[m] * grad[b][m];
-                    adv += cf.cadv[m] * grad[b][m];
+                    if (ADV) adv += cf.cadv[m] * grad[b][m];
                 }
                 const double mass = vol * ((a == b) ? 2.0 : 1.0) / (double)((G + 1) * (G + 2));
-                const double val = cf.cm * mass + cf.ck * vol * dotg + adv * vol / (double)(G + 1);
+                double val = cf.cm * mass + cf.ck * vol * dotg;
+                if (ADV) val += adv * vol / (double)(G + 1);
                 arow[(packed >> (8 * b)) & 255u] += val;
             }
         }
@@ -203,22 +237,40 @@ __global__ void __launch_bounds__(AR_ROWS) k_assemble_p1_rows(const double* __re
 extern "C" int32_t pgd_assemble_p1_rows(pgd_handle_t h, const double* d_coords, const int32_t* d_cell_verts, int64_t n_cells,
                                         int32_t gdim, double c_mass, double c_stiff, const double* h_c_adv,
                                         const int32_t* d_rowptr, const int64_t* d_vptr, const int32_t* d_vent, int64_t n_nodes,
-                                        double* d_values, void* stream) {
+                                        double* d_values, const double* d_coords_soa, int64_t n_verts, void* stream) {
     PGD_CHECK_HANDLE(h);
-    PGD_ARG(h, d_coords && d_cell_verts && d_rowptr && d_vptr && d_vent && d_values, "null pointer");
+    PGD_ARG(h, (d_coords || d_coords_soa) && d_cell_verts && d_rowptr && d_vptr && d_vent && d_values, "null pointer");
     PGD_ARG(h, gdim >= 1 && gdim <= 3, "gdim must be 1, 2 or 3");
+    PGD_ARG(h, !d_coords_soa || n_verts > 0, "n_verts required with component-major coordinates");
     (void)n_cells;
     if (n_nodes <= 0) return 0;
     ArCoef cf;
     cf.cm = c_mass;
     cf.ck = c_stiff;
-    for (int m = 0; m < 3; ++m) cf.cadv[m] = (h_c_adv && m < gdim) ? h_c_adv[m] : 0.0;
+    bool adv = false;
+    for (int m = 0; m < 3; ++m) {
+        cf.cadv[m] = (h_c_adv && m < gdim) ? h_c_adv[m] : 0.0;
+        adv = adv || cf.cadv[m] != 0.0;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned int blocks = pgd_blocks(n_nodes, AR_ROWS);
     const int2* vent = reinterpret_cast<const int2*>(d_vent);
-    if (gdim == 1) k_assemble_p1_rows<1><<<blocks, AR_ROWS, 0, st>>>(d_coords, d_cell_verts, d_rowptr, d_vptr, vent, n_nodes, cf, d_values);
-    else if (gdim == 2) k_assemble_p1_rows<2><<<blocks, AR_ROWS, 0, st>>>(d_coords, d_cell_verts, d_rowptr, d_vptr, vent, n_nodes, cf, d_values);
-    else k_assemble_p1_rows<3><<<blocks, AR_ROWS, 0, st>>>(d_coords, d_cell_verts, d_rowptr, d_vptr, vent, n_nodes, cf, d_values);
+    const bool soa = d_coords_soa != nullptr;
+    const double* xyz = soa ? d_coords_soa : d_coords;
+#define AR_LAUNCH(G, S, A) \
+    k_assemble_p1_rows<G, S, A><<<blocks, AR_ROWS, 0, st>>>(xyz, n_verts, d_cell_verts, d_rowptr, d_vptr, vent, n_nodes, cf, d_values)
+#define AR_DISPATCH(G)                           \
+    do {                                         \
+        if (soa && adv) AR_LAUNCH(G, true, true);        \
+        else if (soa) AR_LAUNCH(G, true, false);         \
+        else if (adv) AR_LAUNCH(G, false, true);         \
+        else AR_LAUNCH(G, false, false);                 \
+    } while (0)
+    if (gdim == 1) AR_DISPATCH(1);
+    else if (gdim == 2) AR_DISPATCH(2);
+    else AR_DISPATCH(3);
+#undef AR_DISPATCH
+#undef AR_LAUNCH
     PGD_LAUNCH_OK(h);
     return 0;
 }

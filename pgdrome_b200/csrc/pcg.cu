@@ -58,8 +58,10 @@ __global__ void __launch_bounds__(256) k_pcg_init(const int32_t* __restrict__ ro
                                                   const double* __restrict__ vals, const double* __restrict__ b,
                                                   double* __restrict__ x, double* r, double* z, double* p0, double* p1,
                                                   double* minv, int64_t n_nodes, double rtol, double atol, double* sc,
-                                                  int* fl, double* part, unsigned int* counter) {
-    double rz = 0.0, bb = 0.0;
+                                                  int* fl, double* part, unsigned int* counter,
+                                                  const double* __restrict__ ax0 = nullptr) {
+    // ax0 != NULL: warm start, x holds the initial guess and ax0 = A x0  (r = b - A x0; bb stays ||b||^2)
+    double rz = 0.0, bb = 0.0, rr = 0.0;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t nd = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; nd < n_nodes; nd += stride) {
         double B[BS][BS], I[BS][BS], rb[BS];
@@ -71,6 +73,8 @@ __global__ void __launch_bounds__(256) k_pcg_init(const int32_t* __restrict__ ro
 #pragma unroll
         for (int i = 0; i < BS; ++i) {
             rb[i] = b[nd * BS + i];
+            bb += rb[i] * rb[i];
+            if (ax0) rb[i] -= ax0[nd * BS + i];
 #pragma unroll
             for (int k = 0; k < BS; ++k) minv[(nd * BS + i) * BS + k] = I[i][k];
         }
@@ -82,17 +86,18 @@ __global__ void __launch_bounds__(256) k_pcg_init(const int32_t* __restrict__ ro
             int64_t d = nd * BS + i;
             r[d] = rb[i];
             z[d] = zi;
-            x[d] = 0.0;
+            if (!ax0) x[d] = 0.0;
             p0[d] = 0.0;
             p1[d] = 0.0;
             rz += rb[i] * zi;
-            bb += rb[i] * rb[i];
+            rr += rb[i] * rb[i];
         }
     }
     rz = block_sum(rz);
     bb = block_sum(bb);
-    double v[2] = {rz, bb};
-    grid_sum_finish<2>(v, part, counter, sc + S_TMP, blockIdx.x, gridDim.x);
+    rr = block_sum(rr);
+    double v[3] = {rz, bb, rr};
+    grid_sum_finish<3>(v, part, counter, sc + S_TMP, blockIdx.x, gridDim.x);
     // the block that finished the reduction publishes the scalars
     if (threadIdx.x == 0) {
         // grid_sum_finish left s_last in shared memory of the last block only; recompute cheaply:
@@ -102,18 +107,18 @@ __global__ void __launch_bounds__(256) k_pcg_init(const int32_t* __restrict__ ro
 
 // single-thread epilogue of init (keeps k_pcg_init simple and race-free)
 __global__ void k_pcg_init_fin(double* sc, int* fl, double rtol, double atol) {
-    double rz = sc[S_TMP], bb = sc[S_TMP + 1];
+    double rz = sc[S_TMP], bb = sc[S_TMP + 1], rr = sc[S_TMP + 2];  // rr = ||b - A x0||^2 (= bb for x0 = 0)
     sc[S_RZ_OLD] = 1.0;
     sc[S_RZ_NEW] = rz;
     sc[S_PQ] = 1.0;
-    sc[S_RR] = bb;
+    sc[S_RR] = rr;
     sc[S_BB] = bb;
     double t2 = rtol * rtol * bb;
     if (atol * atol > t2) t2 = atol * atol;
     sc[S_TOL2] = t2;
     fl[F_ITER] = 0;
     fl[F_BAD] = 0;
-    fl[F_DONE] = (bb <= t2 || bb == 0.0) ? 1 : 0;
+    fl[F_DONE] = (rr <= t2 || bb == 0.0) ? 1 : 0;
 }
 
 template <int LPR>
@@ -267,10 +272,13 @@ __global__ void __launch_bounds__(ST_THREADS) k_pcg_spmv_stream(const int32_t* _
     grid_sum_finish<1>(v, part, counter, sc_out + S_PQ, blockIdx.x, gridDim.x);
 }
 
+int32_t pgd_spmv_internal(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const double* va, const double* x, double* y,
+                          int64_t n, int lpr, cudaStream_t st);
+
 template <int BS>
 static int32_t run_pcg(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const double* va, const double* b, double* x,
                        int64_t n, double rtol, double atol, int maxit, int check_every, int lpr, double* work,
-                       int32_t* h_iters, double* h_relres, cudaStream_t st) {
+                       int32_t* h_iters, double* h_relres, cudaStream_t st, bool warm) {
     const int64_t n_nodes = n / BS;
     double* r = work;
     double* z = r + n;
@@ -287,8 +295,12 @@ static int32_t run_pcg(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const d
     unsigned int sb = pgd_blocks(n, 256 / lpr);
     unsigned int caps = (unsigned int)h->sm_count * 8;
     if (sb > caps) sb = caps;
+    if (warm) {  // q = A x0 (q is free until the first iteration)
+        int32_t rc = pgd_spmv_internal(h, rp, ci, va, x, q, n, lpr, st);
+        if (rc) return rc;
+    }
     k_pcg_init<BS><<<vb, 256, 0, st>>>(rp, ci, va, b, x, r, z, p0, p1, minv, n_nodes, rtol, atol, sc, fl, h->partials,
-                                        h->counters);
+                                        h->counters, warm ? q : nullptr);
     PGD_LAUNCH_OK(h);
     k_pcg_init_fin<<<1, 1, 0, st>>>(sc, fl, rtol, atol);
     PGD_LAUNCH_OK(h);
@@ -357,12 +369,12 @@ static int32_t run_pcg(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const d
 
 int32_t pgd_pcg_resident(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const double* va, const double* b, double* x,
                          int64_t n, int64_t nnz_hint, double rtol, double atol, int maxit, int block, double* work,
-                         int32_t* h_iters, double* h_relres, cudaStream_t st);
+                         int32_t* h_iters, double* h_relres, cudaStream_t st, int warm);
 
-extern "C" int32_t pgd_pcg_sync(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
-                                const double* d_b, double* d_x, int64_t n, double rtol, double atol, int32_t maxit,
-                                int32_t check_every, int32_t block, int32_t lanes_per_row, double* d_work,
-                                int32_t* h_iters, double* h_relres, void* stream) {
+static int32_t pcg_entry(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
+                         const double* d_b, double* d_x, int64_t n, double rtol, double atol, int32_t maxit,
+                         int32_t check_every, int32_t block, int32_t lanes_per_row, double* d_work, int32_t* h_iters,
+                         double* h_relres, void* stream, bool warm) {
     PGD_CHECK_HANDLE(h);
     PGD_ARG(h, d_rowptr && d_colidx && d_values && d_b && d_x && d_work && n > 0, "bad arguments");
     PGD_ARG(h, block >= 1 && block <= 3 && n % block == 0, "block must be 1..3 and divide n");
@@ -377,17 +389,34 @@ extern "C" int32_t pgd_pcg_sync(pgd_handle_t h, const int32_t* d_rowptr, const i
             h->nnz_val = last;
         }
         int32_t rc = pgd_pcg_resident(h, d_rowptr, d_colidx, d_values, d_b, d_x, n, h->nnz_val, rtol, atol, maxit, block,
-                                      d_work, h_iters, h_relres, st);
+                                      d_work, h_iters, h_relres, st, warm ? 1 : 0);
         if (rc != 1) return rc;
     }
     if (block == 1)
         return run_pcg<1>(h, d_rowptr, d_colidx, d_values, d_b, d_x, n, rtol, atol, maxit, check_every, lanes_per_row, d_work,
-                          h_iters, h_relres, st);
+                          h_iters, h_relres, st, warm);
     if (block == 2)
         return run_pcg<2>(h, d_rowptr, d_colidx, d_values, d_b, d_x, n, rtol, atol, maxit, check_every, lanes_per_row, d_work,
-                          h_iters, h_relres, st);
+                          h_iters, h_relres, st, warm);
     return run_pcg<3>(h, d_rowptr, d_colidx, d_values, d_b, d_x, n, rtol, atol, maxit, check_every, lanes_per_row, d_work,
-                      h_iters, h_relres, st);
+                      h_iters, h_relres, st, warm);
+}
+
+extern "C" int32_t pgd_pcg_sync(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
+                                const double* d_b, double* d_x, int64_t n, double rtol, double atol, int32_t maxit,
+                                int32_t check_every, int32_t block, int32_t lanes_per_row, double* d_work,
+                                int32_t* h_iters, double* h_relres, void* stream) {
+    return pcg_entry(h, d_rowptr, d_colidx, d_values, d_b, d_x, n, rtol, atol, maxit, check_every, block, lanes_per_row, d_work,
+                     h_iters, h_relres, stream, false);
+}
+
+/* warm start: d_x holds the initial guess x0 on entry (same stopping rule, relative to ||b||) */
+extern "C" int32_t pgd_pcg_x0_sync(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
+                                   const double* d_b, double* d_x, int64_t n, double rtol, double atol, int32_t maxit,
+                                   int32_t check_every, int32_t block, int32_t lanes_per_row, double* d_work,
+                                   int32_t* h_iters, double* h_relres, void* stream) {
+    return pcg_entry(h, d_rowptr, d_colidx, d_values, d_b, d_x, n, rtol, atol, maxit, check_every, block, lanes_per_row, d_work,
+                     h_iters, h_relres, stream, true);
 }
 
 // ================================================================================================

@@ -35,6 +35,7 @@ struct ResArgs {
     double* out_sc;    // [0]=rr [1]=bb
     int* out_fl;       // [0]=iters [1]=status (0 ok, 1 slice does not fit, 2 NaN)
     int cap_nnz, cap_rows, cap_win;
+    int warm;          // 1: x holds the initial guess x0 (r = b - A x0)
 };
 
 __device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(512, 1) k_pcg_resident(ResArgs a) {
         for (int k = tid; k < nnz; k += nt) s_cols[k] -= cmin;
     __syncthreads();
     // ---- M^-1 (node blocks), r = b, z = M^-1 r, x = 0, p = 0
-    double acc0 = 0.0, acc1 = 0.0;
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
     for (int nd = tid; nd < rows / BS; nd += nt) {
         double B[BS][BS], I[BS][BS], rb[BS];
 #pragma unroll
@@ -170,6 +171,13 @@ __global__ void __launch_bounds__(512, 1) k_pcg_resident(ResArgs a) {
                 }
             }
             rb[i] = a.b[r0 + row];
+            if (a.warm) {  // r = b - A x0: x0 is a read-only input until the final store, no barrier needed
+                double ax = 0.0;
+                for (int k = s_rp[row]; k < s_rp[row + 1]; ++k)
+                    ax = fma(s_vals[k], __ldcg(&a.x[s_cols[k] + (windowed ? cmin : 0)]), ax);
+                acc1 += rb[i] * rb[i];
+                rb[i] -= ax;
+            }
         }
         if constexpr (BS == 1) {
             I[0][0] = 1.0 / B[0][0];
@@ -203,35 +211,43 @@ __global__ void __launch_bounds__(512, 1) k_pcg_resident(ResArgs a) {
                 s_minv[row * BS + k] = I[i][k];
                 zi += I[i][k] * rb[k];
             }
-            s_x[row] = 0.0;
+            s_x[row] = a.warm ? a.x[r0 + row] : 0.0;
             s_r[row] = rb[i];
             s_p[row] = 0.0;
             s_z[row] = zi;
             a.zg[r0 + row] = zi;
             a.pg0[r0 + row] = 0.0;
             acc0 += rb[i] * zi;
-            acc1 += rb[i] * rb[i];
+            if (!a.warm) acc1 += rb[i] * rb[i];
+            acc2 += rb[i] * rb[i];
         }
     }
     acc0 = block_sum(acc0);
     acc1 = block_sum(acc1);
+    acc2 = block_sum(acc2);
     int slot = 0;
     if (tid == 0) {
         a.part[(size_t)(slot * 2 + 0) * G + bid] = acc0;
         a.part[(size_t)(slot * 2 + 1) * G + bid] = acc1;
+        a.part[(size_t)4 * G + bid] = acc2;
     }
     grid_barrier(a.bar, target, G);
     sum_partials<2>(a.part + (size_t)slot * 2 * G, G, s_red);
+    const double rz0 = s_red[0], bb0 = s_red[1];
+    __syncthreads();
+    sum_partials<1>(a.part + (size_t)4 * G, G, s_red);
+    const double rr0 = s_red[0];
+    __syncthreads();
     slot ^= 1;
-    double rz = s_red[0];
-    const double bb = s_red[1];
-    double rr = bb;
+    double rz = rz0;
+    const double bb = bb0;
+    double rr = rr0;  // ||b - A x0||^2 (= bb for a cold start)
     double tol2 = a.rtol * a.rtol * bb;
     if (a.atol * a.atol > tol2) tol2 = a.atol * a.atol;
     int it = 0;
     int status = 0;
     double rz_old = 1.0;
-    if (bb > tol2 && bb > 0.0) {
+    if (rr > tol2 && bb > 0.0) {
         while (it < a.maxit) {
             const double beta = (it == 0) ? 0.0 : rz / rz_old;
             const double* __restrict__ pold = (it & 1) ? a.pg1 : a.pg0;
@@ -324,7 +340,7 @@ __global__ void __launch_bounds__(512, 1) k_pcg_resident(ResArgs a) {
 // returns 0 ok, 1 = not resident (caller falls back), <0 / >1 errors as usual
 int32_t pgd_pcg_resident(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const double* va, const double* b, double* x,
                          int64_t n, int64_t nnz_hint, double rtol, double atol, int maxit, int block, double* work,
-                         int32_t* h_iters, double* h_relres, cudaStream_t st) {
+                         int32_t* h_iters, double* h_relres, cudaStream_t st, int warm) {
     const int G = h->sm_count;
     const size_t smem_max = 200 * 1024;
     // capacity estimate from the mean slice (+25 % slack for uneven rows); the kernel re-checks exactly
@@ -362,6 +378,7 @@ int32_t pgd_pcg_resident(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const
     a.cap_nnz = cap_nnz;
     a.cap_rows = cap_rows;
     a.cap_win = cap_win;
+    a.warm = warm;
     PGD_CUDA(h, cudaMemsetAsync(a.bar, 0, sizeof(unsigned int), st));
     PGD_CUDA(h, cudaMemsetAsync(a.out_fl, 0, 2 * sizeof(int), st));
     void* kargs[] = {&a};

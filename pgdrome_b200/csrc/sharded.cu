@@ -137,7 +137,7 @@ extern "C" int32_t pgd_spcg_solve_sync(pgd_handle_t h, const int32_t* d_rowptr, 
     int* fl = h->flags;
     int32_t rc = pgd_spcg_init(h, d_rowptr, d_colidx, d_values, d_b, d_x, n_owned, n_local, block, d_work, sc, fl, stream);
     if (rc) return rc;
-    if (world > 1) PGD_NCCL(h, g_nccl.AllReduce(sc + 8, sc + 8, 2, ncclDouble, ncclSum, comm, st));
+    if (world > 1) PGD_NCCL(h, g_nccl.AllReduce(sc + 8, sc + 8, 3, ncclDouble, ncclSum, comm, st));
     rc = pgd_spcg_init_fin(h, sc, fl, rtol, atol, stream);
     if (rc) return rc;
     if (check_every < 1) check_every = 1;

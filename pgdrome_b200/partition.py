@@ -211,7 +211,7 @@ def sharded_pcg(A, b, rtol=1e-13, atol=0.0, maxit=10000, check_every=50, block=N
     ops = ops or _DeviceOps(A, block)
     x = torch.zeros(A.n_owned, dtype=F64, device=b.device)
     ops.init(b, x)
-    _allreduce(ops.sc[8:10], group)
+    _allreduce(ops.sc[8:11], group)  # r.z, b.b, r.r
     ops.init_fin(rtol, atol)
 
     def iteration():

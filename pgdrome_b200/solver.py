@@ -336,7 +336,10 @@ class PGDProblem:
             raise ValueError('stopping criterion not defined %s (self.stop_fp = "delta" or "norm")')
         for fpi in range(self.max_fp_it):
             for dim in self.seq_fp:
+                # warm start of the iterative spatial solves: the previous sweep's mode of this dimension
+                self._x0 = Fs[dim].tensor() if (fpi > 0 and (settings or {}).get("warm_start", True)) else None
                 fct_F = self._solve_dimension(dim, Fs, n_enr, _problem, solve_modes, settings)
+                self._x0 = None
                 Fs[dim] = fct_F
                 norms[dim] = self._norm(fct_F, dim, solve_modes)
             if stop == "delta":
@@ -471,8 +474,11 @@ class PGDProblem:
         block = V.bs if (V.bs <= 3 and prec not in ("jacobi", "none_block")) else 1
         if self._use_sharded(V, settings):
             return self._sharded_solve(ds, values, b, block, rtol, atol, maxit, settings)
+        x0 = getattr(self, "_x0", None)
+        if x0 is not None and x0.numel() != b.numel():
+            x0 = None
         x, iters, relres = _lib.pcg(rowptr, colidx, values, b, rtol=rtol, atol=atol, maxit=maxit,
-                                    check_every=int(settings.get("check_every", 50)), block=block, lpr=ds.lpr)
+                                    check_every=int(settings.get("check_every", 50)), block=block, lpr=ds.lpr, x0=x0)
         self.solver_stats["pcg_solves"] += 1
         self.solver_stats["pcg_iterations"] += iters
         if relres > max(rtol, 1e-15) * 10 and iters >= maxit:

@@ -106,7 +106,7 @@ def p1_rowplan_build(rowptr, colidx, cell_dofs, vptr, vidx, n_nodes):
     return cell_dofs  # the stand-in below only needs the cell -> dof table
 
 
-def assemble_p1_rows(coords, cell_verts, gdim, c_mass, c_stiff, c_adv, rowptr, vptr, vent, n_nodes, out=None):
+def assemble_p1_rows(coords, cell_verts, gdim, c_mass, c_stiff, c_adv, rowptr, vptr, vent, n_nodes, out=None, coords_soa=None):
     """closed-form P1 simplex matrices (mass, stiffness, advection) summed into CSR order."""
     import scipy.sparse as sp
 
@@ -221,7 +221,8 @@ def panel_dots(P, n_vecs, x, out=None):
     return d
 
 
-def pcg(rowptr, colidx, values, b, x=None, rtol=1e-12, atol=0.0, maxit=20000, check_every=50, block=1, lpr=0, work=None):
+def pcg(rowptr, colidx, values, b, x=None, rtol=1e-12, atol=0.0, maxit=20000, check_every=50, block=1, lpr=0, work=None,
+        x0=None):
     A = _csr(rowptr, colidx, values)
     bb = _n(b)
     if not np.any(bb):

@@ -128,6 +128,14 @@ def test_fused_p1_operator(kind):
     assert _relerr(_csr(ds, v2).data, Ao.tocsr().data) < MAT_RTOL
     v3 = _lib.assemble_p1_rows(ds.coords, ds.cell_verts, g, cm, ck, cadv, rowptr, ds.vecmap[0], ds.rowplan, ds.n_dofs)
     assert torch.equal(v2, v3)
+    # component-major coordinates (the layout the atom assembly uses) and the no-advection instantiation
+    v4 = _lib.assemble_p1_rows(ds.coords, ds.cell_verts, g, cm, ck, cadv, rowptr, ds.vecmap[0], ds.rowplan, ds.n_dofs,
+                               coords_soa=ds.coords_soa)
+    assert torch.equal(v2, v4)
+    v5 = _lib.assemble_p1_rows(ds.coords, ds.cell_verts, g, cm, ck, None, rowptr, ds.vecmap[0], ds.rowplan, ds.n_dofs,
+                               coords_soa=ds.coords_soa)
+    Ao0 = cm * ofem.assemble_bilinear(S, ofem.T_mass(1, g)) + ck * ofem.assemble_bilinear(S, ofem.T_stiff(1, g))
+    assert _relerr(_csr(ds, v5).data, Ao0.tocsr().data) < MAT_RTOL
     # and it is what the atom assembly of a scalar P1 space uses
     K = ds.assemble_bilinear(ofem.T_stiff(1, g))
     assert _relerr(_csr(ds, K).data, ofem.assemble_bilinear(S, ofem.T_stiff(1, g)).tocsr().data) < MAT_RTOL
@@ -261,6 +269,13 @@ def test_dirichlet_and_pcg(kind, degree, bs, block):
         # zero right-hand side converges immediately to zero
         x0, it0, _ = _lib.pcg(rowptr, colidx, vals, torch.zeros_like(bd), rtol=1e-13, maxit=10, block=block)
         assert it0 == 0 and float(x0.abs().max()) == 0.0
+        # warm start: from the solution itself -> 0 iterations; from a perturbed solution -> fewer iterations, same answer
+        xw, itw, rw = _lib.pcg(rowptr, colidx, vals, bd, rtol=1e-13, maxit=5000, check_every=25, block=block, x0=x)
+        assert itw <= 1 and rw <= 1e-13 and np.linalg.norm(xw.cpu().numpy() - xo) / np.linalg.norm(xo) < 1e-10
+        pert = x * (1.0 + 1e-6 * torch.sin(torch.arange(x.numel(), device=x.device, dtype=x.dtype)))
+        xw, itw, rw = _lib.pcg(rowptr, colidx, vals, bd, rtol=1e-13, maxit=5000, check_every=25, block=block, x0=pert)
+        assert 0 < itw < iters and rw <= 1e-13
+        assert np.linalg.norm(xw.cpu().numpy() - xo) / np.linalg.norm(xo) < 1e-10
     _lib.set_option("pcg_resident", 1)
     assert abs(its[0] - its[1]) <= max(3, its[0] // 20)
 

@@ -40,7 +40,7 @@ class CpuOps:
         self.p.zero_()
         self.sc.zero_()
         self.fl.zero_()
-        self.sc[8], self.sc[9] = float(self.r @ self.z), float(self.r @ self.r)
+        self.sc[8], self.sc[9], self.sc[10] = float(self.r @ self.z), float(self.r @ self.r), float(self.r @ self.r)
 
     def _prec(self, r):
         bs = self.block
@@ -49,8 +49,8 @@ class CpuOps:
         return np.concatenate([self.minv[nd] @ r[nd * bs:(nd + 1) * bs] for nd in range(len(r) // bs)])
 
     def init_fin(self, rtol, atol):
-        rz, bb = float(self.sc[8]), float(self.sc[9])
-        self.sc[0], self.sc[1], self.sc[2], self.sc[3], self.sc[4] = 1.0, rz, 1.0, bb, bb
+        rz, bb, rr = float(self.sc[8]), float(self.sc[9]), float(self.sc[10])
+        self.sc[0], self.sc[1], self.sc[2], self.sc[3], self.sc[4] = 1.0, rz, 1.0, rr, bb
         self.sc[5] = max(rtol * rtol * bb, atol * atol)
         self.fl[0] = 1 if (bb <= float(self.sc[5]) or bb == 0.0) else 0
 

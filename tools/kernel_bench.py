@@ -68,7 +68,9 @@ def run(mesh_n=128, hbm_peak=6451.2, evaluate=True, fp64_peak=None):
     torch.cuda.synchronize()
     out["rowplan_build_s"] = time.perf_counter() - t0
     vptr = ds.vecmap[0]
-    ms = _time(lambda: _lib.assemble_p1_rows(ds.coords, ds.cell_verts, 3, 0.3, 1.7, None, rowptr, vptr, plan, n, out=vals))
+    soa = ds.coords_soa
+    ms = _time(lambda: _lib.assemble_p1_rows(ds.coords, ds.cell_verts, 3, 0.3, 1.7, None, rowptr, vptr, plan, n, out=vals,
+                                             coords_soa=soa))
     entry("assemble_p1_rows", ms, 4 * 4 * nc + 8 * 3 * m.num_vertices() + 8 * nnz,
           note="row-owner kernel; also reads the 8 B/(cell,vertex) plan (%d MB) and re-reads cell vertices 4x through L1/L2"
                % (8 * 4 * nc // 1000000))
