@@ -141,10 +141,12 @@ def heat2d_tk(n=256, nt=199, nk=49, krange=(0.5, 2.0), rho_cp=1.0, a=0.2, xc=(0.
 
 
 # ------------------------------------------------------------------------------- configs[2] / configs[3]
-def _separated_problem(name, name_coord, Vs, ops, coefs, loads, bc_fct, probs, PGD_nmax, MM=None, **attrs):
+def _separated_problem(name, name_coord, Vs, ops, coefs, loads, bc_fct, probs, PGD_nmax, MM=None, lifts=(), **attrs):
     """PGDProblem whose callbacks have the separated shape of every reference example:
-    ops[k][d](u, v) -> bilinear form of term k on dimension d, loads[m][d](w) -> linear form.  The
-    callbacks below are what a PGDrome user writes by hand (cf. test_elastic.py:71-219)."""
+    ops[k][d](u, v) -> bilinear form of term k on dimension d, loads[m][d](w) -> linear form,
+    lifts: known separated functions G = [G_0..G_{D-1}] (inhomogeneous BC / IC lifting,
+    test_heat1D.py:115-139) entering the right-hand side as -sum_k c_k prod_j op_kj(G_j, F_j) op_kd(G_d, v).
+    The callbacks below are what a PGDrome user writes by hand (cf. test_elastic.py:71-219)."""
     D = len(Vs)
     which = {p: i for i, p in enumerate(probs)}
 
@@ -168,13 +170,14 @@ def _separated_problem(name, name_coord, Vs, ops, coefs, loads, bc_fct, probs, P
                 if j != d:
                     c = c * df.assemble(ld[j](Fs[j]))
             l = l + df.Constant(c) * ld[d](var_F)
-        for old in range(nE):
+        known = list(lifts) + [[PGD_func[j][old] for j in range(D)] for old in range(nE)]
+        for G in known:
             for k, op in enumerate(ops):
                 c = coefs[k]
                 for j in range(D):
                     if j != d:
-                        c = c * df.assemble(op[j](PGD_func[j][old], Fs[j]))
-                l = l + (-df.Constant(c)) * op[d](PGD_func[d][old], var_F)
+                        c = c * df.assemble(op[j](G[j], Fs[j]))
+                l = l + (-df.Constant(c)) * op[d](G[d], var_F)
         return l
 
     p = PGDProblem(name=name, name_coord=name_coord, modes_info=["U", "Node", "Vector" if Vs[0].bs > 1 else "Scalar"], Vs=Vs,

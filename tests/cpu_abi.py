@@ -87,7 +87,8 @@ def elem_linear(coords, cell_verts, tdim, gdim, bs, nd, phi, dphi, qw, wq, L, ou
 
 def gather_values(src, gptr, gidx, n_out, out=None):
     s, gp, gi = _n(src), _n(gptr), _n(gidx)
-    res = np.add.reduceat(s[gi], gp[:-1]) if len(gi) else np.zeros(n_out)
+    seg = np.repeat(np.arange(n_out), np.diff(gp))  # empty groups (dofs without contributions) stay 0
+    res = np.bincount(seg, weights=s[gi], minlength=n_out) if len(gi) else np.zeros(n_out)
     res[np.diff(gp) == 0] = 0.0
     r = _t(res)
     if out is not None:
