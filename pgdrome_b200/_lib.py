@@ -91,16 +91,27 @@ def load_library():
         return lib
 
 
+_CUDA_OK = None
+
+
 def require_cuda():
-    if not torch.cuda.is_available():
+    global _CUDA_OK
+    if _CUDA_OK is None:
+        _CUDA_OK = bool(torch.cuda.is_available())
+    if not _CUDA_OK:
         raise PGDB200Error("pgdrome_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
 
 
 def handle(device=None):
     """One library handle per device."""
     require_cuda()
-    lib = load_library()
-    dev = torch.cuda.current_device() if device is None else torch.device(device).index
+    lib = _lib if _lib is not None else load_library()
+    if device is None:
+        dev = torch.cuda.current_device()
+    elif isinstance(device, torch.device):
+        dev = device.index if device.index is not None else torch.cuda.current_device()
+    else:
+        dev = torch.device(device).index
     if dev not in _handles:
         h = c_vp()
         rc = lib.pgd_create(dev, ctypes.byref(h))
@@ -111,17 +122,24 @@ def handle(device=None):
 
 
 def _stream():
-    return c_vp(torch.cuda.current_stream().cuda_stream)
+    """raw cudaStream_t of torch's current stream (the C-level getter: this is called for every launch)"""
+    try:
+        return c_vp(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
+    except AttributeError:
+        return c_vp(torch.cuda.current_stream().cuda_stream)
 
 
-def _p(t, dtype=None):
-    """device pointer of a contiguous CUDA tensor (or NULL)."""
+def _p(t, dtype=None, rows_strided=False):
+    """device pointer of a contiguous CUDA tensor (or NULL).  rows_strided: a 2-D view whose rows are
+    contiguous but spaced by a leading dimension (passed separately to the kernel) is accepted."""
     if t is None:
         return c_vp(0)
     if not t.is_cuda:
         raise PGDB200Error("expected a CUDA tensor (no CPU fallback)")
     if dtype is not None and t.dtype != dtype:
         raise PGDB200Error(f"expected dtype {dtype}, got {t.dtype}")
+    if rows_strided and t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= t.shape[1]:
+        return c_vp(t.data_ptr())
     if not t.is_contiguous():
         raise PGDB200Error("expected a contiguous tensor")
     return c_vp(t.data_ptr())
@@ -492,6 +510,7 @@ def eval_gemm(W, X, R, out=None):
     C, N = W.shape[1], X.shape[1]
     if out is None:
         out = torch.empty((C, N), dtype=F64, device=X.device)
-    _check(lib.pgd_eval_gemm_f64(h, _p(W, F64), W.stride(0), _p(X, F64), X.stride(0), R, C, N, _p(out, F64), out.stride(0),
+    _check(lib.pgd_eval_gemm_f64(h, _p(W, F64, True), W.stride(0), _p(X, F64, True), X.stride(0), R, C, N, _p(out, F64, True),
+                                 out.stride(0),
                                  _stream()), h, "pgd_eval_gemm_f64")
     return out

@@ -367,6 +367,13 @@ def test_evaluate_kernels():
     U = _lib.eval_gemm(W, Xd, R).cpu().numpy()
     assert _relerr(U, Wo.T @ X) < 1e-13
     # ragged sizes around the 128x128 tile and K > 64 (two K chunks)
+    # row-sharded evaluation: a column slab of X / U passed as a strided view (evaluate_batch(rows=...))
+    Xv = Xd[:, 100:612]
+    Us = _lib.eval_gemm(W, Xv, R).cpu().numpy()
+    assert _relerr(Us, (Wo.T @ X)[:, 100:612]) < 1e-13
+    Xv = Xd[:, 101:600]  # odd offset / width: the general kernel
+    Us = _lib.eval_gemm(W, Xv, R).cpu().numpy()
+    assert _relerr(Us, (Wo.T @ X)[:, 101:600]) < 1e-13
     # (even leading dimensions take the cp.async double-buffered kernel, odd ones / K > 64 the general one)
     for (R2, C2, N2) in [(1, 1, 1), (50, 129, 257), (70, 128, 128), (5, 7, 1000), (50, 130, 2050), (13, 300, 1004),
                          (64, 128, 64), (3, 2, 1026), (52, 258, 1090)]:

@@ -48,7 +48,8 @@ def _compare(p, o, n_modes=None, tol=MODE_RTOL, floor_ok=False):
     for d in range(len(p.V)):
         for k in range(n_modes):
             assert _mode_err(p.PGD_func[d][k].vector()[:], o.PGD_func[d][k]) < tol, (d, k)
-    assert np.allclose(p.amplitude[:n_modes], o.amplitude[:n_modes], rtol=1e-7, atol=0)
+    same_counts = list(p.num_fp_it[:n_modes]) == list(o.num_fp_it[:n_modes])
+    assert np.allclose(p.amplitude[:n_modes], o.amplitude[:n_modes], rtol=1e-7 if same_counts else 5e-6, atol=0)
 
 
 def _pgd_point(p, coord):

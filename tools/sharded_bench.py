@@ -96,6 +96,30 @@ def run(mesh_n=128, iters=200, check=False, graph=False, bs=1, hbm_peak=6451.2, 
     out.update(iters=it, ms_per_iteration=per_it, local_bytes_per_iteration=loc_bytes,
                local_gbs=loc_bytes / (per_it * 1e-3) / 1e9, frac_hbm=loc_bytes / (per_it * 1e-3) / 1e9 / hbm_peak,
                global_gbs=(12 * nnz + 4 * n + 56 * n) / (per_it * 1e-3) / 1e9)
+    # configs[4]: the vademecum sweep U[C, N] = W^T X sharded by rows of the spatial dimension -- every rank
+    # reconstructs its own N/world slab, no communication (model.evaluate_batch(rows=...))
+    R, N, C = 50, 100000, 10000
+    n0, n1 = (N * rank) // world, (N * (rank + 1)) // world
+    n0, n1 = n0 - n0 % 2, (n1 - n1 % 2) if rank < world - 1 else n1
+    X = torch.randn((R, N), dtype=torch.float64, device=dev, generator=gen)
+    Wt = torch.randn((R, C), dtype=torch.float64, device=dev, generator=gen)
+    U = torch.empty((C, n1 - n0), dtype=torch.float64, device=dev)
+    Xs = X[:, n0:n1]
+    for _ in range(3):
+        _lib.eval_gemm(Wt, Xs, R, out=U)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0.record()
+    for _ in range(5):
+        _lib.eval_gemm(Wt, Xs, R, out=U)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / 5], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    out["evaluate_sweep"] = {"N": N, "C": C, "R": R, "rows_per_rank": n1 - n0, "ms": float(ms.item()),
+                             "tflops_total": 2.0 * N * C * R / (float(ms.item()) * 1e-3) / 1e12, "collectives": 0}
     if own_pg:
         dist.destroy_process_group()
     return out if rank == 0 else None
