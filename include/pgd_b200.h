@@ -169,7 +169,19 @@ int32_t pgd_spcg_solve_sync(pgd_handle_t h, const int32_t* d_rowptr, const int32
                             const double* d_b, double* d_x, int64_t n_owned, int64_t n_local, int32_t block,
                             const int64_t* d_send_idx, const int64_t* h_send_counts, const int64_t* h_recv_counts,
                             double rtol, double atol, int32_t maxit, int32_t check_every, double* d_work,
-                            int32_t* h_iters, double* h_relres, void* stream);
+                            int32_t* h_iters, double* h_relres, void* stream, const int64_t* h_peer_ghost_base);
+/* NVLink peer window (optional, replaces NCCL inside the iteration): every rank creates a window
+ * (cudaMalloc + CUDA IPC handle, p_capacity >= the largest n_local of all ranks, same value everywhere),
+ * the host all-gathers the 64-byte handles and every rank opens them.  With a window and
+ * h_peer_ghost_base[r] = offset (in doubles) inside rank r's p where this rank's block of ghosts starts
+ * (= n_owned_r + sum of r's recv_counts from lower ranks), pgd_spcg_solve_sync keeps p inside the window:
+ * neighbours store their boundary values of p straight into the ghost tail over NVLink and publish a
+ * sequence flag (st.release.sys); the dot products are reduced by a one-shot mailbox all-reduce summed in
+ * rank order (bitwise identical on all ranks).  pgd_set_option("p2p", 0) falls back to NCCL.  Returns -6 if
+ * a peer does not arrive within ~2 s (instead of hanging the GPU). */
+int32_t pgd_peer_window_create(pgd_handle_t h, int64_t p_capacity, void* h_ipc64);
+int32_t pgd_peer_window_open(pgd_handle_t h, int32_t rank, int32_t world, const void* h_all_ipc);
+int32_t pgd_peer_window_destroy(pgd_handle_t h);
 
 /* Same solve with a warm start: on entry d_x holds the initial guess x0 (r0 = b - A x0); the stopping
  * rule stays relative to ||b||.  The fixed-point sweeps of solver.py:531-757 solve a sequence of nearby

@@ -52,7 +52,10 @@ SIGNATURES = {
     "pgd_comm_init": [c_vp, c_vp, c_i32, c_i32],
     "pgd_comm_destroy": [c_vp],
     "pgd_spcg_solve_sync": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_dbl, c_dbl, c_i32,
-                            c_i32, c_vp, c_vp, c_vp, c_vp],
+                            c_i32, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "pgd_peer_window_create": [c_vp, c_i64, c_vp],
+    "pgd_peer_window_open": [c_vp, c_i32, c_i32, c_vp],
+    "pgd_peer_window_destroy": [c_vp],
     "pgd_pcg_x0_sync": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_dbl, c_dbl, c_i32, c_i32, c_i32, c_i32, c_vp,
                         ctypes.POINTER(c_i32), ctypes.POINTER(c_dbl), c_vp],
     "pgd_banded_solve": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp],
@@ -218,6 +221,47 @@ def comm_init(group=None):
     return _COMM[key]
 
 
+_WINDOW = {}
+
+
+def peer_window(n_local, group=None):
+    """Collective: make sure this device has an NVLink peer window with room for p (n_local doubles on the
+    largest rank) mapped on every rank of `group`; returns (rank, world) or None when P2P is unavailable."""
+    import torch.distributed as dist
+
+    h, lib = handle(None), load_library()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if world > 16:
+        return None
+    dev = torch.cuda.current_device()
+    need = torch.tensor([int(n_local)], dtype=I64, device="cuda")
+    dist.all_reduce(need, op=dist.ReduceOp.MAX, group=group)
+    need = int(need.item())
+    key = (dev, id(group))
+    if key in _WINDOW and _WINDOW[key] >= need:
+        return rank, world
+    cap = max(need + need // 8, 1024)
+    buf = (ctypes.c_ubyte * 64)()
+    _check(lib.pgd_peer_window_create(h, cap, ctypes.cast(buf, c_vp)), h, "pgd_peer_window_create")
+    mine = torch.tensor(list(buf), dtype=torch.uint8, device="cuda")
+    allh = [torch.empty(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+    dist.all_gather(allh, mine, group=group)
+    raw = (ctypes.c_ubyte * (64 * world))(*torch.cat(allh).cpu().tolist())
+    try:
+        _check(lib.pgd_peer_window_open(h, rank, world, ctypes.cast(raw, c_vp)), h, "pgd_peer_window_open")
+        ok = 1
+    except PGDB200Error:
+        ok = 0
+    flag = torch.tensor([ok], dtype=I64, device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if int(flag.item()) == 0:  # some rank could not map a peer: everybody falls back to NCCL
+        lib.pgd_peer_window_destroy(h)
+        _WINDOW.pop(key, None)
+        return None
+    _WINDOW[key] = cap
+    return rank, world
+
+
 def spcg_solve(A, b, rtol=1e-13, atol=0.0, maxit=10000, check_every=50, block=1, work=None):
     """Sharded PCG solve (pgd_spcg_solve_sync): A is a partition.ShardedMatrix, b the owned slice.
     Needs comm_init() when more than one rank takes part."""
@@ -232,11 +276,14 @@ def spcg_solve(A, b, rtol=1e-13, atol=0.0, maxit=10000, check_every=50, block=1,
     sc = (c_i64 * world)(*[int(v) for v in halo.send_counts])
     rc_ = (c_i64 * world)(*[int(v) for v in halo.recv_counts])
     iters, relres = c_i32(0), c_dbl(0.0)
+    gb = getattr(halo, "peer_ghost_base", None)
+    gbase = (c_i64 * world)(*[int(v) for v in gb]) if gb is not None else None
     _check(lib.pgd_spcg_solve_sync(h, _p(A.rowptr, I32), _p(A.colidx, I32), _p(A.values, F64), _p(b, F64), _p(x), A.n_owned,
                                    A.n_local, block, _p(halo.send_idx, I64) if n_send else c_vp(0), ctypes.cast(sc, c_vp),
                                    ctypes.cast(rc_, c_vp), float(rtol), float(atol), int(maxit), int(check_every), _p(work),
                                    ctypes.cast(ctypes.pointer(iters), c_vp), ctypes.cast(ctypes.pointer(relres), c_vp),
-                                   _stream()), h, "pgd_spcg_solve_sync")
+                                   _stream(), ctypes.cast(gbase, c_vp) if gbase is not None else c_vp(0)), h,
+           "pgd_spcg_solve_sync")
     return x, int(iters.value), float(relres.value)
 
 

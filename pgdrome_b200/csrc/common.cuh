@@ -38,6 +38,17 @@ struct pgd_ctx {
     cudaEvent_t ev0, ev1;
     void* comm;              // ncclComm_t of the sharded solves (pgd_comm_init), NULL = single rank
     int comm_rank, comm_world;
+    // NVLink peer window of the sharded solves (pgd_peer_window_*): this rank's cudaMalloc'ed window, the
+    // IPC-mapped windows of the other ranks, and the layout (identical on every rank)
+    void* win_local;
+    void* win_peer[16];
+    int64_t win_pcap;        // doubles reserved for p = [owned | ghost]
+    int win_world, win_rank;
+    unsigned long long win_ar_seq, win_halo_seq;
+    double* p_override;      // when set, the sharded-PCG blocks keep p here (inside the window) instead of in d_work
+    int opt_p2p;             // pgd_set_option("p2p"): 1 (default) = use the peer window when it exists, 0 = NCCL
+    void* cap_stream;        // private stream used to capture the peer-window iteration into a CUDA graph
+    int opt_graph;           // pgd_set_option("graph"): 1 (default) = replay the peer-window iteration from a CUDA graph
 };
 
 void pgd_free_pattern(pgd_ctx* h);

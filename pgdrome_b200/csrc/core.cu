@@ -17,6 +17,8 @@ extern "C" int32_t pgd_create(int32_t device, pgd_handle_t* out) {
     h->device = device;
     h->opt_resident = 1;
     h->opt_stream = 2;
+    h->opt_p2p = 1;
+    h->opt_graph = 1;
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     if ((e = cudaMalloc(&h->partials, sizeof(double) * PGD_MAX_PARTIALS)) != cudaSuccess ||
         (e = cudaMalloc(&h->counters, sizeof(unsigned int) * PGD_MAX_COUNTERS)) != cudaSuccess ||
@@ -72,6 +74,14 @@ extern "C" int32_t pgd_set_option(pgd_handle_t h, const char* name, int64_t valu
     PGD_ARG(h, name != nullptr, "null option name");
     if (strcmp(name, "pcg_resident") == 0) {
         h->opt_resident = value ? 1 : 0;
+        return 0;
+    }
+    if (strcmp(name, "graph") == 0) {
+        h->opt_graph = value ? 1 : 0;
+        return 0;
+    }
+    if (strcmp(name, "p2p") == 0) {
+        h->opt_p2p = value ? 1 : 0;
         return 0;
     }
     if (strcmp(name, "spmv_stream") == 0) {

@@ -493,13 +493,13 @@ __global__ void k_spcg_rotate(double* sc, int* fl) {
 struct SpcgWork {
     double *r, *z, *q, *minv, *p;
 };
-static SpcgWork spcg_work(double* work, int64_t no, int block) {
+static SpcgWork spcg_work(pgd_ctx* h, double* work, int64_t no, int block) {
     SpcgWork w;
     w.r = work;
     w.z = w.r + no;
     w.q = w.z + no;
     w.minv = w.q + no;
-    w.p = w.minv + no * block;
+    w.p = h->p_override ? h->p_override : w.minv + no * block;
     return w;
 }
 
@@ -510,7 +510,7 @@ extern "C" int32_t pgd_spcg_init(pgd_handle_t h, const int32_t* d_rowptr, const 
     PGD_ARG(h, d_rowptr && d_colidx && d_values && d_b && d_x && d_work && d_sc && d_fl, "null pointer");
     PGD_ARG(h, n_owned >= 0 && n_local >= n_owned && block >= 1 && block <= 3 && n_owned % block == 0, "bad sizes");
     cudaStream_t st = (cudaStream_t)stream;
-    SpcgWork w = spcg_work(d_work, n_owned, block);
+    SpcgWork w = spcg_work(h, d_work, n_owned, block);
     PGD_CUDA(h, cudaMemsetAsync(w.p, 0, sizeof(double) * n_local, st));
     PGD_CUDA(h, cudaMemsetAsync(d_sc, 0, sizeof(double) * 16, st));
     PGD_CUDA(h, cudaMemsetAsync(d_fl, 0, sizeof(int32_t) * 4, st));
@@ -541,7 +541,7 @@ extern "C" int32_t pgd_spcg_direction(pgd_handle_t h, double* d_work, int64_t n_
     PGD_CHECK_HANDLE(h);
     PGD_ARG(h, d_work && d_sc && d_fl && n_owned >= 0, "bad arguments");
     if (n_owned == 0) return 0;
-    SpcgWork w = spcg_work(d_work, n_owned, block);
+    SpcgWork w = spcg_work(h, d_work, n_owned, block);
     unsigned int vb = pgd_blocks(n_owned, 256);
     unsigned int capv = (unsigned int)h->sm_count * 16;
     if (vb > capv) vb = capv;
@@ -554,7 +554,7 @@ extern "C" int32_t pgd_spcg_matvec(pgd_handle_t h, const int32_t* d_rowptr, cons
                                    double* d_work, int64_t n_owned, int32_t block, double* d_sc, void* stream) {
     PGD_CHECK_HANDLE(h);
     PGD_ARG(h, d_rowptr && d_colidx && d_values && d_work && d_sc && n_owned >= 0, "bad arguments");
-    SpcgWork w = spcg_work(d_work, n_owned, block);
+    SpcgWork w = spcg_work(h, d_work, n_owned, block);
     if (n_owned == 0) return (int32_t)cudaMemsetAsync(d_sc + S_PQ, 0, sizeof(double), (cudaStream_t)stream);
     // q = A_loc p (p includes the ghost entries), sc[S_PQ] = local p.q     [not skipped when DONE: harmless]
     return pgd_spmv_dot(h, d_rowptr, d_colidx, d_values, w.p, w.q, w.p, d_sc + S_PQ, n_owned, 0, stream);
@@ -565,7 +565,7 @@ extern "C" int32_t pgd_spcg_update(pgd_handle_t h, double* d_x, double* d_work, 
     PGD_CHECK_HANDLE(h);
     PGD_ARG(h, d_x && d_work && d_sc && d_fl && n_owned >= 0 && block >= 1 && block <= 3, "bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    SpcgWork w = spcg_work(d_work, n_owned, block);
+    SpcgWork w = spcg_work(h, d_work, n_owned, block);
     const int64_t n_nodes = n_owned / block;
     if (n_nodes == 0) return (int32_t)cudaMemsetAsync(d_sc + S_TMP, 0, 2 * sizeof(double), st);
     unsigned int vb = pgd_blocks(n_nodes, 256);

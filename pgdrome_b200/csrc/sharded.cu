@@ -110,6 +110,202 @@ __global__ void __launch_bounds__(256) k_halo_pack(const double* __restrict__ v,
     if (i < n) buf[i] = v[idx[i]];
 }
 
+// ================================================================================================
+// NVLink peer window: halo exchange and dot-product all-reduce WITHOUT NCCL in the iteration.
+//
+// Every rank cudaMalloc's one window and maps the windows of the other ranks of the box with CUDA IPC
+// (NVSwitch: every peer at full NVLink bandwidth).  Layout, identical on every rank (win_pcap doubles
+// for p, then the small mailboxes):
+//     p[win_pcap]                      this rank's direction vector [owned | ghost]; neighbours STORE their
+//                                      boundary values straight into the ghost tail (k_halo_push)
+//     ar_slot[2][16][4] doubles        all-reduce mailboxes, double-buffered by sequence parity
+//     ar_flag[2][16], halo_flag[16]    u64 sequence numbers written with st.release.sys by the sender
+// k_halo_push     after p = z + beta p: gathers the boundary entries and stores them into the owners' ghost
+//                 slots over NVLink; the last CTA publishes halo_flag[me] = seq on every destination.
+// k_halo_wait     one warp spins (ld.acquire.sys) until every source has published seq.
+// k_allreduce_p2p one-shot all-reduce of <= 4 doubles: store my partials into everybody's mailbox, flag,
+//                 wait for everybody's flag, sum in RANK ORDER (=> bitwise identical on all ranks).
+// All spins carry a clock64() budget; on expiry they raise the NaN/bad flag instead of hanging the GPU.
+// ================================================================================================
+#define PW_MAXR 16
+#define PW_AR_VALS 4
+#define PW_SPIN_BUDGET (4000000000LL)  // ~2 s at 1.9 GHz
+
+struct PwLayout {
+    int64_t pcap;
+    __host__ __device__ size_t slot_off() const { return (size_t)pcap * 8; }
+    __host__ __device__ size_t arflag_off() const { return slot_off() + 2 * PW_MAXR * PW_AR_VALS * 8; }
+    __host__ __device__ size_t haloflag_off() const { return arflag_off() + 2 * PW_MAXR * 8; }
+    __host__ __device__ size_t bytes() const { return haloflag_off() + PW_MAXR * 8; }
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+struct PwPeers {
+    unsigned char* base[PW_MAXR];
+};
+struct PwHalo {
+    int64_t seg_start[PW_MAXR + 1];  // send entries grouped by destination rank
+    int64_t dst_off[PW_MAXR];        // offset (doubles) inside the destination's p where my block of ghosts starts
+    int recv_from[PW_MAXR];          // 1 if I receive ghosts from that rank
+};
+
+__global__ void __launch_bounds__(256) k_halo_push(const double* __restrict__ p, const int64_t* __restrict__ send_idx,
+                                                   int64_t n_send, PwPeers peers, PwHalo hp, PwLayout lay, int me, int world,
+                                                   const unsigned long long* seq_ctr, unsigned int* counter, const int* fl) {
+    if (fl[0]) return;
+    const unsigned long long seq = *seq_ctr + 1ULL;  // advanced by k_halo_wait (sequence numbers live on the device so
+                                                     // that the iteration can be replayed from a CUDA graph)
+    __shared__ bool s_last;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_send; s += stride) {
+        int r = 0;
+        while (s >= hp.seg_start[r + 1]) ++r;
+        double* dst = reinterpret_cast<double*>(peers.base[r]) + hp.dst_off[r] + (s - hp.seg_start[r]);
+        *dst = p[send_idx[s]];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(counter, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence_system();
+        if ((int)threadIdx.x < world && (int)threadIdx.x != me && hp.seg_start[threadIdx.x + 1] > hp.seg_start[threadIdx.x]) {
+            unsigned long long* f = reinterpret_cast<unsigned long long*>(peers.base[threadIdx.x] + lay.haloflag_off()) + me;
+            st_release_sys(f, seq);
+        }
+        if (threadIdx.x == 0) *counter = 0u;
+    }
+}
+
+__global__ void k_halo_wait(unsigned char* mine, PwHalo hp, PwLayout lay, int world, unsigned long long* seq_ctr, int* fl) {
+    if (fl[0]) return;
+    const unsigned long long seq = *seq_ctr + 1ULL;
+    const int r = threadIdx.x;
+    if (r < world && hp.recv_from[r]) {
+        const unsigned long long* f = reinterpret_cast<const unsigned long long*>(mine + lay.haloflag_off()) + r;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) < seq) {
+            if (clock64() - t0 > PW_SPIN_BUDGET) {
+                fl[2] = 2;  // peer did not arrive: report instead of hanging
+                fl[0] = 1;
+                break;
+            }
+        }
+    }
+    __syncwarp();
+    if (r == 0) *seq_ctr = seq;
+}
+
+// vals: device pointer to nv (<= 4) doubles, reduced in place
+__global__ void k_allreduce_p2p(double* vals, int nv, PwPeers peers, PwLayout lay, int me, int world,
+                                unsigned long long* seq_ctr, int* fl, int skip_when_done) {
+    if (skip_when_done && fl[0]) return;
+    const unsigned long long seq = *seq_ctr + 1ULL;
+    const int par = (int)(seq & 1ULL);
+    const int r = threadIdx.x;
+    __shared__ int s_bad;
+    if (r == 0) s_bad = 0;
+    __syncthreads();
+    if (r < world) {
+        double* slot = reinterpret_cast<double*>(peers.base[r] + lay.slot_off()) + ((size_t)par * PW_MAXR + me) * PW_AR_VALS;
+        for (int k = 0; k < nv; ++k) slot[k] = vals[k];
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<unsigned long long*>(peers.base[r] + lay.arflag_off()) + par * PW_MAXR + me, seq);
+        const unsigned long long* f =
+            reinterpret_cast<const unsigned long long*>(peers.base[me] + lay.arflag_off()) + par * PW_MAXR + r;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) < seq) {
+            if (clock64() - t0 > PW_SPIN_BUDGET) {
+                s_bad = 1;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    if (r == 0) {
+        if (s_bad) {
+            fl[2] = 2;
+            fl[0] = 1;
+        } else {
+            const double* mine = reinterpret_cast<const double*>(peers.base[me] + lay.slot_off()) + (size_t)par * PW_MAXR * PW_AR_VALS;
+            for (int k = 0; k < nv; ++k) {
+                double sum = 0.0;
+                for (int q = 0; q < world; ++q) sum += *((volatile const double*)&mine[q * PW_AR_VALS + k]);
+                vals[k] = sum;
+            }
+        }
+        *seq_ctr = seq;
+    }
+}
+
+extern "C" int32_t pgd_peer_window_create(pgd_handle_t h, int64_t p_capacity, void* h_ipc64) {
+    PGD_CHECK_HANDLE(h);
+    PGD_ARG(h, p_capacity > 0 && h_ipc64, "bad arguments");
+    pgd_set_device(h);
+    if (h->win_local) {
+        cudaFree(h->win_local);
+        h->win_local = nullptr;
+    }
+    PwLayout lay{p_capacity};
+    void* p = nullptr;
+    PGD_CUDA(h, cudaMalloc(&p, lay.bytes()));
+    PGD_CUDA(h, cudaMemset(p, 0, lay.bytes()));
+    cudaIpcMemHandle_t ih;
+    PGD_CUDA(h, cudaIpcGetMemHandle(&ih, p));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(h_ipc64, &ih, 64);
+    h->win_local = p;
+    h->win_pcap = p_capacity;
+    h->win_world = 0;
+    return 0;
+}
+
+extern "C" int32_t pgd_peer_window_open(pgd_handle_t h, int32_t rank, int32_t world, const void* h_all_ipc) {
+    PGD_CHECK_HANDLE(h);
+    PGD_ARG(h, h->win_local && h_all_ipc && world >= 1 && world <= PW_MAXR && rank >= 0 && rank < world, "bad arguments");
+    pgd_set_device(h);
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) {
+            h->win_peer[r] = h->win_local;
+            continue;
+        }
+        cudaIpcMemHandle_t ih;
+        memcpy(&ih, (const char*)h_all_ipc + 64 * r, 64);
+        void* q = nullptr;
+        PGD_CUDA(h, cudaIpcOpenMemHandle(&q, ih, cudaIpcMemLazyEnablePeerAccess));
+        h->win_peer[r] = q;
+    }
+    h->win_world = world;
+    h->win_rank = rank;
+    h->win_ar_seq = 0;
+    h->win_halo_seq = 0;
+    PGD_CUDA(h, cudaMemset(h->scalars + 40, 0, 2 * sizeof(double)));  // device-side sequence counters (halo, all-reduce)
+    return 0;
+}
+
+extern "C" int32_t pgd_peer_window_destroy(pgd_handle_t h) {
+    PGD_CHECK_HANDLE(h);
+    pgd_set_device(h);
+    for (int r = 0; r < h->win_world; ++r)
+        if (r != h->win_rank && h->win_peer[r]) cudaIpcCloseMemHandle(h->win_peer[r]);
+    if (h->win_local) cudaFree(h->win_local);
+    h->win_local = nullptr;
+    h->win_world = 0;
+    h->p_override = nullptr;
+    return 0;
+}
+
 // building blocks defined in pcg.cu
 extern "C" int32_t pgd_spcg_init(pgd_handle_t, const int32_t*, const int32_t*, const double*, const double*, double*, int64_t,
                                  int64_t, int32_t, double*, double*, int32_t*, void*);
@@ -118,11 +314,12 @@ extern "C" int32_t pgd_spcg_solve_sync(pgd_handle_t h, const int32_t* d_rowptr, 
                                        const double* d_b, double* d_x, int64_t n_owned, int64_t n_local, int32_t block,
                                        const int64_t* d_send_idx, const int64_t* h_send_counts, const int64_t* h_recv_counts,
                                        double rtol, double atol, int32_t maxit, int32_t check_every, double* d_work,
-                                       int32_t* h_iters, double* h_relres, void* stream) {
+                                       int32_t* h_iters, double* h_relres, void* stream, const int64_t* h_peer_ghost_base) {
     PGD_CHECK_HANDLE(h);
     PGD_ARG(h, d_rowptr && d_colidx && d_values && d_b && d_x && d_work, "null pointer");
     PGD_ARG(h, n_owned >= 0 && n_local >= n_owned && block >= 1 && block <= 3, "bad sizes");
-    const int world = h->comm ? h->comm_world : 1;
+    const bool p2p = h->opt_p2p && h->win_local && h->win_world > 1 && h_peer_ghost_base && n_local <= h->win_pcap;
+    const int world = p2p ? h->win_world : (h->comm ? h->comm_world : 1);
     PGD_ARG(h, world == 1 || (h_send_counts && h_recv_counts), "split sizes required with more than one rank");
     cudaStream_t st = (cudaStream_t)stream;
     ncclComm_t comm = (ncclComm_t)h->comm;
@@ -130,51 +327,126 @@ extern "C" int32_t pgd_spcg_solve_sync(pgd_handle_t h, const int32_t* d_rowptr, 
     if (world > 1)
         for (int r = 0; r < world; ++r) n_send += h_send_counts[r];
     PGD_ARG(h, n_send == 0 || d_send_idx, "send index list required");
-    // work: r z q minv p[n_local] sendbuf[n_send]
-    double* p = d_work + n_owned * (3 + block);
-    double* sendbuf = p + n_local;
+    // work: r z q minv p[n_local] sendbuf[n_send]   (p2p: p lives in the peer window instead)
+    h->p_override = p2p ? reinterpret_cast<double*>(h->win_local) : nullptr;
+    double* p = p2p ? h->p_override : d_work + n_owned * (3 + block);
+    double* sendbuf = d_work + n_owned * (3 + block) + n_local;
     double* sc = h->scalars;
     int* fl = h->flags;
+    PwPeers peers;
+    PwHalo hp;
+    PwLayout lay{h->win_pcap};
+    const int me = p2p ? h->win_rank : 0;
+    unsigned long long* seq_halo = reinterpret_cast<unsigned long long*>(h->scalars + 40);
+    unsigned long long* seq_ar = reinterpret_cast<unsigned long long*>(h->scalars + 41);
+    if (p2p) {
+        for (int r = 0; r < PW_MAXR; ++r) peers.base[r] = (unsigned char*)(r < world ? h->win_peer[r] : nullptr);
+        hp.seg_start[0] = 0;
+        for (int r = 0; r < PW_MAXR; ++r) {
+            hp.seg_start[r + 1] = hp.seg_start[r] + (r < world ? h_send_counts[r] : 0);
+            hp.dst_off[r] = r < world ? h_peer_ghost_base[r] : 0;
+            hp.recv_from[r] = (r < world && h_recv_counts[r] > 0) ? 1 : 0;
+        }
+    }
+    auto allreduce = [&](double* vals, int nv, int skip_when_done, cudaStream_t st) -> int32_t {
+        if (world <= 1) return 0;
+        if (p2p) {
+            k_allreduce_p2p<<<1, 32, 0, st>>>(vals, nv, peers, lay, me, world, seq_ar, fl, skip_when_done);
+            h->n_launches += 1;
+            return (int32_t)cudaGetLastError();
+        }
+        PGD_NCCL(h, g_nccl.AllReduce(vals, vals, (size_t)nv, ncclDouble, ncclSum, comm, st));
+        return 0;
+    };
     int32_t rc = pgd_spcg_init(h, d_rowptr, d_colidx, d_values, d_b, d_x, n_owned, n_local, block, d_work, sc, fl, stream);
     if (rc) return rc;
-    if (world > 1) PGD_NCCL(h, g_nccl.AllReduce(sc + 8, sc + 8, 3, ncclDouble, ncclSum, comm, st));
+    if ((rc = allreduce(sc + 8, 3, 0, st))) return rc;
     rc = pgd_spcg_init_fin(h, sc, fl, rtol, atol, stream);
     if (rc) return rc;
     if (check_every < 1) check_every = 1;
     int hf[4] = {0, 0, 0, 0};
     int launched = 0;
     PGD_CUDA(h, cudaEventRecord(h->ev0, st));
+    auto enqueue_iteration = [&](cudaStream_t st) -> int32_t {
+        void* stream = (void*)st;
+        int32_t rc2;
+        if ((rc2 = pgd_spcg_direction(h, d_work, n_owned, block, sc, fl, stream))) return rc2;
+        if (p2p) {
+            if (n_send) {
+                unsigned int pb = pgd_blocks(n_send, 256);
+                if (pb > 64) pb = 64;
+                k_halo_push<<<pb, 256, 0, st>>>(p, d_send_idx, n_send, peers, hp, lay, me, world, seq_halo,
+                                                h->counters + (PGD_MAX_COUNTERS - 2), fl);
+            }
+            k_halo_wait<<<1, 32, 0, st>>>((unsigned char*)h->win_local, hp, lay, world, seq_halo, fl);
+            h->n_launches += 2;
+        } else if (world > 1) {
+            if (n_send) {
+                k_halo_pack<<<pgd_blocks(n_send, 256), 256, 0, st>>>(p, d_send_idx, n_send, sendbuf);
+                h->n_launches += 1;
+            }
+            PGD_NCCL(h, g_nccl.GroupStart());
+            int64_t so = 0, ro = 0;
+            for (int r = 0; r < world; ++r) {
+                if (h_send_counts[r]) PGD_NCCL(h, g_nccl.Send(sendbuf + so, (size_t)h_send_counts[r], ncclDouble, r, comm, st));
+                if (h_recv_counts[r]) PGD_NCCL(h, g_nccl.Recv(p + n_owned + ro, (size_t)h_recv_counts[r], ncclDouble, r, comm, st));
+                so += h_send_counts[r];
+                ro += h_recv_counts[r];
+            }
+            PGD_NCCL(h, g_nccl.GroupEnd());
+        }
+        if ((rc2 = pgd_spcg_matvec(h, d_rowptr, d_colidx, d_values, d_work, n_owned, block, sc, stream))) return rc2;
+        if ((rc2 = allreduce(sc + 2, 1, 1, st))) return rc2;
+        if ((rc2 = pgd_spcg_update(h, d_x, d_work, n_owned, block, sc, fl, stream))) return rc2;
+        if ((rc2 = allreduce(sc + 8, 2, 1, st))) return rc2;
+        return pgd_spcg_rotate(h, sc, fl, stream);
+    };
+    // Peer-window path: the iteration is 8 small launches with device-resident sequence numbers and flags, so
+    // it is captured ONCE per solve in a CUDA graph and replayed (the host was the bottleneck at ~7 us per
+    // launch: 59 us per iteration on a 137 k-row slab whose kernels take ~15 us).
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    const bool use_graph = p2p && h->opt_graph;
+    bool warmed = false;
     while (true) {
         PGD_CUDA(h, cudaMemcpyAsync(hf, fl, sizeof(hf), cudaMemcpyDeviceToHost, st));
         PGD_CUDA(h, cudaStreamSynchronize(st));
         if (hf[0] || launched >= maxit) break;
         int todo = maxit - launched;
         if (todo > check_every) todo = check_every;
-        for (int i = 0; i < todo; ++i) {
-            if ((rc = pgd_spcg_direction(h, d_work, n_owned, block, sc, fl, stream))) return rc;
-            if (world > 1) {
-                if (n_send) {
-                    k_halo_pack<<<pgd_blocks(n_send, 256), 256, 0, st>>>(p, d_send_idx, n_send, sendbuf);
-                    h->n_launches += 1;
+        int i = 0;
+        if (use_graph && !warmed) {  // first iteration eagerly (one-time function attributes), then capture
+            if ((rc = enqueue_iteration(st))) return rc;
+            warmed = true;
+            ++i;
+            if (i < todo) {
+                // the caller's stream may be the legacy default stream, which cannot capture: record the
+                // iteration on a private stream and launch the instantiated graph on the caller's stream
+                if (!h->cap_stream) {
+                    cudaStream_t cs;
+                    PGD_CUDA(h, cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+                    h->cap_stream = cs;
                 }
-                PGD_NCCL(h, g_nccl.GroupStart());
-                int64_t so = 0, ro = 0;
-                for (int r = 0; r < world; ++r) {
-                    if (h_send_counts[r]) PGD_NCCL(h, g_nccl.Send(sendbuf + so, (size_t)h_send_counts[r], ncclDouble, r, comm, st));
-                    if (h_recv_counts[r]) PGD_NCCL(h, g_nccl.Recv(p + n_owned + ro, (size_t)h_recv_counts[r], ncclDouble, r, comm, st));
-                    so += h_send_counts[r];
-                    ro += h_recv_counts[r];
-                }
-                PGD_NCCL(h, g_nccl.GroupEnd());
+                cudaStream_t cs = (cudaStream_t)h->cap_stream;
+                PGD_CUDA(h, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+                int32_t rcc = enqueue_iteration(cs);
+                cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+                if (rcc) return rcc;
+                PGD_CUDA(h, ce);
+                PGD_CUDA(h, cudaGraphInstantiate(&gexec, graph, 0));
             }
-            if ((rc = pgd_spcg_matvec(h, d_rowptr, d_colidx, d_values, d_work, n_owned, block, sc, stream))) return rc;
-            if (world > 1) PGD_NCCL(h, g_nccl.AllReduce(sc + 2, sc + 2, 1, ncclDouble, ncclSum, comm, st));
-            if ((rc = pgd_spcg_update(h, d_x, d_work, n_owned, block, sc, fl, stream))) return rc;
-            if (world > 1) PGD_NCCL(h, g_nccl.AllReduce(sc + 8, sc + 8, 2, ncclDouble, ncclSum, comm, st));
-            if ((rc = pgd_spcg_rotate(h, sc, fl, stream))) return rc;
+        }
+        for (; i < todo; ++i) {
+            if (gexec) {
+                PGD_CUDA(h, cudaGraphLaunch(gexec, st));
+            } else if ((rc = enqueue_iteration(st))) {
+                return rc;
+            }
         }
         launched += todo;
     }
+    if (gexec) cudaGraphExecDestroy(gexec);
+    if (graph) cudaGraphDestroy(graph);
     PGD_CUDA(h, cudaEventRecord(h->ev1, st));
     double hs[8];
     PGD_CUDA(h, cudaMemcpyAsync(hs, sc, sizeof(hs), cudaMemcpyDeviceToHost, st));
@@ -183,8 +455,13 @@ extern "C" int32_t pgd_spcg_solve_sync(pgd_handle_t h, const int32_t* d_rowptr, 
     if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->pcg_ms += ms;
     h->pcg_solves += 1;
     h->pcg_iters += hf[1];
+    h->p_override = nullptr;
     if (h_iters) *h_iters = hf[1];
     if (h_relres) *h_relres = (hs[4] > 0.0) ? sqrt(hs[3] / hs[4]) : 0.0;
+    if (hf[2] == 2) {
+        snprintf(h->err, sizeof(h->err), "pgd_spcg_solve_sync: a peer rank did not arrive at a halo / all-reduce flag in time");
+        return -6;
+    }
     if (hf[2]) {
         snprintf(h->err, sizeof(h->err), "pgd_spcg_solve_sync: NaN encountered (matrix not SPD?)");
         return -3;

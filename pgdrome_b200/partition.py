@@ -56,6 +56,24 @@ class HaloPlan:
         self.group = group
         self._buf = torch.empty(int(send_idx.numel()), dtype=F64, device=send_idx.device)
 
+    def ensure_peer_layout(self):
+        """Collective: where this rank's block of ghosts starts inside every neighbour's p
+        (= n_owned_r + the ghosts r receives from lower ranks); needed by the NVLink peer-window path."""
+        import torch.distributed as dist
+
+        if getattr(self, "peer_ghost_base", None) is not None:
+            return
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        dev = self.send_idx.device
+        mine = torch.tensor([self.n_owned] + [int(c) for c in self.recv_counts], dtype=I64, device=dev)
+        allv = [torch.empty(world + 1, dtype=I64, device=dev) for _ in range(world)]
+        dist.all_gather(allv, mine, group=self.group)
+        base = []
+        for r in range(world):
+            v = allv[r].tolist()
+            base.append(int(v[0] + sum(v[1:1 + rank])))
+        self.peer_ghost_base = base
+
     @property
     def bytes_per_exchange(self):
         return 8 * (int(self.send_idx.numel()) + self.n_ghost)
@@ -188,7 +206,8 @@ def _allreduce(t, group):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
 
 
-def sharded_pcg(A, b, rtol=1e-13, atol=0.0, maxit=10000, check_every=50, block=None, ops=None, use_graph=False):
+def sharded_pcg(A, b, rtol=1e-13, atol=0.0, maxit=10000, check_every=50, block=None, ops=None, use_graph=False,
+                use_p2p=True):
     """Solve A x = b over the row partition (A: ShardedMatrix, b: owned slice).  Returns
     (x_owned, iterations, relative residual); identical iteration count on every rank.
 
@@ -207,6 +226,10 @@ def sharded_pcg(A, b, rtol=1e-13, atol=0.0, maxit=10000, check_every=50, block=N
 
         if dist.is_initialized() and dist.get_world_size(group) > 1:
             _lib.comm_init(group)
+            if use_p2p and _lib.peer_window(A.n_local, group) is not None:
+                A.halo.ensure_peer_layout()
+            else:
+                A.halo.peer_ghost_base = None
         return _lib.spcg_solve(A, b, rtol=rtol, atol=atol, maxit=maxit, check_every=check_every, block=block)
     ops = ops or _DeviceOps(A, block)
     x = torch.zeros(A.n_owned, dtype=F64, device=b.device)

@@ -21,7 +21,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
-def run(mesh_n=128, iters=200, check=False, graph=False, bs=1, hbm_peak=6451.2, host_loop=False):
+def run(mesh_n=128, iters=200, check=False, graph=False, bs=1, hbm_peak=6451.2, host_loop=False, p2p=True):
     import torch.distributed as dist
 
     from pgdrome_b200 import _lib, fem, partition as pt
@@ -67,9 +67,9 @@ def run(mesh_n=128, iters=200, check=False, graph=False, bs=1, hbm_peak=6451.2, 
     b = b_full[r0:r1].contiguous()
     out = {"mesh": "BoxMesh %d^3 cells, P1%s" % (mesh_n, "" if bs == 1 else " vector"), "n_dofs": n, "nnz": nnz,
            "world": world, "rows_per_rank": r1 - r0, "ghosts_rank0": A.halo.n_ghost,
-           "halo_bytes_per_exchange_rank0": A.halo.bytes_per_exchange, "cuda_graph": bool(graph), "loop": "host (torch.distributed)" if (host_loop or graph) else "libpgdb200 (NCCL)"}
+           "halo_bytes_per_exchange_rank0": A.halo.bytes_per_exchange, "cuda_graph": bool(graph), "loop": "host (torch.distributed)" if (host_loop or graph) else ("libpgdb200 (NVLink peer window)" if p2p and world > 1 else "libpgdb200 (NCCL)")}
     if check:
-        x, it, rr = pt.sharded_pcg(A, b, rtol=1e-12, maxit=20000, check_every=50, block=bs, use_graph=graph, ops=hops())
+        x, it, rr = pt.sharded_pcg(A, b, rtol=1e-12, maxit=20000, check_every=50, block=bs, use_graph=graph, ops=hops(), use_p2p=p2p)
         full = pt.gather_owned(x, part)
         err = float((full - xs).norm() / xs.norm())
         _lib.set_option("pcg_resident", 0)
@@ -79,13 +79,13 @@ def run(mesh_n=128, iters=200, check=False, graph=False, bs=1, hbm_peak=6451.2, 
         assert rr <= 1e-12 and err < 1e-8 and d < 1e-8 and abs(it - it1) <= max(3, it1 // 20), out["check"]
     del b_full
     # timing: fixed iteration count (rtol 0 never converges), events on the launching stream
-    pt.sharded_pcg(A, b, rtol=0.0, maxit=20, check_every=20, block=bs, use_graph=graph, ops=hops())
+    pt.sharded_pcg(A, b, rtol=0.0, maxit=20, check_every=20, block=bs, use_graph=graph, ops=hops(), use_p2p=p2p)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    _, it, _ = pt.sharded_pcg(A, b, rtol=0.0, maxit=iters, check_every=iters, block=bs, use_graph=graph, ops=hops())
+    _, it, _ = pt.sharded_pcg(A, b, rtol=0.0, maxit=iters, check_every=iters, block=bs, use_graph=graph, ops=hops(), use_p2p=p2p)
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -132,8 +132,15 @@ if __name__ == "__main__":
     ap.add_argument("--bs", type=int, default=1)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--graph", action="store_true")
+    ap.add_argument("--no-cgraph", action="store_true", help="peer-window path without CUDA-graph replay")
+    ap.add_argument("--no-p2p", action="store_true", help="NCCL send/recv + allreduce instead of the NVLink peer window")
     ap.add_argument("--host-loop", action="store_true", help="torch.distributed-driven iteration instead of the C loop")
     a = ap.parse_args()
-    r = run(a.mesh, a.iters, a.check, a.graph, a.bs, host_loop=a.host_loop)
+    if a.no_cgraph:
+        from pgdrome_b200 import _lib as _l
+
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        _l.set_option("graph", 0)
+    r = run(a.mesh, a.iters, a.check, a.graph, a.bs, host_loop=a.host_loop, p2p=not a.no_p2p)
     if r is not None:
         print(json.dumps(r))
