@@ -208,12 +208,22 @@ def run_b200(args):
     it_ms = s["pcg_ms"] / max(s["pcg_iters"], 1)
     achieved = it_bytes / (it_ms * 1e-3) / 1e9 if s["pcg_iters"] else 0.0
     resident = s.get("pcg_resident_solves", 0) >= s["pcg_solves"] > 0
+    traffic = None
+    try:  # DRAM bytes of the dominant kernel from the committed ncu --set full capture (per launch = per solve)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_pcg_resident_traffic.json")))
+        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm",
                 "kernel": ("Jacobi-PCG iteration inside k_pcg_resident (one cooperative launch per solve, matrix slice "
                            "resident in shared memory; figures are per ITERATION)") if resident else
                           "Jacobi-PCG iteration (k_pcg_spmv_bulk + k_pcg_update)",
                 "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "bytes_per_launch": it_bytes, "us_per_launch": 1e3 * it_ms, "launches": s["pcg_iters"],
+                "traffic": traffic if resident else None,
+                "traffic_note": ("ncu dram__bytes_read+write of ONE k_pcg_resident launch = one whole solve (~660 iterations): the "
+                                 "matrix is read from HBM once per solve; a streaming PCG would move bytes_per_launch per "
+                                 "iteration") if resident else None,
+                "bytes_per_launch": it_bytes, "us_per_launch": 1e3 * it_ms, "launches": s["pcg_iters"],
                 "share_of_step": s["pcg_ms"] / total_ms if total_ms else None,
                 "note": "matrix (5.5 MB) + vectors are on-chip at this config (shared memory / L2): the iteration is bound by "
                         "two grid barriers (~2 us each), not by HBM; `kernels` carries the HBM-bound sizes (128^3 mesh: "
