@@ -114,9 +114,10 @@ __global__ void __launch_bounds__(256) k_lincomb(LcArgs a, int64_t n, double* __
 extern "C" int32_t pgd_lincomb(pgd_handle_t h, int32_t n_terms, const double* const* h_xs, const double* h_coefs,
                                int64_t n, double* d_out, int32_t accumulate, void* stream) {
     PGD_CHECK_HANDLE(h);
-    PGD_ARG(h, n_terms >= 0 && n >= 0 && d_out, "bad arguments");
+    PGD_ARG(h, n_terms >= 0 && n >= 0, "bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    if (n == 0) return 0;
+    if (n == 0) return 0;  // empty vectors are a no-op (their device pointers may be NULL)
+    PGD_ARG(h, d_out, "null output");
     if (n_terms == 0 && !accumulate) {
         PGD_CUDA(h, cudaMemsetAsync(d_out, 0, sizeof(double) * n, st));
         return 0;

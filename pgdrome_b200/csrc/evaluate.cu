@@ -303,8 +303,9 @@ __global__ void __launch_bounds__(256, 2) k_eval_gemm2(const double* __restrict_
 extern "C" int32_t pgd_eval_gemm_f64(pgd_handle_t h, const double* d_W, int64_t ldw, const double* d_X, int64_t ldx,
                                      int32_t R, int64_t C, int64_t N, double* d_U, int64_t ldu, void* stream) {
     PGD_CHECK_HANDLE(h);
-    PGD_ARG(h, d_W && d_X && d_U && R > 0 && C >= 0 && N >= 0 && ldw >= C && ldx >= N && ldu >= N, "bad arguments");
-    if (C == 0 || N == 0) return 0;
+    PGD_ARG(h, R > 0 && C >= 0 && N >= 0 && ldw >= C && ldx >= N && ldu >= N, "bad arguments");
+    if (C == 0 || N == 0) return 0;  // empty sweep: nothing to do (pointers of empty tensors may be NULL)
+    PGD_ARG(h, d_W && d_X && d_U, "null pointer");
     const bool aligned = ((ldu | ldx | ldw) % 2 == 0) &&
                          (((reinterpret_cast<uintptr_t>(d_U) | reinterpret_cast<uintptr_t>(d_X) | reinterpret_cast<uintptr_t>(d_W)) % 16) == 0);
     if (aligned && R <= GM2_KMAX) {

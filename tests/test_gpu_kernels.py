@@ -466,3 +466,41 @@ def test_sharded_pcg_single_rank_matches_pcg():
             _lib.set_option("pcg_resident", 1)
         assert abs(it - it1) <= max(2, it1 // 20)
         assert np.linalg.norm(xs.cpu().numpy() - x1.cpu().numpy()) / np.linalg.norm(x) < 1e-10
+
+
+def test_edge_cases_and_error_codes():
+    """Empty and ragged inputs, argument errors reported through the C ABI's return code + pgd_last_error."""
+    from pgdrome_b200 import _lib
+
+    dev = torch.device("cuda")
+    # 1 x 1 system, a row without entries, and an isolated (empty) last row
+    rp = torch.tensor([0, 1, 1, 3, 3], dtype=torch.int32, device=dev)
+    ci = torch.tensor([0, 0, 2], dtype=torch.int32, device=dev)
+    va = torch.tensor([2.0, -1.0, 4.0], dtype=torch.float64, device=dev)
+    x = torch.tensor([1.0, 5.0, 0.5, 7.0], dtype=torch.float64, device=dev)
+    y = _lib.spmv(rp, ci, va, x).cpu().numpy()
+    assert np.array_equal(y, [2.0, 0.0, 1.0, 0.0])
+    assert _lib.bilinear(rp, ci, va, x, x).item() == 2.0 + 0.5 * 1.0
+    # zero-length vectors / zero vectors are no-ops, not errors
+    e = torch.empty(0, dtype=torch.float64, device=dev)
+    assert _lib.lincomb([e], [1.0]).numel() == 0
+    assert _lib.panel_dots(torch.empty((0, 4), dtype=torch.float64, device=dev), 0, x).numel() == 0
+    assert _lib.eval_gemm(torch.empty((3, 0), dtype=torch.float64, device=dev), torch.ones((3, 5), dtype=torch.float64, device=dev),
+                          3).shape == (0, 5)
+    # 1 x 1 PCG
+    x1, it, rr = _lib.pcg(torch.tensor([0, 1], dtype=torch.int32, device=dev), torch.tensor([0], dtype=torch.int32, device=dev),
+                          torch.tensor([4.0], dtype=torch.float64, device=dev), torch.tensor([2.0], dtype=torch.float64, device=dev),
+                          rtol=1e-14, maxit=5)
+    assert abs(x1.item() - 0.5) < 1e-15 and it <= 1
+    # argument errors: negative code and a message naming the function
+    with pytest.raises(_lib.PGDB200Error, match="block must be"):
+        _lib.pcg(rp, ci, va, x, block=3)  # 4 rows are not a multiple of 3
+    with pytest.raises(_lib.PGDB200Error, match="pgd_set_option"):
+        _lib.set_option("no_such_option", 1)
+    with pytest.raises(_lib.PGDB200Error, match="CUDA tensor"):
+        _lib.spmv(rp, ci, va, x.cpu())
+    # a non-SPD matrix is reported (NaN / breakdown), never silently "solved"
+    bad = torch.tensor([0.0], dtype=torch.float64, device=dev)
+    with pytest.raises(_lib.PGDB200Error):
+        _lib.pcg(torch.tensor([0, 1], dtype=torch.int32, device=dev), torch.tensor([0], dtype=torch.int32, device=dev), bad,
+                 torch.tensor([1.0], dtype=torch.float64, device=dev), maxit=3)

@@ -113,3 +113,49 @@ def test_golden_pgdclass_host_logic(cpu):
     from tests import test_gpu_golden as tg
 
     tg.test_pgdclass_evaluate_on_device()
+
+
+# ---- solver options on the FEM path (host logic): normalisations, "delta" criterion, randomised start
+@pytest.mark.parametrize("opts", [dict(norm_modes="l2"), dict(norm_modes="no"), dict(stop_fp="delta", tol_fp_it=1e-6),
+                                  dict(fp_init="randomized")])
+def test_solver_options_match_oracle(cpu, opts):
+    from pgdrome_b200 import configs
+
+    np.random.seed(7)  # fp_init="randomized" draws np.random.rand in dimension order, like solver.py:191-196
+    p = configs.heat2d_tk(n=8, nt=12, nk=5, PGD_nmax=3, **opts)
+    p.solve_PGD(_problem="linear")
+    o, _ = oprob.heat2d_tk(n=8, nt=12, nk=5, PGD_nmax=3, spaces=_ospaces(p), **opts)
+    np.random.seed(7)
+    opgd.solve_pgd(o)
+    _compare(p, o, tol=1e-7 if opts.get("fp_init") else 1e-8)
+    assert np.allclose(p.alpha, o.alpha, rtol=1e-8, atol=0)
+
+
+def test_unknown_options_raise(cpu):
+    from pgdrome_b200 import configs
+
+    p = configs.poisson1d_k(nx=20, nk=4, PGD_nmax=2, stop_fp="chady")
+    with pytest.raises(ValueError):  # solver.py:873-879
+        p.solve_PGD(_problem="linear")
+    q = configs.poisson1d_k(nx=20, nk=4, PGD_nmax=2)
+    with pytest.raises(ValueError):
+        q.solve_PGD(_problem="quadratic")
+    pgd = configs.poisson1d_k(nx=20, nk=4, PGD_nmax=2).solve_PGD(_problem="linear").return_PGD()
+    with pytest.raises(ValueError):  # model.py:737-772
+        pgd.evaluate(0, [1], [1.0, 2.0], 0)
+    with pytest.raises(ValueError):
+        pgd.evaluate(0, [1], [1.0], 5)
+    with pytest.raises(ValueError):  # outside the parameter range (test_pgdclass.py:319-326)
+        pgd.evaluate(0, [1], [9.0], 0)
+
+
+def test_direct_solve_mode(cpu):
+    """solve_modes "direct" (solver.py:909-925): scalar problem b / a broadcast into the dofs."""
+    from pgdrome_b200 import dolfin as df
+    from pgdrome_b200.solver import PGDProblem
+
+    V = df.FunctionSpace(df.IntervalMesh(4, 0.0, 1.0), "P", 1)
+    p = PGDProblem(name="d", name_coord=["X"], modes_info=["U", "Node", "Scalar"], Vs=[V], bc_fct=lambda Vs, dom, param: [0],
+                   load=[], param={}, rhs_fct=None, lhs_fct=None, probs=["r"], PGD_nmax=1)
+    f = p.direct_solve(4.0, 2.0, 0)
+    assert np.array_equal(f.vector()[:], np.full(V.n_dofs, 0.5))
