@@ -265,8 +265,11 @@ def get_atom(space, T, weights, meas, op=None, transpose=False):
     ds = device_space(space)
     if transpose and op is None:
         T = np.ascontiguousarray(T.transpose(2, 3, 0, 1))
+    tb = _TBYTES.get(id(T)) if not transpose else None
+    if tb is None:
+        tb = T.tobytes()
     if op is not None:
-        key = ("op", id(op), op._version, T.tobytes(), bool(transpose))
+        key = ("op", id(op), op._version, tb, bool(transpose))
         a = ds.atoms.get(key)
         if a is None:
             nz = np.argwhere(T != 0.0)
@@ -283,7 +286,7 @@ def get_atom(space, T, weights, meas, op=None, transpose=False):
     if mk != ("dx",):
         raise NotImplementedError("bilinear forms restricted to a cell sub-domain")
     specs = _weight_specs(weights)
-    key = ("atom", T.tobytes(), tuple(s[4] for s in specs))
+    key = ("atom", tb, tuple(s[4] for s in specs))
     a = ds.atoms.get(key)
     if a is None:
         vals = ds.assemble_bilinear(T, weights=specs)
@@ -406,10 +409,69 @@ lazy._flush_hook[0] = _flush
 
 
 # ------------------------------------------------------------------------------- public assemble
+_UNIT_T = {}  # (bs, g, comp_a, slot_a, comp_b, slot_b, coef) -> form tensor (shared, read-only)
+_TBYTES = {}  # id(T) of the shared tensors above -> T.tobytes() (atom cache key)
+
+
+def _fast_functional(meas, m):
+    """Mode integral with exactly two Function operands of one space (F*G*dx, F.dx(i)*G.dx(j)*dx, op(F, G)*dx,
+    times float constants): the overwhelmingly common functional of a separated-form callback.  Builds the
+    LazyScalar leaf directly -- same semantics as compile_form + Group.tensor, ~5x less host work.  Returns
+    None for anything else (the general path then decides or raises)."""
+    coef = m.coef
+    f1 = f2 = op = None
+    for f in m.factors:
+        k = f.leaf.kind
+        if k == "function":
+            if f1 is None:
+                f1 = f
+            elif f2 is None:
+                f2 = f
+            else:
+                return None
+        elif k == "constant":
+            v = f.leaf.value
+            if isinstance(v, float):
+                coef *= v
+            else:
+                return None
+        elif k == "operator":
+            if op is not None:
+                return None
+            op = f.leaf
+        else:
+            return None
+    if f2 is None or coef == 0.0:
+        return None
+    space = f1.leaf.V
+    if not _same_space(f2.leaf.V, space):
+        return None
+    if meas.domain is not None and meas.domain is not space.mesh():
+        return None
+    if meas.kind != "dx" or meas.subdomain_id is not None:
+        return None
+    if op is not None and (f1.deriv is not None or f2.deriv is not None or not _same_space(op.V, space)):
+        return None
+    key = (space.bs, space.mesh().gdim, f1.comp or 0, _slot(f1.deriv), f2.comp or 0, _slot(f2.deriv), coef)
+    T = _UNIT_T.get(key)
+    if T is None:
+        T = np.zeros((key[0], key[1] + 1, key[0], key[1] + 1))
+        T[key[2], key[3], key[4], key[5]] = coef
+        T.setflags(write=False)
+        _UNIT_T[key] = T
+        _TBYTES[id(T)] = T.tobytes()
+    return LazyScalar("leaf", (_Functional("bil", space, T, (), meas, f1.leaf, f2.leaf, op),))
+
+
 def assemble(form):
     """dolfin.assemble: rank 0 -> LazyScalar, rank 1 -> DeviceVector, rank 2 -> AssembledMatrix."""
     if not isinstance(form, Form):
         raise TypeError("assemble expects a Form, got %r" % type(form))
+    ints = form.integrals
+    if len(ints) == 1 and len(ints[0].monos) == 1:
+        fast = _fast_functional(ints[0].measure, ints[0].monos[0])
+        if fast is not None:
+            return fast
     groups = compile_form(form)
     if not groups:
         return lazy.constant(0.0)

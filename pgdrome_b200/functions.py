@@ -17,6 +17,7 @@ from . import _lib
 from .fem import FunctionSpace, tabulate_lagrange
 from . import lazy as _lazy
 from .lazy import LazyScalar
+from .ufl import Expr as _Expr
 from .ufl import Leaf
 
 DOLFIN_EPS = 3.0e-16
@@ -261,9 +262,7 @@ class MatrixOperator(Leaf):
 
     def __call__(self, u, v):
         """Form integrand with u in the trial (column) role and v in the test (row) role."""
-        from .ufl import Expr
-
-        u, v = Expr.wrap(u), Expr.wrap(v)
+        u, v = _Expr.wrap(u), _Expr.wrap(v)
         if u is None or v is None or not (u.is_scalar and v.is_scalar):
             raise NotImplementedError("MatrixOperator needs scalar operands")
         return self * v * u
