@@ -21,10 +21,18 @@ if ROOT not in sys.path:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="thermal3d", choices=["heat2d_tk", "elasticity3d", "thermal3d"])
-    ap.add_argument("--n", type=int, default=None)
+    ap.add_argument("--size", "--n", dest="n", type=int, default=None, help="cells per edge of the spatial mesh")
     ap.add_argument("--modes", type=int, default=3)
     ap.add_argument("--rtol", type=float, default=1e-13)
     a = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world > 1:  # torchrun: the spatial solves are sharded over all ranks (settings["sharded"] = "auto")
+        import torch.distributed as dist
+
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from pgdrome_b200 import _lib, configs
 
     peak = 6451.2
@@ -59,7 +67,7 @@ def main():
     s = _lib.stats()
     it_bytes = 12 * nnz + 4 * (n + 1) + 56 * n
     it_ms = s["pcg_ms"] / max(s["pcg_iters"], 1)
-    out = {"config": a.config, "spatial_dofs": n, "nnz": nnz, "dims": [v.n_dofs for v in p.V], "modes": p.PGD_modes,
+    out = {"config": a.config, "world": world, "sharded_solves": p.solver_stats.get("sharded_solves", 0), "spatial_dofs": n, "nnz": nnz, "dims": [v.n_dofs for v in p.V], "modes": p.PGD_modes,
            "build_problem_s": t_build, "steps": steps, "amplitude": [float(x) for x in p.amplitude],
            "pcg": {"iterations": s["pcg_iters"], "ms_per_iteration": it_ms, "bytes_per_iteration": it_bytes,
                    "gbs": it_bytes / (it_ms * 1e-3) / 1e9 if s["pcg_iters"] else None,
@@ -67,7 +75,12 @@ def main():
                    "share_of_step_time": s["pcg_ms"] / max(sum(x["ms"] for x in steps), 1e-9)},
            "enrichment_steps_per_s": len(steps) / (sum(x["ms"] for x in steps) * 1e-3),
            "device_mem_gb": torch.cuda.max_memory_allocated() / 1e9}
-    print(json.dumps(out))
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
