@@ -17,6 +17,7 @@
 #include <nccl.h>
 
 #include "common.cuh"
+#include "spmv_bulk.cuh"
 
 struct NcclApi {
     void* lib;
@@ -207,19 +208,19 @@ __global__ void k_halo_wait(unsigned char* mine, PwHalo hp, PwLayout lay, int wo
     if (r == 0) *seq_ctr = seq;
 }
 
-// vals: device pointer to nv (<= 4) doubles, reduced in place
-__global__ void k_allreduce_p2p(double* vals, int nv, PwPeers peers, PwLayout lay, int me, int world,
-                                unsigned long long* seq_ctr, int* fl, int skip_when_done) {
-    if (skip_when_done && fl[0]) return;
+// One-shot mailbox all-reduce executed by ONE CTA (threads 0..world-1 talk to one peer each):
+// vals: nv (<= 4) doubles, reduced in place; every rank sums the mailboxes in rank order.
+__device__ __forceinline__ void ar_p2p_block(double* vals, int nv, const PwPeers& peers, const PwLayout& lay, int me,
+                                             int world, unsigned long long* seq_ctr, int* fl) {
+    __shared__ int s_bad;
     const unsigned long long seq = *seq_ctr + 1ULL;
     const int par = (int)(seq & 1ULL);
     const int r = threadIdx.x;
-    __shared__ int s_bad;
     if (r == 0) s_bad = 0;
     __syncthreads();
     if (r < world) {
         double* slot = reinterpret_cast<double*>(peers.base[r] + lay.slot_off()) + ((size_t)par * PW_MAXR + me) * PW_AR_VALS;
-        for (int k = 0; k < nv; ++k) slot[k] = vals[k];
+        for (int k = 0; k < nv; ++k) slot[k] = *((volatile double*)&vals[k]);
         __threadfence_system();
         st_release_sys(reinterpret_cast<unsigned long long*>(peers.base[r] + lay.arflag_off()) + par * PW_MAXR + me, seq);
         const unsigned long long* f =
@@ -246,6 +247,157 @@ __global__ void k_allreduce_p2p(double* vals, int nv, PwPeers peers, PwLayout la
             }
         }
         *seq_ctr = seq;
+    }
+    __syncthreads();
+}
+
+__global__ void k_allreduce_p2p(double* vals, int nv, PwPeers peers, PwLayout lay, int me, int world,
+                                unsigned long long* seq_ctr, int* fl, int skip_when_done) {
+    if (skip_when_done && fl[0]) return;
+    ar_p2p_block(vals, nv, peers, lay, me, world, seq_ctr, fl);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused iteration of the peer-window path: 4 launches, the collectives inside the compute kernels.
+//   k_halo_push_pre        boundary entries of p = z + beta p_old stored into the neighbours' ghost slots over
+//                          NVLink (+ flag), then the plain direction kernel updates p in place
+//   k_spcg_matvec_p2p      every CTA first acquires the neighbours' halo flags, then the TMA-pipelined
+//                          SpMV q = A_loc p with the local p.q; the CTA that finishes the grid reduction
+//                          runs the mailbox all-reduce of p.q with the other GPUs
+//   k_spcg_update_p2p      x, r, z update with local r.z, r.r; the finishing CTA all-reduces both and rotates
+//                          the CG scalars / iteration counter / convergence flag
+// ------------------------------------------------------------------------------------------------
+enum { S_RZ_OLD = 0, S_RZ_NEW = 1, S_PQ = 2, S_RR = 3, S_BB = 4, S_TOL2 = 5, S_TMP = 8 };
+enum { F_DONE = 0, F_ITER = 1, F_BAD = 2 };
+
+// boundary entries of the NEW direction p = z + beta p_old, formed from z and p_old (the same fma the direction
+// kernel evaluates right afterwards => bitwise identical) and stored into the neighbours' ghost slots
+__global__ void __launch_bounds__(256) k_halo_push_pre(const double* __restrict__ z, const double* __restrict__ p_old,
+                                                       const double* sc, const int* fl,
+                                                       const int64_t* __restrict__ send_idx, int64_t n_send, PwPeers peers,
+                                                       PwHalo hp, PwLayout lay, int me, int world,
+                                                       const unsigned long long* halo_ctr, unsigned int* counter) {
+    if (fl[F_DONE]) return;
+    __shared__ bool s_last;
+    const double beta = (fl[F_ITER] == 0) ? 0.0 : sc[S_RZ_NEW] / sc[S_RZ_OLD];
+    const unsigned long long seq = *halo_ctr + 1ULL;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_send; s += stride) {
+        int r = 0;
+        while (s >= hp.seg_start[r + 1]) ++r;
+        const int64_t i = send_idx[s];
+        double* dst = reinterpret_cast<double*>(peers.base[r]) + hp.dst_off[r] + (s - hp.seg_start[r]);
+        *dst = fma(beta, p_old[i], z[i]);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(counter, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence_system();
+    if ((int)threadIdx.x < world && (int)threadIdx.x != me && hp.seg_start[threadIdx.x + 1] > hp.seg_start[threadIdx.x]) {
+        unsigned long long* f = reinterpret_cast<unsigned long long*>(peers.base[threadIdx.x] + lay.haloflag_off()) + me;
+        st_release_sys(f, seq);
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+}
+
+__global__ void __launch_bounds__(BK_THREADS, 2) k_spcg_matvec_p2p(const int32_t* __restrict__ rowptr,
+                                                                   const int32_t* __restrict__ colidx,
+                                                                   const double* __restrict__ vals, const double* p,
+                                                                   double* __restrict__ q, int64_t n, double* sc, int* fl,
+                                                                   double* part, unsigned int* counter, PwPeers peers,
+                                                                   PwHalo hp, PwLayout lay, int me, int world,
+                                                                   unsigned long long* halo_ctr, unsigned long long* ar_ctr) {
+    extern __shared__ __align__(128) unsigned char bk_smem[];
+    if (fl[F_DONE]) return;
+    // ---- acquire the halo of p (the neighbours stored it into this rank's ghost slots)
+    const unsigned long long hseq = *halo_ctr + 1ULL;
+    if ((int)threadIdx.x < world && hp.recv_from[threadIdx.x]) {
+        const unsigned long long* f =
+            reinterpret_cast<const unsigned long long*>(peers.base[me] + lay.haloflag_off()) + threadIdx.x;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) < hseq) {
+            if (clock64() - t0 > PW_SPIN_BUDGET) {
+                fl[F_BAD] = 2;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- q = A_loc p (p is read through L2: its ghost tail was written by peers), local p.q
+    double acc = 0.0;
+    struct GatherCG {
+        const double* x;
+        // plain (L1-cached, not .nc) loads: peers write p's ghost tail while this kernel is resident, but no line
+        // of p is touched by this SM before the acquire above
+        __device__ __forceinline__ double operator()(int c) const { return x[c]; }
+    };
+    bk_spmv_rows(rowptr, colidx, vals, n, GatherCG{p},
+                 [&](int64_t row, double s) {
+                     q[row] = s;
+                     acc = fma(p[row], s, acc);
+                 },
+                 bk_smem);
+    acc = block_sum(acc);
+    double v[1] = {acc};
+    const bool last = grid_sum_finish<1>(v, part, counter, sc + S_PQ, blockIdx.x, gridDim.x);
+    if (!last) return;
+    __syncthreads();
+    if (threadIdx.x == 0) *halo_ctr = hseq;  // every CTA has passed its wait (it arrived at the reduction counter)
+    ar_p2p_block(sc + S_PQ, 1, peers, lay, me, world, ar_ctr, fl);
+    if (threadIdx.x == 0 && fl[F_BAD] == 2) fl[F_DONE] = 1;
+}
+
+template <int BS>
+__global__ void __launch_bounds__(256) k_spcg_update_p2p(double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
+                                                         const double* p, const double* __restrict__ q,
+                                                         const double* __restrict__ minv, int64_t n_nodes, double* sc, int* fl,
+                                                         double* part, unsigned int* counter, PwPeers peers, PwLayout lay,
+                                                         int me, int world, unsigned long long* ar_ctr) {
+    if (fl[F_DONE]) return;
+    const double alpha = sc[S_RZ_NEW] / sc[S_PQ];
+    const double rz_cur = sc[S_RZ_NEW];
+    const int it = fl[F_ITER];
+    double rz = 0.0, rr = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t nd = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; nd < n_nodes; nd += stride) {
+        double rn[BS];
+#pragma unroll
+        for (int i = 0; i < BS; ++i) {
+            const int64_t d = nd * BS + i;
+            x[d] = fma(alpha, p[d], x[d]);
+            rn[i] = fma(-alpha, q[d], r[d]);
+            r[d] = rn[i];
+            rr = fma(rn[i], rn[i], rr);
+        }
+#pragma unroll
+        for (int i = 0; i < BS; ++i) {
+            double zi = 0.0;
+#pragma unroll
+            for (int k = 0; k < BS; ++k) zi = fma(__ldg(&minv[(nd * BS + i) * BS + k]), rn[k], zi);
+            z[nd * BS + i] = zi;
+            rz = fma(rn[i], zi, rz);
+        }
+    }
+    rz = block_sum(rz);
+    rr = block_sum(rr);
+    double v[2] = {rz, rr};
+    const bool last = grid_sum_finish<2>(v, part, counter, sc + S_TMP, blockIdx.x, gridDim.x);
+    if (!last) return;
+    __syncthreads();
+    ar_p2p_block(sc + S_TMP, 2, peers, lay, me, world, ar_ctr, fl);
+    if (threadIdx.x == 0 && !fl[F_DONE]) {  // scalar rotation (identical on every rank)
+        const double rz_next = sc[S_TMP], rr_new = sc[S_TMP + 1];
+        sc[S_RZ_OLD] = rz_cur;
+        sc[S_RZ_NEW] = rz_next;
+        sc[S_RR] = rr_new;
+        fl[F_ITER] = it + 1;
+        if (!(rr_new > sc[S_TOL2])) fl[F_DONE] = 1;
+        if (!(rr_new == rr_new) || !(rz_next == rz_next)) fl[F_BAD] = 1;
     }
 }
 
@@ -367,9 +519,43 @@ extern "C" int32_t pgd_spcg_solve_sync(pgd_handle_t h, const int32_t* d_rowptr, 
     int hf[4] = {0, 0, 0, 0};
     int launched = 0;
     PGD_CUDA(h, cudaEventRecord(h->ev0, st));
+    const bool fused = p2p && h->opt_fused;
+    if (fused) PGD_CUDA(h, cudaFuncSetAttribute(k_spcg_matvec_p2p, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM_BYTES));
     auto enqueue_iteration = [&](cudaStream_t st) -> int32_t {
         void* stream = (void*)st;
         int32_t rc2;
+        if (fused) {
+            double* w_r = d_work;
+            double* w_z = w_r + n_owned;
+            double* w_q = w_z + n_owned;
+            double* w_minv = w_q + n_owned;
+            if (n_send) {
+                unsigned int pb = pgd_blocks(n_send, 256);
+                if (pb > 64) pb = 64;
+                k_halo_push_pre<<<pb, 256, 0, st>>>(w_z, p, sc, fl, d_send_idx, n_send, peers, hp, lay, me, world, seq_halo,
+                                                    h->counters + (PGD_MAX_COUNTERS - 2));
+            }
+            if ((rc2 = pgd_spcg_direction(h, d_work, n_owned, block, sc, fl, stream))) return rc2;
+            k_spcg_matvec_p2p<<<2 * h->sm_count, BK_THREADS, BK_SMEM_BYTES, st>>>(d_rowptr, d_colidx, d_values, p, w_q, n_owned, sc,
+                                                                                   fl, h->partials, h->counters, peers, hp, lay,
+                                                                                   me, world, seq_halo, seq_ar);
+            const int64_t n_nodes = n_owned / block;
+            unsigned int vb = pgd_blocks(n_nodes, 256);
+            unsigned int capv = (unsigned int)h->sm_count * 8;
+            if (vb > capv) vb = capv;
+            if (vb < 1) vb = 1;
+            if (block == 1)
+                k_spcg_update_p2p<1><<<vb, 256, 0, st>>>(d_x, w_r, w_z, p, w_q, w_minv, n_nodes, sc, fl, h->partials, h->counters,
+                                                         peers, lay, me, world, seq_ar);
+            else if (block == 2)
+                k_spcg_update_p2p<2><<<vb, 256, 0, st>>>(d_x, w_r, w_z, p, w_q, w_minv, n_nodes, sc, fl, h->partials, h->counters,
+                                                         peers, lay, me, world, seq_ar);
+            else
+                k_spcg_update_p2p<3><<<vb, 256, 0, st>>>(d_x, w_r, w_z, p, w_q, w_minv, n_nodes, sc, fl, h->partials, h->counters,
+                                                         peers, lay, me, world, seq_ar);
+            h->n_launches += 3;
+            return (int32_t)cudaGetLastError();
+        }
         if ((rc2 = pgd_spcg_direction(h, d_work, n_owned, block, sc, fl, stream))) return rc2;
         if (p2p) {
             if (n_send) {

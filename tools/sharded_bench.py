@@ -132,15 +132,19 @@ if __name__ == "__main__":
     ap.add_argument("--bs", type=int, default=1)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--graph", action="store_true")
+    ap.add_argument("--fused", action="store_true", help="peer-window path with the collectives fused into the SpMV / update kernels")
     ap.add_argument("--no-cgraph", action="store_true", help="peer-window path without CUDA-graph replay")
     ap.add_argument("--no-p2p", action="store_true", help="NCCL send/recv + allreduce instead of the NVLink peer window")
     ap.add_argument("--host-loop", action="store_true", help="torch.distributed-driven iteration instead of the C loop")
     a = ap.parse_args()
-    if a.no_cgraph:
+    if a.no_cgraph or a.fused:
         from pgdrome_b200 import _lib as _l
 
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-        _l.set_option("graph", 0)
+        if a.no_cgraph:
+            _l.set_option("graph", 0)
+        if a.fused:
+            _l.set_option("fused", 1)
     r = run(a.mesh, a.iters, a.check, a.graph, a.bs, host_loop=a.host_loop, p2p=not a.no_p2p)
     if r is not None:
         print(json.dumps(r))
