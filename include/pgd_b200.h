@@ -125,7 +125,7 @@ int32_t pgd_panel_dots(pgd_handle_t h, const double* d_P, int64_t ld, int32_t n_
  * solver.py:579-595,627-636,651-674,704-716; FD_solve spsolve solver.py:927-943).
  * Jacobi-PCG, x0 = 0, stop ||r|| <= max(rtol*||b||, atol); convergence flag and iteration counter
  * live on the device, the host only polls them every check_every iterations.
- * d_work: 6*n doubles.  block = 1 (point Jacobi) or bs (bs x bs node-block Jacobi, bs <= 3). */
+ * d_work: (5+block)*n + 8 doubles.  block = 1 (point Jacobi) or bs (bs x bs node-block Jacobi, bs <= 3). */
 int32_t pgd_pcg_sync(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
                      const double* d_b, double* d_x, int64_t n, double rtol, double atol, int32_t maxit,
                      int32_t check_every, int32_t block, int32_t lanes_per_row, double* d_work,

@@ -493,8 +493,8 @@ def pcg(rowptr, colidx, values, b, x=None, rtol=1e-12, atol=0.0, maxit=20000, ch
         x = x0.detach().clone() if x is None else x.copy_(x0)
     elif x is None:
         x = torch.empty(n, dtype=F64, device=b.device)
-    if work is None or work.numel() < (5 + block) * n:
-        work = torch.empty((5 + block) * n, dtype=F64, device=b.device)
+    if work is None or work.numel() < (5 + block) * n + 8:
+        work = torch.empty((5 + block) * n + 8, dtype=F64, device=b.device)
     iters, relres = c_i32(0), c_dbl(0.0)
     fn = lib.pgd_pcg_x0_sync if x0 is not None else lib.pgd_pcg_sync
     _check(fn(h, _p(rowptr, I32), _p(colidx, I32), _p(values, F64), _p(b, F64), _p(x, F64), n, rtol, atol,

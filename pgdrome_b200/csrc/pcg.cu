@@ -175,7 +175,53 @@ __global__ void __launch_bounds__(256) k_pcg_update(double* __restrict__ x, doub
     const double alpha = rz_cur / sc[S_PQ];
     double rz = 0.0, rr = 0.0;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t nd = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; nd < n_nodes; nd += stride) {
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool vec = false;
+    if constexpr (BS == 1) {
+        // point Jacobi: two rows per thread with 128-bit loads/stores when the six arrays are 16-byte aligned
+        vec = (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(z) |
+                 reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(minv)) & 15) == 0);
+        if (vec) {
+            const int64_t n2 = n_nodes >> 1;
+            double2* x2 = reinterpret_cast<double2*>(x);
+            double2* r2 = reinterpret_cast<double2*>(r);
+            double2* z2 = reinterpret_cast<double2*>(z);
+            const double2* p2 = reinterpret_cast<const double2*>(p);
+            const double2* q2 = reinterpret_cast<const double2*>(q);
+            const double2* m2 = reinterpret_cast<const double2*>(minv);
+            double rz1 = 0.0, rr1 = 0.0;
+#pragma unroll 2
+            for (int64_t i = gtid; i < n2; i += stride) {
+                const double2 pv = p2[i], qv = q2[i], mv = __ldg(m2 + i);
+                double2 xv = x2[i], rv = r2[i];
+                xv.x = fma(alpha, pv.x, xv.x);
+                xv.y = fma(alpha, pv.y, xv.y);
+                rv.x = fma(-alpha, qv.x, rv.x);
+                rv.y = fma(-alpha, qv.y, rv.y);
+                const double2 zv = make_double2(mv.x * rv.x, mv.y * rv.y);
+                x2[i] = xv;
+                r2[i] = rv;
+                z2[i] = zv;
+                rr = fma(rv.x, rv.x, rr);
+                rr1 = fma(rv.y, rv.y, rr1);
+                rz = fma(rv.x, zv.x, rz);
+                rz1 = fma(rv.y, zv.y, rz1);
+            }
+            rr += rr1;
+            rz += rz1;
+            if ((n_nodes & 1) && gtid == 0) {
+                const int64_t d = n_nodes - 1;
+                x[d] = fma(alpha, p[d], x[d]);
+                const double rn = fma(-alpha, q[d], r[d]);
+                r[d] = rn;
+                const double zi = minv[d] * rn;
+                z[d] = zi;
+                rr = fma(rn, rn, rr);
+                rz = fma(rn, zi, rz);
+            }
+        }
+    }
+    for (int64_t nd = vec ? n_nodes : gtid; nd < n_nodes; nd += stride) {
         double rn[BS];
 #pragma unroll
         for (int i = 0; i < BS; ++i) {
@@ -280,12 +326,13 @@ static int32_t run_pcg(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const d
                        int64_t n, double rtol, double atol, int maxit, int check_every, int lpr, double* work,
                        int32_t* h_iters, double* h_relres, cudaStream_t st, bool warm) {
     const int64_t n_nodes = n / BS;
+    const int64_t ns = (n + 1) & ~(int64_t)1;  // even stride: the work arrays stay 16-byte aligned (128-bit vector path)
     double* r = work;
-    double* z = r + n;
-    double* p0 = z + n;
-    double* p1 = p0 + n;
-    double* q = p1 + n;
-    double* minv = q + n;  // n*BS
+    double* z = r + ns;
+    double* p0 = z + ns;
+    double* p1 = p0 + ns;
+    double* q = p1 + ns;
+    double* minv = q + ns;  // n*BS
     double* sc = h->scalars;
     int* fl = h->flags;
     unsigned int vb = pgd_blocks(n_nodes, 256);

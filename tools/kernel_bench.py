@@ -101,7 +101,7 @@ def run(mesh_n=128, hbm_peak=6451.2, evaluate=True, fp64_peak=None):
     entry("bilinear_functional", ms, spmv_bytes, lanes_per_row=lpr)
     # PCG iteration (device time from the library's own events)
     b = _lib.spmv(rowptr, colidx, vals, x, lpr=lpr)
-    work = torch.empty(6 * n, dtype=torch.float64, device=dev)
+    work = torch.empty(6 * n + 8, dtype=torch.float64, device=dev)
     _lib.pcg(rowptr, colidx, vals, b, rtol=1e-30, maxit=20, check_every=20, lpr=lpr, work=work)
     _lib.stats(reset=True)
     _lib.pcg(rowptr, colidx, vals, b, rtol=1e-30, maxit=100, check_every=100, lpr=lpr, work=work)
