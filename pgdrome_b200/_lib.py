@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpgdb200.so")
+LIB_PATH = os.environ.get("PGD_LIB_PATH") or os.path.join(_HERE, "libpgdb200.so")  # override: kernel-variant experiments only
 
 c_i32, c_i64, c_dbl, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
 

@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(256) k_pcg_update(double* __restrict__ x, doub
 }
 
 // TMA-pipelined variant of k_pcg_spmv (spmv_bulk.cuh)
-__global__ void __launch_bounds__(BK_THREADS, 2) k_pcg_spmv_bulk(const int32_t* __restrict__ rowptr,
+__global__ void __launch_bounds__(BK_THREADS, BK_CTAS_PER_SM) k_pcg_spmv_bulk(const int32_t* __restrict__ rowptr,
                                                                  const int32_t* __restrict__ colidx,
                                                                  const double* __restrict__ vals,
                                                                  const double* __restrict__ z, double* pa, double* pb,
@@ -369,7 +369,7 @@ static int32_t run_pcg(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const d
             PGD_CUDA(h, cudaFuncSetAttribute(k_pcg_spmv_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM_BYTES));
         for (int i = 0; i < todo; ++i) {
             if (bulk) {
-                k_pcg_spmv_bulk<<<2 * h->sm_count, BK_THREADS, BK_SMEM_BYTES, st>>>(rp, ci, va, z, p0, p1, q, n, sc, fl, sc,
+                k_pcg_spmv_bulk<<<BK_CTAS_PER_SM * h->sm_count, BK_THREADS, BK_SMEM_BYTES, st>>>(rp, ci, va, z, p0, p1, q, n, sc, fl, sc,
                                                                                     h->partials, h->counters);
             } else if (stream) {
                 k_pcg_spmv_stream<<<stb, ST_THREADS, 0, st>>>(rp, ci, va, z, p0, p1, q, n, sc, fl, sc, h->partials,

@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(256) k_halo_push_pre(const double* __restrict_
     if (threadIdx.x == 0) *counter = 0u;
 }
 
-__global__ void __launch_bounds__(BK_THREADS, 2) k_spcg_matvec_p2p(const int32_t* __restrict__ rowptr,
+__global__ void __launch_bounds__(BK_THREADS, BK_CTAS_PER_SM) k_spcg_matvec_p2p(const int32_t* __restrict__ rowptr,
                                                                    const int32_t* __restrict__ colidx,
                                                                    const double* __restrict__ vals, const double* p,
                                                                    double* __restrict__ q, int64_t n, double* sc, int* fl,
@@ -536,7 +536,7 @@ extern "C" int32_t pgd_spcg_solve_sync(pgd_handle_t h, const int32_t* d_rowptr, 
                                                     h->counters + (PGD_MAX_COUNTERS - 2));
             }
             if ((rc2 = pgd_spcg_direction(h, d_work, n_owned, block, sc, fl, stream))) return rc2;
-            k_spcg_matvec_p2p<<<2 * h->sm_count, BK_THREADS, BK_SMEM_BYTES, st>>>(d_rowptr, d_colidx, d_values, p, w_q, n_owned, sc,
+            k_spcg_matvec_p2p<<<BK_CTAS_PER_SM * h->sm_count, BK_THREADS, BK_SMEM_BYTES, st>>>(d_rowptr, d_colidx, d_values, p, w_q, n_owned, sc,
                                                                                    fl, h->partials, h->counters, peers, hp, lay,
                                                                                    me, world, seq_halo, seq_ar);
             const int64_t n_nodes = n_owned / block;

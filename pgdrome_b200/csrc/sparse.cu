@@ -7,20 +7,20 @@
 #include "spmv_stream.cuh"
 
 // TMA-pipelined SpMV (spmv_bulk.cuh).  MODE as in k_spmv below.
+#define SPMV_BULK_THREADS 512
 template <int MODE>
-__global__ void __launch_bounds__(BK_THREADS, 2) k_spmv_bulk(const int32_t* __restrict__ rowptr,
+__global__ void __launch_bounds__(SPMV_BULK_THREADS, BK_CTAS_PER_SM) k_spmv_bulk(const int32_t* __restrict__ rowptr,
                                                              const int32_t* __restrict__ colidx,
                                                              const double* __restrict__ vals, const double* __restrict__ x,
                                                              double* __restrict__ y, const double* __restrict__ w, int64_t n,
                                                              double* dot, double* part, unsigned int* counter) {
     extern __shared__ __align__(128) unsigned char bk_smem[];
     double acc = 0.0;
-    bk_spmv_rows(rowptr, colidx, vals, n, BkGatherX{x},
-                 [&](int64_t row, double s) {
-                     if (MODE != 2) y[row] = s;
-                     if (MODE != 0) acc = fma(__ldg(&w[row]), s, acc);
-                 },
-                 bk_smem);
+    auto epi = [&](int64_t row, double s) {
+        if (MODE != 2) y[row] = s;
+        if (MODE != 0) acc = fma(__ldg(&w[row]), s, acc);
+    };
+    bk_spmv_rows<BkGatherX, decltype(epi)&, SPMV_BULK_THREADS>(rowptr, colidx, vals, n, BkGatherX{x}, epi, bk_smem);
     if (MODE != 0) {
         acc = block_sum(acc);
         double v[1] = {acc};
@@ -116,7 +116,7 @@ static int32_t launch_spmv(pgd_ctx* h, const int32_t* rp, const int32_t* ci, con
             PGD_CUDA(h, cudaFuncSetAttribute(k_spmv_bulk<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM_BYTES));
             attr_set = true;
         }
-        k_spmv_bulk<MODE><<<2 * h->sm_count, BK_THREADS, BK_SMEM_BYTES, st>>>(rp, ci, va, x, y, w, n, dot, h->partials,
+        k_spmv_bulk<MODE><<<BK_CTAS_PER_SM * h->sm_count, SPMV_BULK_THREADS, BK_SMEM_BYTES, st>>>(rp, ci, va, x, y, w, n, dot, h->partials,
                                                                               h->counters);
         PGD_LAUNCH_OK(h);
         return 0;
