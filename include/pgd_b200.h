@@ -139,8 +139,8 @@ int32_t pgd_pcg_sync(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_c
  * allocates, so an iteration can be captured in a CUDA graph.  Caller-owned device state:
  *   d_sc (>= 16 doubles): [0] r.z old, [1] r.z, [2] p.q, [3] r.r, [4] b.b, [5] tol^2, [8..9] partial sums
  *   d_fl (>= 4 int32):    [0] done, [1] iterations, [2] NaN seen
- *   d_work: n_owned*(3+block) + n_local doubles; p (with its ghost tail) starts at
- *           d_work + n_owned*(3+block); d_x [n_owned] is the solution (x0 = 0).
+ *   d_work: n_owned*(3+block) + n_local + 8 doubles, laid out r, z, q (stride ns = n_owned rounded up to even),
+ *           M^-1, then p with its ghost tail at d_work + 3*ns + even(n_owned*block); d_x [n_owned] is the solution.
  * pgd_spcg_init leaves the local (r.z, b.b, r.r) in d_sc[8..10]: all-reduce them, then pgd_spcg_init_fin. */
 int32_t pgd_spcg_init(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
                       const double* d_b, double* d_x, int64_t n_owned, int64_t n_local, int32_t block, double* d_work,
@@ -161,7 +161,7 @@ int32_t pgd_spcg_rotate(pgd_handle_t h, double* d_sc, int32_t* d_fl, void* strea
  * torch.distributed.broadcast) and every rank calls pgd_comm_init on its handle.  Without a communicator
  * the call is the single-rank solve.  d_send_idx: int64 local owned indices grouped by destination
  * rank; h_send_counts / h_recv_counts: [world] host arrays.
- * d_work: n_owned*(3+block) + n_local + sum(send_counts) doubles. */
+ * d_work: n_owned*(3+block) + n_local + sum(send_counts) + 8 doubles. */
 int32_t pgd_comm_unique_id(void* h_id128);
 int32_t pgd_comm_init(pgd_handle_t h, const void* h_id128, int32_t rank, int32_t world);
 int32_t pgd_comm_destroy(pgd_handle_t h);

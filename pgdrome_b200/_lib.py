@@ -269,7 +269,7 @@ def spcg_solve(A, b, rtol=1e-13, atol=0.0, maxit=10000, check_every=50, block=1,
     halo = A.halo
     world = len(halo.send_counts)
     n_send = int(sum(halo.send_counts))
-    need = A.n_owned * (3 + block) + A.n_local + n_send
+    need = A.n_owned * (3 + block) + A.n_local + n_send + 8
     if work is None or work.numel() < need:
         work = torch.empty(need, dtype=F64, device=b.device)
     x = torch.empty(A.n_owned, dtype=F64, device=b.device)

@@ -163,17 +163,13 @@ __global__ void __launch_bounds__(256) k_pcg_spmv(const int32_t* __restrict__ ro
     grid_sum_finish<1>(v, part, counter, sc_out + S_PQ, blockIdx.x, gridDim.x);
 }
 
+// x += alpha p ; r -= alpha q ; z = M^-1 r over the rows of this grid; accumulates the thread's r.z and r.r.
+// Point Jacobi takes two rows per thread with 128-bit accesses when the six arrays are 16-byte aligned.
 template <int BS>
-__global__ void __launch_bounds__(256) k_pcg_update(double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
-                                                    const double* pa, const double* pb, const double* __restrict__ q,
-                                                    const double* __restrict__ minv, int64_t n_nodes, double* sc, int* fl,
-                                                    double* part, unsigned int* counter) {
-    if (fl[F_DONE]) return;
-    const int it = fl[F_ITER];
-    const double* __restrict__ p = (it & 1) ? pa : pb;  // the p_new written by k_pcg_spmv
-    const double rz_cur = sc[S_RZ_NEW];
-    const double alpha = rz_cur / sc[S_PQ];
-    double rz = 0.0, rr = 0.0;
+__device__ __forceinline__ void pcg_update_rows(double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
+                                                const double* __restrict__ p, const double* __restrict__ q,
+                                                const double* __restrict__ minv, int64_t n_nodes, double alpha, double& rz,
+                                                double& rr) {
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool vec = false;
@@ -240,6 +236,20 @@ __global__ void __launch_bounds__(256) k_pcg_update(double* __restrict__ x, doub
             rz = fma(rn[i], zi, rz);
         }
     }
+}
+
+template <int BS>
+__global__ void __launch_bounds__(256) k_pcg_update(double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
+                                                    const double* pa, const double* pb, const double* __restrict__ q,
+                                                    const double* __restrict__ minv, int64_t n_nodes, double* sc, int* fl,
+                                                    double* part, unsigned int* counter) {
+    if (fl[F_DONE]) return;
+    const int it = fl[F_ITER];
+    const double* __restrict__ p = (it & 1) ? pa : pb;  // the p_new written by k_pcg_spmv
+    const double rz_cur = sc[S_RZ_NEW];
+    const double alpha = rz_cur / sc[S_PQ];
+    double rz = 0.0, rr = 0.0;
+    pcg_update_rows<BS>(x, r, z, p, q, minv, n_nodes, alpha, rz, rr);
     rz = block_sum(rz);
     rr = block_sum(rr);
     double v[2] = {rz, rr};
@@ -496,7 +506,8 @@ extern "C" int32_t pgd_pcg_x0_sync(pgd_handle_t h, const int32_t* d_rowptr, cons
 // All calls are asynchronous launches without host synchronisation or allocation, so the host can
 // capture an iteration (kernels + NCCL collectives) in a CUDA graph.  d_sc: >= 16 doubles, d_fl: >= 4
 // ints, both caller-owned (the collectives operate on slices of d_sc).
-// work layout: r[no] z[no] q[no] minv[no*block] p[nl]   (no = owned rows, nl = owned + ghost)
+// work layout: r[ns] z[ns] q[ns] minv[even(no*block)] p[nl]   (no = owned rows, ns = no rounded up to even,
+// nl = owned + ghost)
 // ================================================================================================
 __global__ void __launch_bounds__(256) k_spcg_direction(const double* __restrict__ z, double* __restrict__ p, int64_t n,
                                                         const double* sc, const int* fl) {
@@ -531,26 +542,7 @@ __global__ void __launch_bounds__(256) k_spcg_update(double* __restrict__ x, dou
     if (fl[F_DONE]) return;
     const double alpha = sc[S_RZ_NEW] / sc[S_PQ];
     double rz = 0.0, rr = 0.0;
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t nd = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; nd < n_nodes; nd += stride) {
-        double rn[BS];
-#pragma unroll
-        for (int i = 0; i < BS; ++i) {
-            int64_t d = nd * BS + i;
-            x[d] = fma(alpha, p[d], x[d]);
-            rn[i] = fma(-alpha, q[d], r[d]);
-            r[d] = rn[i];
-            rr = fma(rn[i], rn[i], rr);
-        }
-#pragma unroll
-        for (int i = 0; i < BS; ++i) {
-            double zi = 0.0;
-#pragma unroll
-            for (int k = 0; k < BS; ++k) zi = fma(__ldg(&minv[(nd * BS + i) * BS + k]), rn[k], zi);
-            z[nd * BS + i] = zi;
-            rz = fma(rn[i], zi, rz);
-        }
-    }
+    pcg_update_rows<BS>(x, r, z, p, q, minv, n_nodes, alpha, rz, rr);
     rz = block_sum(rz);
     rr = block_sum(rr);
     double v[2] = {rz, rr};
@@ -573,11 +565,12 @@ struct SpcgWork {
 };
 static SpcgWork spcg_work(pgd_ctx* h, double* work, int64_t no, int block) {
     SpcgWork w;
+    const int64_t ns = (no + 1) & ~(int64_t)1;  // even strides keep every array 16-byte aligned (128-bit vector paths)
     w.r = work;
-    w.z = w.r + no;
-    w.q = w.z + no;
-    w.minv = w.q + no;
-    w.p = h->p_override ? h->p_override : w.minv + no * block;
+    w.z = w.r + ns;
+    w.q = w.z + ns;
+    w.minv = w.q + ns;
+    w.p = h->p_override ? h->p_override : w.minv + ((no * block + 1) & ~(int64_t)1);
     return w;
 }
 

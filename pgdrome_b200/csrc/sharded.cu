@@ -479,10 +479,12 @@ extern "C" int32_t pgd_spcg_solve_sync(pgd_handle_t h, const int32_t* d_rowptr, 
     if (world > 1)
         for (int r = 0; r < world; ++r) n_send += h_send_counts[r];
     PGD_ARG(h, n_send == 0 || d_send_idx, "send index list required");
-    // work: r z q minv p[n_local] sendbuf[n_send]   (p2p: p lives in the peer window instead)
+    // work: r z q minv p[n_local] sendbuf[n_send]   (p2p: p lives in the peer window instead); even strides
+    const int64_t ns = (n_owned + 1) & ~(int64_t)1;
+    const int64_t p_off = 3 * ns + ((n_owned * block + 1) & ~(int64_t)1);
     h->p_override = p2p ? reinterpret_cast<double*>(h->win_local) : nullptr;
-    double* p = p2p ? h->p_override : d_work + n_owned * (3 + block);
-    double* sendbuf = d_work + n_owned * (3 + block) + n_local;
+    double* p = p2p ? h->p_override : d_work + p_off;
+    double* sendbuf = d_work + p_off + ((n_local + 1) & ~(int64_t)1);
     double* sc = h->scalars;
     int* fl = h->flags;
     PwPeers peers;
@@ -526,9 +528,9 @@ extern "C" int32_t pgd_spcg_solve_sync(pgd_handle_t h, const int32_t* d_rowptr, 
         int32_t rc2;
         if (fused) {
             double* w_r = d_work;
-            double* w_z = w_r + n_owned;
-            double* w_q = w_z + n_owned;
-            double* w_minv = w_q + n_owned;
+            double* w_z = w_r + ns;
+            double* w_q = w_z + ns;
+            double* w_minv = w_q + ns;
             if (n_send) {
                 unsigned int pb = pgd_blocks(n_send, 256);
                 if (pb > 64) pb = 64;

@@ -160,8 +160,10 @@ class _DeviceOps:
         self._lib, self.A, self.block = _lib, A, block
         dev = A.rowptr.device
         no, nl = A.n_owned, A.n_local
-        self.work = torch.empty(no * (3 + block) + nl, dtype=F64, device=dev)
-        self.p = self.work[no * (3 + block):]
+        ns = (no + 1) & ~1  # the library keeps every work array on an even offset (pgd_b200.h)
+        p_off = 3 * ns + ((no * block + 1) & ~1)
+        self.work = torch.empty(p_off + nl + 8, dtype=F64, device=dev)
+        self.p = self.work[p_off:p_off + nl]
         self.sc = torch.zeros(16, dtype=F64, device=dev)
         self.fl = torch.zeros(4, dtype=I32, device=dev)
 
