@@ -12,7 +12,9 @@
  *   - return 0 = OK, >0 = cudaError_t, <0 = argument error; pgd_last_error(h) gives the text.
  *   - asynchronous on `stream` (a cudaStream_t passed as void*) unless the name ends in _sync.
  *   - one host thread and one stream at a time per handle; one handle per GPU / rank.
- *   - reductions are deterministic (fixed-order two-stage sums, no floating-point atomics).
+ *   - reductions are deterministic (fixed-order two-stage sums, no floating-point atomics); the one exception is
+ *     the right-hand-side lifting of NON-ZERO Dirichlet values in pgd_apply_dirichlet (atomicAdd per touched row;
+ *     every reference example prescribes 0, for which nothing is added).
  */
 #ifndef PGD_B200_H
 #define PGD_B200_H

@@ -1,11 +1,15 @@
-// Jacobi / node-block-Jacobi preconditioned CG, two kernels per iteration, all scalars and the
-// convergence flag on the device (the host polls once per `check_every` iterations).
-//   k_pcg_spmv[_stream]: p_new = z + beta p_old (fused into the gather), q = A p_new, pq = p_new.q
-//   k_pcg_update       : alpha = rz/pq; x += alpha p; r -= alpha q; z = M^-1 r; rz' = r.z, rr = r.r;
-//                        the block that finishes the reduction rotates rz, bumps the iteration
-//                        counter and sets DONE (every other block has consumed the old scalars
-//                        before it deposited its partials, so there is no ordering hazard).
-// Reductions are fixed-order two-stage sums (bitwise reproducible).
+// Jacobi / node-block-Jacobi preconditioned CG with all scalars and the convergence flag on the device
+// (the host polls once per `check_every` iterations).  Three regimes, chosen per solve:
+//   * the system fits on chip            -> pcg_resident.cu: ONE cooperative kernel per solve
+//   * n >= PGD_BULK_MIN_ROWS (HBM-bound) -> 3 launches per iteration: k_spcg_direction (p = z + beta p),
+//                                           k_spmv_bulk<1> (q = A p with p.q, TMA ring, 512-thread CTAs), k_pcg_update
+//   * in between                         -> 2 launches: k_pcg_spmv[_stream|_bulk] (p_new = z + beta p_old fused into
+//                                           the gather, q = A p_new, p.q) and k_pcg_update
+//   k_pcg_update: alpha = rz/pq; x += alpha p; r -= alpha q; z = M^-1 r; rz' = r.z, rr = r.r; the block that
+//                 finishes the reduction rotates rz, bumps the iteration counter and sets DONE (every other
+//                 block has consumed the old scalars before it deposited its partials: no ordering hazard).
+// Reductions are fixed-order two-stage sums (bitwise reproducible).  The sharded (multi-GPU) building blocks
+// pgd_spcg_* at the end of this file reuse the same kernels with the reductions completed across ranks.
 #include "common.cuh"
 #include "spmv_bulk.cuh"
 #include "spmv_stream.cuh"
@@ -97,12 +101,7 @@ __global__ void __launch_bounds__(256) k_pcg_init(const int32_t* __restrict__ ro
     bb = block_sum(bb);
     rr = block_sum(rr);
     double v[3] = {rz, bb, rr};
-    grid_sum_finish<3>(v, part, counter, sc + S_TMP, blockIdx.x, gridDim.x);
-    // the block that finished the reduction publishes the scalars
-    if (threadIdx.x == 0) {
-        // grid_sum_finish left s_last in shared memory of the last block only; recompute cheaply:
-        // the last block is the one that reset the counter, detectable through sc[S_TMP] being final.
-    }
+    grid_sum_finish<3>(v, part, counter, sc + S_TMP, blockIdx.x, gridDim.x);  // k_pcg_init_fin publishes the scalars
 }
 
 // single-thread epilogue of init (keeps k_pcg_init simple and race-free)

@@ -1,7 +1,7 @@
-// CSR kernels: SpMV (sub-warp per row), fused SpMV+dot, bilinear functional x^T A y, Dirichlet.
-// All are HBM-bound: matrix values/indices are streamed once (ld.global.cs), x is gathered through
-// the read-only path and stays L2-resident; rows are processed by LPR-lane groups so that a warp
-// reads a contiguous run of the CSR arrays.
+// CSR kernels: SpMV, fused SpMV+dot, bilinear functional x^T A y (one template, three modes), Dirichlet.
+// Three SpMV cores by size: k_spmv_bulk (n >= 32 768 rows: TMA ring, spmv_bulk.cuh), k_spmv_stream (n >= 8 192:
+// register-staged row blocks, spmv_stream.cuh) and k_spmv (sub-warp per row, latency-bound small systems).
+// Matrix values/indices are streamed once, x is gathered through the read-only path and stays L2-resident.
 #include "common.cuh"
 #include "spmv_bulk.cuh"
 #include "spmv_stream.cuh"
@@ -96,15 +96,6 @@ __global__ void __launch_bounds__(256) k_spmv(const int32_t* __restrict__ rowptr
         double v[1] = {acc};
         grid_sum_finish<1>(v, part, counter, dot, blockIdx.x, gridDim.x);
     }
-}
-
-static int auto_lpr(int64_t n, int64_t nnz_hint) {
-    double m = (n > 0) ? (double)nnz_hint / (double)n : 8.0;
-    if (m <= 3.0) return 2;
-    if (m <= 6.0) return 4;
-    if (m <= 12.0) return 8;
-    if (m <= 24.0) return 16;
-    return 32;
 }
 
 template <int MODE>
