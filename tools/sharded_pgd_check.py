@@ -16,7 +16,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
-def main(n=96, nmax=3):
+def main():
     import torch.distributed as dist
 
     from pgdrome_b200 import configs
@@ -24,15 +24,28 @@ def main(n=96, nmax=3):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cases = [("heat2d_tk", lambda: configs.heat2d_tk(n=96, nt=40, nk=10, PGD_nmax=3)),
+             ("elasticity3d (vector P1, node-block Jacobi)", lambda: configs.elasticity3d(n=12, nE=8, nF=2, PGD_nmax=2)),
+             ("thermal3d", lambda: configs.thermal3d(n=20, nt=30, nP=4, nv=4, n_src=3, PGD_nmax=2))]
+    for name, make in cases:
+        check(name, make)
+    dist.destroy_process_group()
+
+
+def check(name, make):
+    import torch.distributed as dist
+
     rank = dist.get_rank()
-    a = configs.heat2d_tk(n=n, nt=40, nk=10, PGD_nmax=nmax)
+    n = 0
+    nmax = 0
+    a = make()
     a.solve_PGD(_problem="linear", settings={"sharded": False})
-    b = configs.heat2d_tk(n=n, nt=40, nk=10, PGD_nmax=nmax)
+    b = make()
     b.solve_PGD(_problem="linear", settings={"sharded": True})
     assert b.solver_stats.get("sharded_solves", 0) > 0 and a.solver_stats.get("sharded_solves", 0) == 0
     assert a.PGD_modes == b.PGD_modes and a.num_fp_it == b.num_fp_it, (a.num_fp_it, b.num_fp_it)
     worst = 0.0
-    for d in range(3):
+    for d in range(len(a.V)):
         for k in range(a.PGD_modes):
             u, v = a.PGD_func[d][k].vector()[:], b.PGD_func[d][k].vector()[:]
             worst = max(worst, min(np.linalg.norm(u - v), np.linalg.norm(u + v)) / np.linalg.norm(u))
@@ -45,10 +58,9 @@ def main(n=96, nmax=3):
     dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     assert float(lo) == float(hi)
     if rank == 0:
-        print(json.dumps({"ok": True, "world": dist.get_world_size(), "spatial_dofs": (n + 1) ** 2, "modes": a.PGD_modes,
+        print(json.dumps({"ok": True, "case": name, "world": dist.get_world_size(), "spatial_dofs": a.V[0].n_dofs, "modes": a.PGD_modes,
                           "fp_iterations": a.num_fp_it, "worst_mode_diff": worst, "sharded_solves": b.solver_stats["sharded_solves"],
                           "pcg_iterations": [a.solver_stats["pcg_iterations"], b.solver_stats["pcg_iterations"]]}))
-    dist.destroy_process_group()
 
 
 if __name__ == "__main__":
