@@ -12,10 +12,14 @@ model.py:798,838) and ``pgd_eval_gemv`` (one point) or the FP64 tensor-core GEMM
 ``pgd_eval_gemm_f64`` (a batch of points: ``evaluate_batch`` -- the vademecum sweep the reference
 performs as a Python loop of single evaluations, model.py:1785-1803).
 
-Out of scope (C13-C15): PXDMF/XDMF/HDF5 I/O, sensor/derivative evaluation -- the
-methods exist and raise NotImplementedError naming themselves.
+PXDMF I/O: ``write_pxdmf`` / ``load_pxdmf`` in the self-contained
+``Format="XML"`` variant (model.py:202-575).  Out of scope (C13, C15): DOLFIN HDF5 /
+XDMF side files, sensor/derivative evaluation -- the methods exist and raise NotImplementedError
+naming themselves.
 """
 import logging
+import os
+import xml.etree.ElementTree as et
 
 import numpy as np
 import torch
@@ -146,6 +150,31 @@ class PGDMesh(object):
         print("\n")
 
 
+def _rows_text(a, fmt):
+    """One text line per row, blank-separated (the layout ``data_to_array`` at model.py:419-437 parses)."""
+    return "".join(" ".join(fmt % v for v in row) + "\n" for row in a.tolist())
+
+
+def _read_item(item, folder, typ):
+    """A <DataItem>: XML text (first and last line of the text are dropped like model.py:423-425) or an
+    ``file.h5:/path`` HDF reference."""
+    fmt = item.get("Format")
+    if fmt == "XML":
+        lines = item.text.split("\n")[1:-1]
+        rows = [[typ(tok) for tok in ln.split(" ") if tok] for ln in lines]
+        return np.array(rows)
+    if fmt == "HDF":
+        try:
+            import h5py
+        except ImportError as exc:
+            raise ImportError("PGD.load_pxdmf: DataItem '%s' is Format=\"HDF\" and h5py is not installed; "
+                              "re-export the file with Format=\"XML\" DataItems (PGD.write_pxdmf)" % item.text) from exc
+        fname, dset = item.text.split(":")
+        with h5py.File(os.path.join(folder, fname), "r") as hf:
+            return np.array(hf.get(dset))
+    raise ValueError("PGD.load_pxdmf: unknown DataItem Format %r" % fmt)
+
+
 def _as_f64(a):
     return _lib.to_device(np.ascontiguousarray(a, dtype=np.float64))
 
@@ -229,11 +258,115 @@ class PGD:
     def write_hdf5(self, *a, **k):
         self._out_of_scope("write_hdf5")
 
-    def write_pxdmf(self, *a, **k):
-        self._out_of_scope("write_pxdmf")
+    def write_pxdmf(self, folder, xdmf_exist=False):
+        """Write ``<folder>/<name>.pxdmf`` (layout of model.py:202-404: one <Grid> per PGD coordinate with
+        its Dims/Dim0/Unit0 information, topology, geometry and one ``<name>_<mode>`` attribute per mode).
 
-    def load_pxdmf(self, *a, **k):
-        self._out_of_scope("load_pxdmf")
+        The reference merges DOLFIN's XDMF/HDF5 side files (``Format="HDF"``, needs h5py + DOLFIN); this
+        writer is self-contained: every DataItem is ``Format="XML"`` -- the variant the reference loader
+        already reads (model.py:475-480, 498-501, 534-537) -- with 17 significant digits so that
+        write -> load -> evaluate reproduces the modes bit for bit.  ``xdmf_exist`` is accepted for
+        signature compatibility and ignored (there are no side files)."""
+        os.makedirs(folder, exist_ok=True)
+        path = os.path.join(folder, str(self.name) + ".pxdmf")
+        with open(path, "w") as fo:
+            fo.write('<?xml version="1.0"?><!--pxdmf written by pgdrome_b200 (all DataItems Format="XML")-->\n')
+            fo.write('<!DOCTYPE Xdmf SYSTEM "Xdmf.dtd" []>\n')
+            fo.write('<Xdmf Version="3.0" xmlns:xi="http://www.w3.org/2001/XInclude">\n')
+            fo.write('  <Domain Name="%s.pxdmf">\n' % self.name)
+            for m in self.mesh:
+                info = m.info
+                if info and isinstance(info[0], (list, tuple)):  # loaded files keep [name, value] pairs
+                    info = [v for _, v in info]
+                fo.write('    <Grid Name="%s">\n' % m.name)
+                fo.write('      <Information Name="Dims" Value="%s" />\n' % info[0])
+                fo.write('      <Information Name="Dim0" Value="%s" />\n' % info[1])
+                fo.write('      <Information Name="Unit0" Value="%s" />\n' % info[2])
+                topo = np.asarray(m.topology, dtype=np.int64)
+                fo.write('        <Topology NumberOfElements = "%d" TopologyType = "%s" NodesPerElement = "%d" >\n'
+                         % (m.numElements, m.typElements, topo.shape[1]))
+                fo.write('          <DataItem Dimensions = "%d %d" NumberType = "UInt" Format = "XML">\n' % topo.shape)
+                fo.write(_rows_text(topo, "%d"))
+                fo.write("          </DataItem>\n        </Topology>\n")
+                if int(info[0]) == 2:
+                    geom, gt = np.column_stack([m.dataX, m.dataY]), "XY"
+                else:
+                    geom, gt = np.column_stack([m.dataX, m.dataY, m.dataZ]), "XYZ"
+                fo.write('        <Geometry GeometryType = "%s">\n' % gt)
+                fo.write('          <DataItem Dimensions = "%d %d" Format = "XML">\n' % geom.shape)
+                fo.write(_rows_text(geom, "%.17g"))
+                fo.write("          </DataItem>\n        </Geometry>\n")
+                for att in m.attributes:
+                    for k in range(len(att.data)):
+                        dat = np.asarray(att.data[k], dtype=np.float64)
+                        dat = dat.reshape(len(dat), -1)
+                        fo.write('        <Attribute Name="%s_%d" AttributeType="%s" Center="%s">\n'
+                                 % (att.name, k, att.field, att._type))
+                        fo.write('          <DataItem Dimensions="%d %d" Format="XML" NumberType="float" >\n' % dat.shape)
+                        fo.write(_rows_text(dat, "%.17g"))
+                        fo.write("          </DataItem>\n        </Attribute>\n")
+                fo.write("    </Grid>\n")
+            fo.write("  </Domain>\n</Xdmf>")
+        self.logger.info("Wrote %s ", path)
+        return path
+
+    def load_pxdmf(self, filepath, verbose=False):
+        """Read a PXDMF file into this instance (model.py:406-575): ``PGD().load_pxdmf(path)``.  Meshes,
+        topology, geometry and the per-mode attribute arrays land in ``PGDMesh``/``PGDAttribute`` exactly
+        as the reference stores them (``info`` as [name, value] pairs, ``data`` as a list of
+        [numNodes, ncols] arrays); follow with ``create_interpolation_fcts`` (interpolationInfo name 0)
+        and ``evaluate`` / ``evaluate_batch`` run on the device.  ``Format="XML"`` DataItems are parsed
+        here; ``Format="HDF"`` ones need h5py, which is imported on demand and reported if absent."""
+        folder = os.path.dirname(os.path.abspath(filepath))
+        root = et.parse(filepath).getroot()
+        self.folder = folder
+        self.name = root.findall("Domain")[0].attrib.get("Name")
+        self.mesh = list()
+        for g in root.iter("Grid"):
+            m = PGDMesh(g.get("Name"))
+            m.fenics_mesh = None
+            m.info = [[e.attrib.get("Name"), e.attrib.get("Value")] for e in g.iter("Information")]
+            m.meshdim = int(m.info[0][1])
+            for e in g.iter("Topology"):
+                m.numElements = int(e.attrib.get("NumberOfElements"))
+                m.typElements = e.attrib.get("TopologyType")
+                m.topology = _read_item(e[0], folder, int)
+            for e in g.iter("Geometry"):
+                m.typGeometry = e.attrib.get("GeometryType", m.typGeometry)
+                geom = _read_item(e[0], folder, float)
+                m.numNodes = geom.shape[0]
+                m.dataX = geom[:, 0]
+                if geom.shape[1] >= 2:
+                    m.dataY = geom[:, 1]
+                else:
+                    m.dataY = np.zeros(m.numNodes)
+                m.dataZ = geom[:, 2] if geom.shape[1] == 3 else np.zeros(m.numNodes)
+            m.attributes = list()
+            for e in g.iter("Attribute"):
+                name = "_".join(e.attrib.get("Name").split("_")[:-1])
+                dat = _read_item(e[0], folder, float)
+                for att in m.attributes:
+                    if att.name == name:
+                        att.data.append(dat)
+                        break
+                else:
+                    att = PGDAttribute()
+                    att.name = name
+                    att._type = e.attrib.get("Center")
+                    att.field = e.attrib.get("AttributeType")
+                    att.data = [dat]
+                    m.attributes.append(att)
+            self.mesh.append(m)
+        self.numModes = len(self.mesh[0].attributes[0].data)
+        self.used_numModes = self.numModes
+        self.invalidate_device_cache()
+        if verbose:
+            self.print_info()
+            for m in self.mesh:
+                m.print_info()
+                for att in m.attributes:
+                    att.print_info()
+        return self
 
     def evaluate_sensor_response(self, *a, **k):
         self._out_of_scope("evaluate_sensor_response")

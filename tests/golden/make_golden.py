@@ -178,9 +178,82 @@ def pgdclass(out):
     out["lhs_samples"] = np.array(ec.sampling_LHS())
 
 
+def pxdmf(out):
+    """PXDMF round trip across the two implementations: the PRODUCT writer (pgdrome_b200 PGD.write_pxdmf,
+    Format="XML") produces tests/golden/pxdmf/PGDsolution.pxdmf; the UNMODIFIED reference loader
+    (model.py:406-575) reads it back, and what it stored (and what the reference then evaluates from it)
+    is the golden data the product loader / device evaluate are compared with."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from pgdrome_b200 import model as pm
+
+    from pgdrome.model import PGD as RefPGD
+
+    rng = np.random.default_rng(11)
+    R = 3
+    nx, ny = 4, 3
+    X, Y = np.meshgrid(np.linspace(0.0, 2.0, nx + 1), np.linspace(0.0, 1.0, ny + 1))
+    tri = []
+    for j in range(ny):
+        for i in range(nx):
+            v0 = j * (nx + 1) + i
+            v1, v2, v3 = v0 + 1, v0 + nx + 1, v0 + nx + 2
+            tri += [[v0, v1, v3], [v0, v2, v3]]
+    x1 = np.array([0.0, 2.0, 0.35, 0.8, 1.1, 1.45, 1.9])  # deliberately not sorted
+    x2 = np.linspace(1.0, 3.0, 5)
+    grids = [("PGD1", 2, "Triangle", np.array(tri), X.ravel(), Y.ravel(), "X"),
+             ("PGD2", 1, "Polyline", np.column_stack([np.argsort(x1)[:-1], np.argsort(x1)[1:]]), x1, 0 * x1, "E"),
+             ("PGD3", 1, "Polyline", np.column_stack([np.arange(4), np.arange(1, 5)]), x2, 0 * x2, "F")]
+    pgd = pm.PGD()
+    pgd.name, pgd.numModes, pgd.used_numModes = "PGDsolution", R, R
+    for name, dim, typ, topo, gx, gy, cname in grids:
+        m = pm.PGDMesh(name)
+        m.meshdim, m.info = dim, [dim, cname, "-?-"]
+        m.topology, m.numElements, m.typElements = topo, len(topo), typ
+        m.dataX, m.dataY, m.dataZ, m.numNodes = gx, gy, np.zeros(len(gx)), len(gx)
+        m.attributes = []
+        for an in ("U_x", "Sig_x"):
+            a = pm.PGDAttribute()
+            a.name, a._type, a.field = an, "Node", "Scalar"
+            a.data = [rng.standard_normal((len(gx), 1)) * 10.0 ** rng.integers(-3, 3) for _ in range(R)]
+            m.attributes.append(a)
+        pgd.mesh.append(m)
+    folder = os.path.join(HERE, "pxdmf")
+    path = pgd.write_pxdmf(folder)
+    ref = RefPGD().load_pxdmf(path)
+    out["name"] = np.array(ref.name)
+    out["num_modes"] = np.array(ref.numModes)
+    for d, m in enumerate(ref.mesh):
+        out["g%d_name" % d] = np.array(m.name)
+        out["g%d_info" % d] = np.array(m.info)
+        out["g%d_meshdim" % d] = np.array(m.meshdim)
+        out["g%d_num_elements" % d] = np.array(m.numElements)
+        out["g%d_typ_elements" % d] = np.array(m.typElements)
+        out["g%d_topology" % d] = np.asarray(m.topology)
+        out["g%d_num_nodes" % d] = np.array(m.numNodes)
+        out["g%d_x" % d] = np.asarray(m.dataX)
+        out["g%d_y" % d] = np.asarray(m.dataY)
+        for a, att in enumerate(m.attributes):
+            out["g%d_a%d_meta" % (d, a)] = np.array([att.name, att._type, att.field])
+            out["g%d_a%d_data" % (d, a)] = np.array(att.data)
+        # the reference read back exactly what the product wrote (17 significant digits)
+        assert np.array_equal(np.asarray(m.dataX), pgd.mesh[d].dataX)
+        for a, att in enumerate(m.attributes):
+            assert all(np.array_equal(att.data[k], pgd.mesh[d].attributes[a].data[k]) for k in range(R))
+    pts = [[0.0, 1.0], [2.0, 3.0], [0.35, 1.5], [1.0, 2.25], [1.777, 2.999], [0.1234, 1.001]]
+    out["points"] = np.array(pts)
+    for at in (0, 1):
+        for d in (1, 2):
+            ref.mesh[d].attributes[at].interpolationInfo = {"name": 0, "kind": "linear"}
+        ref.create_interpolation_fcts([1, 2], at)
+        out["eval_%d" % at] = np.array([np.asarray(ref.evaluate(0, [1, 2], p, at)).copy() for p in pts])
+
+
 def main():
     _install_stub()
-    for name, fn in (("fd_matrices", fd_matrices), ("laplace_fd", laplace_fd), ("pgdclass", pgdclass)):
+    only = sys.argv[1:]
+    for name, fn in (("fd_matrices", fd_matrices), ("laplace_fd", laplace_fd), ("pgdclass", pgdclass), ("pxdmf", pxdmf)):
+        if only and name not in only:
+            continue
         out = {}
         fn(out)
         path = os.path.join(HERE, name + ".npz")
