@@ -214,6 +214,22 @@ int32_t pgd_eval_gemv(pgd_handle_t h, const double* d_X, int64_t ldx, int32_t R,
 int32_t pgd_eval_gemm_f64(pgd_handle_t h, const double* d_W, int64_t ldw, const double* d_X, int64_t ldx,
                           int32_t R, int64_t C, int64_t N, double* d_U, int64_t ldu, void* stream);
 
+/* ---- sensor evaluation (PGD.evaluate_sensor_response, model.py:862-953; eval_fixed_modes with
+ * fenicstools.Probes, model.py:107-130).
+ * pgd_locate_points: for each of n_points points [n_points, gdim] find the LOWEST-numbered simplex
+ * (d_cells int32 [n_cells, gdim+1] into d_coords [n_verts, gdim]) whose barycentric coordinates are all
+ * >= -tol; d_cell[i] = that cell or -1 (outside the mesh), d_bary[i, 0..gdim] = barycentric coordinates
+ * w.r.t. the cell's vertices in d_cells order (zeros when outside).  Deterministic (atomicMin on the id).
+ * d_cells must be aligned to one row (8 B for gdim 1, 16 B for gdim 3: rows are read as one vector load). */
+int32_t pgd_locate_points(pgd_handle_t h, const double* d_coords, const int32_t* d_cells, int64_t n_cells, int32_t gdim,
+                          const double* d_points, int32_t n_points, double tol, int32_t* d_cell, double* d_bary,
+                          void* stream);
+/* E[k, r] = sum_j w[r, j] X[k, dofs[r, j]]   (k < R modes, r < n_rows probe rows, nd basis functions per
+ * row): every mode of the fixed dimension evaluated at the located points; E [R, lde] is laid out as the X
+ * operand of pgd_eval_gemv / pgd_eval_gemm_f64. */
+int32_t pgd_probe_modes(pgd_handle_t h, const double* d_X, int64_t ldx, int32_t R, const int32_t* d_dofs,
+                        const double* d_w, int64_t n_rows, int32_t nd, double* d_E, int64_t lde, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,7 +24,9 @@ PARITY STATUS: **partly pinned**.
     finite-difference paths touch): ``FD_matrices``; the enrichment loop in FD mode (get_Fsinit,
     residual check, FP_solve with both stopping criteria, the three normalisations, the stopping
     test); ``PGD.evaluate`` interp1d path and mode point-evaluation loop; evaluate_min/max; LHS
-    sampling; the error loop.  Checked in tests/test_oracle_golden.py.
+    sampling; the error loop.  Checked in tests/test_oracle_golden.py.  Also pinned: the mode
+    combination / return shapes of ``evaluate_sensor_response`` (tests/golden/sensor.npz) and the PXDMF
+    XML layout (a product-written file read back by the unmodified reference loader, pxdmf.npz).
   * **parity unpinned** for everything that goes through DOLFIN's finite-element assembly
     (sparsity bit-exact, matrices 1e-12): fenics=2019.1.0 (environment.yml:8) cannot be imported
     here (Python 3.12, no dolfin/ufl/ffc/petsc4py) and the reference ships no stored matrices.

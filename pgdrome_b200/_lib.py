@@ -62,6 +62,8 @@ SIGNATURES = {
     "pgd_eval_weights": [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp],
     "pgd_eval_gemv": [c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_vp, c_vp],
     "pgd_eval_gemm_f64": [c_vp, c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i64, c_vp, c_i64, c_vp],
+    "pgd_locate_points": [c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_i32, c_dbl, c_vp, c_vp, c_vp],
+    "pgd_probe_modes": [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_vp],
 }
 
 _lib = None
@@ -549,6 +551,29 @@ def eval_gemv(X, R, w, out=None):
         out = torch.empty(N, dtype=F64, device=X.device)
     _check(lib.pgd_eval_gemv(h, _p(X, F64), X.stride(0), R, _p(w, F64), N, _p(out, F64), _stream()), h, "pgd_eval_gemv")
     return out
+
+
+def locate_points(coords, cells, points, tol=1e-10):
+    """coords [n_verts, g] f64, cells [n_cells, g+1] i32, points [n_pts, g] f64 (device) -> (cell i32 [n_pts]
+    with -1 = outside, bary f64 [n_pts, g+1]); the lowest-numbered containing cell wins."""
+    h, lib = handle(coords.device), load_library()
+    g = coords.shape[1]
+    n_pts = points.shape[0]
+    cell = torch.empty(n_pts, dtype=I32, device=coords.device)
+    bary = torch.empty((n_pts, g + 1), dtype=F64, device=coords.device)
+    _check(lib.pgd_locate_points(h, _p(coords, F64), _p(cells, I32), cells.shape[0], g, _p(points, F64), n_pts, float(tol),
+                                 _p(cell, I32), _p(bary, F64), _stream()), h, "pgd_locate_points")
+    return cell, bary
+
+
+def probe_modes(X, R, dofs, w):
+    """X [>=R, ld] modes, dofs i32 [n_rows, nd], w f64 [n_rows, nd] -> E [R, n_rows], E[k, r] = sum_j w[r, j] X[k, dofs[r, j]]."""
+    h, lib = handle(X.device), load_library()
+    n_rows, nd = dofs.shape
+    E = torch.empty((R, n_rows), dtype=F64, device=X.device)
+    _check(lib.pgd_probe_modes(h, _p(X, F64, True), X.stride(0), R, _p(dofs, I32), _p(w, F64), n_rows, nd, _p(E, F64), n_rows,
+                               _stream()), h, "pgd_probe_modes")
+    return E
 
 
 def eval_gemm(W, X, R, out=None):

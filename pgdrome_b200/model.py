@@ -13,9 +13,10 @@ model.py:798,838) and ``pgd_eval_gemv`` (one point) or the FP64 tensor-core GEMM
 performs as a Python loop of single evaluations, model.py:1785-1803).
 
 PXDMF I/O: ``write_pxdmf`` / ``load_pxdmf`` in the self-contained
-``Format="XML"`` variant (model.py:202-575).  Out of scope (C13, C15): DOLFIN HDF5 /
-XDMF side files, sensor/derivative evaluation -- the methods exist and raise NotImplementedError
-naming themselves.
+``Format="XML"`` variant (model.py:202-575).  Sensor evaluation:
+``eval_fixed_modes`` / ``evaluate_sensor_response`` (model.py:107-130, 862-953) with device point location.
+Out of scope (C13, C15): DOLFIN HDF5 / XDMF side files and derivative evaluation (needs
+``dolfin.project``) -- the methods exist and raise NotImplementedError naming themselves.
 """
 import logging
 import os
@@ -214,6 +215,7 @@ class PGD:
         self.problem = None
         self.pos = 0
         self._eval_fixed_modes = {}
+        self._sensor_digest = {}
         self._dev_cache = {}
 
     def __str__(self):
@@ -368,8 +370,80 @@ class PGD:
                     att.print_info()
         return self
 
-    def evaluate_sensor_response(self, *a, **k):
-        self._out_of_scope("evaluate_sensor_response")
+    # ------------------------------------------------------------------ sensor evaluation
+    def eval_fixed_modes(self, sensor_points, fixed_dim, attri):
+        """All modes of the fixed dimension at the sensor points (model.py:107-130, fenicstools.Probes):
+        ``[n_pts, R]`` for a scalar space, ``[n_pts, bs, R]`` for a vector space (``[n_pts]`` / ``[n_pts, bs]``
+        when there is a single mode, like ``probes.array()``).  Point location (``pgd_locate_points``) and the
+        basis evaluation of every mode (``pgd_probe_modes``) run on the device once per sensor set; the result is
+        cached under the reference's key ``(sum(points), fixed_dim, attri)`` -- guarded here by a digest of the
+        points, so two sensor sets with the same coordinate sum do not alias."""
+        pts = np.ascontiguousarray(np.asarray(sensor_points, dtype=np.float64))
+        key = (float(np.sum(pts.flatten())), fixed_dim, attri)
+        digest = hash(pts.tobytes())
+        if key in self._eval_fixed_modes and self._sensor_digest.get(key, digest) == digest:
+            return self._eval_fixed_modes[key]
+        modes = self.mesh[fixed_dim].attributes[attri].interpolationfct
+        if not modes or not hasattr(modes[0], "function_space"):
+            raise ValueError("sensor evaluation needs the fixed dimension's modes as finite-element functions")
+        V = modes[0].function_space()
+        m = V.mesh()
+        g = m.tdim
+        pts = pts.reshape(-1, g)
+        cell, bary = _lib.locate_points(_as_f64(m.coordinates()[:, :g]), _as_i32(m.cells()), _as_f64(pts))
+        cell_h, bary_h = _lib.to_host(cell).astype(np.int64), _lib.to_host(bary)
+        if np.any(cell_h < 0):
+            bad = pts[np.nonzero(cell_h < 0)[0][0]]
+            raise RuntimeError("sensor point %s is outside the mesh (allow_extrapolation is not supported)" % (bad,))
+        from .fem import tabulate_lagrange
+
+        phi, _ = tabulate_lagrange(g, V.degree, bary_h[:, 1:])  # [n_pts, nd]
+        nodes = V.cell_nodes[cell_h]  # [n_pts, nd]
+        bs, R = V.bs, self.numModes
+        dofs = (nodes[:, None, :] * bs + np.arange(bs)[None, :, None]).reshape(-1, nodes.shape[1])  # rows (point, comp)
+        w = np.repeat(phi, bs, axis=0)
+        X = self._fixed_dev(fixed_dim, attri, 1)
+        E = _lib.probe_modes(X, R, _as_i32(dofs), _as_f64(w))  # [R, n_pts * bs]
+        self._dev_cache[("sensor", key)] = (digest, E)
+        out = _lib.to_host(E).T.reshape(len(pts), bs, R)
+        out = out[:, 0, :] if bs == 1 else out
+        if R == 1:
+            out = out[..., 0]
+        self._eval_fixed_modes[key] = out
+        self._sensor_digest[key] = digest
+        return out
+
+    def evaluate_sensor_response(self, fixed_dim, free_dim, coord, attri, sensor_points):
+        """PGD solution of the fixed variable at the sensor points only (model.py:862-953); returns an ndarray
+        ``[n_pts]`` (scalar field) or ``[n_pts, bs]``.  The probed modes stay on the device as the X operand of
+        ``pgd_eval_gemv``: one weight kernel + one GEMV per call."""
+        if len(coord) != self.num_pgd_var - 1:
+            raise ValueError("given variables are missing or to much, coord=%s <-> num_pgd_var=%s", coord,
+                             self.num_pgd_var - 1)
+        for d in free_dim:
+            if sum(self.mesh[d].dataY) != 0 and sum(self.mesh[d].dataZ) != 0:
+                raise ValueError("free Dimensions are not 1D, interpolation not possible")
+        if attri >= len(self.mesh[fixed_dim].attributes):
+            raise ValueError("attribute number not possible")
+        for idx in free_dim:
+            if len(self.mesh[idx].attributes[attri].interpolationfct) == 0:
+                self.create_interpolation_fcts(free_dim, attri)
+                break
+        E_host = self.eval_fixed_modes(sensor_points, fixed_dim, attri)
+        pts = np.ascontiguousarray(np.asarray(sensor_points, dtype=np.float64))
+        key = (float(np.sum(pts.flatten())), fixed_dim, attri)
+        ent = self._dev_cache.get(("sensor", key))
+        R = self.numModes
+        if ent is None or ent[1].shape[0] != R or ent[0] != self._sensor_digest.get(key, ent[0]):
+            # cache entry injected on the host (or device cache invalidated): rebuild the [R, rows] operand
+            Eh = np.asarray(E_host, dtype=np.float64)
+            Eh = Eh[..., None] if R == 1 else Eh
+            ent = (self._sensor_digest.get(key), _as_f64(Eh.reshape(-1, R).T))
+            self._dev_cache[("sensor", key)] = ent
+        W = self._weights(free_dim, [coord], attri)
+        u = _lib.to_host(_lib.eval_gemv(ent[1], self.used_numModes, W[:, 0].contiguous()))
+        shape = np.asarray(E_host).shape
+        return u.reshape(shape if R == 1 else shape[:-1])
 
     def evaluate_derivative(self, *a, **k):
         self._out_of_scope("evaluate_derivative")

@@ -273,10 +273,22 @@ def eval_gemm(W, X, R, out=None):
     return r
 
 
+def locate_points(coords, cells, points, tol=1e-10):
+    from oracle.evaluate import locate_points as ref
+
+    c, b = ref(_n(coords), _n(cells), _n(points), tol)
+    return torch.as_tensor(c.astype(np.int32)), _t(b)
+
+
+def probe_modes(X, R, dofs, w):
+    Xn, d, wn = _n(X)[:R], _n(dofs), _n(w)
+    return _t(np.einsum("rj,krj->kr", wn, Xn[:, d]))
+
+
 NAMES = ["pattern_build", "vecmap_build", "elem_bilinear", "elem_linear", "gather_values", "assemble_p1",
          "p1_rowplan_build", "assemble_p1_rows", "lincomb",
          "apply_dirichlet", "set_entries", "spmv", "spmv_dot", "bilinear", "dot", "panel_dots", "pcg", "banded_solve",
-         "eval_weights", "eval_gemv", "eval_gemm"]
+         "eval_weights", "eval_gemv", "eval_gemm", "locate_points", "probe_modes"]
 
 
 def install(monkeypatch):

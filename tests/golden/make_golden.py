@@ -248,10 +248,50 @@ def pxdmf(out):
         out["eval_%d" % at] = np.array([np.asarray(ref.evaluate(0, [1, 2], p, at)).copy() for p in pts])
 
 
+def sensor(out):
+    """evaluate_sensor_response (model.py:862-953) of the UNMODIFIED reference with the Probes result injected into
+    its own cache (model.py:115-117; fenicstools is absent): pins how the probed fixed modes are combined with the
+    free-dimension factors and which shapes come back (scalar / vector field, one mode / several)."""
+    from pgdrome.model import PGD as RefPGD
+
+    rng = np.random.default_rng(5)
+    ref = RefPGD().load_pxdmf(os.path.join(HERE, "pxdmf", "PGDsolution.pxdmf"))  # 3 modes, free dims 1-D
+    for d in (1, 2):
+        ref.mesh[d].attributes[0].interpolationInfo = {"name": 0, "kind": "linear"}
+    ref.create_interpolation_fcts([1, 2], 0)
+    pts = rng.random((5, 2))
+    coords = [[0.35, 1.5], [1.777, 2.999], [0.0, 1.0]]
+    out["points"], out["coords"] = pts, np.array(coords)
+    key = (np.sum(pts.flatten()), 0, 0)
+    for tag, E in (("scalar", rng.standard_normal((5, 3))), ("vector", rng.standard_normal((5, 2, 3)))):
+        ref._eval_fixed_modes = {key: E}
+        out["E_" + tag] = E
+        out["resp_" + tag] = np.array([ref.evaluate_sensor_response(0, [1, 2], c, 0, pts) for c in coords])
+        ref.used_numModes = 2  # truncated evaluation (model.py:911-921 loops over used_numModes)
+        out["resp2_" + tag] = np.array([ref.evaluate_sensor_response(0, [1, 2], c, 0, pts) for c in coords])
+        ref.used_numModes = 3
+    # single mode: probes.array() drops the mode axis (model.py:930-935)
+    tp = _load(os.path.join(REF, "tests/unit/test_pgdclass.py"), "ref_test_pgdclass_s")
+    one = tp.create_example_pgd_solution({"A": 1, "n": 1, "lae": 1})
+    for d in (1, 2):
+        one.mesh[d].attributes[0].interpolationInfo = {"name": 0, "kind": "linear"}
+    one.create_interpolation_fcts([1, 2], 0)
+    pts1 = np.array([[0.25], [0.5], [0.9]])
+    out["one_points"] = pts1
+    out["one_coord"] = np.array([0.737, 0.93])
+    for tag, E in (("scalar", rng.standard_normal(3)), ("vector", rng.standard_normal((3, 2)))):
+        one._eval_fixed_modes = {(np.sum(pts1.flatten()), 0, 0): E}
+        out["one_E_" + tag] = E
+        out["one_resp_" + tag] = np.asarray(one.evaluate_sensor_response(0, [1, 2], [0.737, 0.93], 0, pts1))
+    for d in range(3):
+        out["one_x%d" % d] = np.asarray(one.mesh[d].dataX, dtype=np.float64)
+        out["one_data%d" % d] = np.array([np.asarray(m, dtype=np.float64) for m in one.mesh[d].attributes[0].data])
+
+
 def main():
     _install_stub()
     only = sys.argv[1:]
-    for name, fn in (("fd_matrices", fd_matrices), ("laplace_fd", laplace_fd), ("pgdclass", pgdclass), ("pxdmf", pxdmf)):
+    for name, fn in (("fd_matrices", fd_matrices), ("laplace_fd", laplace_fd), ("pgdclass", pgdclass), ("pxdmf", pxdmf), ("sensor", sensor)):
         if only and name not in only:
             continue
         out = {}

@@ -163,5 +163,7 @@ def test_solved_problem_written_loaded_evaluated(tmp_path):
     k = pgd.mesh[2].dataX
     for pt in ([float(t[3]), float(k[2])], [0.5 * (t.min() + t.max()), 0.3 * k.min() + 0.7 * k.max()], [t.max(), k.min()]):
         u_ref = pgd.evaluate(0, [1, 2], pt, 0).compute_vertex_values()
-        u = np.asarray(back.evaluate(0, [1, 2], pt, 0)).reshape(-1)
+        u = np.asarray(back.evaluate(0, [1, 2], pt, 0))  # vertex data [numNodes, meshdim], values in column 0 (model.py:1510-1556)
+        assert u.shape == (pgd.mesh[0].numNodes, 2) and not u[:, 1].any()
+        u = u[:, 0]
         assert np.abs(u - u_ref).max() <= 1e-12 * max(np.abs(u_ref).max(), 1e-300)

@@ -113,6 +113,10 @@ def run(mesh_n=128, hbm_peak=6451.2, evaluate=True, fp64_peak=None):
     ms = _time(lambda: _lib.panel_dots(P, 16, x, out=res))
     entry("panel_dots_16", ms, 8 * n * 16 + 8 * n)
     del P, K, M, vals, work
+    # sensor point location: one pass over the cells for 64 sensors
+    pts = torch.rand((64, 3), dtype=torch.float64, device=dev, generator=g)
+    ms = _time(lambda: _lib.locate_points(ds.coords, ds.cell_verts, pts))
+    entry("locate_points_64", ms, 4 * 4 * nc + 8 * 3 * m.num_vertices(), kernel="k_locate<3> (+ fill, finalise)")
     if evaluate:
         R, N, C = 50, 100000, 10000
         X = torch.randn((R, N), dtype=torch.float64, device=dev, generator=g)
