@@ -29,7 +29,7 @@ import torch
 
 from . import _lib, lazy
 from .assembly import device_space
-from .functions import Constant, DeviceVector, Expression, Function, _DofOwner, _device
+from .functions import DeviceVector, Expression, Function, _DofOwner, _device
 from .lazy import LazyScalar
 from .ufl import Form
 

@@ -27,7 +27,7 @@ import torch
 from scipy.stats import qmc
 
 from . import _lib
-from .functions import Function, _device
+from .functions import Function
 
 LOGGER = logging.getLogger(__name__)
 

@@ -24,10 +24,9 @@ import numpy as np
 import scipy.sparse as sp
 import torch
 
-from . import _lib, forms, lazy
+from . import _lib, forms
 from .assembly import device_space
-from .functions import (Constant, DeviceVector, Expression, Function, MatrixOperator, bc_list, interpolate,
-                        merged_bc_dofs)
+from .functions import Function, MatrixOperator, bc_list, merged_bc_dofs
 from .lazy import LazyScalar
 from .ufl import Form, TestFunction, TrialFunction, derivative
 from .ufl import dx as forms_dx
