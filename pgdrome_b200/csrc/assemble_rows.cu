@@ -68,8 +68,7 @@ extern "C" int32_t pgd_p1_rowplan_build_sync(pgd_handle_t h, const int32_t* d_ro
     else k_p1_rowplan<4><<<blocks, 256, 0, st>>>(d_rowptr, d_colidx, d_cell_dofs, d_vptr, d_vidx, n_nodes, vent, flag);
     PGD_LAUNCH_OK(h);
     int hf = 0;
-    PGD_CUDA(h, cudaMemcpyAsync(&hf, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
-    PGD_CUDA(h, cudaStreamSynchronize(st));
+    PGD_CUDA(h, pgd_fetch(h, &hf, flag, sizeof(int), nullptr, nullptr, 0, st));
     if (hf) {
         snprintf(h->err, sizeof(h->err), "pgd_p1_rowplan_build_sync: a row has more than 255 entries");
         return -4;

@@ -29,6 +29,10 @@ struct pgd_ctx {
     // statistics (pgd_get_stats): kernel launches, PCG solves / iterations / device time
     int64_t n_launches, pcg_solves, pcg_iters, pcg_resident_solves;
     double pcg_ms;
+    void* pinned;            // 256 B of page-locked host memory: staging for the small device->host reads of the *_sync calls
+    void* arena;             // grow-only device scratch of the set-up calls (pattern / vecmap builds), see pgd_arena
+    size_t arena_cap;
+    int pat_in_arena;        // the pending pattern lives in the arena (nothing to free)
     int opt_resident;        // pgd_set_option("pcg_resident"): 1 = use the SM-resident PCG when the system fits
     int opt_stream;          // pgd_set_option("spmv_stream"): 0 = sub-warp-per-row kernels only; 1 = register-staged row-block
                              // streaming for n >= PGD_STREAM_MIN_ROWS; 2 (default) = additionally the TMA-pipelined kernel
@@ -83,6 +87,45 @@ void pgd_free_pattern(pgd_ctx* h);
         (h)->n_launches += 1;            \
         PGD_CUDA(h, cudaGetLastError()); \
     } while (0)
+
+// Device -> host read of up to two small items (<= 128 B each) followed by a stream synchronise, staged through the
+// handle's page-locked buffer: a pageable destination sends cudaMemcpyAsync down the driver's blocking staging path,
+// which showed up as sporadic 100+ ms stalls of the *_sync entry points on a busy host.
+static inline cudaError_t pgd_fetch(pgd_ctx* h, void* dst0, const void* src0, size_t n0, void* dst1, const void* src1,
+                                    size_t n1, cudaStream_t st) {
+    char* pin = static_cast<char*>(h->pinned);
+    cudaError_t e = cudaMemcpyAsync(pin, src0, n0, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && n1) e = cudaMemcpyAsync(pin + 128, src1, n1, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return e;
+    memcpy(dst0, pin, n0);
+    if (n1) memcpy(dst1, pin + 128, n1);
+    return cudaSuccess;
+}
+
+// Scratch for the set-up calls.  Requests up to PGD_ARENA_KEEP bytes are served from one grow-only block that stays
+// with the handle (no cudaMalloc / cudaFree per call: both are blocking driver calls); larger ones (the 4 M-dof
+// patterns need GBs for a moment) are allocated for the call and must be returned with pgd_arena_release.
+#define PGD_ARENA_KEEP ((size_t)512 << 20)
+static inline cudaError_t pgd_arena(pgd_ctx* h, size_t bytes, void** out, bool* temporary) {
+    *temporary = false;
+    if (bytes > PGD_ARENA_KEEP) {
+        *temporary = true;
+        return cudaMalloc(out, bytes);
+    }
+    if (bytes > h->arena_cap) {
+        if (h->arena) cudaFree(h->arena);
+        h->arena = nullptr;
+        h->arena_cap = 0;
+        size_t cap = bytes + bytes / 4;
+        if (cap > PGD_ARENA_KEEP) cap = PGD_ARENA_KEEP;
+        cudaError_t e = cudaMalloc(&h->arena, cap);
+        if (e != cudaSuccess) return e;
+        h->arena_cap = cap;
+    }
+    *out = h->arena;
+    return cudaSuccess;
+}
 
 static inline int pgd_set_device(pgd_ctx* h) { return (int)cudaSetDevice(h->device); }
 

@@ -25,7 +25,8 @@ extern "C" int32_t pgd_create(int32_t device, pgd_handle_t* out) {
     if ((e = cudaMalloc(&h->partials, sizeof(double) * PGD_MAX_PARTIALS)) != cudaSuccess ||
         (e = cudaMalloc(&h->counters, sizeof(unsigned int) * PGD_MAX_COUNTERS)) != cudaSuccess ||
         (e = cudaMalloc(&h->scalars, sizeof(double) * 64)) != cudaSuccess ||
-        (e = cudaMalloc(&h->flags, sizeof(int) * 16)) != cudaSuccess) {
+        (e = cudaMalloc(&h->flags, sizeof(int) * 16)) != cudaSuccess ||
+        (e = cudaMallocHost(&h->pinned, 256)) != cudaSuccess) {
         delete h;
         return (int32_t)e;
     }
@@ -44,6 +45,8 @@ extern "C" int32_t pgd_destroy(pgd_handle_t h) {
     cudaSetDevice(h->device);
     pgd_free_pattern(h);
     cudaFree(h->partials);
+    if (h->arena) cudaFree(h->arena);
+    if (h->pinned) cudaFreeHost(h->pinned);
     cudaFree(h->counters);
     cudaFree(h->scalars);
     cudaFree(h->flags);

@@ -6,10 +6,13 @@
 #include "common.cuh"
 
 void pgd_free_pattern(pgd_ctx* h) {
-    cudaFree(h->pat_rowptr);
-    cudaFree(h->pat_colidx);
-    cudaFree(h->pat_gptr);
-    cudaFree(h->pat_gidx);
+    if (!h->pat_in_arena) {
+        cudaFree(h->pat_rowptr);
+        cudaFree(h->pat_colidx);
+        cudaFree(h->pat_gptr);
+        cudaFree(h->pat_gidx);
+    }
+    h->pat_in_arena = 0;
     h->pat_rowptr = h->pat_colidx = h->pat_gidx = nullptr;
     h->pat_gptr = nullptr;
     h->pat_nnz = 0;
@@ -83,12 +86,27 @@ struct SortBufs {
     int64_t *k0 = nullptr, *k1 = nullptr;
     int32_t *v0 = nullptr, *v1 = nullptr;
     void* temp = nullptr;
+    bool owned = true;  // false: carved out of the handle's arena
     ~SortBufs() {
+        if (!owned) return;
         cudaFree(k0);
         cudaFree(k1);
         cudaFree(v0);
         cudaFree(v1);
         cudaFree(temp);
+    }
+};
+
+static inline size_t up256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+// bump allocator over one block
+struct Carver {
+    char* p;
+    template <typename T>
+    T* take(size_t count) {
+        T* r = reinterpret_cast<T*>(p);
+        p += up256(sizeof(T) * count);
+        return r;
     }
 };
 
@@ -103,40 +121,59 @@ extern "C" int32_t pgd_pattern_build_sync(pgd_handle_t h, const int32_t* d_cell_
     pgd_set_device(h);
     pgd_free_pattern(h);
     SortBufs B;
-    PGD_CUDA(h, cudaMalloc(&B.k0, sizeof(int64_t) * n));
-    PGD_CUDA(h, cudaMalloc(&B.k1, sizeof(int64_t) * n));
-    PGD_CUDA(h, cudaMalloc(&B.v0, sizeof(int32_t) * n));
-    PGD_CUDA(h, cudaMalloc(&B.v1, sizeof(int32_t) * n));
+    size_t tb = 0, tb2 = 0;
+    const int end_bit = bits_for(n_dofs * n_dofs);
+    PGD_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tb, B.k0, B.k1, B.v0, B.v1, (int)n, 0, end_bit, st));
+    PGD_CUDA(h, cub::DeviceScan::InclusiveSum(nullptr, tb2, B.v0, B.v0, (int)n, st));
+    if (tb2 > tb) tb = tb2;
+    // everything (sort buffers, CUB scratch, the pattern with nnz bounded by the contribution count) in the handle's
+    // arena when that is small enough to keep; otherwise per-call allocations sized by the real nnz
+    const size_t need = 2 * up256(sizeof(int64_t) * n) + 2 * up256(sizeof(int32_t) * n) + up256(tb) +
+                        up256(sizeof(int32_t) * (n_dofs + 1)) + up256(sizeof(int32_t) * n) + up256(sizeof(int64_t) * (n + 1));
+    const bool in_arena = need <= PGD_ARENA_KEEP;
+    Carver cv{nullptr};
+    if (in_arena) {
+        void* base = nullptr;
+        bool temporary = false;
+        PGD_CUDA(h, pgd_arena(h, need, &base, &temporary));
+        cv.p = static_cast<char*>(base);
+        B.owned = false;
+        B.k0 = cv.take<int64_t>(n);
+        B.k1 = cv.take<int64_t>(n);
+        B.v0 = cv.take<int32_t>(n);
+        B.v1 = cv.take<int32_t>(n);
+        B.temp = cv.take<char>(tb);
+    } else {
+        PGD_CUDA(h, cudaMalloc(&B.k0, sizeof(int64_t) * n));
+        PGD_CUDA(h, cudaMalloc(&B.k1, sizeof(int64_t) * n));
+        PGD_CUDA(h, cudaMalloc(&B.v0, sizeof(int32_t) * n));
+        PGD_CUDA(h, cudaMalloc(&B.v1, sizeof(int32_t) * n));
+        PGD_CUDA(h, cudaMalloc(&B.temp, tb));
+    }
     k_make_pair_keys<<<pgd_blocks(n, 256), 256, 0, st>>>(d_cell_dofs, n, ndl, n_dofs, B.k0, B.v0);
     PGD_LAUNCH_OK(h);
-    size_t tb = 0;
-    int end_bit = bits_for(n_dofs * n_dofs);
-    PGD_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tb, B.k0, B.k1, B.v0, B.v1, (int)n, 0, end_bit, st));
-    PGD_CUDA(h, cudaMalloc(&B.temp, tb));
     PGD_CUDA(h, cub::DeviceRadixSort::SortPairs(B.temp, tb, B.k0, B.k1, B.v0, B.v1, (int)n, 0, end_bit, st));
     // sorted keys in k1, contribution ids in v1.  reuse v0 as flags/gid.
     k_head_flags<<<pgd_blocks(n, 256), 256, 0, st>>>(B.k1, n, B.v0);
     PGD_LAUNCH_OK(h);
-    size_t tb2 = 0;
-    PGD_CUDA(h, cub::DeviceScan::InclusiveSum(nullptr, tb2, B.v0, B.v0, (int)n, st));
-    if (tb2 > tb) {
-        cudaFree(B.temp);
-        B.temp = nullptr;
-        PGD_CUDA(h, cudaMalloc(&B.temp, tb2));
-        tb = tb2;
-    }
-    PGD_CUDA(h, cub::DeviceScan::InclusiveSum(B.temp, tb2, B.v0, B.v0, (int)n, st));
+    PGD_CUDA(h, cub::DeviceScan::InclusiveSum(B.temp, tb, B.v0, B.v0, (int)n, st));
     int32_t nnz32 = 0;
-    PGD_CUDA(h, cudaMemcpyAsync(&nnz32, B.v0 + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    PGD_CUDA(h, cudaStreamSynchronize(st));
+    PGD_CUDA(h, pgd_fetch(h, &nnz32, B.v0 + (n - 1), sizeof(int32_t), nullptr, nullptr, 0, st));
     int64_t nnz = nnz32;
-    PGD_CUDA(h, cudaMalloc(&h->pat_rowptr, sizeof(int32_t) * (n_dofs + 1)));
-    PGD_CUDA(h, cudaMalloc(&h->pat_colidx, sizeof(int32_t) * nnz));
-    PGD_CUDA(h, cudaMalloc(&h->pat_gptr, sizeof(int64_t) * (nnz + 1)));
+    if (in_arena) {
+        h->pat_rowptr = cv.take<int32_t>(n_dofs + 1);
+        h->pat_colidx = cv.take<int32_t>(n);
+        h->pat_gptr = cv.take<int64_t>(n + 1);
+        h->pat_in_arena = 1;
+    } else {
+        PGD_CUDA(h, cudaMalloc(&h->pat_rowptr, sizeof(int32_t) * (n_dofs + 1)));
+        PGD_CUDA(h, cudaMalloc(&h->pat_colidx, sizeof(int32_t) * nnz));
+        PGD_CUDA(h, cudaMalloc(&h->pat_gptr, sizeof(int64_t) * (nnz + 1)));
+    }
     k_groups<<<pgd_blocks(n, 256), 256, 0, st>>>(B.k1, B.v0, n, n_dofs, nnz, h->pat_gptr, h->pat_colidx, h->pat_rowptr);
     PGD_LAUNCH_OK(h);
     h->pat_gidx = B.v1;  // keep the sorted contribution ids
-    B.v1 = nullptr;
+    if (B.owned) B.v1 = nullptr;
     h->pat_nnz = nnz;
     h->pat_ndofs = n_dofs;
     h->pat_ncontrib = n;
@@ -168,16 +205,30 @@ extern "C" int32_t pgd_vecmap_build_sync(pgd_handle_t h, const int32_t* d_cell_d
     PGD_ARG(h, n < ((int64_t)1 << 31), "n_cells*ndl must be < 2^31");
     cudaStream_t st = (cudaStream_t)stream;
     pgd_set_device(h);
+    PGD_ARG(h, !h->pat_in_arena, "a pattern is pending in the handle's scratch (call pgd_pattern_export first)");
     SortBufs B;
-    PGD_CUDA(h, cudaMalloc(&B.k0, sizeof(int64_t) * n));
-    PGD_CUDA(h, cudaMalloc(&B.k1, sizeof(int64_t) * n));
-    PGD_CUDA(h, cudaMalloc(&B.v0, sizeof(int32_t) * n));
+    size_t tb = 0;
+    const int end_bit = bits_for(n_dofs);
+    PGD_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tb, B.k0, B.k1, B.v0, d_vidx, (int)n, 0, end_bit, st));
+    const size_t need = 2 * up256(sizeof(int64_t) * n) + up256(sizeof(int32_t) * n) + up256(tb);
+    if (need <= PGD_ARENA_KEEP) {
+        void* base = nullptr;
+        bool temporary = false;
+        PGD_CUDA(h, pgd_arena(h, need, &base, &temporary));
+        Carver cv{static_cast<char*>(base)};
+        B.owned = false;
+        B.k0 = cv.take<int64_t>(n);
+        B.k1 = cv.take<int64_t>(n);
+        B.v0 = cv.take<int32_t>(n);
+        B.temp = cv.take<char>(tb);
+    } else {
+        PGD_CUDA(h, cudaMalloc(&B.k0, sizeof(int64_t) * n));
+        PGD_CUDA(h, cudaMalloc(&B.k1, sizeof(int64_t) * n));
+        PGD_CUDA(h, cudaMalloc(&B.v0, sizeof(int32_t) * n));
+        PGD_CUDA(h, cudaMalloc(&B.temp, tb));
+    }
     k_make_dof_keys<<<pgd_blocks(n, 256), 256, 0, st>>>(d_cell_dofs, n, B.k0, B.v0);
     PGD_LAUNCH_OK(h);
-    size_t tb = 0;
-    int end_bit = bits_for(n_dofs);
-    PGD_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tb, B.k0, B.k1, B.v0, d_vidx, (int)n, 0, end_bit, st));
-    PGD_CUDA(h, cudaMalloc(&B.temp, tb));
     PGD_CUDA(h, cub::DeviceRadixSort::SortPairs(B.temp, tb, B.k0, B.k1, B.v0, d_vidx, (int)n, 0, end_bit, st));
     k_vecmap_ptr<<<pgd_blocks(n, 256), 256, 0, st>>>(B.k1, n, n_dofs, d_vptr);
     PGD_LAUNCH_OK(h);

@@ -368,8 +368,7 @@ static int32_t run_pcg(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const d
     if (check_every < 1) check_every = 1;
     PGD_CUDA(h, cudaEventRecord(h->ev0, st));
     while (true) {
-        PGD_CUDA(h, cudaMemcpyAsync(hf, fl, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
-        PGD_CUDA(h, cudaStreamSynchronize(st));
+        PGD_CUDA(h, pgd_fetch(h, hf, fl, sizeof(int) * 4, nullptr, nullptr, 0, st));
         if (hf[F_DONE] || launched >= maxit) break;
         int todo = maxit - launched;
         if (todo > check_every) todo = check_every;
@@ -421,8 +420,7 @@ static int32_t run_pcg(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const d
         launched += todo;
     }
     PGD_CUDA(h, cudaEventRecord(h->ev1, st));
-    PGD_CUDA(h, cudaMemcpyAsync(hs, sc, sizeof(double) * 8, cudaMemcpyDeviceToHost, st));
-    PGD_CUDA(h, cudaStreamSynchronize(st));
+    PGD_CUDA(h, pgd_fetch(h, hs, sc, sizeof(double) * 8, nullptr, nullptr, 0, st));
     {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->pcg_ms += ms;
@@ -453,8 +451,7 @@ static int32_t pcg_entry(pgd_handle_t h, const int32_t* d_rowptr, const int32_t*
     if (h->opt_resident && n <= ((int64_t)1 << 22)) {
         if (h->nnz_key != (const void*)d_rowptr || h->nnz_key_n != n) {
             int32_t last = 0;
-            PGD_CUDA(h, cudaMemcpyAsync(&last, d_rowptr + n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-            PGD_CUDA(h, cudaStreamSynchronize(st));
+            PGD_CUDA(h, pgd_fetch(h, &last, d_rowptr + n, sizeof(int32_t), nullptr, nullptr, 0, st));
             h->nnz_key = (const void*)d_rowptr;
             h->nnz_key_n = n;
             h->nnz_val = last;

@@ -391,9 +391,7 @@ int32_t pgd_pcg_resident(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const
     PGD_CUDA(h, cudaEventRecord(h->ev1, st));
     int hf[2];
     double hs[2];
-    PGD_CUDA(h, cudaMemcpyAsync(hf, a.out_fl, sizeof(hf), cudaMemcpyDeviceToHost, st));
-    PGD_CUDA(h, cudaMemcpyAsync(hs, a.out_sc, sizeof(hs), cudaMemcpyDeviceToHost, st));
-    PGD_CUDA(h, cudaStreamSynchronize(st));
+    PGD_CUDA(h, pgd_fetch(h, hf, a.out_fl, sizeof(hf), hs, a.out_sc, sizeof(hs), st));
     if (hf[1] == 1) return 1;
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->pcg_ms += ms;

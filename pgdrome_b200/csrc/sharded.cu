@@ -597,8 +597,7 @@ extern "C" int32_t pgd_spcg_solve_sync(pgd_handle_t h, const int32_t* d_rowptr, 
     const bool use_graph = p2p && h->opt_graph;
     bool warmed = false;
     while (true) {
-        PGD_CUDA(h, cudaMemcpyAsync(hf, fl, sizeof(hf), cudaMemcpyDeviceToHost, st));
-        PGD_CUDA(h, cudaStreamSynchronize(st));
+        PGD_CUDA(h, pgd_fetch(h, hf, fl, sizeof(hf), nullptr, nullptr, 0, st));
         if (hf[0] || launched >= maxit) break;
         int todo = maxit - launched;
         if (todo > check_every) todo = check_every;
@@ -637,8 +636,7 @@ extern "C" int32_t pgd_spcg_solve_sync(pgd_handle_t h, const int32_t* d_rowptr, 
     if (graph) cudaGraphDestroy(graph);
     PGD_CUDA(h, cudaEventRecord(h->ev1, st));
     double hs[8];
-    PGD_CUDA(h, cudaMemcpyAsync(hs, sc, sizeof(hs), cudaMemcpyDeviceToHost, st));
-    PGD_CUDA(h, cudaStreamSynchronize(st));
+    PGD_CUDA(h, pgd_fetch(h, hs, sc, sizeof(hs), nullptr, nullptr, 0, st));
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->pcg_ms += ms;
     h->pcg_solves += 1;

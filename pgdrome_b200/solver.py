@@ -18,6 +18,7 @@ Deviations, all forced by "no CPU, no direct sparse solver on the device" (see D
   * with ``_problem="linear"`` the callbacks are invoked once per sub-problem (with a
     TrialFunction), not twice; ``bc_fct`` / ``dom_fct`` are evaluated once per ``solve_PGD``.
 """
+import gc
 import logging
 
 import numpy as np
@@ -59,6 +60,40 @@ class _CsrOnDevice:
     def product(self, x, y):
         """device scalar tensor x^T A y"""
         return _lib.bilinear(self.rowptr, self.colidx, self.values, x, y, lpr=self.lpr)
+
+
+class _ParkedHeap:
+    """While an enrichment step runs, every object that existed before it sits in the collector's permanent
+    generation (``gc.freeze``), and goes back afterwards (``gc.unfreeze``; both are O(1) list splices).
+
+    A step creates ~10^5 short-lived Python objects (form nodes, deferred scalars).  They die by reference count,
+    but their allocation still drives CPython's generational collector, and a full collection walks every tracked
+    object of the process -- ~2*10^5 for torch + scipy + this package, measured 0.13 s, i.e. several enrichment
+    steps of configs[1] -- whenever the long-lived heuristic fires.  With the old objects parked, collections
+    inside the step only see what the step itself allocated.  ``settings={"gc_freeze": False}`` turns it off; a
+    heap the caller froze is left as it is."""
+    depth = 0
+    base = gc.get_freeze_count()  # what the interpreter itself keeps frozen (a few hundred start-up objects here)
+
+    def __init__(self, on):
+        self.on = bool(on)
+        self.mine = False
+
+    def __enter__(self):
+        if self.on:
+            if _ParkedHeap.depth == 0 and gc.get_freeze_count() == _ParkedHeap.base:
+                gc.freeze()
+                self.mine = True
+            _ParkedHeap.depth += 1
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            _ParkedHeap.depth -= 1
+            if self.mine:
+                gc.unfreeze()
+                _ParkedHeap.base = gc.get_freeze_count()
+        return False
 
 
 class PGDProblem:
@@ -236,6 +271,10 @@ class PGDProblem:
     def enrichment_step(self, n_enr, normConv, relConv, _problem="nonlinear", solve_modes=None,
                         settings={"linear_solver": "mumps"}):
         """One pass of the enrichment loop body (one new mode per dimension). True = stop."""
+        with _ParkedHeap(settings.get("gc_freeze", True)):
+            return self._enrichment_step(n_enr, normConv, relConv, _problem, solve_modes, settings)
+
+    def _enrichment_step(self, n_enr, normConv, relConv, _problem, solve_modes, settings):
         D = self.num_pgd_var
         Fs_init = self.get_Fsinit(self.V, self.bc, solve_modes)
         norm_Fs = np.ones(D)

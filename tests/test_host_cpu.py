@@ -159,3 +159,30 @@ def test_direct_solve_mode(cpu):
                    load=[], param={}, rhs_fct=None, lhs_fct=None, probs=["r"], PGD_nmax=1)
     f = p.direct_solve(4.0, 2.0, 0)
     assert np.array_equal(f.vector()[:], np.full(V.n_dofs, 0.5))
+
+
+def test_parked_heap_restores_collector_state():
+    """The enrichment step parks the existing heap in the collector's permanent generation and puts it back."""
+    import gc
+
+    from pgdrome_b200.solver import _ParkedHeap
+
+    before = gc.get_freeze_count()
+    with _ParkedHeap(True) as outer:
+        assert outer.mine and gc.get_freeze_count() > before
+        with _ParkedHeap(True) as inner:  # nested steps (normalisation callbacks) do not freeze twice
+            assert not inner.mine
+        assert gc.get_freeze_count() > before
+    after = gc.get_freeze_count()
+    assert after <= before and _ParkedHeap.depth == 0
+    with _ParkedHeap(False) as off:
+        assert not off.mine and gc.get_freeze_count() == after
+    gc.freeze()  # a heap frozen by the caller is left alone
+    try:
+        n = gc.get_freeze_count()
+        with _ParkedHeap(True) as p:
+            assert not p.mine
+        assert gc.get_freeze_count() == n
+    finally:
+        gc.unfreeze()
+        _ParkedHeap.base = gc.get_freeze_count()
