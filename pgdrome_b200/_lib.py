@@ -164,18 +164,59 @@ F64, I32, I64 = torch.float64, torch.int32, torch.int64
 traffic = {"h2d": 0, "d2h": 0}
 
 
+_STAGE_BYTES = 32 << 20  # page-locked staging block per direction (larger arrays are copied in pieces)
+_stage = {}
+
+
+def _staging(kind):
+    """The package's page-locked host block for one direction ("h2d" / "d2h"), allocated on first use:
+    (tensor, NumPy byte view of the same memory -- host-side copies are plain single-threaded memcpys)."""
+    ent = _stage.get(kind)
+    if ent is None:
+        buf = torch.empty(_STAGE_BYTES, dtype=torch.uint8).pin_memory()
+        ent = (buf, buf.numpy())
+        _stage[kind] = ent
+    return ent
+
+
 def to_device(a, dtype=None):
-    """NumPy array / tensor -> contiguous CUDA tensor (counted as host->device traffic)."""
+    """NumPy array / tensor -> contiguous CUDA tensor (counted as host->device traffic).  The bytes travel through a
+    page-locked staging block, so the copy is a real DMA from pinned memory instead of the driver's blocking
+    pageable path."""
     require_cuda()
-    t = torch.as_tensor(a if isinstance(a, torch.Tensor) else np.ascontiguousarray(a), dtype=dtype)
-    traffic["h2d"] += t.numel() * t.element_size()
-    return t.to(torch.device("cuda", torch.cuda.current_device()))
+    t = torch.as_tensor(a if isinstance(a, torch.Tensor) else np.ascontiguousarray(a), dtype=dtype).contiguous()
+    nbytes = t.numel() * t.element_size()
+    traffic["h2d"] += nbytes
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if t.is_cuda or nbytes == 0 or t.is_pinned():
+        return t.to(dev)
+    out = torch.empty(t.shape, dtype=t.dtype, device=dev)
+    src = t.view(-1).view(torch.uint8).numpy()
+    dst = out.view(-1).view(torch.uint8)
+    stage, stage_np = _staging("h2d")
+    for o in range(0, nbytes, _STAGE_BYTES):
+        m = min(_STAGE_BYTES, nbytes - o)
+        stage_np[:m] = src[o:o + m]
+        dst[o:o + m].copy_(stage[:m], non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the block is reused by the next piece / call
+    return out
 
 
 def to_host(t):
-    """CUDA tensor -> NumPy array (counted as device->host traffic; synchronises)."""
-    traffic["d2h"] += t.numel() * t.element_size()
-    return t.cpu().numpy()
+    """CUDA tensor -> NumPy array (counted as device->host traffic; synchronises).  Staged through page-locked memory."""
+    nbytes = t.numel() * t.element_size()
+    traffic["d2h"] += nbytes
+    if not t.is_cuda or nbytes == 0 or nbytes > _STAGE_BYTES:
+        return t.cpu().numpy()
+    t = t.contiguous()
+    stage, stage_np = _staging("d2h")
+    stage[:nbytes].copy_(t.view(-1).view(torch.uint8), non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return stage_np[:nbytes].copy().view(_NP_DTYPE[t.dtype]).reshape(tuple(t.shape))
+
+
+_NP_DTYPE = {torch.float64: np.float64, torch.float32: np.float32, torch.int32: np.int32, torch.int64: np.int64,
+             torch.uint8: np.uint8, torch.bool: np.bool_, torch.int8: np.int8, torch.int16: np.int16}
 
 
 def stats(device=None, reset=False):

@@ -7,6 +7,8 @@ arrays, or the fused P1 kernel ``_lib.assemble_p1``), cf. SURVEY.md 7.1 and
 pgdrome/solver.py:547-556.  All arithmetic happens in libpgdb200.so; this module only stages the
 host tables (basis tabulation, quadrature, coefficient samples) that FFC would have generated.
 """
+import weakref
+
 import numpy as np
 import torch
 
@@ -27,8 +29,8 @@ class DeviceSpace:
     """GPU mirror of a FunctionSpace: mesh arrays, CSR pattern, gather lists, cached atoms."""
 
     def __init__(self, space):
-        self.space = space
-        m = space.mesh()
+        self._space = weakref.ref(space)  # the space owns this object (space._dev): no strong back-reference, so
+        m = space.mesh()                  # dropping the space frees the device arrays by reference count alone
         self.coords = _up(m.coordinates(), torch.float64)
         self.cell_verts = _up(m.cells(), torch.int32)
         self.cell_dofs = _up(space.cell_dofs, torch.int32)
@@ -40,6 +42,10 @@ class DeviceSpace:
         self._facet = {}
         self.atoms = {}  # key -> values tensor
         self.band = None
+
+    @property
+    def space(self):
+        return self._space()
 
     # ---- structure
     @property

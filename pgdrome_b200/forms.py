@@ -23,6 +23,7 @@ with coef_g = float constants x the mode integrals of the other dimensions (Lazy
 in one batch per system, one device->host copy).
 """
 import math
+import weakref
 
 import numpy as np
 import torch
@@ -209,14 +210,22 @@ class Atom:
     """One assembled operator K[T, weights] on a space + the panel of cached products K @ f."""
 
     def __init__(self, ds, values, symmetric):
-        self.ds, self.values, self.symmetric = ds, values, symmetric
+        # the DeviceSpace owns its atoms and the Functions own their space: back-references are weak so that the
+        # whole structure is released by reference counting when the user drops the problem and its spaces
+        self._ds, self.values, self.symmetric = weakref.ref(ds), values, symmetric
         self.panel = None  # [cap, n_dofs]
-        self.rows = {}  # id(fn) -> (row, version, fn)  (keeps fn alive)
+        self.rows = {}  # id(fn) -> (row, version, weakref(fn))
         self.n_rows = 0
+
+    @property
+    def ds(self):
+        return self._ds()
 
     def product(self, fn):
         """Cached K @ fn (a row of the panel); recomputed if fn changed."""
         ent = self.rows.get(id(fn))
+        if ent is not None and ent[2]() is not fn:  # the id was recycled by another Function: reuse the row
+            ent = (ent[0], -1, None)
         if ent is not None and ent[1] == fn._version:
             return ent[0]
         if ent is None:
@@ -232,12 +241,12 @@ class Atom:
             row = ent[0]
         rowptr, colidx, _, _ = self.ds.pattern
         _lib.spmv(rowptr, colidx, self.values, fn.tensor(), self.panel[row], lpr=self.ds.lpr)
-        self.rows[id(fn)] = (row, fn._version, fn)
+        self.rows[id(fn)] = (row, fn._version, weakref.ref(fn))
         return row
 
     def has_fresh(self, fn):
         ent = self.rows.get(id(fn))
-        return ent is not None and ent[1] == fn._version
+        return ent is not None and ent[2]() is fn and ent[1] == fn._version
 
 
 def _embed_operator(ds, op, scale, transpose):
@@ -271,13 +280,15 @@ def get_atom(space, T, weights, meas, op=None, transpose=False):
     if op is not None:
         key = ("op", id(op), op._version, tb, bool(transpose))
         a = ds.atoms.get(key)
+        if a is not None and a.keepalive() is not op:  # id recycled by another operator object
+            a = None
         if a is None:
             nz = np.argwhere(T != 0.0)
             if len(nz) != 1 or tuple(nz[0]) != (0, 0, 0, 0):
                 raise NotImplementedError("MatrixOperator applied to derivatives / vector components")
             vals, sym = _embed_operator(ds, op, float(T[0, 0, 0, 0]), bool(transpose))
             a = Atom(ds, vals, sym)
-            a.keepalive = op
+            a.keepalive = weakref.ref(op)  # weak: the operator owns its space, the space owns this atom
             ds.atoms[key] = a
         return a
     if meas.kind != "dx":

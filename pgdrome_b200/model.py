@@ -20,6 +20,7 @@ Out of scope (C13, C15): DOLFIN HDF5 / XDMF side files and deriva
 """
 import logging
 import os
+import weakref
 import xml.etree.ElementTree as et
 
 import numpy as np
@@ -37,7 +38,10 @@ class _LazyData:
     (model.py:1510-1556) are only materialised when somebody indexes them."""
 
     def __init__(self, attr, num_modes, mesh, pgd_modes):
-        self._attr, self._n, self._mesh, self._modes = attr, num_modes, mesh, pgd_modes
+        # the attribute owns this object and the PGDMesh owns the attribute: weak back-references (no cycles, so a
+        # dropped model releases its modes by reference counting)
+        self._attr, self._mesh = weakref.ref(attr), weakref.ref(mesh)
+        self._n, self._modes = num_modes, pgd_modes
         self._cache = {}
 
     def __len__(self):
@@ -51,7 +55,7 @@ class _LazyData:
         if not 0 <= k < self._n:
             raise IndexError(k)
         if k not in self._cache:
-            self._cache[k] = self._attr._vertex_data(self._mesh, self._modes[k])
+            self._cache[k] = self._attr()._vertex_data(self._mesh(), self._modes[k])
         return self._cache[k]
 
     def __iter__(self):

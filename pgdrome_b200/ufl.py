@@ -195,10 +195,17 @@ class Leaf(Expr):
     kind = "leaf"
 
     def _init_leaf(self, n_comp):
-        if n_comp in (None, 0, 1):
-            Expr.__init__(self, (), [[Mono(1.0, (Factor(self, None, None),))]])
-        else:
-            Expr.__init__(self, (n_comp,), [[Mono(1.0, (Factor(self, i, None),))] for i in range(n_comp)])
+        self._n_comp = 1 if n_comp in (None, 0, 1) else int(n_comp)
+        self.ufl_shape = () if self._n_comp == 1 else (self._n_comp,)
+
+    @property
+    def comps(self):
+        """The leaf as a polynomial in itself -- built per use, not stored: a stored copy would make every Function /
+        Constant / Expression a reference cycle (leaf -> monomial -> factor -> leaf), i.e. device vectors that only
+        the cycle collector can free."""
+        if self._n_comp == 1:
+            return [[Mono(1.0, (Factor(self, None, None),))]]
+        return [[Mono(1.0, (Factor(self, i, None),))] for i in range(self._n_comp)]
 
 
 class _LazyLeaf(Leaf):

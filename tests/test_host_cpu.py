@@ -186,3 +186,39 @@ def test_parked_heap_restores_collector_state():
     finally:
         gc.unfreeze()
         _ParkedHeap.base = gc.get_freeze_count()
+
+
+@pytest.mark.parametrize("make", [
+    lambda c: c.heat2d_tk(n=10, nt=20, nk=6, PGD_nmax=2, PGD_tol=0.0),
+    lambda c: c.elasticity3d(n=3, nE=5, nF=2, PGD_nmax=2),
+    lambda c: c.thermal3d(n=4, nt=10, nP=3, nv=3, n_src=2, PGD_nmax=2),
+    lambda c: c.poisson1d_k(nx=40, nk=10, PGD_nmax=2),
+])
+def test_dropped_problem_is_freed_by_reference_counting(cpu, make):
+    """No reference cycles through the package's objects: dropping a solved problem (and its PGD model) releases its
+    spaces, device arrays and modes immediately -- device memory must not wait for the cycle collector."""
+    import gc
+    import weakref
+
+    from pgdrome_b200 import configs
+
+    gc.collect()
+    gc.disable()
+    try:
+        def run():
+            p = make(configs)
+            p.solve_PGD(_problem="linear")
+            pgd = p.return_PGD()
+            pgd.evaluate_batch(0, list(range(1, len(p.V))), [[float(v.mesh().coordinates()[1, 0]) for v in p.V[1:]]], 0)
+            return [weakref.ref(o) for o in (p, pgd, p.V[0], p.V[0]._dev["device_space"], p.PGD_func[0][0])]
+
+        refs = run()
+        assert [r() is None for r in refs] == [True] * 5
+        gc.set_debug(gc.DEBUG_SAVEALL)
+        gc.collect()
+        mine = [o for o in gc.garbage if type(o).__module__.startswith("pgdrome_b200")]
+        assert not mine, sorted({type(o).__name__ for o in mine})
+    finally:
+        gc.set_debug(0)
+        gc.garbage.clear()
+        gc.enable()

@@ -35,6 +35,9 @@ for rep in range(int(sys.argv[1]) if len(sys.argv) > 1 else 8):
     q.solve_PGD(_problem="linear")
     modes = [[f.vector().get_local() for f in q.PGD_func[d]] for d in range(3)]
     e1.record(); torch.cuda.synchronize()
+    ms_ = torch.cuda.memory_stats()
+    print("    device allocs %d frees %d (cumulative), reserved %.0f MB, host pinned stage %s" % (
+        ms_.get("num_device_alloc", 0), ms_.get("num_device_free", 0), ms_.get("reserved_bytes.all.current", 0) / 1e6, list(_lib._stage)))
     st = _lib.stats(reset=True)
     print("   ", {k: round(1e3 * v, 1) for k, v in tim.items()}); tim.clear()
     print("rep %d: device %.1f ms wall %.1f ms (make %.1f ms) full collections %d (%.1f ms) pcg_iters %d pcg_ms %.1f solves %d cpu %.1f ms" % (
