@@ -424,16 +424,18 @@ _UNIT_T = {}  # (bs, g, comp_a, slot_a, comp_b, slot_b, coef) -> form tensor (sh
 _TBYTES = {}  # id(T) of the shared tensors above -> T.tobytes() (atom cache key)
 
 
-def _fast_functional(meas, m):
-    """Mode integral with exactly two Function operands of one space (F*G*dx, F.dx(i)*G.dx(j)*dx, op(F, G)*dx,
-    times float constants): the overwhelmingly common functional of a separated-form callback.  Builds the
-    LazyScalar leaf directly -- same semantics as compile_form + Group.tensor, ~5x less host work.  Returns
-    None for anything else (the general path then decides or raises)."""
+def _parse_functional_mono(m):
+    """(coef, f1, f2, op, weights) of one monomial with exactly two Function operands, or None."""
     coef = m.coef
     f1 = f2 = op = None
+    weights = ()
     for f in m.factors:
         k = f.leaf.kind
-        if k == "function":
+        if k == "expression":  # weight, e.g. u*k(x)*v*dx (same bookkeeping as compile_form)
+            if f.deriv is not None:
+                return None
+            weights += ((f.leaf, f.comp),)
+        elif k == "function":
             if f1 is None:
                 f1 = f
             elif f2 is None:
@@ -452,8 +454,21 @@ def _fast_functional(meas, m):
             op = f.leaf
         else:
             return None
-    if f2 is None or coef == 0.0:
+    if f2 is None:
         return None
+    return coef, f1, f2, op, weights
+
+
+def _fast_functional(meas, monos):
+    """Mode integral whose monomials all pair the same two Functions of one space (F*G*dx, F.dx(i)*G.dx(j)*dx,
+    inner(grad(F), grad(G))*dx, F*k(x)*G*dx, op(F, G)*dx, times float constants): the overwhelmingly common
+    functional of a separated-form callback.  Builds the LazyScalar leaf directly -- same semantics as
+    compile_form + Group.tensor, ~5x less host work.  Returns None for anything else (the general path then
+    decides or raises)."""
+    first = _parse_functional_mono(monos[0])
+    if first is None:
+        return None
+    coef, f1, f2, op, weights = first
     space = f1.leaf.V
     if not _same_space(f2.leaf.V, space):
         return None
@@ -461,17 +476,34 @@ def _fast_functional(meas, m):
         return None
     if meas.kind != "dx" or meas.subdomain_id is not None:
         return None
-    if op is not None and (f1.deriv is not None or f2.deriv is not None or not _same_space(op.V, space)):
+    if op is not None and (weights or f1.deriv is not None or f2.deriv is not None or not _same_space(op.V, space)):
         return None
+    if len(weights) > 1:
+        weights = tuple(sorted(weights, key=lambda wc: (id(wc[0]), wc[1] or 0)))
     key = (space.bs, space.mesh().gdim, f1.comp or 0, _slot(f1.deriv), f2.comp or 0, _slot(f2.deriv), coef)
+    for m in monos[1:]:
+        nxt = _parse_functional_mono(m)
+        if nxt is None:
+            return None
+        c, g1, g2, op2, w2 = nxt
+        if g1.leaf is not f1.leaf or g2.leaf is not f2.leaf or op2 is not None or op is not None:
+            return None
+        if len(w2) > 1:
+            w2 = tuple(sorted(w2, key=lambda wc: (id(wc[0]), wc[1] or 0)))
+        if w2 != weights:
+            return None
+        key += (g1.comp or 0, _slot(g1.deriv), g2.comp or 0, _slot(g2.deriv), c)
     T = _UNIT_T.get(key)
     if T is None:
         T = np.zeros((key[0], key[1] + 1, key[0], key[1] + 1))
-        T[key[2], key[3], key[4], key[5]] = coef
+        for i in range(2, len(key), 5):
+            T[key[i], key[i + 1], key[i + 2], key[i + 3]] += key[i + 4]
         T.setflags(write=False)
         _UNIT_T[key] = T
         _TBYTES[id(T)] = T.tobytes()
-    return LazyScalar("leaf", (_Functional("bil", space, T, (), meas, f1.leaf, f2.leaf, op),))
+    if not T.any():
+        return None
+    return LazyScalar("leaf", (_Functional("bil", space, T, weights, meas, f1.leaf, f2.leaf, op),))
 
 
 def assemble(form):
@@ -479,8 +511,8 @@ def assemble(form):
     if not isinstance(form, Form):
         raise TypeError("assemble expects a Form, got %r" % type(form))
     ints = form.integrals
-    if len(ints) == 1 and len(ints[0].monos) == 1:
-        fast = _fast_functional(ints[0].measure, ints[0].monos[0])
+    if len(ints) == 1 and 1 <= len(ints[0].monos) <= 9:
+        fast = _fast_functional(ints[0].measure, ints[0].monos)
         if fast is not None:
             return fast
     groups = compile_form(form)
