@@ -260,6 +260,7 @@ def run_b200(args):
     e2e = None
     if rank == 0 or world > 1:
         Ke = min(K, args.e2e_steps) if args.e2e_steps else min(K, NMAX)
+        p = st = None  # the device-resident problem is done: its memory goes back to the allocator before the next one
         q = make(Ke)
         for V in q.V:
             V._dev.pop("device_space", None)

@@ -35,6 +35,7 @@ from .lazy import LazyScalar
 from .ufl import Form
 
 MAX_PANEL_ROWS = 8
+panel_rows_hint = [MAX_PANEL_ROWS]  # first allocation of a product panel (the solver sets it from PGD_nmax)
 
 
 # ------------------------------------------------------------------------------- compile (host)
@@ -230,7 +231,7 @@ class Atom:
             return ent[0]
         if ent is None:
             if self.panel is None or self.n_rows == self.panel.shape[0]:
-                cap = MAX_PANEL_ROWS if self.panel is None else 2 * self.panel.shape[0]
+                cap = panel_rows_hint[0] if self.panel is None else 2 * self.panel.shape[0]
                 new = torch.empty((cap, self.ds.n_dofs), dtype=torch.float64, device=self.values.device)
                 if self.panel is not None:
                     new[: self.n_rows].copy_(self.panel[: self.n_rows])

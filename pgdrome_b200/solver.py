@@ -62,6 +62,9 @@ class _CsrOnDevice:
         return _lib.bilinear(self.rowptr, self.colidx, self.values, x, y, lpr=self.lpr)
 
 
+MODE_ARENA_ROWS = 64  # rows per block of the mode arenas / first allocation of the product panels
+
+
 class _ParkedHeap:
     """While an enrichment step runs, every object that existed before it sits in the collector's permanent
     generation (``gc.freeze``), and goes back afterwards (``gc.unfreeze``; both are O(1) list splices).
@@ -162,6 +165,8 @@ class PGDProblem:
     def invalidate_caches(self):
         self._bc_cache = self._dom_cache = None
         self._bcd = {}
+        self._mode_arena = {}
+        forms.panel_rows_hint[0] = max(forms.MAX_PANEL_ROWS, min(int(self.PGD_nmax), MODE_ARENA_ROWS))
 
     def _bc_dev(self, dim):
         """(dofs int32 tensor, values tensor | None) of dimension dim, or None."""
@@ -355,7 +360,20 @@ class PGDProblem:
         return False
 
     def _store(self, dim, f):
+        """Keep a converged mode.  Its values move into the dimension's mode arena -- [rows, n_dofs] blocks sized
+        from PGD_nmax and allocated when the first mode arrives -- so that a run does not grow the device heap mode
+        by mode (every new allocator segment is a blocking cudaMalloc), and all modes of a dimension are rows of one
+        matrix (the X operand of evaluate)."""
         f.stable = True  # K @ U_i products of stored modes are cached in the atom panels
+        arena = self.__dict__.setdefault("_mode_arena", {}).setdefault(dim, [None, 0])  # [current block, rows used]
+        t = f.tensor()
+        if arena[0] is None or arena[1] == arena[0].shape[0]:
+            rows = max(1, min(int(self.PGD_nmax) - len(self.PGD_func[dim]), MODE_ARENA_ROWS))
+            arena[0], arena[1] = torch.empty((rows, t.numel()), dtype=t.dtype, device=t.device), 0
+        row = arena[0][arena[1]]
+        arena[1] += 1
+        row.copy_(t)
+        f.set_tensor(row)
         self.PGD_func[dim].append(f)
 
     def _csr(self, A):
