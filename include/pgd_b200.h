@@ -214,6 +214,18 @@ int32_t pgd_eval_gemv(pgd_handle_t h, const double* d_X, int64_t ldx, int32_t R,
 int32_t pgd_eval_gemm_f64(pgd_handle_t h, const double* d_W, int64_t ldw, const double* d_X, int64_t ldx,
                           int32_t R, int64_t C, int64_t N, double* d_U, int64_t ldu, void* stream);
 
+/* Started / finished solve: pgd_pcg_start enqueues the SM-resident PCG (one cooperative kernel, the result lands in
+ * d_x in stream order) and returns without waiting, so the host can record the next sub-problem's forms while the
+ * GPU iterates; pgd_pcg_finish waits for it and reports iterations / relative residual (*h_iters = -1 when nothing
+ * was started).  Returns 1 (nothing enqueued) unless an earlier pgd_pcg[_x0]_sync call on the same d_rowptr / n /
+ * block ran SM-resident, i.e. the system is known to fit; the caller then uses the _sync entry points.  One solve
+ * in flight per handle; every other pcg entry point finishes a pending one first.  d_work as for pgd_pcg_sync;
+ * warm != 0: d_x holds the initial guess. */
+int32_t pgd_pcg_start(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
+                      const double* d_b, double* d_x, int64_t n, double rtol, double atol, int32_t maxit, int32_t block,
+                      double* d_work, int32_t warm, void* stream);
+int32_t pgd_pcg_finish(pgd_handle_t h, int32_t* h_iters, double* h_relres);
+
 /* ---- sensor evaluation (PGD.evaluate_sensor_response, model.py:862-953; eval_fixed_modes with
  * fenicstools.Probes, model.py:107-130).
  * pgd_locate_points: for each of n_points points [n_points, gdim] find the LOWEST-numbered simplex

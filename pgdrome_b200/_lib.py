@@ -62,6 +62,8 @@ SIGNATURES = {
     "pgd_eval_weights": [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp],
     "pgd_eval_gemv": [c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_vp, c_vp],
     "pgd_eval_gemm_f64": [c_vp, c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i64, c_vp, c_i64, c_vp],
+    "pgd_pcg_start": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_dbl, c_dbl, c_i32, c_i32, c_vp, c_i32, c_vp],
+    "pgd_pcg_finish": [c_vp, ctypes.POINTER(c_i32), ctypes.POINTER(c_dbl)],
     "pgd_locate_points": [c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_i32, c_dbl, c_vp, c_vp, c_vp],
     "pgd_probe_modes": [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_vp],
 }
@@ -544,6 +546,30 @@ def pcg(rowptr, colidx, values, b, x=None, rtol=1e-12, atol=0.0, maxit=20000, ch
               maxit, check_every, block, lpr, _p(work, F64), ctypes.byref(iters), ctypes.byref(relres),
               _stream()), h, "pgd_pcg_sync")
     return x, iters.value, relres.value
+
+
+def pcg_start(rowptr, colidx, values, b, rtol=1e-12, atol=0.0, maxit=20000, block=1, x0=None):
+    """Enqueue the SM-resident PCG without waiting (pgd_pcg_start).  Returns the solution tensor (valid in stream
+    order) or None when the system is not known to fit the resident solver -- then call ``pcg``.  Collect iterations
+    and residual with ``pcg_finish`` before the next solve."""
+    h, lib = handle(b.device), load_library()
+    n = b.numel()
+    x = x0.detach().clone() if x0 is not None else torch.empty(n, dtype=F64, device=b.device)
+    work = torch.empty((5 + block) * n + 8, dtype=F64, device=b.device)
+    rc = lib.pgd_pcg_start(h, _p(rowptr, I32), _p(colidx, I32), _p(values, F64), _p(b, F64), _p(x, F64), n, rtol, atol,
+                           maxit, block, _p(work, F64), 1 if x0 is not None else 0, _stream())
+    if rc == 1:
+        return None
+    _check(rc, h, "pgd_pcg_start")
+    return x
+
+
+def pcg_finish(device=None):
+    """(iterations, relative residual) of the solve started with ``pcg_start``; (-1, 0.0) if none is pending."""
+    h, lib = handle(device), load_library()
+    iters, relres = c_i32(0), c_dbl(0.0)
+    _check(lib.pgd_pcg_finish(h, ctypes.byref(iters), ctypes.byref(relres)), h, "pgd_pcg_finish")
+    return iters.value, relres.value
 
 
 def banded_solve(rowptr, colidx, values, b, perm, kl, ku, x=None, work=None, info=None):

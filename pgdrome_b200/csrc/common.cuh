@@ -29,7 +29,13 @@ struct pgd_ctx {
     // statistics (pgd_get_stats): kernel launches, PCG solves / iterations / device time
     int64_t n_launches, pcg_solves, pcg_iters, pcg_resident_solves;
     double pcg_ms;
-    void* pinned;            // 256 B of page-locked host memory: staging for the small device->host reads of the *_sync calls
+    void* pinned;            // 512 B of page-locked host memory: [0,256) staging for the small device->host reads of the *_sync
+                             // calls, [256,512) results of a started (pgd_pcg_start) solve
+    int res_pending;         // a solve started with pgd_pcg_start has not been finished yet
+    void* res_stream;        // ... on this stream
+    const void* fit_key;     // rowptr / n / block of the last system the SM-resident PCG solved (=> it fits: eligible for start)
+    int64_t fit_n;
+    int fit_block;
     void* arena;             // grow-only device scratch of the set-up calls (pattern / vecmap builds), see pgd_arena
     size_t arena_cap;
     int pat_in_arena;        // the pending pattern lives in the arena (nothing to free)

@@ -26,7 +26,7 @@ extern "C" int32_t pgd_create(int32_t device, pgd_handle_t* out) {
         (e = cudaMalloc(&h->counters, sizeof(unsigned int) * PGD_MAX_COUNTERS)) != cudaSuccess ||
         (e = cudaMalloc(&h->scalars, sizeof(double) * 64)) != cudaSuccess ||
         (e = cudaMalloc(&h->flags, sizeof(int) * 16)) != cudaSuccess ||
-        (e = cudaMallocHost(&h->pinned, 256)) != cudaSuccess) {
+        (e = cudaMallocHost(&h->pinned, 512)) != cudaSuccess) {
         delete h;
         return (int32_t)e;
     }

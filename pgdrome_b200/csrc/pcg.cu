@@ -438,7 +438,8 @@ static int32_t run_pcg(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const d
 
 int32_t pgd_pcg_resident(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const double* va, const double* b, double* x,
                          int64_t n, int64_t nnz_hint, double rtol, double atol, int maxit, int block, double* work,
-                         int32_t* h_iters, double* h_relres, cudaStream_t st, int warm);
+                         int32_t* h_iters, double* h_relres, cudaStream_t st, int warm, int defer);
+int32_t pgd_pcg_finish_impl(pgd_ctx* h, int32_t* h_iters, double* h_relres);
 
 static int32_t pcg_entry(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
                          const double* d_b, double* d_x, int64_t n, double rtol, double atol, int32_t maxit,
@@ -448,6 +449,10 @@ static int32_t pcg_entry(pgd_handle_t h, const int32_t* d_rowptr, const int32_t*
     PGD_ARG(h, d_rowptr && d_colidx && d_values && d_b && d_x && d_work && n > 0, "bad arguments");
     PGD_ARG(h, block >= 1 && block <= 3 && n % block == 0, "block must be 1..3 and divide n");
     cudaStream_t st = (cudaStream_t)stream;
+    {  // a solve started earlier and never collected: finish it first (its counters are kept, its status is dropped)
+        int32_t rc0 = pgd_pcg_finish_impl(h, nullptr, nullptr);
+        if (rc0 < 0) return rc0;
+    }
     if (h->opt_resident && n <= ((int64_t)1 << 22)) {
         if (h->nnz_key != (const void*)d_rowptr || h->nnz_key_n != n) {
             int32_t last = 0;
@@ -457,7 +462,7 @@ static int32_t pcg_entry(pgd_handle_t h, const int32_t* d_rowptr, const int32_t*
             h->nnz_val = last;
         }
         int32_t rc = pgd_pcg_resident(h, d_rowptr, d_colidx, d_values, d_b, d_x, n, h->nnz_val, rtol, atol, maxit, block,
-                                      d_work, h_iters, h_relres, st, warm ? 1 : 0);
+                                      d_work, h_iters, h_relres, st, warm ? 1 : 0, 0);
         if (rc != 1) return rc;
     }
     if (block == 1)
@@ -651,4 +656,28 @@ extern "C" int32_t pgd_spcg_rotate(pgd_handle_t h, double* d_sc, int32_t* d_fl, 
     k_spcg_rotate<<<1, 1, 0, (cudaStream_t)stream>>>(d_sc, d_fl);
     PGD_LAUNCH_OK(h);
     return 0;
+}
+
+/* Started / finished solve (see include/pgd_b200.h). */
+extern "C" int32_t pgd_pcg_start(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
+                                 const double* d_b, double* d_x, int64_t n, double rtol, double atol, int32_t maxit,
+                                 int32_t block, double* d_work, int32_t warm, void* stream) {
+    PGD_CHECK_HANDLE(h);
+    PGD_ARG(h, d_rowptr && d_colidx && d_values && d_b && d_x && d_work && n > 0, "bad arguments");
+    PGD_ARG(h, block >= 1 && block <= 3 && n % block == 0, "block must be 1..3 and divide n");
+    if (!h->opt_resident || h->fit_key != (const void*)d_rowptr || h->fit_n != n || h->fit_block != block ||
+        h->nnz_key != (const void*)d_rowptr || h->nnz_key_n != n)
+        return 1;  // not known to fit the SM-resident solver: use pgd_pcg_sync / pgd_pcg_x0_sync
+    return pgd_pcg_resident(h, d_rowptr, d_colidx, d_values, d_b, d_x, n, h->nnz_val, rtol, atol, maxit, block, d_work, nullptr,
+                            nullptr, (cudaStream_t)stream, warm ? 1 : 0, 1);
+}
+
+extern "C" int32_t pgd_pcg_finish(pgd_handle_t h, int32_t* h_iters, double* h_relres) {
+    PGD_CHECK_HANDLE(h);
+    int32_t rc = pgd_pcg_finish_impl(h, h_iters, h_relres);
+    if (rc == 1) {
+        snprintf(h->err, sizeof(h->err), "pgd_pcg_finish: the started system no longer fits the SM-resident solver");
+        return -5;
+    }
+    return rc;
 }

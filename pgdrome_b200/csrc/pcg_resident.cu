@@ -337,10 +337,17 @@ __global__ void __launch_bounds__(512, 1) k_pcg_resident(ResArgs a) {
     }
 }
 
-// returns 0 ok, 1 = not resident (caller falls back), <0 / >1 errors as usual
+int32_t pgd_pcg_finish_impl(pgd_ctx* h, int32_t* h_iters, double* h_relres);
+
+// returns 0 ok, 1 = not resident (caller falls back), <0 / >1 errors as usual.  defer != 0: enqueue only, the
+// results are collected by pgd_pcg_finish_impl (the caller knows from an earlier solve that the system fits)
 int32_t pgd_pcg_resident(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const double* va, const double* b, double* x,
                          int64_t n, int64_t nnz_hint, double rtol, double atol, int maxit, int block, double* work,
-                         int32_t* h_iters, double* h_relres, cudaStream_t st, int warm) {
+                         int32_t* h_iters, double* h_relres, cudaStream_t st, int warm, int defer) {
+    {  // one solve in flight per handle: its results sit in the page-locked block until they are collected
+        int32_t rc0 = pgd_pcg_finish_impl(h, nullptr, nullptr);
+        if (rc0 < 0) return rc0;
+    }
     const int G = h->sm_count;
     const size_t smem_max = 200 * 1024;
     // capacity estimate from the mean slice (+25 % slack for uneven rows); the kernel re-checks exactly
@@ -389,9 +396,38 @@ int32_t pgd_pcg_resident(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const
     PGD_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3(G), dim3(512), kargs, bytes, st));
     h->n_launches += 1;
     PGD_CUDA(h, cudaEventRecord(h->ev1, st));
+    // results -> the handle's page-locked block; read by pgd_pcg_finish_impl after the stream has drained
+    char* pin = static_cast<char*>(h->pinned) + 256;
+    PGD_CUDA(h, cudaMemcpyAsync(pin, a.out_fl, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    PGD_CUDA(h, cudaMemcpyAsync(pin + 64, a.out_sc, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    h->res_pending = 1;
+    h->res_stream = (void*)st;
+    if (defer) {
+        if (h_iters) *h_iters = -1;
+        return 0;
+    }
+    int32_t rc = pgd_pcg_finish_impl(h, h_iters, h_relres);
+    if (rc == 0) {  // this system fits the SMs: later solves on it may be started without waiting
+        h->fit_key = (const void*)rp;
+        h->fit_n = n;
+        h->fit_block = block;
+    }
+    return rc;
+}
+
+// waits for a started solve; 0 ok, 1 = the slices did not fit (nothing was solved), -3 NaN; *h_iters = -1 if none was pending
+int32_t pgd_pcg_finish_impl(pgd_ctx* h, int32_t* h_iters, double* h_relres) {
+    if (!h->res_pending) {
+        if (h_iters) *h_iters = -1;
+        return 0;
+    }
+    h->res_pending = 0;
+    PGD_CUDA(h, cudaStreamSynchronize((cudaStream_t)h->res_stream));
+    const char* pin = static_cast<const char*>(h->pinned) + 256;
     int hf[2];
     double hs[2];
-    PGD_CUDA(h, pgd_fetch(h, hf, a.out_fl, sizeof(hf), hs, a.out_sc, sizeof(hs), st));
+    memcpy(hf, pin, sizeof(hf));
+    memcpy(hs, pin + 64, sizeof(hs));
     if (hf[1] == 1) return 1;
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->pcg_ms += ms;
@@ -401,7 +437,7 @@ int32_t pgd_pcg_resident(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const
     if (h_iters) *h_iters = hf[0];
     if (h_relres) *h_relres = (hs[1] > 0.0) ? sqrt(hs[0] / hs[1]) : 0.0;
     if (hf[1] == 2) {
-        snprintf(h->err, sizeof(h->err), "pgd_pcg_sync: NaN encountered (matrix not SPD?)");
+        snprintf(h->err, sizeof(h->err), "pgd_pcg: NaN encountered (matrix not SPD?)");
         return -3;
     }
     return 0;

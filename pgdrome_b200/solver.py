@@ -277,7 +277,10 @@ class PGDProblem:
                         settings={"linear_solver": "mumps"}):
         """One pass of the enrichment loop body (one new mode per dimension). True = stop."""
         with _ParkedHeap(settings.get("gc_freeze", True)):
-            return self._enrichment_step(n_enr, normConv, relConv, _problem, solve_modes, settings)
+            try:
+                return self._enrichment_step(n_enr, normConv, relConv, _problem, solve_modes, settings)
+            finally:
+                self._collect_solve()
 
     def _enrichment_step(self, n_enr, normConv, relConv, _problem, solve_modes, settings):
         D = self.num_pgd_var
@@ -533,13 +536,32 @@ class PGDProblem:
         x0 = getattr(self, "_x0", None)
         if x0 is not None and x0.numel() != b.numel():
             x0 = None
+        self._collect_solve()
+        if settings.get("async_solve", True):
+            # SM-resident systems (known to fit from an earlier solve): enqueue and go on recording the next
+            # sub-problem's forms while the GPU iterates; iterations / residual are collected before the next solve
+            x = _lib.pcg_start(rowptr, colidx, values, b, rtol=rtol, atol=atol, maxit=maxit, block=block, x0=x0)
+            if x is not None:
+                self._pending_solve = (rtol, maxit)
+                return x
         x, iters, relres = _lib.pcg(rowptr, colidx, values, b, rtol=rtol, atol=atol, maxit=maxit,
                                     check_every=int(settings.get("check_every", 50)), block=block, lpr=ds.lpr, x0=x0)
+        self._account_solve(iters, relres, rtol, maxit)
+        return x
+
+    def _account_solve(self, iters, relres, rtol, maxit):
         self.solver_stats["pcg_solves"] += 1
         self.solver_stats["pcg_iterations"] += iters
         if relres > max(rtol, 1e-15) * 10 and iters >= maxit:
             self.logger.warning("PCG stopped at relative residual %.3e after %d iterations", relres, iters)
-        return x
+
+    def _collect_solve(self):
+        """Wait for a solve started with pgd_pcg_start and book its iteration count."""
+        pend = self.__dict__.pop("_pending_solve", None)
+        if pend is not None:
+            iters, relres = _lib.pcg_finish()
+            if iters >= 0:
+                self._account_solve(iters, relres, *pend)
 
     # ---- multi-GPU: the spatial solve sharded by rows over the ranks of torch.distributed
     @staticmethod

@@ -285,10 +285,18 @@ def probe_modes(X, R, dofs, w):
     return _t(np.einsum("rj,krj->kr", wn, Xn[:, d]))
 
 
+def pcg_start(*a, **k):
+    return None  # the stand-in has no resident solver: the host logic falls back to pcg()
+
+
+def pcg_finish(device=None):
+    return -1, 0.0
+
+
 NAMES = ["pattern_build", "vecmap_build", "elem_bilinear", "elem_linear", "gather_values", "assemble_p1",
          "p1_rowplan_build", "assemble_p1_rows", "lincomb",
          "apply_dirichlet", "set_entries", "spmv", "spmv_dot", "bilinear", "dot", "panel_dots", "pcg", "banded_solve",
-         "eval_weights", "eval_gemv", "eval_gemm", "locate_points", "probe_modes"]
+         "eval_weights", "eval_gemv", "eval_gemm", "locate_points", "probe_modes", "pcg_start", "pcg_finish"]
 
 
 def install(monkeypatch):
