@@ -278,6 +278,25 @@ def test_dirichlet_and_pcg(kind, degree, bs, block):
         assert np.linalg.norm(xw.cpu().numpy() - xo) / np.linalg.norm(xo) < 1e-10
     _lib.set_option("pcg_resident", 1)
     assert abs(its[0] - its[1]) <= max(3, its[0] // 20)
+    # started / finished solve: only after a blocking solve showed that the system fits the SM-resident solver
+    other = rowptr.clone()
+    assert _lib.pcg_start(other, colidx, vals, bd, rtol=1e-13, maxit=5000, block=block) is None
+    assert _lib.pcg_finish() == (-1, 0.0)
+    xs, it_s, _ = _lib.pcg(rowptr, colidx, vals, bd, rtol=1e-13, maxit=5000, check_every=25, block=block)
+    _lib.stats(reset=True)
+    xa = _lib.pcg_start(rowptr, colidx, vals, bd, rtol=1e-13, maxit=5000, block=block)
+    assert xa is not None
+    it_a, rr_a = _lib.pcg_finish()
+    assert it_a == it_s and rr_a <= 1e-13 and torch.equal(xa, xs)  # same kernel, bitwise the same answer
+    assert _lib.pcg_finish() == (-1, 0.0)
+    pert = xs * (1.0 + 1e-6 * torch.cos(torch.arange(xs.numel(), device=xs.device, dtype=xs.dtype)))
+    xw = _lib.pcg_start(rowptr, colidx, vals, bd, rtol=1e-13, maxit=5000, block=block, x0=pert)
+    # a blocking call while a started solve is pending collects it first (its counters are kept)
+    xz, itz, _ = _lib.pcg(rowptr, colidx, vals, torch.zeros_like(bd), rtol=1e-13, maxit=10, block=block)
+    assert itz == 0 and _lib.pcg_finish() == (-1, 0.0)
+    st = _lib.stats()
+    assert st["pcg_solves"] == 3 and 0 < st["pcg_iters"] - it_a < it_s
+    assert np.linalg.norm(xw.cpu().numpy() - xo) / np.linalg.norm(xo) < 1e-10
 
 
 @pytest.mark.parametrize("degree", [1, 2])
