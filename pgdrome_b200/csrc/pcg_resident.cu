@@ -6,7 +6,8 @@
 // nnz-balanced row slice of (values, columns) into its shared memory ONCE (up to ~200 KB per SM, i.e.
 // ~2.5 M nonzeros chip-wide) together with its slices of x, r, p, q, M^-1, and then iterates
 //
-//     S2: q_i = sum_j A_ij (z_j + beta p_j)      gathers of z, p_old from L2 (ld.global.cg)
+//     S2: q_i = sum_j A_ij (z_j + beta p_j)      z, p_old over the slice's column window: cp.async.cg started right
+//                                                  after the previous barrier, overlapping the reduction round trip
 //         p_i = z_i + beta p_i ; pq = sum p_i q_i                         -> grid barrier (reduces pq)
 //     S3: x += alpha p ; r -= alpha q ; z = M^-1 r ; rz, rr                -> grid barrier (reduces rz, rr)
 //
@@ -17,6 +18,15 @@
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+
+// 16-byte asynchronous global -> shared copy that bypasses L1 (.cg): the window of p / z is written by other CTAs
+__device__ __forceinline__ void cp_async_cg16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
 
 struct ResArgs {
     const int32_t* rowptr;
@@ -37,6 +47,7 @@ struct ResArgs {
     int cap_nnz, cap_rows, cap_win;
     int warm;          // 1: x holds the initial guess x0 (r = b - A x0)
 };
+// zg / pg0 / pg1 are spaced by an even number of doubles so that 16-byte copies of a window stay aligned
 
 __device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
     unsigned int v;
@@ -46,13 +57,55 @@ __device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
 
 // all threads call; returns after every CTA of the grid has arrived (and their prior global writes
 // are visible).  `target` is this CTA's private running arrival target.
+// LEAD = false: the caller has already executed a __syncthreads after the CTA's last global write (block_sum does).
+template <bool LEAD = true>
 __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& target, unsigned int G) {
-    __syncthreads();
+    if (LEAD) __syncthreads();
     target += G;
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(bar, 1u);
         while (ld_acquire(bar) < target) {
+        }
+    }
+    __syncthreads();
+}
+
+// Sum over the block of two values at once (same tree per value as block_sum); results valid in thread 0.
+__device__ __forceinline__ void block_sum2(double& a, double& b) {
+    __shared__ double sh2[2][32];
+    __syncthreads();
+    a = warp_sum(a);
+    b = warp_sum(b);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) {
+        sh2[0][w] = a;
+        sh2[1][w] = b;
+    }
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    a = (threadIdx.x < nw) ? sh2[0][threadIdx.x] : 0.0;
+    b = (threadIdx.x < nw) ? sh2[1][threadIdx.x] : 0.0;
+    if (w == 0) {
+        a = warp_sum(a);
+        b = warp_sum(b);
+    }
+}
+
+// two values per CTA stored side by side (one 16-byte load per CTA fetches both): same per-value order as sum_partials
+__device__ __forceinline__ void sum_partials_pair(const double2* part, unsigned int G, double* s_out) {
+    if (threadIdx.x < 32) {
+        double s0 = 0.0, s1 = 0.0;
+        for (unsigned int i = threadIdx.x; i < G; i += 32) {
+            const double2 v = __ldcg(&part[i]);
+            s0 += v.x;
+            s1 += v.y;
+        }
+        s0 = warp_sum(s0);
+        s1 = warp_sum(s1);
+        if (threadIdx.x == 0) {
+            s_out[0] = s0;
+            s_out[1] = s1;
         }
     }
     __syncthreads();
@@ -111,8 +164,9 @@ __global__ void __launch_bounds__(512, 1) k_pcg_resident(ResArgs a) {
     double* s_q = s_p + a.cap_rows;
     double* s_z = s_q + a.cap_rows;
     double* s_minv = s_z + a.cap_rows;  // [cap_rows * BS]
-    double* s_win = s_minv + (size_t)a.cap_rows * BS;  // [cap_win] window of p_new over the slice's column range
-    int* s_cols = reinterpret_cast<int*>(s_win + a.cap_win);
+    double* s_zw = s_minv + (size_t)a.cap_rows * BS;  // [cap_win] window of z over the slice's column range
+    double* s_pw = s_zw + a.cap_win;                   // [cap_win] window of p_old
+    int* s_cols = reinterpret_cast<int*>(s_pw + a.cap_win);
     int* s_rp = s_cols + a.cap_nnz;  // [cap_rows + 1], relative to k0
 
     if (tid == 0) s_bad = (nnz > a.cap_nnz || rows > a.cap_rows) ? 1 : 0;
@@ -129,7 +183,7 @@ __global__ void __launch_bounds__(512, 1) k_pcg_resident(ResArgs a) {
     for (int i = tid; i <= rows; i += nt) s_rp[i] = a.rowptr[r0 + i] - k0;
     __syncthreads();
     // column range of the slice: if it fits, every iteration first loads p_new = z + beta p_old over
-    // [cmin, cmax] with coalesced L2 reads into s_win and the SpMV then runs entirely out of shared memory
+    // [cmin, cmax] into shared memory (asynchronous 16-byte copies) and the SpMV then runs entirely out of shared memory
     int cmin = 0x7fffffff, cmax = -1;
     for (int k = tid; k < nnz; k += nt) {
         cmin = min(cmin, s_cols[k]);
@@ -148,8 +202,18 @@ __global__ void __launch_bounds__(512, 1) k_pcg_resident(ResArgs a) {
         cmin = s_mm[0];
         cmax = s_mm[1];
     }
-    const int wlen = cmax - cmin + 1;
+    cmin &= ~1;                                   // even start and even length: 16-byte copies
+    const int wlen = ((cmax + 2) & ~1) - cmin;
     const bool windowed = (rows > 0) && (wlen <= a.cap_win);
+    // after a grid barrier: start copying the window of z and of the given p into shared memory (no registers, L1
+    // bypassed); it is waited for at the top of the next S2, so the round trip overlaps the reduction of the partials
+    auto prefetch_window = [&](const double* psrc) {
+        if (!windowed) return;
+        for (int j = 2 * tid; j < wlen; j += 2 * nt) {
+            cp_async_cg16(&s_zw[j], &a.zg[cmin + j]);
+            cp_async_cg16(&s_pw[j], &psrc[cmin + j]);
+        }
+    };
     if (windowed)
         for (int k = tid; k < nnz; k += nt) s_cols[k] -= cmin;
     __syncthreads();
@@ -232,6 +296,7 @@ __global__ void __launch_bounds__(512, 1) k_pcg_resident(ResArgs a) {
         a.part[(size_t)4 * G + bid] = acc2;
     }
     grid_barrier(a.bar, target, G);
+    prefetch_window(a.pg0);
     sum_partials<2>(a.part + (size_t)slot * 2 * G, G, s_red);
     const double rz0 = s_red[0], bb0 = s_red[1];
     __syncthreads();
@@ -255,14 +320,16 @@ __global__ void __launch_bounds__(512, 1) k_pcg_resident(ResArgs a) {
             // ---- S2
             double pq = 0.0;
             if (windowed) {
-                for (int j = tid; j < wlen; j += nt) s_win[j] = fma(beta, __ldcg(&pold[cmin + j]), __ldcg(&a.zg[cmin + j]));
+                cp_async_commit_wait_all();  // the window copies started after the previous barrier
                 __syncthreads();
-                const int off = (int)r0 - cmin;
                 for (int i = tid; i < rows; i += nt) {
                     const int ka = s_rp[i], kb = s_rp[i + 1];
                     double s = 0.0;
-                    for (int k = ka; k < kb; ++k) s = fma(s_vals[k], s_win[s_cols[k]], s);
-                    const double pi = s_win[off + i];
+                    for (int k = ka; k < kb; ++k) {
+                        const int c = s_cols[k];
+                        s = fma(s_vals[k], fma(beta, s_pw[c], s_zw[c]), s);
+                    }
+                    const double pi = fma(beta, s_p[i], s_z[i]);
                     s_p[i] = pi;
                     pnew[r0 + i] = pi;
                     s_q[i] = s;
@@ -286,7 +353,7 @@ __global__ void __launch_bounds__(512, 1) k_pcg_resident(ResArgs a) {
             }
             pq = block_sum(pq);
             if (tid == 0) a.part[(size_t)(slot * 2 + 0) * G + bid] = pq;
-            grid_barrier(a.bar, target, G);
+            grid_barrier<false>(a.bar, target, G);
             sum_partials<1>(a.part + (size_t)slot * 2 * G, G, s_red);
             slot ^= 1;
             const double alpha = rz / s_red[0];
@@ -308,14 +375,12 @@ __global__ void __launch_bounds__(512, 1) k_pcg_resident(ResArgs a) {
                 a0 = fma(ri, zi, a0);
                 a1 = fma(ri, ri, a1);
             }
-            a0 = block_sum(a0);
-            a1 = block_sum(a1);
-            if (tid == 0) {
-                a.part[(size_t)(slot * 2 + 0) * G + bid] = a0;
-                a.part[(size_t)(slot * 2 + 1) * G + bid] = a1;
-            }
-            grid_barrier(a.bar, target, G);
-            sum_partials<2>(a.part + (size_t)slot * 2 * G, G, s_red);
+            block_sum2(a0, a1);
+            double2* pair = reinterpret_cast<double2*>(a.part + (size_t)6 * G) + (size_t)slot * G;  // [2 slots][G] pairs
+            if (tid == 0) pair[bid] = make_double2(a0, a1);
+            grid_barrier<false>(a.bar, target, G);
+            prefetch_window(pnew);  // p of this iteration = p_old of the next
+            sum_partials_pair(pair, G, s_red);
             slot ^= 1;
             rz_old = rz;
             rz = s_red[0];
@@ -328,6 +393,7 @@ __global__ void __launch_bounds__(512, 1) k_pcg_resident(ResArgs a) {
             if (!(rr > tol2)) break;
         }
     }
+    cp_async_commit_wait_all();  // a window copy may still be in flight when the loop exits
     for (int i = tid; i < rows; i += nt) a.x[r0 + i] = (bb > 0.0) ? s_x[i] : 0.0;
     if (bid == 0 && tid == 0) {
         a.out_sc[0] = rr;
@@ -352,7 +418,8 @@ int32_t pgd_pcg_resident(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const
     const size_t smem_max = 200 * 1024;
     // capacity estimate from the mean slice (+25 % slack for uneven rows); the kernel re-checks exactly
     int cap_rows = (int)((n + G - 1) / G);
-    cap_rows = cap_rows + cap_rows / 4 + 8 * block;
+    cap_rows = (cap_rows + cap_rows / 4 + 8 * block + 1) & ~1;  // even: the windows behind the row arrays stay 16-byte aligned
+    if ((reinterpret_cast<uintptr_t>(work) & 15) != 0) return 1;  // the window copies are 16-byte transfers
     int64_t cap_nnz64 = (nnz_hint + G - 1) / G;
     cap_nnz64 = cap_nnz64 + cap_nnz64 / 4 + 64;
     if (cap_nnz64 > (1 << 22)) return 1;
@@ -361,10 +428,10 @@ int32_t pgd_pcg_resident(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const
                    sizeof(int) * ((size_t)cap_nnz + cap_rows + 1);
     if (bytes > smem_max) return 1;
     // whatever shared memory is left becomes the p-window (column range of the slice)
-    int cap_win = (int)((smem_max - bytes) / sizeof(double));
-    if (cap_win > 16384) cap_win = 16384;
+    int cap_win = (int)((smem_max - bytes) / (2 * sizeof(double)));
+    if (cap_win > 8192) cap_win = 8192;
     cap_win &= ~1;
-    bytes += sizeof(double) * (size_t)cap_win;
+    bytes += 2 * sizeof(double) * (size_t)cap_win;
     ResArgs a;
     a.rowptr = rp;
     a.colidx = ci;
@@ -375,9 +442,10 @@ int32_t pgd_pcg_resident(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const
     a.rtol = rtol;
     a.atol = atol;
     a.maxit = maxit;
+    const int64_t ns = n + (n & 1);  // even spacing (work holds (5 + block) n + 8 doubles)
     a.zg = work;
-    a.pg0 = work + n;
-    a.pg1 = work + 2 * n;
+    a.pg0 = work + ns;
+    a.pg1 = work + 2 * ns;
     a.part = h->partials;
     a.bar = h->counters + (PGD_MAX_COUNTERS - 1);
     a.out_sc = h->scalars + 32;
