@@ -28,6 +28,10 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
+#ifndef RES_THREADS
+#define RES_THREADS 512
+#endif
+
 struct ResArgs {
     const int32_t* rowptr;
     const int32_t* colidx;
@@ -461,7 +465,7 @@ int32_t pgd_pcg_resident(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const
                                   : (block == 2 ? (const void*)k_pcg_resident<2> : (const void*)k_pcg_resident<3>);
     PGD_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     PGD_CUDA(h, cudaEventRecord(h->ev0, st));
-    PGD_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3(G), dim3(512), kargs, bytes, st));
+    PGD_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3(G), dim3(RES_THREADS), kargs, bytes, st));
     h->n_launches += 1;
     PGD_CUDA(h, cudaEventRecord(h->ev1, st));
     // results -> the handle's page-locked block; read by pgd_pcg_finish_impl after the stream has drained
