@@ -331,6 +331,31 @@ def test_banded_solve_nonsymmetric(degree):
     xs = spla.spsolve(T.tocsc(), bb)
     assert int(info.item()) == 0
     assert np.linalg.norm(xt.cpu().numpy() - xs) / np.linalg.norm(xs) < 1e-10
+    # wide band (kl = ku = 6 > 3: the warp-parallel recurrences), random entries, weak diagonal => interchanges
+    n, w = 150, 6
+    diags = [rng.uniform(-1, 1, n - abs(o)) * (0.05 if o == 0 else 1.0) for o in range(-w, w + 1)]
+    Wm = sp.diags(diags, list(range(-w, w + 1))).tocsr()
+    Wm.sort_indices()
+    bb = rng.uniform(-1, 1, n)
+    xw, info = _lib.banded_solve(torch.as_tensor(Wm.indptr.astype(np.int32)).to(dev), torch.as_tensor(Wm.indices.astype(np.int32)).to(dev),
+                                 torch.as_tensor(Wm.data).to(dev), torch.as_tensor(bb).to(dev),
+                                 torch.arange(n, dtype=torch.int32, device=dev), w, w)
+    xs = spla.spsolve(Wm.tocsc(), bb)
+    assert int(info.item()) == 0
+    assert np.linalg.norm(Wm @ xw.cpu().numpy() - bb) / np.linalg.norm(bb) < 1e-10
+    assert np.linalg.norm(xw.cpu().numpy() - xs) / np.linalg.norm(xs) < 1e-7
+    # singular matrix: zero pivot reported, no exception
+    Z = sp.diags([np.ones(9), np.zeros(10), np.ones(9)], [-1, 0, 1]).tolil()
+    Z[3, :] = 0.0
+    Z[:, 3] = 0.0
+    Z = Z.tocsr()
+    Z.sort_indices()
+    pat = sp.diags([np.ones(9), np.ones(10), np.ones(9)], [-1, 0, 1]).tocsr()
+    dat = np.array([Z[i, j] for i, j in zip(*pat.nonzero())])
+    _, info = _lib.banded_solve(torch.as_tensor(pat.indptr.astype(np.int32)).to(dev), torch.as_tensor(pat.indices.astype(np.int32)).to(dev),
+                                torch.as_tensor(dat).to(dev), torch.ones(10, dtype=torch.float64, device=dev),
+                                torch.arange(10, dtype=torch.int32, device=dev), 1, 1)
+    assert int(info.item()) > 0
 
 
 def test_evaluate_kernels():
