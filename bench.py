@@ -254,7 +254,7 @@ def run_b200(args):
                 "share_of_step": s["pcg_ms"] / total_ms if total_ms else None,
                 "note": "matrix (5.5 MB) + vectors are on-chip at this config (shared memory / L2): the iteration is bound by "
                         "two grid barriers (~2 us each), not by HBM; `kernels` carries the HBM-bound sizes (128^3 mesh: "
-                        "SpMV 74 %, PCG iteration 55 % of the measured HBM peak)"}
+                        "SpMV 80 %, PCG iteration 63 % of the measured HBM peak)"}
 
     # ---------------- end-to-end arm: host arrays in, modes out, everything inside the timed region
     e2e = None
