@@ -186,7 +186,11 @@ def to_device(a, dtype=None):
     page-locked staging block, so the copy is a real DMA from pinned memory instead of the driver's blocking
     pageable path."""
     require_cuda()
-    t = torch.as_tensor(a if isinstance(a, torch.Tensor) else np.ascontiguousarray(a), dtype=dtype).contiguous()
+    if not isinstance(a, torch.Tensor):
+        a = np.ascontiguousarray(a)
+        if not a.flags.writeable:  # torch refuses to alias read-only arrays silently; the bytes are copied below anyway
+            a = a.copy()
+    t = torch.as_tensor(a, dtype=dtype).contiguous()
     nbytes = t.numel() * t.element_size()
     traffic["h2d"] += nbytes
     dev = torch.device("cuda", torch.cuda.current_device())
