@@ -35,6 +35,7 @@ from .lazy import LazyScalar
 from .ufl import Form
 
 MAX_PANEL_ROWS = 8
+functional_memo = [None]  # dict while an enrichment step runs (see _fast_functional), else None
 panel_rows_hint = [MAX_PANEL_ROWS]  # first allocation of a product panel (the solver sets it from PGD_nmax)
 
 
@@ -504,7 +505,18 @@ def _fast_functional(meas, monos):
         _TBYTES[id(T)] = T.tobytes()
     if not T.any():
         return None
-    return LazyScalar("leaf", (_Functional("bil", space, T, weights, meas, f1.leaf, f2.leaf, op),))
+    memo = functional_memo[0]
+    if memo is None:
+        return LazyScalar("leaf", (_Functional("bil", space, T, weights, meas, f1.leaf, f2.leaf, op),))
+    # inside an enrichment step: the same integral of the same (unchanged) functions is asked for again and again
+    # (every other dimension's sub-problem needs it) -- hand out the one deferred scalar.  The entry keeps its operands
+    # alive, so an id cannot be recycled while it is in the table; the solver clears the table at the end of the step.
+    mkey = (id(T), id(f1.leaf), f1.leaf._version, id(f2.leaf), f2.leaf._version, id(op), weights and tuple((id(w), c, getattr(w, "_version", 0)) for w, c in weights))
+    hit = memo.get(mkey)
+    if hit is None:
+        hit = LazyScalar("leaf", (_Functional("bil", space, T, weights, meas, f1.leaf, f2.leaf, op),))
+        memo[mkey] = hit
+    return hit
 
 
 def assemble(form):

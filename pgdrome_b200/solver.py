@@ -277,9 +277,13 @@ class PGDProblem:
                         settings={"linear_solver": "mumps"}):
         """One pass of the enrichment loop body (one new mode per dimension). True = stop."""
         with _ParkedHeap(settings.get("gc_freeze", True)):
+            outer = forms.functional_memo[0]
+            if outer is None and settings.get("memo_functionals", True):
+                forms.functional_memo[0] = {}
             try:
                 return self._enrichment_step(n_enr, normConv, relConv, _problem, solve_modes, settings)
             finally:
+                forms.functional_memo[0] = outer
                 self._collect_solve()
 
     def _enrichment_step(self, n_enr, normConv, relConv, _problem, solve_modes, settings):
