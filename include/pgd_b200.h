@@ -95,6 +95,18 @@ int32_t pgd_assemble_p1_rows(pgd_handle_t h, const double* d_coords, const int32
  * SURVEY.md 7.1).  h_xs: HOST array of n_terms device pointers; h_coefs: HOST array. */
 int32_t pgd_lincomb(pgd_handle_t h, int32_t n_terms, const double* const* h_xs, const double* h_coefs,
                     int64_t n, double* d_out, int32_t accumulate, void* stream);
+/* Same with the coefficients in device memory (d_coefs[n_terms]), e.g. produced by pgd_scalar_programs. */
+int32_t pgd_lincomb_dev(pgd_handle_t h, int32_t n_terms, const double* const* h_xs, const double* d_coefs, int64_t n,
+                        double* d_out, int32_t accumulate, void* stream);
+/* Evaluate up to 32 small arithmetic expressions over device-resident scalars: program g is the postfix code
+ * h_code[h_off[g] .. h_off[g+1]) with instructions (opcode << 24) | operand; opcodes 0 = push h_consts[operand],
+ * 1 = push d_pool[operand], 2 = mul, 3 = add, 4 = sub, 5 = div, 6 = negate; d_out[g] = the value left on the stack.
+ * Each operation is one IEEE-754 double operation in program order (no contraction): the result is bitwise what the
+ * host obtains for the same expression.  Limits: 640 instructions, 128 constants, stack depth 16 per call.  The code
+ * travels as kernel parameters (no copy); used for the coefficients c_k of A_d = sum_k c_k K_{d,k}
+ * (solver.py:598-621), which are products of mode integrals (pgd_bilinear / pgd_panel_dots results). */
+int32_t pgd_scalar_programs(pgd_handle_t h, int32_t n_prog, const int32_t* h_off, const int32_t* h_code,
+                            const double* h_consts, int32_t n_consts, const double* d_pool, double* d_out, void* stream);
 
 /* ---- Dirichlet (DirichletBC.apply / assemble_system symmetric elimination, solver.py:186-191,
  * 364-372,704-716): zero row+col of every bc dof, diagonal 1, b lifted and set.  d_bc_vals may be

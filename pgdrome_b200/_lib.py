@@ -62,6 +62,8 @@ SIGNATURES = {
     "pgd_eval_weights": [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp],
     "pgd_eval_gemv": [c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_vp, c_vp],
     "pgd_eval_gemm_f64": [c_vp, c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i64, c_vp, c_i64, c_vp],
+    "pgd_lincomb_dev": [c_vp, c_i32, c_vp, c_vp, c_i64, c_vp, c_i32, c_vp],
+    "pgd_scalar_programs": [c_vp, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp],
     "pgd_pcg_start": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_dbl, c_dbl, c_i32, c_i32, c_vp, c_i32, c_vp],
     "pgd_pcg_finish": [c_vp, ctypes.POINTER(c_i32), ctypes.POINTER(c_dbl)],
     "pgd_locate_points": [c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_i32, c_dbl, c_vp, c_vp, c_vp],
@@ -456,9 +458,44 @@ def lincomb(xs, coefs, out=None, accumulate=False):
     if out is None:
         out = torch.empty(n, dtype=F64, device=ref.device)
     ptrs = (c_vp * max(1, n_terms))(*[_p(x, F64).value for x in xs])
+    if isinstance(coefs, torch.Tensor):  # coefficients computed on the device (scalar_programs): no host round trip
+        _check(lib.pgd_lincomb_dev(h, n_terms, ctypes.cast(ptrs, c_vp), _p(coefs, F64), n, _p(out, F64),
+                                   1 if accumulate else 0, _stream()), h, "pgd_lincomb_dev")
+        return out
     cs = (c_dbl * max(1, n_terms))(*[float(c) for c in coefs])
     _check(lib.pgd_lincomb(h, n_terms, ctypes.cast(ptrs, c_vp), ctypes.cast(cs, c_vp), n, _p(out, F64),
                            1 if accumulate else 0, _stream()), h, "pgd_lincomb")
+    return out
+
+
+SP_MAX_PROG, SP_MAX_CODE, SP_MAX_CONST = 32, 640, 128
+OP_CONST, OP_LOAD, OP_MUL, OP_ADD, OP_SUB, OP_DIV, OP_NEG = range(7)
+
+
+def scalar_programs(programs, consts, pool, out):
+    """programs: list of postfix instruction lists [(opcode << 24) | operand, ...] (pgd_scalar_programs); consts: list of
+    floats; pool: device tensor the LOAD operands index; out: device tensor [len(programs)] (filled in place, chunked
+    to the 32-program / 640-instruction limit of one call)."""
+    h, lib = handle(out.device), load_library()
+    g0 = 0
+    cs = (c_dbl * max(1, len(consts)))(*consts)
+    while g0 < len(programs):
+        g1, n_code = g0, 0
+        while g1 < len(programs) and g1 - g0 < SP_MAX_PROG and n_code + len(programs[g1]) <= SP_MAX_CODE:
+            n_code += len(programs[g1])
+            g1 += 1
+        if g1 == g0:
+            raise ValueError("scalar program longer than %d instructions" % SP_MAX_CODE)
+        off, code = [0], []
+        for p in programs[g0:g1]:
+            code.extend(p)
+            off.append(len(code))
+        a_off = (c_i32 * len(off))(*off)
+        a_code = (c_i32 * max(1, len(code)))(*code)
+        _check(lib.pgd_scalar_programs(h, g1 - g0, ctypes.cast(a_off, c_vp), ctypes.cast(a_code, c_vp), ctypes.cast(cs, c_vp),
+                                       len(consts), _p(pool, F64) if pool is not None else c_vp(0),
+                                       c_vp(out.data_ptr() + 8 * g0), _stream()), h, "pgd_scalar_programs")
+        g0 = g1
     return out
 
 

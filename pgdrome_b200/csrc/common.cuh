@@ -46,6 +46,8 @@ struct pgd_ctx {
     const void* nnz_key;     // cache of rowptr[n] (one 4-byte D2H per new matrix)
     int64_t nnz_key_n, nnz_val;
     cudaEvent_t ev0, ev1;
+    cudaEvent_t ev_done;     // recorded behind the result copies of a started solve: pgd_pcg_finish waits for it only, not for
+                             // whatever else has been enqueued on the stream since
     void* comm;              // ncclComm_t of the sharded solves (pgd_comm_init), NULL = single rank
     int comm_rank, comm_world;
     // NVLink peer window of the sharded solves (pgd_peer_window_*): this rank's cudaMalloc'ed window, the

@@ -32,6 +32,7 @@ extern "C" int32_t pgd_create(int32_t device, pgd_handle_t* out) {
     }
     cudaEventCreate(&h->ev0);
     cudaEventCreate(&h->ev1);
+    cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming);
     cudaMemset(h->counters, 0, sizeof(unsigned int) * PGD_MAX_COUNTERS);
     cudaMemset(h->scalars, 0, sizeof(double) * 64);
     cudaMemset(h->flags, 0, sizeof(int) * 16);
@@ -52,6 +53,7 @@ extern "C" int32_t pgd_destroy(pgd_handle_t h) {
     cudaFree(h->flags);
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
+    cudaEventDestroy(h->ev_done);
     delete h;
     return 0;
 }
@@ -110,6 +112,7 @@ extern "C" int32_t pgd_set_option(pgd_handle_t h, const char* name, int64_t valu
 struct LcArgs {
     const double* x[LC_MAX];
     double c[LC_MAX];
+    const double* dc;  // when set: the coefficients of this chunk live on the device (pgd_lincomb_dev)
     int n_terms;
 };
 
@@ -117,6 +120,10 @@ struct LcArgs {
 // (torch.dot reads at 7.1 TB/s on this box, the scalar version of this kernel reached 5.2: tools/micro/bw_probe.py)
 template <bool VEC>
 __global__ void __launch_bounds__(256) k_lincomb(LcArgs a, int64_t n, double* __restrict__ out, int accumulate) {
+    if (a.dc) {
+#pragma unroll 4
+        for (int t = 0; t < a.n_terms; ++t) a.c[t] = __ldg(&a.dc[t]);
+    }
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (VEC) {
@@ -148,9 +155,8 @@ __global__ void __launch_bounds__(256) k_lincomb(LcArgs a, int64_t n, double* __
     }
 }
 
-extern "C" int32_t pgd_lincomb(pgd_handle_t h, int32_t n_terms, const double* const* h_xs, const double* h_coefs,
-                               int64_t n, double* d_out, int32_t accumulate, void* stream) {
-    PGD_CHECK_HANDLE(h);
+static int32_t lincomb_impl(pgd_ctx* h, int32_t n_terms, const double* const* h_xs, const double* h_coefs,
+                            const double* d_coefs, int64_t n, double* d_out, int32_t accumulate, void* stream) {
     PGD_ARG(h, n_terms >= 0 && n >= 0, "bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) return 0;  // empty vectors are a no-op (their device pointers may be NULL)
@@ -166,16 +172,110 @@ extern "C" int32_t pgd_lincomb(pgd_handle_t h, int32_t n_terms, const double* co
     for (int t0 = 0; t0 < n_terms; t0 += LC_MAX) {
         LcArgs a;
         a.n_terms = (n_terms - t0 < LC_MAX) ? (n_terms - t0) : LC_MAX;
+        a.dc = d_coefs ? d_coefs + t0 : nullptr;
         uintptr_t al = reinterpret_cast<uintptr_t>(d_out);
         for (int t = 0; t < a.n_terms; ++t) {
             a.x[t] = h_xs[t0 + t];
-            a.c[t] = h_coefs[t0 + t];
+            a.c[t] = h_coefs ? h_coefs[t0 + t] : 0.0;
             al |= reinterpret_cast<uintptr_t>(a.x[t]);
         }
         if ((al & 15) == 0) k_lincomb<true><<<blocks, 256, 0, st>>>(a, n, d_out, (accumulate || t0 > 0) ? 1 : 0);
         else k_lincomb<false><<<blocks, 256, 0, st>>>(a, n, d_out, (accumulate || t0 > 0) ? 1 : 0);
         PGD_LAUNCH_OK(h);
     }
+    return 0;
+}
+
+extern "C" int32_t pgd_lincomb(pgd_handle_t h, int32_t n_terms, const double* const* h_xs, const double* h_coefs,
+                               int64_t n, double* d_out, int32_t accumulate, void* stream) {
+    PGD_CHECK_HANDLE(h);
+    PGD_ARG(h, n_terms == 0 || h_coefs, "null coefficients");
+    return lincomb_impl(h, n_terms, h_xs, h_coefs, nullptr, n, d_out, accumulate, stream);
+}
+
+extern "C" int32_t pgd_lincomb_dev(pgd_handle_t h, int32_t n_terms, const double* const* h_xs, const double* d_coefs,
+                                   int64_t n, double* d_out, int32_t accumulate, void* stream) {
+    PGD_CHECK_HANDLE(h);
+    PGD_ARG(h, n_terms == 0 || d_coefs, "null coefficients");
+    return lincomb_impl(h, n_terms, h_xs, nullptr, d_coefs, n, d_out, accumulate, stream);
+}
+
+// ----------------------------------------------------------------------------- scalar programs
+// The separated form's coefficients  c_g = (+-) c0 * prod_j <mode integral j>  are tiny arithmetic expressions over
+// mode integrals that already sit in device memory.  Evaluating them here (one thread per coefficient, postfix code
+// passed as kernel parameters) instead of on the host removes the device->host round trip between the functionals of
+// a sub-problem and its operator / right-hand-side assembly.  Every operation is a separately rounded IEEE double
+// operation in the order the host would apply it, so the result is bitwise the host's.
+#define SP_MAX_CODE 640
+#define SP_MAX_CONST 128
+#define SP_MAX_PROG 32
+struct SpArgs {
+    int n_prog;
+    int off[SP_MAX_PROG + 1];
+    int code[SP_MAX_CODE];  // (opcode << 24) | operand
+    double consts[SP_MAX_CONST];
+};
+enum { SP_CONST = 0, SP_LOAD = 1, SP_MUL = 2, SP_ADD = 3, SP_SUB = 4, SP_DIV = 5, SP_NEG = 6 };
+
+__global__ void k_scalar_programs(SpArgs a, const double* __restrict__ pool, double* __restrict__ out) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.n_prog) return;
+    double st[16];
+    int sp = 0;
+    for (int i = a.off[g]; i < a.off[g + 1]; ++i) {
+        const int op = a.code[i] >> 24, arg = a.code[i] & 0xffffff;
+        if (op == SP_CONST) st[sp++ & 15] = a.consts[arg];
+        else if (op == SP_LOAD) st[sp++ & 15] = pool[arg];
+        else if (op == SP_NEG) st[(sp - 1) & 15] = -st[(sp - 1) & 15];
+        else {
+            const double y = st[(sp - 1) & 15], x = st[(sp - 2) & 15];
+            double r;
+            if (op == SP_MUL) r = __dmul_rn(x, y);
+            else if (op == SP_ADD) r = __dadd_rn(x, y);
+            else if (op == SP_SUB) r = __dsub_rn(x, y);
+            else r = __ddiv_rn(x, y);
+            sp -= 1;
+            st[(sp - 1) & 15] = r;
+        }
+    }
+    out[g] = st[(sp - 1) & 15];
+}
+
+extern "C" int32_t pgd_scalar_programs(pgd_handle_t h, int32_t n_prog, const int32_t* h_off, const int32_t* h_code,
+                                       const double* h_consts, int32_t n_consts, const double* d_pool, double* d_out,
+                                       void* stream) {
+    PGD_CHECK_HANDLE(h);
+    PGD_ARG(h, n_prog >= 0 && n_prog <= SP_MAX_PROG && h_off && d_out, "bad arguments (at most 32 programs per call)");
+    if (n_prog == 0) return 0;
+    PGD_ARG(h, h_off[n_prog] <= SP_MAX_CODE && n_consts <= SP_MAX_CONST && h_off[0] == 0, "program too long");
+    SpArgs a;
+    a.n_prog = n_prog;
+    for (int i = 0; i <= n_prog; ++i) a.off[i] = h_off[i];
+    // validate: operands in range, stack depth within 1..16, exactly one value left
+    for (int g = 0; g < n_prog; ++g) {
+        int depth = 0;
+        for (int i = h_off[g]; i < h_off[g + 1]; ++i) {
+            const int op = h_code[i] >> 24, arg = h_code[i] & 0xffffff;
+            if (op == SP_CONST) {
+                PGD_ARG(h, arg < n_consts, "constant index out of range");
+                ++depth;
+            } else if (op == SP_LOAD) {
+                PGD_ARG(h, d_pool != nullptr, "program loads from a null pool");
+                ++depth;
+            } else if (op == SP_NEG) {
+                PGD_ARG(h, depth >= 1, "stack underflow");
+            } else {
+                PGD_ARG(h, op >= SP_MUL && op <= SP_DIV && depth >= 2, "bad opcode / stack underflow");
+                --depth;
+            }
+            PGD_ARG(h, depth <= 16, "expression too deep");
+            a.code[i] = h_code[i];
+        }
+        PGD_ARG(h, depth == 1, "program must leave exactly one value");
+    }
+    for (int i = 0; i < n_consts; ++i) a.consts[i] = h_consts[i];
+    k_scalar_programs<<<1, SP_MAX_PROG, 0, (cudaStream_t)stream>>>(a, d_pool, d_out);
+    PGD_LAUNCH_OK(h);
     return 0;
 }
 

@@ -472,6 +472,7 @@ int32_t pgd_pcg_resident(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const
     char* pin = static_cast<char*>(h->pinned) + 256;
     PGD_CUDA(h, cudaMemcpyAsync(pin, a.out_fl, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     PGD_CUDA(h, cudaMemcpyAsync(pin + 64, a.out_sc, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PGD_CUDA(h, cudaEventRecord(h->ev_done, st));
     h->res_pending = 1;
     h->res_stream = (void*)st;
     if (defer) {
@@ -494,7 +495,7 @@ int32_t pgd_pcg_finish_impl(pgd_ctx* h, int32_t* h_iters, double* h_relres) {
         return 0;
     }
     h->res_pending = 0;
-    PGD_CUDA(h, cudaStreamSynchronize((cudaStream_t)h->res_stream));
+    PGD_CUDA(h, cudaEventSynchronize(h->ev_done));
     const char* pin = static_cast<const char*>(h->pinned) + 256;
     int hf[2];
     double hs[2];

@@ -359,8 +359,28 @@ def _functional_value(g):
     return LazyScalar("leaf", (p,))
 
 
-def _flush(leaves):
-    """Evaluate all pending functionals: batched device launches, ONE device->host copy."""
+POOL_DOUBLES = 1 << 16
+_pool = {}  # device -> [tensor POOL_DOUBLES, cursor]: where the functionals of the current step deposit their values
+
+
+def _pool_take(dev, n):
+    """n consecutive slots of the device scalar pool (absolute index of the first one)."""
+    ent = _pool.get(dev)
+    if ent is None:
+        ent = [torch.empty(POOL_DOUBLES, dtype=torch.float64, device=dev), 0]
+        _pool[dev] = ent
+    if n > POOL_DOUBLES:
+        raise ValueError("more than %d functionals in one batch" % POOL_DOUBLES)
+    if ent[1] + n > POOL_DOUBLES:
+        lazy.fetch()  # everything still living in the pool goes to the host first, then the pool is reused
+        ent[1] = 0
+    base = ent[1]
+    ent[1] += n
+    return ent[0], base
+
+
+def _launch(leaves):
+    """Enqueue the evaluation of the given functionals: batched device launches writing into the scalar pool."""
     dev = _device()
     plan = []  # (leaf, slot)
     n_slots = 0
@@ -403,7 +423,8 @@ def _flush(leaves):
         for leaf, row in job[3]:
             plan.append((leaf, n_slots + row))
         n_slots += at.n_rows
-    res = torch.empty(max(n_slots, 1), dtype=torch.float64, device=dev)
+    pool, base0 = _pool_take(dev, max(n_slots, 1))
+    res = pool[base0:base0 + max(n_slots, 1)]
     for slot, kind, args in direct:
         if kind == "dot":
             _lib.dot(args[0], args[1], out=res[slot:slot + 1])
@@ -413,12 +434,22 @@ def _flush(leaves):
             _lib.bilinear(rowptr, colidx, atom.values, args[1], args[2], out=res[slot:slot + 1], lpr=atom.ds.lpr)
     for at, x, base, _ in panel_jobs.values():
         _lib.panel_dots(at.panel, at.n_rows, x.tensor(), out=res[base:base + at.n_rows])
-    host = _lib.to_host(res)
     for leaf, slot in plan:
-        leaf._value = float(host[slot])
+        leaf._dev = base0 + slot
 
 
-lazy._flush_hook[0] = _flush
+def _fetch(leaves):
+    """ONE device->host copy of the pool range that holds the given (launched) functionals."""
+    lo = min(l._dev for l in leaves)
+    hi = max(l._dev for l in leaves) + 1
+    host = _lib.to_host(_pool[_device()][0][lo:hi])
+    for leaf in leaves:
+        leaf._value = float(host[leaf._dev - lo])
+        leaf._dev = None
+
+
+lazy._launch_hook[0] = _launch
+lazy._fetch_hook[0] = _fetch
 
 
 # ------------------------------------------------------------------------------- public assemble
@@ -552,6 +583,80 @@ def _coefs(groups):
     return [float(g.coefficient()) for g in groups]
 
 
+device_coefficients = [False]  # set by the solver for the duration of an enrichment step (settings["device_coefficients"])
+_OPS = {"mul": _lib.OP_MUL, "add": _lib.OP_ADD, "sub": _lib.OP_SUB, "div": _lib.OP_DIV}
+
+
+def _coefs_dev(groups):
+    """The groups' scalar coefficients as a DEVICE tensor, computed by pgd_scalar_programs from the functionals'
+    values in the scalar pool -- no device->host round trip between recording a sub-problem's mode integrals and
+    assembling its operator / right-hand side.  Returns None (-> host path) for expressions the device evaluator
+    does not cover (pow / sqrt / abs, very deep trees) or when nothing is pending on the device anyway."""
+    lazy.launch()
+    consts, cidx, programs = [], {}, []
+    uses_pool = False
+
+    def const(v):
+        v = float(v)
+        k = cidx.get(v)
+        if k is None:
+            k = cidx[v] = len(consts)
+            consts.append(v)
+        return (_lib.OP_CONST << 24) | k
+
+    def emit(node, code, depth):
+        """postfix code for node; returns the stack depth needed, or -1 if unsupported"""
+        nonlocal uses_pool
+        if not isinstance(node, LazyScalar):
+            code.append(const(node))
+            return depth + 1
+        if node._value is not None:
+            code.append(const(node._value))
+            return depth + 1
+        op = node.op
+        if op == "leaf":
+            if node._dev is None:
+                return -1
+            uses_pool = True
+            code.append((_lib.OP_LOAD << 24) | node._dev)
+            return depth + 1
+        if op == "neg":
+            d = emit(node.args[0], code, depth)
+            code.append(_lib.OP_NEG << 24)
+            return d
+        bop = _OPS.get(op)
+        if bop is None:
+            return -1
+        d0 = emit(node.args[0], code, depth)
+        if d0 < 0:
+            return -1
+        d1 = emit(node.args[1], code, depth + 1)
+        if d1 < 0:
+            return -1
+        code.append(bop << 24)
+        return max(d0, d1)
+
+    for g in groups:
+        code = []
+        need = emit(g.coefficient(), code, 0)
+        if need < 0 or need > 16 or len(code) > _lib.SP_MAX_CODE or len(consts) > _lib.SP_MAX_CONST:
+            return None
+        programs.append(code)
+    if not uses_pool:
+        return None  # all values are already on the host: nothing to gain
+    dev = _device()
+    out = torch.empty(len(programs), dtype=torch.float64, device=dev)
+    return _lib.scalar_programs(programs, consts, _pool[dev][0], out)
+
+
+def _coefficients(groups):
+    if device_coefficients[0]:
+        c = _coefs_dev(groups)
+        if c is not None:
+            return c
+    return _coefs(groups)
+
+
 def assemble_vector(groups, out=None):
     """b = sum_g coef_g * (load_g | K_g @ f_g)  on the device."""
     space = groups[0].space
@@ -572,7 +677,7 @@ def assemble_vector(groups, out=None):
                 vecs.append(_lib.spmv(rowptr, colidx, atom.values, f.tensor(), lpr=atom.ds.lpr))
         else:
             raise NotImplementedError("linear form with two Function operands in one term")
-    coefs = _coefs(groups)
+    coefs = _coefficients(groups)
     return _lib.lincomb(vecs, coefs, out=out)
 
 
@@ -599,7 +704,7 @@ def assemble_matrix(groups, out=None):
         if not _same_space(g.space, space) or g.operands:
             raise NotImplementedError("bilinear form with Function operands (non-linear form?)")
         atoms.append(get_atom(g.space, g.tensor(), g.weights, g.measure, g.op))
-    coefs = _coefs(groups)
+    coefs = _coefficients(groups)
     vals = _lib.lincomb([a.values for a in atoms], coefs, out=out)
     m = AssembledMatrix(ds, vals)
     m.symmetric = all(a.symmetric for a in atoms)

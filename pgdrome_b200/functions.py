@@ -408,7 +408,7 @@ class _DofOwner:
     def before_write(self):
         """Functionals recorded against the current values must be evaluated before they change."""
         if _lazy.has_pending():
-            _lazy.flush()
+            _lazy.launch()  # enqueued before the write in stream order; the values are read back when somebody asks
 
     def touch(self):
         self._version += 1

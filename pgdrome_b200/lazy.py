@@ -12,9 +12,11 @@ import math
 
 import numpy as np
 
-_pending = []  # leaves whose device evaluation has not happened yet
-_flush_hook = [None]  # set by forms.py: callable(list_of_leaves) -> fills leaf._value
-stats = {"flushes": 0, "leaves": 0}
+_pending = []  # leaves recorded by a callback, nothing launched yet
+_launched = []  # leaves whose kernels are enqueued (value in the device scalar pool, leaf._dev = slot), not read back
+_launch_hook = [None]  # set by forms.py: callable(list_of_leaves) -> enqueues the kernels, sets leaf._dev
+_fetch_hook = [None]  # set by forms.py: callable(list_of_leaves) -> ONE device->host copy, fills leaf._value
+stats = {"flushes": 0, "leaves": 0, "fetches": 0}
 
 
 def _num(x):
@@ -24,10 +26,10 @@ def _num(x):
 class LazyScalar:
     __array_ufunc__ = None
     __array_priority__ = 2000
-    __slots__ = ("op", "args", "_value", "__weakref__")
+    __slots__ = ("op", "args", "_value", "_dev", "__weakref__")
 
     def __init__(self, op, args, value=None):
-        self.op, self.args, self._value = op, args, value
+        self.op, self.args, self._value, self._dev = op, args, value, None
         if op == "leaf" and value is None:
             _pending.append(self)
 
@@ -150,20 +152,40 @@ def constant(v):
     return LazyScalar("const", (float(v),), float(v))
 
 
-def flush():
-    """Evaluate every pending functional on the device in one batch."""
+def launch():
+    """Enqueue the device evaluation of every recorded functional (no host synchronisation): afterwards the values
+    exist in stream order in the device scalar pool, where device-side consumers (forms._coefs_dev) read them."""
     global _pending
     if not _pending:
         return
     leaves, _pending = _pending, []
-    leaves = [l for l in leaves if l._value is None]
+    leaves = [l for l in leaves if l._value is None and l._dev is None]
     if not leaves:
         return
-    if _flush_hook[0] is None:
+    if _launch_hook[0] is None:
         raise RuntimeError("no device evaluator registered (pgdrome_b200.forms not imported)")
     stats["flushes"] += 1
     stats["leaves"] += len(leaves)
-    _flush_hook[0](leaves)
+    _launch_hook[0](leaves)
+    _launched.extend(leaves)
+
+
+def fetch():
+    """Read the launched functionals back with ONE device->host copy (synchronises)."""
+    global _launched
+    if not _launched:
+        return
+    leaves, _launched = _launched, []
+    leaves = [l for l in leaves if l._value is None]
+    if leaves:
+        stats["fetches"] += 1
+        _fetch_hook[0](leaves)
+
+
+def flush():
+    """Evaluate every pending functional on the device in one batch and bring the values to the host."""
+    launch()
+    fetch()
 
 
 def has_pending():

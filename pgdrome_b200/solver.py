@@ -25,7 +25,7 @@ import numpy as np
 import scipy.sparse as sp
 import torch
 
-from . import _lib, forms
+from . import _lib, forms, lazy
 from .assembly import device_space
 from .functions import Function, MatrixOperator, bc_list, merged_bc_dofs
 from .lazy import LazyScalar
@@ -278,13 +278,17 @@ class PGDProblem:
         """One pass of the enrichment loop body (one new mode per dimension). True = stop."""
         with _ParkedHeap(settings.get("gc_freeze", True)):
             outer = forms.functional_memo[0]
+            outer_dc = forms.device_coefficients[0]
             if outer is None and settings.get("memo_functionals", True):
                 forms.functional_memo[0] = {}
+            forms.device_coefficients[0] = bool(settings.get("device_coefficients", True))
             try:
                 return self._enrichment_step(n_enr, normConv, relConv, _problem, solve_modes, settings)
             finally:
                 forms.functional_memo[0] = outer
+                forms.device_coefficients[0] = outer_dc
                 self._collect_solve()
+                lazy.fetch()  # functionals that were only consumed on the device: bring their values home, release them
 
     def _enrichment_step(self, n_enr, normConv, relConv, _problem, solve_modes, settings):
         D = self.num_pgd_var

@@ -285,6 +285,26 @@ def probe_modes(X, R, dofs, w):
     return _t(np.einsum("rj,krj->kr", wn, Xn[:, d]))
 
 
+def scalar_programs(programs, consts, pool, out):
+    P = _n(pool) if pool is not None else None
+    for g, code in enumerate(programs):
+        st = []
+        for ins in code:
+            op, arg = ins >> 24, ins & 0xffffff
+            if op == 0:
+                st.append(np.float64(consts[arg]))
+            elif op == 1:
+                st.append(np.float64(P[arg]))
+            elif op == 6:
+                st[-1] = -st[-1]
+            else:
+                y, x = st.pop(), st.pop()
+                st.append(x * y if op == 2 else x + y if op == 3 else x - y if op == 4 else x / y)
+        assert len(st) == 1
+        out[g] = float(st[0])
+    return out
+
+
 def pcg_start(*a, **k):
     return None  # the stand-in has no resident solver: the host logic falls back to pcg()
 
@@ -296,7 +316,7 @@ def pcg_finish(device=None):
 NAMES = ["pattern_build", "vecmap_build", "elem_bilinear", "elem_linear", "gather_values", "assemble_p1",
          "p1_rowplan_build", "assemble_p1_rows", "lincomb",
          "apply_dirichlet", "set_entries", "spmv", "spmv_dot", "bilinear", "dot", "panel_dots", "pcg", "banded_solve",
-         "eval_weights", "eval_gemv", "eval_gemm", "locate_points", "probe_modes", "pcg_start", "pcg_finish"]
+         "eval_weights", "eval_gemv", "eval_gemm", "locate_points", "probe_modes", "pcg_start", "pcg_finish", "scalar_programs"]
 
 
 def install(monkeypatch):
