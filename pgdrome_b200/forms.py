@@ -532,9 +532,12 @@ def _fast_functional(meas, monos):
         for i in range(2, len(key), 5):
             T[key[i], key[i + 1], key[i + 2], key[i + 3]] += key[i + 4]
         T.setflags(write=False)
+        if not T.any():
+            T = False  # the monomials cancel: let the general path produce the zero
+        else:
+            _TBYTES[id(T)] = T.tobytes()
         _UNIT_T[key] = T
-        _TBYTES[id(T)] = T.tobytes()
-    if not T.any():
+    if T is False:
         return None
     memo = functional_memo[0]
     if memo is None:

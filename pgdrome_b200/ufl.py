@@ -114,6 +114,9 @@ class Expr:
     def __mul__(self, other):
         if isinstance(other, (Measure, Form)):
             return NotImplemented
+        if isinstance(other, Leaf) and other._n_comp == 1 and isinstance(self, Leaf) and self._n_comp == 1:
+            # scalar leaf * scalar leaf (F*G, Constant*F, ...): the product monomial directly
+            return Expr((), [[Mono(1.0, (Factor(self, None, None), Factor(other, None, None)))]])
         o = Expr.wrap(other)
         if o is None:
             return NotImplemented
