@@ -548,3 +548,54 @@ def test_edge_cases_and_error_codes():
     with pytest.raises(_lib.PGDB200Error):
         _lib.pcg(torch.tensor([0, 1], dtype=torch.int32, device=dev), torch.tensor([0], dtype=torch.int32, device=dev), bad,
                  torch.tensor([1.0], dtype=torch.float64, device=dev), maxit=3)
+
+
+def test_scalar_programs_bitwise_and_lincomb_dev():
+    """pgd_scalar_programs evaluates postfix expressions over device scalars with separately rounded IEEE operations in
+    program order: bitwise equal to the same expression evaluated by Python floats; pgd_lincomb_dev with those
+    coefficients equals pgd_lincomb with the host values bit for bit.  More programs than one launch takes (32) and an
+    argument error (stack underflow) are covered."""
+    from pgdrome_b200 import _lib
+
+    dev = torch.device("cuda")
+    rng = np.random.default_rng(21)
+    pool_h = rng.standard_normal(500) * 10.0 ** rng.integers(-8, 8, 500)
+    pool = torch.as_tensor(pool_h).to(dev)
+    consts = [float(v) for v in rng.standard_normal(20)] + [1.0, -1.0, 0.5]
+    C, L, MUL, ADD, SUB, DIV, NEG = (_lib.OP_CONST << 24, _lib.OP_LOAD << 24, _lib.OP_MUL << 24, _lib.OP_ADD << 24,
+                                     _lib.OP_SUB << 24, _lib.OP_DIV << 24, _lib.OP_NEG << 24)
+    programs, expect = [], []
+    for g in range(75):
+        # ((c * p_a) * p_b) [- / +] (p_c * p_d) ... a left-deep chain like the separated-form coefficients, random ops
+        ia = rng.integers(0, 500, 6)
+        ic = int(rng.integers(0, len(consts)))
+        code = [C | ic, L | int(ia[0]), MUL]
+        val = consts[ic] * pool_h[ia[0]]
+        for k in range(1, 6):
+            op = int(rng.integers(0, 4))
+            code += [L | int(ia[k]), (MUL, ADD, SUB, DIV)[op]]
+            x = float(pool_h[ia[k]])
+            val = (val * x, val + x, val - x, val / x)[op]
+            if rng.random() < 0.3:
+                code.append(NEG)
+                val = -val
+        programs.append(code)
+        expect.append(val)
+    out = torch.empty(75, dtype=torch.float64, device=dev)
+    _lib.scalar_programs(programs, consts, pool, out)
+    assert np.array_equal(out.cpu().numpy(), np.array(expect))  # bitwise
+    # nested (right operand is itself an expression): stack depth 3
+    deep = [[L | 1, L | 2, L | 3, L | 4, ADD, MUL, SUB]]
+    o1 = torch.empty(1, dtype=torch.float64, device=dev)
+    _lib.scalar_programs(deep, consts, pool, o1)
+    assert float(o1.item()) == pool_h[1] - pool_h[2] * (pool_h[3] + pool_h[4])
+    with pytest.raises(_lib.PGDB200Error):
+        _lib.scalar_programs([[L | 1, MUL]], consts, pool, o1)
+    # device coefficients in the linear combination == host coefficients, bit for bit
+    xs = [torch.as_tensor(rng.standard_normal(100003)).to(dev) for _ in range(30)]  # more terms than one lincomb launch
+    coefs_dev = out[:30].contiguous()
+    a = _lib.lincomb(xs, coefs_dev)
+    b = _lib.lincomb(xs, expect[:30])
+    assert torch.equal(a, b)
+    acc = _lib.lincomb(xs[:3], coefs_dev[:3], out=a.clone(), accumulate=True)
+    assert torch.equal(acc, _lib.lincomb(xs[:3], expect[:3], out=b.clone(), accumulate=True))
