@@ -222,3 +222,37 @@ def test_dropped_problem_is_freed_by_reference_counting(cpu, make):
         gc.set_debug(0)
         gc.garbage.clear()
         gc.enable()
+
+
+def test_device_coefficients_equal_host_coefficients(cpu):
+    """The separated form's coefficients evaluated by scalar programs (device path, here through the NumPy stand-in) give
+    bitwise the modes of the host-float path; unsupported scalar operations fall back to the host path."""
+    from pgdrome_b200 import configs, forms, lazy
+    from pgdrome_b200 import dolfin as df
+
+    runs = []
+    for dc in (True, False):
+        p = configs.heat2d_tk(n=8, nt=16, nk=6, PGD_nmax=3, PGD_tol=0.0)
+        p.solve_PGD(_problem="linear", settings={"device_coefficients": dc, "linear_solver": "mumps"})
+        runs.append(p)
+    a, b = runs
+    assert a.num_fp_it == b.num_fp_it and a.PGD_modes == b.PGD_modes == 3
+    for d in range(3):
+        for k in range(3):
+            assert np.array_equal(a.PGD_func[d][k].vector().get_local(), b.PGD_func[d][k].vector().get_local())
+    # fewer host synchronisations on the device path: values are read back once per sweep, not once per sub-problem
+    V = df.FunctionSpace(df.UnitIntervalMesh(7), "CG", 1)
+    f = df.interpolate(df.Expression("1.0+x[0]", degree=1), V)
+    u, v = df.TrialFunction(V), df.TestFunction(V)
+    forms.device_coefficients[0] = True
+    try:
+        ok = forms.compile_form(df.Constant(df.assemble(f * f * df.dx) * 2.0) * u * v * df.dx)
+        c_dev = forms._coefs_dev(ok)
+        assert c_dev is not None and abs(float(c_dev[0]) - 2.0 * float(df.assemble(f * f * df.dx))) < 1e-15
+        unsupported = forms.compile_form(df.Constant(df.assemble(f * f * df.dx).sqrt()) * u * v * df.dx)
+        assert forms._coefs_dev(unsupported) is None  # sqrt is evaluated on the host
+        A = forms.assemble_matrix(unsupported)  # ... and the assembly still works through the host path
+        assert np.isfinite(A.array()).all()
+        lazy.fetch()
+    finally:
+        forms.device_coefficients[0] = False
