@@ -115,20 +115,31 @@ __global__ void __launch_bounds__(256) k_locate(const double* __restrict__ coord
             for (int d = 0; d < G; ++d) s_p[rank * G + d] = s_raw[i * G + d];
         }
         __syncthreads();
-        for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += (int64_t)gridDim.x * blockDim.x) {
+        // the index row of the NEXT cell of this thread is requested one iteration ahead: the vertex gathers of a
+        // cell then only wait for one memory latency instead of two dependent ones (index row -> coordinates)
+        auto load_row = [&](int64_t c, int32_t (&v)[G + 1]) {
+            if constexpr (G == 3) {  // one 16-byte row
+                const int4 q = __ldcs(reinterpret_cast<const int4*>(cells) + c);
+                v[0] = q.x, v[1] = q.y, v[2] = q.z, v[3] = q.w;
+            } else if constexpr (G == 1) {
+                const int2 q = __ldcs(reinterpret_cast<const int2*>(cells) + c);
+                v[0] = q.x, v[1] = q.y;
+            } else {
+#pragma unroll
+                for (int k = 0; k <= G; ++k) v[k] = __ldcs(&cells[c * (G + 1) + k]);
+            }
+        };
+        const int64_t cstride = (int64_t)gridDim.x * blockDim.x;
+        const int64_t c_first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        int32_t vnext[G + 1];
+        if (c_first < n_cells) load_row(c_first, vnext);
+        for (int64_t c = c_first; c < n_cells; c += cstride) {
             double X[G + 1][G];
             double lo[G], hi[G];
             int32_t vids[G + 1];
-            if constexpr (G == 3) {  // one 16-byte row
-                const int4 q = __ldcs(reinterpret_cast<const int4*>(cells) + c);
-                vids[0] = q.x, vids[1] = q.y, vids[2] = q.z, vids[3] = q.w;
-            } else if constexpr (G == 1) {
-                const int2 q = __ldcs(reinterpret_cast<const int2*>(cells) + c);
-                vids[0] = q.x, vids[1] = q.y;
-            } else {
 #pragma unroll
-                for (int v = 0; v <= G; ++v) vids[v] = __ldcs(&cells[c * (G + 1) + v]);
-            }
+            for (int k = 0; k <= G; ++k) vids[k] = vnext[k];
+            if (c + cstride < n_cells) load_row(c + cstride, vnext);
 #pragma unroll
             for (int v = 0; v <= G; ++v) {
                 const int32_t vid = vids[v];
