@@ -330,7 +330,7 @@ def install(monkeypatch):
         monkeypatch.setattr(_lib, name, getattr(me, name))
     monkeypatch.setattr(_lib, "require_cuda", lambda: None)
     monkeypatch.setattr(_lib, "to_device", lambda a, dtype=None: torch.as_tensor(
-        a if isinstance(a, torch.Tensor) else np.ascontiguousarray(a), dtype=dtype).clone())
+        a if isinstance(a, torch.Tensor) else np.array(a, copy=True, order="C"), dtype=dtype).clone())
     monkeypatch.setattr(_lib, "to_host", lambda t: t.detach().cpu().numpy())
     cpu = torch.device("cpu")
     monkeypatch.setattr(assembly, "_dev", lambda: cpu)

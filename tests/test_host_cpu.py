@@ -256,3 +256,26 @@ def test_device_coefficients_equal_host_coefficients(cpu):
         lazy.fetch()
     finally:
         forms.device_coefficients[0] = False
+
+
+def test_scalar_pool_wraps_around(cpu, monkeypatch):
+    """A pool far smaller than a step's functionals: when it is full the launched values are read back and the pool
+    is reused -- same modes, bit for bit, as with the large pool."""
+    from pgdrome_b200 import configs, forms, lazy
+
+    def run():
+        p = configs.heat2d_tk(n=8, nt=16, nk=6, PGD_nmax=3, PGD_tol=0.0)
+        p.solve_PGD(_problem="linear")
+        return p
+
+    ref = run()
+    f0 = lazy.stats["fetches"]
+    monkeypatch.setattr(forms, "POOL_DOUBLES", 24)
+    monkeypatch.setattr(forms, "_pool", {})
+    small = run()
+    assert lazy.stats["fetches"] - f0 > 0
+    assert forms._pool and next(iter(forms._pool.values()))[0].numel() == 24
+    assert small.num_fp_it == ref.num_fp_it
+    for d in range(3):
+        for k in range(3):
+            assert np.array_equal(small.PGD_func[d][k].vector().get_local(), ref.PGD_func[d][k].vector().get_local())
