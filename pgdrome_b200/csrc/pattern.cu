@@ -194,6 +194,10 @@ extern "C" int32_t pgd_pattern_export(pgd_handle_t h, int32_t* d_rowptr, int32_t
     if (d_gidx) PGD_CUDA(h, cudaMemcpyAsync(d_gidx, h->pat_gidx, sizeof(int32_t) * h->pat_ncontrib, k, st));
     PGD_CUDA(h, cudaStreamSynchronize(st));
     pgd_free_pattern(h);
+    // a new sparsity structure exists: whatever the solver remembered about an older one (nnz, "fits the SM-resident
+    // PCG") may belong to freed memory whose address the caller's allocator hands out again
+    h->nnz_key = nullptr;
+    h->fit_key = nullptr;
     return 0;
 }
 
