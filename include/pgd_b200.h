@@ -30,7 +30,10 @@ int32_t pgd_create(int32_t device, pgd_handle_t* out);
 int32_t pgd_destroy(pgd_handle_t h);
 const char* pgd_last_error(pgd_handle_t h);
 /* options: "pcg_resident" (default 1) = solve with the single-kernel SM-resident PCG whenever the
- * matrix slice of every SM fits in its shared memory (else, and with 0, the multi-kernel PCG). */
+ * matrix slice of every SM fits in its shared memory; "persist" (default 1) = larger systems (>= 32 768 rows) run in the
+ * persistent streaming kernel of pgd_pcg_persist_sync (0: three launches per iteration); "bsr" (default 1) = node-block
+ * walk inside that kernel when a block-column list is supplied; "spin_ms" = budget of every in-kernel wait;
+ * "p2p", "graph", "fused", "pcg3", "spmv_stream": variants of the older multi-launch paths. */
 int32_t pgd_set_option(pgd_handle_t h, const char* name, int64_t value);
 /* library-side counters since the last reset: h_counts[0] kernels launched, [1] PCG solves,
  * [2] PCG iterations, [3] solves done by the SM-resident kernel; *h_pcg_ms device time (CUDA events on the solve's stream) spent in the PCG
@@ -204,6 +207,31 @@ int32_t pgd_pcg_x0_sync(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* 
                         const double* d_b, double* d_x, int64_t n, double rtol, double atol, int32_t maxit,
                         int32_t check_every, int32_t block, int32_t lanes_per_row, double* d_work,
                         int32_t* h_iters, double* h_relres, void* stream);
+
+/* Persistent PCG for systems that do not fit on chip (the HBM-bound regime of configs[2]-[3]): ONE cooperative kernel
+ * per solve -- direction update, TMA-pipelined SpMV, vector update and all reductions inside, CG scalars in registers,
+ * stop test on the device -- on one GPU or on every GPU of a row-sharded system (same settings-forwarding call site as
+ * pgd_pcg_sync: solver.py:634-635).  Local layout as for the sharded blocks: d_rowptr has n_owned rows, columns and
+ * d_x [n_local] in [owned | ghost] numbering (single GPU: n_local = n_owned, the four halo arguments NULL).
+ *   warm != 0: d_x holds the initial guess INCLUDING valid ghost entries; on return d_x holds the solution and, sharded,
+ *   its ghost entries are up to date as well (exchanged through the peer window inside the kernel).
+ *   Sharded: needs an opened peer window (pgd_peer_window_create with p_capacity >= 2 * max n_local + 8) and the halo
+ *   description of pgd_spcg_solve_sync.  Neighbour values of the direction vector are stored straight into the peers'
+ *   ghost slots over NVLink, the dot products are summed through per-rank mailboxes in rank order (bitwise identical on
+ *   all ranks).  Every in-kernel wait has a wall-clock budget (pgd_set_option "spin_ms", default 20 000): a missing peer
+ *   ends the call with -6 instead of hanging, and the peer window is disabled afterwards (the ranks' sequence numbers
+ *   may have diverged; pgd_spcg_solve_sync over NCCL keeps working).
+ *   d_bcol / max_blocks_per_row (optional, block > 1): block-column list of the node-block walk -- d_bcol[j] = node of the
+ *   j-th block x block block, block rows in order (nnz / block^2 entries); the kernel then streams 8 B per nonzero plus
+ *   4 B per block instead of 12 B per nonzero.  Requires a block-structured pattern (every node pair coupled by a full
+ *   block, as produced by pgd_pattern_build_sync on a node-blocked vector space).
+ *   d_work: 3 * even(n_owned) + even(n_owned * block) + 2 * even(n_local) + 8 doubles, 16-byte aligned. */
+int32_t pgd_pcg_persist_sync(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
+                             const double* d_b, double* d_x, int64_t n_owned, int64_t n_local, int32_t block, double rtol,
+                             double atol, int32_t maxit, int32_t warm, double* d_work, const int64_t* d_send_idx,
+                             const int64_t* h_send_counts, const int64_t* h_recv_counts, const int64_t* h_peer_ghost_base,
+                             const int32_t* d_bcol, int32_t max_blocks_per_row, int32_t* h_iters, double* h_relres,
+                             void* stream);
 
 /* General banded LU with partial pivoting, one CTA, for the 1-D parameter / time dimensions
  * (tiny, possibly non-symmetric).  d_perm[new] = old dof (band ordering), kl/ku bandwidths in the

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("PGD_LIB_PATH") or os.path.join(HERE, "libpgdb200.so")
-SOURCES = ["core.cu", "pattern.cu", "assemble.cu", "assemble_rows.cu", "sparse.cu", "pcg.cu", "pcg_resident.cu", "sharded.cu", "banded.cu", "evaluate.cu", "probe.cu"]
+SOURCES = ["core.cu", "pattern.cu", "assemble.cu", "assemble_rows.cu", "sparse.cu", "pcg.cu", "pcg_resident.cu", "pcg_persist.cu", "sharded.cu", "banded.cu", "evaluate.cu", "probe.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -58,6 +58,8 @@ SIGNATURES = {
     "pgd_peer_window_destroy": [c_vp],
     "pgd_pcg_x0_sync": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_dbl, c_dbl, c_i32, c_i32, c_i32, c_i32, c_vp,
                         ctypes.POINTER(c_i32), ctypes.POINTER(c_dbl), c_vp],
+    "pgd_pcg_persist_sync": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_dbl, c_dbl, c_i32, c_i32, c_vp, c_vp, c_vp,
+                             c_vp, c_vp, c_vp, c_i32, ctypes.POINTER(c_i32), ctypes.POINTER(c_dbl), c_vp],
     "pgd_banded_solve": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp],
     "pgd_eval_weights": [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp],
     "pgd_eval_gemv": [c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_vp, c_vp],
@@ -586,6 +588,72 @@ def pcg(rowptr, colidx, values, b, x=None, rtol=1e-12, atol=0.0, maxit=20000, ch
     _check(fn(h, _p(rowptr, I32), _p(colidx, I32), _p(values, F64), _p(b, F64), _p(x, F64), n, rtol, atol,
               maxit, check_every, block, lpr, _p(work, F64), ctypes.byref(iters), ctypes.byref(relres),
               _stream()), h, "pgd_pcg_sync")
+    return x, iters.value, relres.value
+
+
+def bsr_plan(rowptr, colidx, bs):
+    """Block-column list of a node-blocked CSR pattern for the node-block walk of pgd_pcg_persist_sync: (bcol int32
+    [nnz / bs^2], longest block row), or None when the pattern is not a union of full bs x bs blocks."""
+    n = rowptr.numel() - 1
+    if bs < 2 or n % bs:
+        return None
+    rp = rowptr.to(I64)
+    lens = rp[1:] - rp[:-1]
+    if bool((lens.view(-1, bs) != lens.view(-1, bs)[:, :1]).any()) or bool((lens % bs != 0).any()):
+        return None
+    # entries of the first row of every node whose column is a first component: one per block, in block order
+    first = torch.repeat_interleave(torch.arange(n, device=rowptr.device) % bs == 0, lens)
+    sel = first & (colidx % bs == 0)
+    bcol = torch.div(colidx[sel], bs, rounding_mode="floor").to(I32).contiguous()
+    nnz = int(colidx.numel())
+    if bcol.numel() * bs * bs != nnz:
+        return None
+    # every block must be full: columns of a row = bs * bcol + (0..bs-1), identical for the bs rows of a node
+    exp = (bcol.to(I64).repeat_interleave(bs) * bs + torch.arange(bs, device=bcol.device).repeat(bcol.numel()))
+    nb = (lens.view(-1, bs)[:, 0] // bs)
+    for i in range(bs):
+        rows_i = torch.arange(i, n, bs, device=rowptr.device)
+        seg = torch.repeat_interleave(rp[rows_i], lens[rows_i]) + _ramp(lens[rows_i])
+        if not torch.equal(colidx[seg].to(I64), exp):
+            return None
+    return bcol, int(nb.max().item())
+
+
+def _ramp(lens):
+    """0..len-1 for every segment, concatenated (device)."""
+    ends = torch.cumsum(lens, 0)
+    return torch.arange(int(ends[-1].item()), device=lens.device) - torch.repeat_interleave(ends - lens, lens)
+
+
+def pcg_persist(rowptr, colidx, values, b, x=None, n_owned=None, block=1, rtol=1e-13, atol=0.0, maxit=20000, x0=None,
+                halo=None, bsr=None, work=None):
+    """Persistent streaming PCG (pgd_pcg_persist_sync).  rowptr: the n_owned local rows; x / x0: [n_local] (ghosts of
+    x0 valid); halo: partition.HaloPlan with its peer layout (sharded solves) or None; bsr: result of ``bsr_plan``.
+    Returns (x [n_local], iterations, relative residual)."""
+    h, lib = handle(b.device), load_library()
+    no = rowptr.numel() - 1 if n_owned is None else int(n_owned)
+    nl = no if halo is None else int(halo.n_local)
+    if x is None:
+        x = torch.empty(nl, dtype=F64, device=b.device)
+    if x0 is not None and x0.data_ptr() != x.data_ptr():
+        x.copy_(x0)
+    need = 3 * ((no + 1) & ~1) + ((no * block + 1) & ~1) + 2 * ((nl + 1) & ~1) + 8
+    if work is None or work.numel() < need:
+        work = torch.empty(need, dtype=F64, device=b.device)
+    send_idx = sc = rc_ = gbase = None
+    if halo is not None:
+        world = len(halo.send_counts)
+        sc = (c_i64 * world)(*[int(v) for v in halo.send_counts])
+        rc_ = (c_i64 * world)(*[int(v) for v in halo.recv_counts])
+        gbase = (c_i64 * world)(*[int(v) for v in halo.peer_ghost_base])
+        send_idx = halo.send_idx if halo.send_idx.numel() else None
+    iters, relres = c_i32(0), c_dbl(0.0)
+    cast = lambda a: ctypes.cast(a, c_vp) if a is not None else c_vp(0)
+    _check(lib.pgd_pcg_persist_sync(h, _p(rowptr, I32), _p(colidx, I32), _p(values, F64), _p(b, F64), _p(x, F64), no, nl, block,
+                                    float(rtol), float(atol), int(maxit), 1 if x0 is not None else 0, _p(work, F64),
+                                    _p(send_idx, I64), cast(sc), cast(rc_), cast(gbase),
+                                    _p(bsr[0], I32) if bsr else c_vp(0), int(bsr[1]) if bsr else 0,
+                                    ctypes.byref(iters), ctypes.byref(relres), _stream()), h, "pgd_pcg_persist_sync")
     return x, iters.value, relres.value
 
 

@@ -66,6 +66,10 @@ struct pgd_ctx {
                              // launches, CUDA-graph replayed) -- measured 7 % faster at 2 GPUs: the fused SpMV has to gather p
                              // with coherent loads instead of ld.global.nc
     int opt_graph;           // pgd_set_option("graph"): 1 (default) = replay the peer-window iteration from a CUDA graph
+    int opt_persist;         // pgd_set_option("persist"): 1 (default) = HBM-bound solves run in the persistent cooperative kernel
+    int opt_bsr;             // pgd_set_option("bsr"): 1 (default) = node-block walk of vector operators inside that kernel
+    int opt_spin_ms;         // pgd_set_option("spin_ms"): budget of every in-kernel wait (default 20 000 ms)
+    void* mailbox;           // single-GPU stand-in for the peer window's mailboxes (PwLayout{0}: slots + flags, 2 KB)
 };
 
 void pgd_free_pattern(pgd_ctx* h);

@@ -21,11 +21,15 @@ extern "C" int32_t pgd_create(int32_t device, pgd_handle_t* out) {
     h->opt_graph = 1;
     h->opt_pcg3 = 1;
     h->opt_fused = 0;
+    h->opt_persist = 1;
+    h->opt_bsr = 1;
+    h->opt_spin_ms = 20000;
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     if ((e = cudaMalloc(&h->partials, sizeof(double) * PGD_MAX_PARTIALS)) != cudaSuccess ||
         (e = cudaMalloc(&h->counters, sizeof(unsigned int) * PGD_MAX_COUNTERS)) != cudaSuccess ||
         (e = cudaMalloc(&h->scalars, sizeof(double) * 64)) != cudaSuccess ||
         (e = cudaMalloc(&h->flags, sizeof(int) * 16)) != cudaSuccess ||
+        (e = cudaMalloc(&h->mailbox, 2048)) != cudaSuccess ||
         (e = cudaMallocHost(&h->pinned, 512)) != cudaSuccess) {
         delete h;
         return (int32_t)e;
@@ -36,6 +40,7 @@ extern "C" int32_t pgd_create(int32_t device, pgd_handle_t* out) {
     cudaMemset(h->counters, 0, sizeof(unsigned int) * PGD_MAX_COUNTERS);
     cudaMemset(h->scalars, 0, sizeof(double) * 64);
     cudaMemset(h->flags, 0, sizeof(int) * 16);
+    cudaMemset(h->mailbox, 0, 2048);
     cudaDeviceSynchronize();
     *out = h;
     return 0;
@@ -51,6 +56,7 @@ extern "C" int32_t pgd_destroy(pgd_handle_t h) {
     cudaFree(h->counters);
     cudaFree(h->scalars);
     cudaFree(h->flags);
+    cudaFree(h->mailbox);
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
     cudaEventDestroy(h->ev_done);
@@ -97,6 +103,18 @@ extern "C" int32_t pgd_set_option(pgd_handle_t h, const char* name, int64_t valu
     }
     if (strcmp(name, "p2p") == 0) {
         h->opt_p2p = value ? 1 : 0;
+        return 0;
+    }
+    if (strcmp(name, "persist") == 0) {
+        h->opt_persist = value ? 1 : 0;
+        return 0;
+    }
+    if (strcmp(name, "bsr") == 0) {
+        h->opt_bsr = value ? 1 : 0;
+        return 0;
+    }
+    if (strcmp(name, "spin_ms") == 0) {
+        h->opt_spin_ms = value < 1 ? 1 : (value > 600000 ? 600000 : (int)value);
         return 0;
     }
     if (strcmp(name, "spmv_stream") == 0) {

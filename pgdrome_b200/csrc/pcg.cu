@@ -14,47 +14,7 @@
 #include "spmv_bulk.cuh"
 #include "spmv_stream.cuh"
 
-enum { S_RZ_OLD = 0, S_RZ_NEW = 1, S_PQ = 2, S_RR = 3, S_BB = 4, S_TOL2 = 5, S_TMP = 8 };
-enum { F_DONE = 0, F_ITER = 1, F_BAD = 2 };
-
-template <int BS>
-__device__ __forceinline__ void invert_block(const double (&B)[BS][BS], double (&I)[BS][BS]) {
-    if constexpr (BS == 1) {
-        I[0][0] = 1.0 / B[0][0];
-    } else if constexpr (BS == 2) {
-        double id = 1.0 / (B[0][0] * B[1][1] - B[0][1] * B[1][0]);
-        I[0][0] = B[1][1] * id;
-        I[0][1] = -B[0][1] * id;
-        I[1][0] = -B[1][0] * id;
-        I[1][1] = B[0][0] * id;
-    } else {
-        double c00 = B[1][1] * B[2][2] - B[1][2] * B[2][1];
-        double c01 = B[1][2] * B[2][0] - B[1][0] * B[2][2];
-        double c02 = B[1][0] * B[2][1] - B[1][1] * B[2][0];
-        double id = 1.0 / (B[0][0] * c00 + B[0][1] * c01 + B[0][2] * c02);
-        I[0][0] = c00 * id;
-        I[1][0] = c01 * id;
-        I[2][0] = c02 * id;
-        I[0][1] = (B[0][2] * B[2][1] - B[0][1] * B[2][2]) * id;
-        I[1][1] = (B[0][0] * B[2][2] - B[0][2] * B[2][0]) * id;
-        I[2][1] = (B[0][1] * B[2][0] - B[0][0] * B[2][1]) * id;
-        I[0][2] = (B[0][1] * B[1][2] - B[0][2] * B[1][1]) * id;
-        I[1][2] = (B[0][2] * B[1][0] - B[0][0] * B[1][2]) * id;
-        I[2][2] = (B[0][0] * B[1][1] - B[0][1] * B[1][0]) * id;
-    }
-}
-
-__device__ __forceinline__ double csr_entry(const int32_t* rowptr, const int32_t* colidx, const double* vals, int r, int c) {
-    int lo = rowptr[r], hi = rowptr[r + 1] - 1;
-    while (lo <= hi) {
-        int mid = (lo + hi) >> 1;
-        int cc = colidx[mid];
-        if (cc == c) return vals[mid];
-        if (cc < c) lo = mid + 1;
-        else hi = mid - 1;
-    }
-    return 0.0;
-}
+#include "pcg_blocks.cuh"
 
 // thread per node: Minv (BSxBS per node), r = b, z = Minv r, x = 0, p0 = p1 = 0; rz, bb
 template <int BS>
@@ -160,81 +120,6 @@ __global__ void __launch_bounds__(256) k_pcg_spmv(const int32_t* __restrict__ ro
     acc = block_sum(acc);
     double v[1] = {acc};
     grid_sum_finish<1>(v, part, counter, sc_out + S_PQ, blockIdx.x, gridDim.x);
-}
-
-// x += alpha p ; r -= alpha q ; z = M^-1 r over the rows of this grid; accumulates the thread's r.z and r.r.
-// Point Jacobi takes two rows per thread with 128-bit accesses when the six arrays are 16-byte aligned.
-template <int BS>
-__device__ __forceinline__ void pcg_update_rows(double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
-                                                const double* __restrict__ p, const double* __restrict__ q,
-                                                const double* __restrict__ minv, int64_t n_nodes, double alpha, double& rz,
-                                                double& rr) {
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool vec = false;
-    if constexpr (BS == 1) {
-        // point Jacobi: two rows per thread with 128-bit loads/stores when the six arrays are 16-byte aligned
-        vec = (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(z) |
-                 reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(minv)) & 15) == 0);
-        if (vec) {
-            const int64_t n2 = n_nodes >> 1;
-            double2* x2 = reinterpret_cast<double2*>(x);
-            double2* r2 = reinterpret_cast<double2*>(r);
-            double2* z2 = reinterpret_cast<double2*>(z);
-            const double2* p2 = reinterpret_cast<const double2*>(p);
-            const double2* q2 = reinterpret_cast<const double2*>(q);
-            const double2* m2 = reinterpret_cast<const double2*>(minv);
-            double rz1 = 0.0, rr1 = 0.0;
-#pragma unroll 2
-            for (int64_t i = gtid; i < n2; i += stride) {
-                const double2 pv = p2[i], qv = q2[i], mv = __ldg(m2 + i);
-                double2 xv = x2[i], rv = r2[i];
-                xv.x = fma(alpha, pv.x, xv.x);
-                xv.y = fma(alpha, pv.y, xv.y);
-                rv.x = fma(-alpha, qv.x, rv.x);
-                rv.y = fma(-alpha, qv.y, rv.y);
-                const double2 zv = make_double2(mv.x * rv.x, mv.y * rv.y);
-                x2[i] = xv;
-                r2[i] = rv;
-                z2[i] = zv;
-                rr = fma(rv.x, rv.x, rr);
-                rr1 = fma(rv.y, rv.y, rr1);
-                rz = fma(rv.x, zv.x, rz);
-                rz1 = fma(rv.y, zv.y, rz1);
-            }
-            rr += rr1;
-            rz += rz1;
-            if ((n_nodes & 1) && gtid == 0) {
-                const int64_t d = n_nodes - 1;
-                x[d] = fma(alpha, p[d], x[d]);
-                const double rn = fma(-alpha, q[d], r[d]);
-                r[d] = rn;
-                const double zi = minv[d] * rn;
-                z[d] = zi;
-                rr = fma(rn, rn, rr);
-                rz = fma(rn, zi, rz);
-            }
-        }
-    }
-    for (int64_t nd = vec ? n_nodes : gtid; nd < n_nodes; nd += stride) {
-        double rn[BS];
-#pragma unroll
-        for (int i = 0; i < BS; ++i) {
-            int64_t d = nd * BS + i;
-            x[d] = fma(alpha, p[d], x[d]);
-            rn[i] = fma(-alpha, q[d], r[d]);
-            r[d] = rn[i];
-            rr = fma(rn[i], rn[i], rr);
-        }
-#pragma unroll
-        for (int i = 0; i < BS; ++i) {
-            double zi = 0.0;
-#pragma unroll
-            for (int k = 0; k < BS; ++k) zi = fma(__ldg(&minv[(nd * BS + i) * BS + k]), rn[k], zi);
-            z[nd * BS + i] = zi;
-            rz = fma(rn[i], zi, rz);
-        }
-    }
 }
 
 template <int BS>
@@ -465,6 +350,11 @@ static int32_t pcg_entry(pgd_handle_t h, const int32_t* d_rowptr, const int32_t*
                                       d_work, h_iters, h_relres, st, warm ? 1 : 0, 0);
         if (rc != 1) return rc;
     }
+    if (h->opt_persist && n >= PGD_BULK_MIN_ROWS && (((uintptr_t)d_colidx | (uintptr_t)d_values | (uintptr_t)d_work) & 15) == 0)
+        // HBM-bound regime: the whole solve in one persistent cooperative kernel (pcg_persist.cu); d_work of
+        // (5 + block) n + 8 doubles covers its layout for n_local = n
+        return pgd_pcg_persist_sync(h, d_rowptr, d_colidx, d_values, d_b, d_x, n, n, block, rtol, atol, maxit, warm ? 1 : 0,
+                                    d_work, nullptr, nullptr, nullptr, nullptr, nullptr, 0, h_iters, h_relres, stream);
     if (block == 1)
         return run_pcg<1>(h, d_rowptr, d_colidx, d_values, d_b, d_x, n, rtol, atol, maxit, check_every, lanes_per_row, d_work,
                           h_iters, h_relres, st, warm);

@@ -1,0 +1,549 @@
+// Persistent Jacobi / node-block-Jacobi PCG for the HBM-bound regime: ONE cooperative kernel per solve, on one
+// GPU or on every GPU of a row-sharded system (the multi-GPU form of pcg_resident.cu).
+//
+// The matrix does not fit on chip here (configs[2]: 520 MB, configs[3]: 720 MB, 1/N of that per rank), so every
+// iteration streams the local CSR rows through the TMA ring of spmv_bulk.cuh; what the persistent form removes
+// is everything BETWEEN the streams: kernel launches, host polling, and -- sharded -- the 8 dependent launches
+// and three host-visible flag round trips of pgd_spcg_solve_sync (55 us floor per iteration).  All CG scalars
+// live in registers, identical in every CTA of every rank.
+//
+// One iteration (p is kept in two buffers pa / pb that alternate, both with a ghost tail):
+//   D  boundary entries of p_new = z + beta p_old are formed FIRST and stored straight into the neighbours'
+//      ghost slots over NVLink (+ sequence flag), then the owned part of p_new is written
+//      -> grid barrier (arrival counter), halo flags of the neighbours acquired
+//   S  q = A_loc p_new through the TMA ring, local p.q            -> reduce-broadcast #1 (alpha)
+//   U  x += alpha p ; r -= alpha q ; z = M^-1 r ; local r.z, r.r  -> reduce-broadcast #2 (beta, stop test)
+// reduce-broadcast: every CTA deposits its partials and arrives; CTA 0 sums them in a fixed order and stores
+// the rank's sum into the mailbox of every rank (its own included) with a release flag; every CTA of every
+// rank acquires the `world` flags and adds the mailboxes in RANK ORDER => bitwise identical scalars
+// everywhere, deterministic run to run, one uniform stop decision and no host round trip.  On a single GPU the
+// mailbox is a block of the handle's own memory and the scheme degenerates to a grid barrier.
+// Every spin carries a wall-clock budget (globaltimer) and watches a local abort word, so a missing peer ends
+// the solve with -6 instead of hanging the GPU; the window is then marked unusable (sequence numbers may have
+// diverged) and later solves use the NCCL path.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+#include "pcg_blocks.cuh"
+#include "peer_window.cuh"
+#include "spmv_bulk.cuh"
+#include "spmv_bsr.cuh"
+
+#define PS_THREADS 512
+
+int32_t pgd_pcg_finish_impl(pgd_ctx* h, int32_t* h_iters, double* h_relres);
+
+struct PersistArgs {
+    const int32_t* rowptr;
+    const int32_t* colidx;
+    const double* vals;
+    const double* b;
+    double* x;                 // [n_local]; warm: initial guess with valid ghosts on entry
+    int64_t n_owned, n_local;
+    double rtol, atol;
+    int maxit, warm;
+    double *r, *z, *q, *minv;  // [n_owned] (minv: n_owned * BS)
+    double *pa, *pb;           // [n_local] each; inside the peer window when world > 1
+    double* part;              // [2][4][G] partial sums, double-buffered by sync parity
+    unsigned int* arrive;      // monotonic arrival counter, 0 at launch
+    unsigned int* push_ctr;    // "last pushing CTA" ticket, 0 at launch and whenever idle
+    int* abort_word;           // != 0: leave (set by a spin that ran out of budget)
+    double* out_sc;            // [0] rr, [1] bb
+    int* out_fl;               // [0] iterations, [1] status (0 ok, 2 NaN, 3 peer timeout)
+    unsigned long long* seq_ar;    // device-resident sequence numbers (shared with pgd_spcg_solve_sync)
+    unsigned long long* seq_halo;
+    int world, me;
+    PwPeers peers;             // window base of every rank (world == 1: base[0] = the handle's local mailbox block)
+    PwLayout lay;
+    PwHalo hp;
+    const int64_t* send_idx;
+    int64_t n_send;
+    int64_t pb_off;            // offset (doubles) of pb inside a window (pa sits at 0)
+    unsigned long long spin_ns;
+    BsrPlan bsr;               // node-block walk of the CSR arrays (BSR template only)
+};
+
+__device__ __forceinline__ unsigned long long ps_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned int ps_ld_acquire_gpu(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+struct PsSync {
+    unsigned int target;           // arrival target of this CTA (monotonic)
+    unsigned long long seq_ar;     // last completed reduce-broadcast
+    unsigned long long seq_halo;   // last completed halo exchange
+    int parity;                    // partial-sum buffer of the next reduce
+};
+
+// Spin until pred() or the budget / abort word ends it; returns false when aborted (and raises the abort word).
+template <class Pred>
+__device__ __forceinline__ bool ps_spin(Pred&& pred, const PersistArgs& a) {
+    if (pred()) return true;
+    const unsigned long long t0 = ps_now();
+    unsigned int k = 0;
+    while (!pred()) {
+        if ((++k & 63u) == 0u) {
+            if (*((volatile int*)a.abort_word) != 0) return false;
+            if (ps_now() - t0 > a.spin_ns) {
+                atomicExch(a.abort_word, 1);
+                return false;
+            }
+        }
+    }
+    return true;
+}
+
+// grid barrier: all threads call; false = aborted (uniform per CTA)
+__device__ __forceinline__ bool ps_grid_barrier(const PersistArgs& a, PsSync& sy, unsigned int G) {
+    __shared__ int s_ok;
+    __syncthreads();
+    sy.target += G;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(a.arrive, 1u);
+        const unsigned int tgt = sy.target;
+        s_ok = ps_spin([&] { return ps_ld_acquire_gpu(a.arrive) >= tgt; }, a) ? 1 : 0;
+    }
+    __syncthreads();
+    return s_ok != 0;
+}
+
+// Deterministic all-CTA (and all-rank) sum of NV per-thread values; the result lands in out[0..NV) of every thread.
+// false = aborted.
+template <int NV>
+__device__ __forceinline__ bool ps_reduce_bcast(double (&v)[NV], const PersistArgs& a, PsSync& sy, unsigned int G) {
+    __shared__ double s_res[4];
+    __shared__ int s_ok;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_ok = 1;  // (ordered before every later write by the barriers inside block_sum)
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = block_sum(v[k]);
+    double* part = a.part + (size_t)sy.parity * 4 * G;
+    sy.parity ^= 1;
+    sy.target += G;
+    const unsigned long long seq = ++sy.seq_ar;
+    const int par = (int)(seq & 1ULL);
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) part[(size_t)k * G + blockIdx.x] = v[k];
+        __threadfence();
+        atomicAdd(a.arrive, 1u);
+    }
+    if (blockIdx.x == 0) {
+        // CTA 0: wait for every CTA of this rank, sum the partials in a fixed order, publish to all ranks
+        if (tid == 0) {
+            const unsigned int tgt = sy.target;
+            if (!ps_spin([&] { return ps_ld_acquire_gpu(a.arrive) >= tgt; }, a)) s_ok = 0;
+        }
+        __syncthreads();
+        if (tid < 32) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                double s = 0.0;
+                for (unsigned int i = tid; i < G; i += 32) s += __ldcg(&part[(size_t)k * G + i]);
+                s = warp_sum(s);
+                if (tid == 0) s_res[k] = s;
+            }
+        }
+        __syncthreads();
+        if (tid < a.world) {
+            double* slot = reinterpret_cast<double*>(a.peers.base[tid] + a.lay.slot_off()) +
+                           ((size_t)par * PW_MAXR + a.me) * PW_AR_VALS;
+#pragma unroll
+            for (int k = 0; k < NV; ++k) slot[k] = s_res[k];
+            __threadfence_system();
+            st_release_sys(reinterpret_cast<unsigned long long*>(a.peers.base[tid] + a.lay.arflag_off()) + par * PW_MAXR + a.me,
+                           seq);
+        }
+    }
+    // every CTA: acquire the flag of every rank in the LOCAL window, then add the mailboxes in rank order
+    if (tid < a.world) {
+        const unsigned long long* f =
+            reinterpret_cast<const unsigned long long*>(a.peers.base[a.me] + a.lay.arflag_off()) + par * PW_MAXR + tid;
+        if (!ps_spin([&] { return ld_acquire_sys(f) >= seq; }, a)) s_ok = 0;
+    }
+    __syncthreads();
+    if (tid == 0 && s_ok) {
+        const double* mine = reinterpret_cast<const double*>(a.peers.base[a.me] + a.lay.slot_off()) + (size_t)par * PW_MAXR * PW_AR_VALS;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double s = 0.0;
+            for (int q = 0; q < a.world; ++q) s += *((volatile const double*)&mine[q * PW_AR_VALS + k]);
+            s_res[k] = s;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = s_res[k];
+    const bool ok = s_ok != 0;
+    __syncthreads();  // s_res / s_ok are reused by the next call
+    return ok;
+}
+
+// boundary entries of v (or of z + beta p_old when z != NULL) -> the neighbours' ghost slots of buffer `dst_off`
+// (doubles from the window base); the last CTA to finish publishes the halo flag on every destination.
+__device__ __forceinline__ void ps_halo_push(const PersistArgs& a, const double* __restrict__ z, const double* __restrict__ v,
+                                             double beta, int64_t dst_buf_off, unsigned long long seq, unsigned int G) {
+    if (a.n_send == 0 || a.world <= 1) return;
+    __shared__ bool s_last;
+    const int64_t stride = (int64_t)G * blockDim.x;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < a.n_send; s += stride) {
+        int r = 0;
+        while (s >= a.hp.seg_start[r + 1]) ++r;
+        const int64_t i = a.send_idx[s];
+        double* dst = reinterpret_cast<double*>(a.peers.base[r]) + dst_buf_off + a.hp.dst_off[r] + (s - a.hp.seg_start[r]);
+        *dst = z ? fma(beta, v[i], z[i]) : v[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(a.push_ctr, 1u);
+        s_last = (t == G - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence_system();
+        const int r = threadIdx.x;
+        if (r < a.world && r != a.me && a.hp.seg_start[r + 1] > a.hp.seg_start[r])
+            st_release_sys(reinterpret_cast<unsigned long long*>(a.peers.base[r] + a.lay.haloflag_off()) + a.me, seq);
+        if (threadIdx.x == 0) *a.push_ctr = 0u;
+    }
+}
+
+// all threads call; the threads r < world acquire the halo flag of rank r; false = aborted
+__device__ __forceinline__ bool ps_halo_wait(const PersistArgs& a, unsigned long long seq) {
+    __shared__ int s_ok2;
+    if (a.world <= 1) return true;
+    if (threadIdx.x == 0) s_ok2 = 1;
+    __syncthreads();
+    const int r = threadIdx.x;
+    if (r < a.world && a.hp.recv_from[r]) {
+        const unsigned long long* f = reinterpret_cast<const unsigned long long*>(a.peers.base[a.me] + a.lay.haloflag_off()) + r;
+        if (!ps_spin([&] { return ld_acquire_sys(f) >= seq; }, a)) s_ok2 = 0;
+    }
+    __syncthreads();
+    return s_ok2 != 0;
+}
+
+// Gather of the direction vector.  Plain global loads (L1-cached, NOT the read-only .nc path): p is rewritten every
+// iteration by other CTAs and -- its ghost tail -- by peer GPUs; every phase that reads it starts behind an acquire
+// (grid barrier / halo flag) followed by a CTA barrier, which orders these weak loads after the writers' stores.
+struct PsGather {
+    const double* x;
+    __device__ __forceinline__ double operator()(int c) const { return x[c]; }
+};
+
+// q-type pass over the local rows: epi(row, (A v)[row]) through the CSR ring or the node-block walk
+template <int BS, bool BSR, class Epi>
+__device__ __forceinline__ void ps_spmv(const PersistArgs& a, const double* v, Epi&& epi, unsigned char* smem, uint32_t* tile) {
+    if constexpr (BSR)
+        bb_spmv_rows<BS, PsGather, Epi, PS_THREADS>(a.rowptr, a.vals, a.bsr, a.n_owned, PsGather{v}, epi, smem, tile);
+    else
+        bk_spmv_rows<PsGather, Epi, PS_THREADS>(a.rowptr, a.colidx, a.vals, a.n_owned, PsGather{v}, epi, smem, tile);
+}
+
+template <int BS, bool BSR>
+__global__ void __launch_bounds__(PS_THREADS, BK_CTAS_PER_SM) k_pcg_persist(PersistArgs a) {
+    extern __shared__ __align__(128) unsigned char bk_smem[];
+    const unsigned int G = gridDim.x;
+    const int tid = threadIdx.x;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + tid;
+    const int64_t gstride = (int64_t)G * blockDim.x;
+    const int64_t no = a.n_owned, n_nodes = a.n_owned / BS;
+    PsSync sy;
+    sy.target = 0;
+    sy.seq_ar = *a.seq_ar;      // nobody writes these before the very end of the kernel
+    sy.seq_halo = *a.seq_halo;
+    sy.parity = 0;
+    uint32_t tile = 0;
+    if (tid == 0) {
+        if constexpr (BSR) bb_init_barriers(bk_smem);
+        else bk_init_barriers(bk_smem);
+    }
+    __syncthreads();
+    int status = 0;
+    int it = 0;
+    double rz = 0.0, rz_old = 1.0, rr = 0.0, bb = 0.0, tol2 = 0.0;
+
+    // ---- r = b - A x0 (warm) | b ; M^-1 ; z = M^-1 r ; pa = pb = 0
+    if (a.warm) {
+        auto epi = [&](int64_t row, double s) { a.q[row] = s; };
+        ps_spmv<BS, BSR>(a, a.x, epi, bk_smem, &tile);
+        __syncthreads();
+        if (!ps_grid_barrier(a, sy, G)) status = 3;
+    }
+    {
+        double v[3] = {0.0, 0.0, 0.0};  // r.z, b.b, r.r
+        if (status == 0) {
+            for (int64_t nd = gtid; nd < n_nodes; nd += gstride) {
+                double B[BS][BS], I[BS][BS], rb[BS];
+#pragma unroll
+                for (int i = 0; i < BS; ++i)
+#pragma unroll
+                    for (int k = 0; k < BS; ++k)
+                        B[i][k] = csr_entry(a.rowptr, a.colidx, a.vals, (int)(nd * BS + i), (int)(nd * BS + k));
+                invert_block<BS>(B, I);
+#pragma unroll
+                for (int i = 0; i < BS; ++i) {
+                    rb[i] = a.b[nd * BS + i];
+                    v[1] += rb[i] * rb[i];
+                    if (a.warm) rb[i] -= a.q[nd * BS + i];
+#pragma unroll
+                    for (int k = 0; k < BS; ++k) a.minv[(nd * BS + i) * BS + k] = I[i][k];
+                }
+#pragma unroll
+                for (int i = 0; i < BS; ++i) {
+                    double zi = 0.0;
+#pragma unroll
+                    for (int k = 0; k < BS; ++k) zi += I[i][k] * rb[k];
+                    const int64_t d = nd * BS + i;
+                    a.r[d] = rb[i];
+                    a.z[d] = zi;
+                    if (!a.warm) a.x[d] = 0.0;
+                    v[0] += rb[i] * zi;
+                    v[2] += rb[i] * rb[i];
+                }
+            }
+            for (int64_t i = gtid; i < a.n_local; i += gstride) {
+                a.pa[i] = 0.0;
+                a.pb[i] = 0.0;
+            }
+            if (!ps_reduce_bcast<3>(v, a, sy, G)) status = 3;
+        }
+        rz = v[0];
+        bb = v[1];
+        rr = v[2];
+        tol2 = a.rtol * a.rtol * bb;
+        if (a.atol * a.atol > tol2) tol2 = a.atol * a.atol;
+    }
+
+    if (status == 0 && rr > tol2 && bb > 0.0) {
+        while (it < a.maxit) {
+            const double beta = (it == 0) ? 0.0 : rz / rz_old;
+            const double* __restrict__ p_old = (it & 1) ? a.pb : a.pa;
+            double* __restrict__ p_new = (it & 1) ? a.pa : a.pb;
+            const int64_t new_off = (it & 1) ? 0 : a.pb_off;
+            // ---- D: boundary entries to the neighbours first, then the owned direction
+            const unsigned long long hseq = ++sy.seq_halo;
+            ps_halo_push(a, a.z, p_old, beta, new_off, hseq, G);
+            if ((((uintptr_t)a.z | (uintptr_t)p_old | (uintptr_t)p_new) & 15) == 0) {
+                const int64_t n2 = no >> 1;
+                const double2* z2 = reinterpret_cast<const double2*>(a.z);
+                const double2* o2 = reinterpret_cast<const double2*>(p_old);
+                double2* p2 = reinterpret_cast<double2*>(p_new);
+                for (int64_t i = gtid; i < n2; i += gstride) {
+                    const double2 zv = z2[i], ov = o2[i];
+                    p2[i] = make_double2(fma(beta, ov.x, zv.x), fma(beta, ov.y, zv.y));
+                }
+                if ((no & 1) && gtid == 0) p_new[no - 1] = fma(beta, p_old[no - 1], a.z[no - 1]);
+            } else {
+                for (int64_t i = gtid; i < no; i += gstride) p_new[i] = fma(beta, p_old[i], a.z[i]);
+            }
+            if (!ps_grid_barrier(a, sy, G) || !ps_halo_wait(a, hseq)) {
+                status = 3;
+                break;
+            }
+            // ---- S: q = A p, p.q
+            double pq = 0.0;
+            {
+                auto epi = [&](int64_t row, double s) {
+                    a.q[row] = s;
+                    pq = fma(p_new[row], s, pq);
+                };
+                ps_spmv<BS, BSR>(a, p_new, epi, bk_smem, &tile);
+            }
+            double v1[1] = {pq};
+            if (!ps_reduce_bcast<1>(v1, a, sy, G)) {
+                status = 3;
+                break;
+            }
+            const double alpha = rz / v1[0];
+            // ---- U: x, r, z, r.z, r.r
+            double v2[2] = {0.0, 0.0};
+            pcg_update_rows<BS>(a.x, a.r, a.z, p_new, a.q, a.minv, n_nodes, alpha, v2[0], v2[1]);
+            if (!ps_reduce_bcast<2>(v2, a, sy, G)) {
+                status = 3;
+                break;
+            }
+            rz_old = rz;
+            rz = v2[0];
+            rr = v2[1];
+            ++it;
+            if (!(rr == rr) || !(rz == rz)) {
+                status = 2;
+                break;
+            }
+            if (!(rr > tol2)) break;
+        }
+    }
+    // ---- ghosts of the solution: the boundary entries of x travel through the pa buffer of the window
+    if (a.world > 1 && status != 3) {
+        const unsigned long long hseq = ++sy.seq_halo;
+        if (bb > 0.0) {
+            ps_halo_push(a, nullptr, a.x, 0.0, 0, hseq, G);
+        } else {
+            ps_halo_push(a, nullptr, a.pa, 0.0, 0, hseq, G);  // b = 0: x = 0 (pa is still all zero)
+        }
+        if (!ps_halo_wait(a, hseq)) status = 3;
+        else
+            for (int64_t i = no + gtid; i < a.n_local; i += gstride) a.x[i] = a.pa[i];
+        // nobody may start the next solve's pushes into pa before every rank has copied its ghosts: one more
+        // reduce-broadcast acts as the closing barrier across ranks
+        double v0[1] = {0.0};
+        if (status != 3 && !ps_reduce_bcast<1>(v0, a, sy, G)) status = 3;
+    }
+    if (!(bb > 0.0) && status == 0)
+        for (int64_t i = gtid; i < no; i += gstride) a.x[i] = 0.0;  // b = 0: the solution is 0 whatever x0 was
+    if (blockIdx.x == 0 && tid == 0) {
+        a.out_sc[0] = rr;
+        a.out_sc[1] = bb;
+        a.out_fl[0] = it;
+        a.out_fl[1] = status;
+        *a.seq_ar = sy.seq_ar;
+        *a.seq_halo = sy.seq_halo;
+    }
+}
+
+/* d_work: r z q (stride ns = n_owned rounded up to even) | M^-1 (even(n_owned*block)) | pa pb (even(n_local) each, used
+ * only without a peer window) => 3*ns + even(n_owned*block) + 2*even(n_local) + 8 doubles. */
+extern "C" int32_t pgd_pcg_persist_sync(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
+                                        const double* d_b, double* d_x, int64_t n_owned, int64_t n_local, int32_t block,
+                                        double rtol, double atol, int32_t maxit, int32_t warm, double* d_work,
+                                        const int64_t* d_send_idx, const int64_t* h_send_counts, const int64_t* h_recv_counts,
+                                        const int64_t* h_peer_ghost_base, const int32_t* d_bcol, int32_t max_blocks_per_row,
+                                        int32_t* h_iters, double* h_relres, void* stream) {
+    PGD_CHECK_HANDLE(h);
+    PGD_ARG(h, d_rowptr && d_colidx && d_values && d_b && d_x && d_work, "null pointer");
+    PGD_ARG(h, n_owned > 0 && n_local >= n_owned && block >= 1 && block <= 3 && n_owned % block == 0, "bad sizes");
+    PGD_ARG(h, (((uintptr_t)d_colidx | (uintptr_t)d_values) & 15) == 0, "colidx / values must be 16-byte aligned (bulk copies)");
+    cudaStream_t st = (cudaStream_t)stream;
+    {  // a solve started earlier with pgd_pcg_start and never collected: finish it first
+        int32_t rc0 = pgd_pcg_finish_impl(h, nullptr, nullptr);
+        if (rc0 < 0) return rc0;
+    }
+    const bool multi = h_send_counts && h_recv_counts && h_peer_ghost_base && h->win_local && h->win_world > 1;
+    PGD_ARG(h, multi || n_local == n_owned, "ghost columns need an opened peer window (pgd_peer_window_open)");
+    const int world = multi ? h->win_world : 1;
+    PersistArgs a;
+    memset(&a, 0, sizeof(a));
+    a.rowptr = d_rowptr;
+    a.colidx = d_colidx;
+    a.vals = d_values;
+    a.b = d_b;
+    a.x = d_x;
+    a.n_owned = n_owned;
+    a.n_local = n_local;
+    a.rtol = rtol;
+    a.atol = atol;
+    a.maxit = maxit;
+    a.warm = warm ? 1 : 0;
+    const int64_t ns = (n_owned + 1) & ~(int64_t)1;
+    const int64_t nl2 = (n_local + 1) & ~(int64_t)1;
+    a.r = d_work;
+    a.z = a.r + ns;
+    a.q = a.z + ns;
+    a.minv = a.q + ns;
+    double* ploc = a.minv + ((n_owned * block + 1) & ~(int64_t)1);
+    a.world = world;
+    a.me = multi ? h->win_rank : 0;
+    a.lay = PwLayout{multi ? h->win_pcap : 0};
+    if (multi) {
+        const int64_t half = (h->win_pcap / 2) & ~(int64_t)1;
+        PGD_ARG(h, n_local <= half, "peer window too small for two direction buffers");
+        a.pb_off = half;
+        a.pa = reinterpret_cast<double*>(h->win_local);
+        a.pb = a.pa + half;
+        int64_t n_send = 0;
+        a.hp.seg_start[0] = 0;
+        for (int r = 0; r < PW_MAXR; ++r) {
+            a.peers.base[r] = (unsigned char*)(r < world ? h->win_peer[r] : nullptr);
+            a.hp.seg_start[r + 1] = a.hp.seg_start[r] + (r < world ? h_send_counts[r] : 0);
+            a.hp.dst_off[r] = r < world ? h_peer_ghost_base[r] : 0;
+            a.hp.recv_from[r] = (r < world && h_recv_counts[r] > 0) ? 1 : 0;
+            if (r < world) n_send += h_send_counts[r];
+        }
+        PGD_ARG(h, n_send == 0 || d_send_idx, "send index list required");
+        a.send_idx = d_send_idx;
+        a.n_send = n_send;
+    } else {
+        a.pa = ploc;
+        a.pb = ploc + nl2;
+        a.pb_off = nl2;
+        a.peers.base[0] = reinterpret_cast<unsigned char*>(h->mailbox);
+    }
+    a.part = h->partials;
+    a.arrive = h->counters + (PGD_MAX_COUNTERS - 3);
+    a.push_ctr = h->counters + (PGD_MAX_COUNTERS - 4);
+    a.abort_word = h->flags + 12;
+    a.out_sc = h->scalars + 32;
+    a.out_fl = h->flags + 8;
+    a.seq_halo = reinterpret_cast<unsigned long long*>(h->scalars + 40);
+    a.seq_ar = reinterpret_cast<unsigned long long*>(h->scalars + (multi ? 41 : 42));  // the local mailbox has its own sequence
+    a.spin_ns = (unsigned long long)h->opt_spin_ms * 1000000ULL;
+    PGD_CUDA(h, cudaMemsetAsync(a.arrive - 1, 0, 2 * sizeof(unsigned int), st));  // push_ctr, arrive
+    PGD_CUDA(h, cudaMemsetAsync(a.out_fl, 0, 2 * sizeof(int), st));
+    PGD_CUDA(h, cudaMemsetAsync(a.abort_word, 0, sizeof(int), st));
+    // node-block walk: lanes per block row = the power of two covering the longest block row (<= 32), block rows per
+    // tile = CTA size / lanes; the tile (nbr * block^2 * longest row entries) must fit one stage of the ring
+    bool bsr = false;
+    if (d_bcol && block > 1 && max_blocks_per_row > 0 && h->opt_bsr) {
+        int lpr = 1;
+        while (lpr < 32 && lpr < max_blocks_per_row) lpr *= 2;
+        const int nbr = PS_THREADS / lpr;
+        if (nbr <= BB_MAXNBR && (int64_t)nbr * block * block * max_blocks_per_row <= BK_CAP &&
+            (((uintptr_t)d_bcol) & 15) == 0) {
+            bsr = true;
+            a.bsr.bcol = d_bcol;
+            a.bsr.nbr = nbr;
+            a.bsr.lpr = lpr;
+        }
+    }
+    const void* fn = nullptr;
+    if (block == 1) fn = (const void*)k_pcg_persist<1, false>;
+    else if (block == 2) fn = bsr ? (const void*)k_pcg_persist<2, true> : (const void*)k_pcg_persist<2, false>;
+    else fn = bsr ? (const void*)k_pcg_persist<3, true> : (const void*)k_pcg_persist<3, false>;
+    const size_t smem = bsr ? BB_SMEM_BYTES : BK_SMEM_BYTES;
+    PGD_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    PGD_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PS_THREADS, smem));
+    if (per_sm < 1) {
+        snprintf(h->err, sizeof(h->err), "pgd_pcg_persist_sync: kernel does not fit an SM");
+        return -4;
+    }
+    if (per_sm > BK_CTAS_PER_SM) per_sm = BK_CTAS_PER_SM;
+    const int G = per_sm * h->sm_count;
+    if ((size_t)G * 8 > PGD_MAX_PARTIALS) return -4;
+    void* kargs[] = {&a};
+    PGD_CUDA(h, cudaEventRecord(h->ev0, st));
+    PGD_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3(G), dim3(PS_THREADS), kargs, smem, st));
+    h->n_launches += 1;
+    PGD_CUDA(h, cudaEventRecord(h->ev1, st));
+    int hf[2] = {0, 0};
+    double hs[2] = {0.0, 0.0};
+    PGD_CUDA(h, pgd_fetch(h, hf, a.out_fl, sizeof(hf), hs, a.out_sc, sizeof(hs), st));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->pcg_ms += ms;
+    h->pcg_solves += 1;
+    h->pcg_iters += hf[0];
+    if (h_iters) *h_iters = hf[0];
+    if (h_relres) *h_relres = (hs[1] > 0.0) ? sqrt(hs[0] / hs[1]) : 0.0;
+    if (hf[1] == 3) {
+        // sequence numbers of the ranks may have diverged: the window is not usable any more (NCCL path from now on)
+        if (multi) h->win_world = 0;
+        snprintf(h->err, sizeof(h->err),
+                 "pgd_pcg_persist_sync: a CTA or peer rank did not arrive within %d ms; the peer window has been disabled",
+                 h->opt_spin_ms);
+        return -6;
+    }
+    if (hf[1] == 2) {
+        snprintf(h->err, sizeof(h->err), "pgd_pcg_persist_sync: NaN encountered (matrix not SPD?)");
+        return -3;
+    }
+    return 0;
+}

@@ -17,6 +17,7 @@
 #include <nccl.h>
 
 #include "common.cuh"
+#include "pcg_blocks.cuh"
 #include "spmv_bulk.cuh"
 
 struct NcclApi {
@@ -128,35 +129,7 @@ __global__ void __launch_bounds__(256) k_halo_pack(const double* __restrict__ v,
 //                 wait for everybody's flag, sum in RANK ORDER (=> bitwise identical on all ranks).
 // All spins carry a clock64() budget; on expiry they raise the NaN/bad flag instead of hanging the GPU.
 // ================================================================================================
-#define PW_MAXR 16
-#define PW_AR_VALS 4
-#define PW_SPIN_BUDGET (4000000000LL)  // ~2 s at 1.9 GHz
-
-struct PwLayout {
-    int64_t pcap;
-    __host__ __device__ size_t slot_off() const { return (size_t)pcap * 8; }
-    __host__ __device__ size_t arflag_off() const { return slot_off() + 2 * PW_MAXR * PW_AR_VALS * 8; }
-    __host__ __device__ size_t haloflag_off() const { return arflag_off() + 2 * PW_MAXR * 8; }
-    __host__ __device__ size_t bytes() const { return haloflag_off() + PW_MAXR * 8; }
-};
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-struct PwPeers {
-    unsigned char* base[PW_MAXR];
-};
-struct PwHalo {
-    int64_t seg_start[PW_MAXR + 1];  // send entries grouped by destination rank
-    int64_t dst_off[PW_MAXR];        // offset (doubles) inside the destination's p where my block of ghosts starts
-    int recv_from[PW_MAXR];          // 1 if I receive ghosts from that rank
-};
+#include "peer_window.cuh"
 
 __global__ void __launch_bounds__(256) k_halo_push(const double* __restrict__ p, const int64_t* __restrict__ send_idx,
                                                    int64_t n_send, PwPeers peers, PwHalo hp, PwLayout lay, int me, int world,
@@ -267,8 +240,6 @@ __global__ void k_allreduce_p2p(double* vals, int nv, PwPeers peers, PwLayout la
 //   k_spcg_update_p2p      x, r, z update with local r.z, r.r; the finishing CTA all-reduces both and rotates
 //                          the CG scalars / iteration counter / convergence flag
 // ------------------------------------------------------------------------------------------------
-enum { S_RZ_OLD = 0, S_RZ_NEW = 1, S_PQ = 2, S_RR = 3, S_BB = 4, S_TOL2 = 5, S_TMP = 8 };
-enum { F_DONE = 0, F_ITER = 1, F_BAD = 2 };
 
 // boundary entries of the NEW direction p = z + beta p_old, formed from z and p_old (the same fma the direction
 // kernel evaluates right afterwards => bitwise identical) and stored into the neighbours' ghost slots

@@ -47,18 +47,24 @@ __device__ __forceinline__ void bk_bulk_g2s(void* dst, const void* src, uint32_t
                  "l"(src), "r"(bytes), "r"(bk_smem_u32(bar))
                  : "memory");
 }
+// Wait for the phase with the given parity.  The poll is bounded: a copy that never completes (a bug, never seen in
+// a correct run) traps after ~4 s instead of hanging the GPU.
 __device__ __forceinline__ void bk_mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "BK_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra BK_DONE_%=;\n"
-        "bra BK_WAIT_%=;\n"
-        "BK_DONE_%=:\n"
-        "}\n" ::"r"(bk_smem_u32(bar)),
-        "r"(parity)
-        : "memory");
+    const uint32_t addr = bk_smem_u32(bar);
+    uint32_t done = 0;
+    for (uint32_t spins = 0;; ++spins) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (spins > (1u << 22)) __trap();  // each failed try_wait already waits a hardware-defined interval (~1 us)
+    }
 }
 
 struct BkGatherX {
@@ -90,7 +96,7 @@ __device__ __forceinline__ int bk_pick_lpr(int64_t n, int64_t nnz) {
 template <class Gather, class Epi, int THREADS = BK_THREADS>
 __device__ __forceinline__ void bk_spmv_rows(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                                              const double* __restrict__ vals, int64_t n, const Gather& g, Epi&& epi,
-                                             unsigned char* smem) {
+                                             unsigned char* smem, uint32_t* t_state = nullptr) {
     double* const s_vals0 = reinterpret_cast<double*>(smem);             // [2][BK_BUF]
     int* const s_cols0 = reinterpret_cast<int*>(s_vals0 + 2 * BK_BUF);   // [2][BK_BUF]
     int* const s_rp0 = s_cols0 + 2 * BK_BUF;                             // [2][260]
@@ -126,7 +132,9 @@ __device__ __forceinline__ void bk_spmv_rows(const int32_t* __restrict__ rowptr,
     int64_t r0 = rb * RB;
     int nr = (int)min((int64_t)RB, n - r0);
     for (int i = tid; i <= nr; i += THREADS) s_rp(0)[i] = __ldg(&rowptr[r0 + i]);
-    if (tid == 0) {
+    // t_state (persistent callers): the mbarriers were initialised once by bk_init_barriers and the running tile
+    // counter (stage = t & 1, phase parity = (t >> 1) & 1) carries over from call to call
+    if (tid == 0 && !t_state) {
         bk_mbar_init(&bars[0], 1);
         bk_mbar_init(&bars[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -134,8 +142,8 @@ __device__ __forceinline__ void bk_spmv_rows(const int32_t* __restrict__ rowptr,
     __syncthreads();
     int pb = 0;
     int k0 = s_rp(0)[0], k1 = s_rp(0)[nr];
-    uint32_t t = 0;
-    if (tid == 0) issue(0, k0, min(k0 + BK_CAP, k1));
+    uint32_t t = t_state ? *t_state : 0u;
+    if (tid == 0) issue(t, k0, min(k0 + BK_CAP, k1));
 
     while (true) {
         // prefetch the NEXT row block's rowptr slice into registers (RB + 1 <= BK_THREADS + 1 entries)
@@ -208,6 +216,18 @@ __device__ __forceinline__ void bk_spmv_rows(const int32_t* __restrict__ rowptr,
         k0 = s_rp(pb)[0];
         k1 = s_rp(pb)[nr];
     }
+    if (t_state) *t_state = t;
+}
+
+// one-time initialisation of the two stage barriers for persistent callers of bk_spmv_rows (thread 0; follow with
+// __syncthreads before the first call)
+__device__ __forceinline__ void bk_init_barriers(unsigned char* smem) {
+    double* const s_vals0 = reinterpret_cast<double*>(smem);
+    int* const s_cols0 = reinterpret_cast<int*>(s_vals0 + 2 * BK_BUF);
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(s_cols0 + 2 * BK_BUF + 2 * 260);
+    bk_mbar_init(&bars[0], 1);
+    bk_mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 #undef s_vals
 #undef s_cols

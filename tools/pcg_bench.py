@@ -1,0 +1,143 @@
+"""Streaming (HBM-bound) PCG iteration on the operators of BASELINE configs[2] / configs[3]: per-kernel and
+per-iteration device times against the byte model of DESIGN.md.
+
+  python -m tools.pcg_bench --mesh 68 --bs 3            configs[2] pattern (vector P1, 985 527 dofs, 45 nnz/row)
+  python -m tools.pcg_bench --mesh 158 --bs 1           configs[3] pattern (scalar P1, 4 019 679 dofs, 15 nnz/row)
+  ... --profile                                          few launches only (for ncu captures)
+
+Prints one JSON line.  CUDA events on the launching stream, >= 3 warm-ups, CSR arrays >> L2."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def operator(mesh_n, bs):
+    from pgdrome_b200 import fem
+    from pgdrome_b200.assembly import device_space
+
+    m = fem.UnitCubeMesh(mesh_n, mesh_n, mesh_n)
+    V = fem.FunctionSpace(m, "P", 1) if bs == 1 else fem.VectorFunctionSpace(m, "P", 1)
+    ds = device_space(V)
+    g = 3
+    if bs == 1:
+        T = np.zeros((1, g + 1, 1, g + 1))
+        T[0, 0, 0, 0] = 0.3
+        for k in range(1, g + 1):
+            T[0, k, 0, k] = 1.7
+    else:  # isotropic elasticity + mass shift (SPD without boundary conditions)
+        lam, mu = 1.3, 0.7
+        T = np.zeros((bs, g + 1, bs, g + 1))
+        for i in range(bs):
+            T[i, 0, i, 0] = 0.3
+            for j in range(bs):
+                T[i, 1 + i, j, 1 + j] += lam
+                T[i, 1 + j, j, 1 + i] += mu
+                T[i, 1 + j, i, 1 + j] += mu
+    vals = ds.assemble_bilinear(T)
+    return V, ds, vals
+
+
+def run(mesh_n=68, bs=3, iters=200, profile=False, hbm_peak=6451.2):
+    from pgdrome_b200 import _lib
+
+    V, ds, vals = operator(mesh_n, bs)
+    rowptr, colidx, _, _ = ds.pattern
+    n, nnz = ds.n_dofs, ds.nnz
+    dev = rowptr.device
+    gen = torch.Generator(device=dev).manual_seed(0)
+    x = torch.rand(n, dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+    b = _lib.spmv(rowptr, colidx, vals, x, lpr=ds.lpr)
+    out = {"mesh": "BoxMesh %d^3, P1 bs=%d" % (mesh_n, bs), "n_dofs": n, "nnz": nnz, "hbm_peak_gbs": hbm_peak}
+
+    def timed(fn, reps=20, warm=3):
+        if profile:
+            reps, warm = 1, 1
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for a, c in evs:
+            a.record()
+            fn()
+            c.record()
+        torch.cuda.synchronize()
+        ms = sorted(a.elapsed_time(c) for a, c in evs)
+        return ms[len(ms) // 2]
+
+    def entry(name, ms, nbytes, **kw):
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out[name] = dict(ms=ms, bytes=nbytes, gbs=gbs, frac_hbm=gbs / hbm_peak, **kw)
+
+    y = torch.empty(n, dtype=torch.float64, device=dev)
+    sc = torch.empty(1, dtype=torch.float64, device=dev)
+    spmv_bytes = 12 * nnz + 4 * (n + 1) + 16 * n
+    entry("spmv", timed(lambda: _lib.spmv(rowptr, colidx, vals, x, y=y)), spmv_bytes)
+    entry("spmv_dot", timed(lambda: _lib.spmv_dot(rowptr, colidx, vals, x, x, y=y, out=sc)), spmv_bytes)
+    it_bytes = 12 * nnz + 4 * (n + 1) + 56 * n
+    work = torch.empty((5 + bs) * n + 16, dtype=torch.float64, device=dev)
+    _lib.set_option("pcg_resident", 0)
+    _lib.set_option("spin_ms", 3000)
+    k = 3 if profile else iters
+    plan = _lib.bsr_plan(rowptr, colidx, bs) if bs > 1 else None
+    out["bsr_plan"] = None if plan is None else {"blocks": int(plan[0].numel()), "max_blocks_per_row": plan[1]}
+    variants = [("pcg_3launch", dict(persist=0), None), ("pcg_persist_csr", dict(persist=1, bsr=0), None)]
+    if plan is not None:
+        variants.append(("pcg_persist_bsr", dict(persist=1, bsr=1), plan))
+    sols = {}
+    for name, opts, pl in variants:
+        for o, v in opts.items():
+            _lib.set_option(o, v)
+
+        def solve(rtol, maxit):
+            if pl is not None:
+                return _lib.pcg_persist(rowptr, colidx, vals, b, block=bs, rtol=rtol, maxit=maxit, bsr=pl, work=work)
+            return _lib.pcg(rowptr, colidx, vals, b, rtol=rtol, maxit=maxit, check_every=maxit, block=bs, work=work)
+
+        solve(1e-30, 10)
+        _lib.stats(reset=True)
+        solve(1e-30, k)
+        s = _lib.stats()
+        bytes_moved = it_bytes if pl is None else (8 * nnz + 4 * (nnz // (bs * bs)) + 4 * (n + 1) + 56 * n)
+        entry(name, s["pcg_ms"] / max(s["pcg_iters"], 1), it_bytes, iters=s["pcg_iters"], launches=s["launches"],
+              bytes_of_format=bytes_moved, frac_hbm_of_format=bytes_moved / (s["pcg_ms"] / max(s["pcg_iters"], 1) * 1e-3) / 1e9 / hbm_peak)
+        if not profile:
+            _lib.stats(reset=True)
+            xs, its, rr = solve(1e-13, 20000)
+            s = _lib.stats()
+            sols[name] = xs[:n].clone()
+            out[name]["solve"] = {"iters": its, "relres": rr, "err": float((xs[:n] - x).norm() / x.norm()), "ms": s["pcg_ms"]}
+            # warm start from the converged solution: must stop at once
+            if pl is not None:
+                _, its2, rr2 = _lib.pcg_persist(rowptr, colidx, vals, b, block=bs, rtol=1e-12, maxit=100, x0=xs, bsr=pl, work=work)
+            else:
+                _, its2, rr2 = _lib.pcg(rowptr, colidx, vals, b, rtol=1e-12, maxit=100, check_every=50, block=bs, work=work, x0=xs)
+            out[name]["warm_restart"] = {"iters": its2, "relres": rr2}
+    if len(sols) > 1:
+        ref = sols["pcg_3launch"]
+        out["max_rel_diff_vs_3launch"] = {kk: float((v - ref).norm() / ref.norm()) for kk, v in sols.items()}
+    _lib.set_option("persist", 1)
+    _lib.set_option("bsr", 1)
+    return out
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mesh", type=int, default=68)
+    ap.add_argument("--bs", type=int, default=3)
+    ap.add_argument("--iters", type=int, default=200)
+    ap.add_argument("--profile", action="store_true")
+    a = ap.parse_args()
+    peak = 6451.2
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", peak)
+    except Exception:
+        pass
+    print(json.dumps(run(a.mesh, a.bs, a.iters, a.profile, peak)))
