@@ -233,6 +233,11 @@ int32_t pgd_pcg_persist_sync(pgd_handle_t h, const int32_t* d_rowptr, const int3
                              const int32_t* d_bcol, int32_t max_blocks_per_row, int32_t* h_iters, double* h_relres,
                              void* stream);
 
+/* Phase profile of that kernel (pgd_set_option "prof" = 1): accumulated nanoseconds as seen by CTA 0 in
+ * [0] direction update + halo push, [1] grid barrier + halo wait, [2] SpMV, [3] reduce-broadcast of p.q,
+ * [4] vector update, [5] reduce-broadcast of r.z / r.r.  Diagnostic (tools/pcg_bench.py); synchronises. */
+int32_t pgd_get_phase_ns(pgd_handle_t h, int64_t* h_ns6, int32_t reset);
+
 /* General banded LU with partial pivoting, one CTA, for the 1-D parameter / time dimensions
  * (tiny, possibly non-symmetric).  d_perm[new] = old dof (band ordering), kl/ku bandwidths in the
  * permuted numbering; d_work: (2*kl+ku+1)*n + n doubles; *d_info != 0 on a zero pivot. */

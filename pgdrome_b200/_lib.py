@@ -60,6 +60,7 @@ SIGNATURES = {
                         ctypes.POINTER(c_i32), ctypes.POINTER(c_dbl), c_vp],
     "pgd_pcg_persist_sync": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_dbl, c_dbl, c_i32, c_i32, c_vp, c_vp, c_vp,
                              c_vp, c_vp, c_vp, c_i32, ctypes.POINTER(c_i32), ctypes.POINTER(c_dbl), c_vp],
+    "pgd_get_phase_ns": [c_vp, c_vp, c_i32],
     "pgd_banded_solve": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp],
     "pgd_eval_weights": [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp],
     "pgd_eval_gemv": [c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_vp, c_vp],
@@ -425,11 +426,13 @@ def p1_rowplan_build(rowptr, colidx, cell_dofs, vptr, vidx, n_nodes):
     return vent
 
 
-def assemble_p1_rows(coords, cell_verts, gdim, c_mass, c_stiff, c_adv, rowptr, vptr, vent, n_nodes, out=None, coords_soa=None):
-    """coords_soa: optional component-major copy [gdim, n_verts] of coords (faster coordinate gathers)."""
+def assemble_p1_rows(coords, cell_verts, gdim, c_mass, c_stiff, c_adv, rowptr, vptr, vent, n_nodes, out=None, coords_soa=None,
+                     nnz=None):
+    """coords_soa: optional component-major copy [gdim, n_verts] of coords (faster coordinate gathers).  nnz: size of the
+    value array (known to the owner of the pattern; read back from rowptr[-1] when neither it nor ``out`` is given)."""
     h, lib = handle(coords.device), load_library()
     if out is None:
-        out = torch.empty(_nnz_of(rowptr), dtype=F64, device=coords.device)
+        out = torch.empty(int(rowptr[-1].item()) if nnz is None else int(nnz), dtype=F64, device=coords.device)
     adv = None
     if c_adv is not None:
         adv = (c_dbl * 3)(*[float(v) for v in list(c_adv) + [0.0] * (3 - len(c_adv))])
@@ -439,16 +442,6 @@ def assemble_p1_rows(coords, cell_verts, gdim, c_mass, c_stiff, c_adv, rowptr, v
                                     _p(coords_soa, F64) if coords_soa is not None else c_vp(0),
                                     coords_soa.shape[1] if coords_soa is not None else 0, _stream()), h, "pgd_assemble_p1_rows")
     return out
-
-
-_NNZ_CACHE = {}
-
-
-def _nnz_of(rowptr):
-    key = (rowptr.data_ptr(), rowptr.numel())
-    if key not in _NNZ_CACHE:
-        _NNZ_CACHE[key] = int(rowptr[-1].item())
-    return _NNZ_CACHE[key]
 
 
 def lincomb(xs, coefs, out=None, accumulate=False):
@@ -655,6 +648,14 @@ def pcg_persist(rowptr, colidx, values, b, x=None, n_owned=None, block=1, rtol=1
                                     _p(bsr[0], I32) if bsr else c_vp(0), int(bsr[1]) if bsr else 0,
                                     ctypes.byref(iters), ctypes.byref(relres), _stream()), h, "pgd_pcg_persist_sync")
     return x, iters.value, relres.value
+
+
+def phase_ns(reset=True, device=None):
+    """per-phase nanoseconds of the persistent PCG kernel (set_option("prof", 1)): D, barrier, S, reduce1, U, reduce2"""
+    h, lib = handle(device), load_library()
+    ns = (c_i64 * 6)()
+    _check(lib.pgd_get_phase_ns(h, ctypes.cast(ns, c_vp), 1 if reset else 0), h, "pgd_get_phase_ns")
+    return dict(zip(["direction", "barrier", "spmv", "reduce_pq", "update", "reduce_rz"], [int(v) for v in ns]))
 
 
 def pcg_start(rowptr, colidx, values, b, rtol=1e-12, atol=0.0, maxit=20000, block=1, x0=None):

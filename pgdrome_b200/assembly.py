@@ -42,6 +42,9 @@ class DeviceSpace:
         self._facet = {}
         self.atoms = {}  # key -> values tensor
         self.band = None
+        self.shard = None        # sharding.SpaceShard on an element-partitioned space (ShardedDeviceSpace)
+        self.n_owned = self.n_dofs
+        self._bsr = 0
 
     @property
     def space(self):
@@ -57,6 +60,28 @@ class DeviceSpace:
     @property
     def nnz(self):
         return self.pattern[1].numel()
+
+    @property
+    def rowptr_owned(self):
+        """row pointers of the rows this rank owns (all rows on a replicated space): what SpMV-type kernels iterate"""
+        rp = self.pattern[0]
+        return rp if self.n_owned == self.n_dofs else rp[: self.n_owned + 1]
+
+    @property
+    def bsr(self):
+        """block-column plan of the node-block walk (vector spaces; None when the pattern is not block structured)"""
+        if self._bsr == 0:
+            s = self.space
+            self._bsr = _lib.bsr_plan(self.rowptr_owned, self.pattern[1][: self.nnz_owned], s.bs) if 1 < s.bs <= 3 else None
+        return self._bsr
+
+    @property
+    def nnz_owned(self):
+        if self.n_owned == self.n_dofs:
+            return self.nnz
+        if getattr(self, "_nnz_owned", None) is None:
+            self._nnz_owned = int(self.pattern[0][self.n_owned].item())
+        return self._nnz_owned
 
     @property
     def lpr(self):
@@ -184,7 +209,8 @@ class DeviceSpace:
                 # constant-coefficient P1 operator: one fused kernel straight into the CSR pattern
                 rowptr = self.pattern[0]
                 return _lib.assemble_p1_rows(self.coords, self.cell_verts, g, cf[0], cf[1], cf[2] if any(cf[2]) else None,
-                                             rowptr, self.vecmap[0], self.rowplan, self.n_dofs, coords_soa=self.coords_soa)
+                                             rowptr, self.vecmap[0], self.rowplan, self.n_dofs, coords_soa=self.coords_soa,
+                                             nnz=self.nnz)
         # polynomial degree of the integrand on an affine simplex
         dv = s.degree if np.any(T[:, 0, :, :] != 0) else s.degree - 1
         du = s.degree if np.any(T[:, :, :, 0] != 0) else s.degree - 1
@@ -247,10 +273,46 @@ class DeviceSpace:
         return _lib.gather_values(be, vptr, vidx, self.n_dofs, out=out)
 
 
+class ShardedDeviceSpace(DeviceSpace):
+    """DeviceSpace of an element-partitioned space: the device arrays are those of this rank's sub-mesh (cells that
+    touch an owned node, nodes numbered [owned | ghost], sharding.SpaceShard.local), so pattern, atoms and loads are
+    built by the unchanged code above on 1/world of the cells.  Rows of owned dofs are complete; rows of ghost dofs
+    are partial and never enter a product (``rowptr_owned`` ends at n_owned)."""
+
+    def __init__(self, gspace, shard):
+        super().__init__(shard.local)
+        self._gspace = weakref.ref(gspace)
+        self.shard = shard
+        self.n_owned = shard.n_owned
+
+    def facet_set(self, key, cell, loc):
+        """(cell, local facet) pairs arrive in GLOBAL cell numbers (MeshFunction / boundary_facets of the user's mesh)"""
+        if key not in self._facet:
+            lc = self.shard.local_cells(cell)
+            keep = lc >= 0
+            return super().facet_set(key, lc[keep], np.asarray(loc)[keep])
+        return self._facet[key]
+
+    def _sample_function(self, f, comp, pts):
+        from . import sharding
+
+        V = f.V
+        sh = sharding.shard_of(V)
+        if sh is not self.shard:
+            raise NotImplementedError("coefficient Function from a different space than the (partitioned) form space")
+        phi, _ = tabulate_lagrange(V.mesh().tdim, V.degree, pts)
+        loc = sh.local
+        vals = _lib.to_host(f.tensor()).reshape(loc.n_nodes, loc.bs)[:, comp or 0]
+        return vals[loc.cell_nodes] @ phi.T
+
+
 def device_space(space):
     """Lazily attach (and cache) the DeviceSpace of a FunctionSpace."""
     ds = space._dev.get("device_space")
     if ds is None:
-        ds = DeviceSpace(space)
+        from . import sharding
+
+        sh = sharding.shard_of(space)
+        ds = DeviceSpace(space) if sh is None else ShardedDeviceSpace(space, sh)
         space._dev["device_space"] = ds
     return ds

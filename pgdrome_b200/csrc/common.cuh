@@ -69,6 +69,7 @@ struct pgd_ctx {
     int opt_persist;         // pgd_set_option("persist"): 1 (default) = HBM-bound solves run in the persistent cooperative kernel
     int opt_bsr;             // pgd_set_option("bsr"): 1 (default) = node-block walk of vector operators inside that kernel
     int opt_spin_ms;         // pgd_set_option("spin_ms"): budget of every in-kernel wait (default 20 000 ms)
+    int opt_prof;            // pgd_set_option("prof"): 1 = the persistent kernel accumulates per-phase times (pgd_get_phase_ns)
     void* mailbox;           // single-GPU stand-in for the peer window's mailboxes (PwLayout{0}: slots + flags, 2 KB)
 };
 

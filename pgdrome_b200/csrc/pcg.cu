@@ -350,9 +350,12 @@ static int32_t pcg_entry(pgd_handle_t h, const int32_t* d_rowptr, const int32_t*
                                       d_work, h_iters, h_relres, st, warm ? 1 : 0, 0);
         if (rc != 1) return rc;
     }
-    if (h->opt_persist && n >= PGD_BULK_MIN_ROWS && (((uintptr_t)d_colidx | (uintptr_t)d_values | (uintptr_t)d_work) & 15) == 0)
-        // HBM-bound regime: the whole solve in one persistent cooperative kernel (pcg_persist.cu); d_work of
-        // (5 + block) n + 8 doubles covers its layout for n_local = n
+    if (h->opt_persist >= 2 && n >= PGD_BULK_MIN_ROWS && (((uintptr_t)d_colidx | (uintptr_t)d_values | (uintptr_t)d_work) & 15) == 0)
+        // pgd_set_option("persist", 2): the whole solve in one persistent cooperative kernel (pcg_persist.cu) also for
+        // plain CSR on one GPU.  Not the default: measured 0.235 ms against 0.215 ms per iteration for the three-launch
+        // form on the 4 M-dof scalar operator (the persistent kernel must gather p with coherent loads and pays three
+        // grid-wide waits; it wins with the node-block walk and on sharded systems, where the caller selects it).
+        // d_work of (5 + block) n + 8 doubles covers its layout for n_local = n
         return pgd_pcg_persist_sync(h, d_rowptr, d_colidx, d_values, d_b, d_x, n, n, block, rtol, atol, maxit, warm ? 1 : 0,
                                     d_work, nullptr, nullptr, nullptr, nullptr, nullptr, 0, h_iters, h_relres, stream);
     if (block == 1)

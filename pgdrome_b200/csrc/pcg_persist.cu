@@ -61,7 +61,17 @@ struct PersistArgs {
     int64_t pb_off;            // offset (doubles) of pb inside a window (pa sits at 0)
     unsigned long long spin_ns;
     BsrPlan bsr;               // node-block walk of the CSR arrays (BSR template only)
+    unsigned long long* prof;  // optional [8]: ns spent (as seen by CTA 0) in D, barrier, S, reduce 1, U, reduce 2
 };
+
+#define PS_MARK(slot)                                              \
+    do {                                                           \
+        if (a.prof && blockIdx.x == 0 && tid == 0) {               \
+            const unsigned long long _t = ps_now();                \
+            a.prof[slot] += _t - t_mark;                           \
+            t_mark = _t;                                           \
+        }                                                          \
+    } while (0)
 
 __device__ __forceinline__ unsigned long long ps_now() {
     unsigned long long t;
@@ -114,7 +124,12 @@ __device__ __forceinline__ bool ps_grid_barrier(const PersistArgs& a, PsSync& sy
     return s_ok != 0;
 }
 
-// Deterministic all-CTA (and all-rank) sum of NV per-thread values; the result lands in out[0..NV) of every thread.
+// Deterministic all-CTA (and all-rank) sum of NV per-thread values; the result lands in v[0..NV) of every thread.
+// Two L2 round trips on one GPU (arrival counter, then every CTA adds the G partials itself in the same fixed order:
+// the first version, in which CTA 0 alone summed and everybody waited for its mailbox flag, cost 10.5 us per call on
+// a B200 -- five dependent round trips and a system-scope fence -- against ~3 us for this one).  Sharded: CTA 0 also
+// stores the rank's sum into the other ranks' mailboxes with a release flag, and every CTA acquires the `world - 1`
+// foreign flags in its LOCAL window and adds the rank sums in RANK ORDER (its own from the partials).
 // false = aborted.
 template <int NV>
 __device__ __forceinline__ bool ps_reduce_bcast(double (&v)[NV], const PersistArgs& a, PsSync& sy, unsigned int G) {
@@ -134,25 +149,22 @@ __device__ __forceinline__ bool ps_reduce_bcast(double (&v)[NV], const PersistAr
         for (int k = 0; k < NV; ++k) part[(size_t)k * G + blockIdx.x] = v[k];
         __threadfence();
         atomicAdd(a.arrive, 1u);
+        const unsigned int tgt = sy.target;
+        if (!ps_spin([&] { return ps_ld_acquire_gpu(a.arrive) >= tgt; }, a)) s_ok = 0;
     }
-    if (blockIdx.x == 0) {
-        // CTA 0: wait for every CTA of this rank, sum the partials in a fixed order, publish to all ranks
-        if (tid == 0) {
-            const unsigned int tgt = sy.target;
-            if (!ps_spin([&] { return ps_ld_acquire_gpu(a.arrive) >= tgt; }, a)) s_ok = 0;
-        }
-        __syncthreads();
-        if (tid < 32) {
+    __syncthreads();
+    if (tid < 32) {  // every CTA: the rank's sum, same order everywhere
 #pragma unroll
-            for (int k = 0; k < NV; ++k) {
-                double s = 0.0;
-                for (unsigned int i = tid; i < G; i += 32) s += __ldcg(&part[(size_t)k * G + i]);
-                s = warp_sum(s);
-                if (tid == 0) s_res[k] = s;
-            }
+        for (int k = 0; k < NV; ++k) {
+            double s = 0.0;
+            for (unsigned int i = tid; i < G; i += 32) s += __ldcg(&part[(size_t)k * G + i]);
+            s = warp_sum(s);
+            if (tid == 0) s_res[k] = s;
         }
-        __syncthreads();
-        if (tid < a.world) {
+    }
+    __syncthreads();
+    if (a.world > 1) {
+        if (blockIdx.x == 0 && tid < a.world && tid != a.me) {
             double* slot = reinterpret_cast<double*>(a.peers.base[tid] + a.lay.slot_off()) +
                            ((size_t)par * PW_MAXR + a.me) * PW_AR_VALS;
 #pragma unroll
@@ -161,24 +173,25 @@ __device__ __forceinline__ bool ps_reduce_bcast(double (&v)[NV], const PersistAr
             st_release_sys(reinterpret_cast<unsigned long long*>(a.peers.base[tid] + a.lay.arflag_off()) + par * PW_MAXR + a.me,
                            seq);
         }
-    }
-    // every CTA: acquire the flag of every rank in the LOCAL window, then add the mailboxes in rank order
-    if (tid < a.world) {
-        const unsigned long long* f =
-            reinterpret_cast<const unsigned long long*>(a.peers.base[a.me] + a.lay.arflag_off()) + par * PW_MAXR + tid;
-        if (!ps_spin([&] { return ld_acquire_sys(f) >= seq; }, a)) s_ok = 0;
-    }
-    __syncthreads();
-    if (tid == 0 && s_ok) {
-        const double* mine = reinterpret_cast<const double*>(a.peers.base[a.me] + a.lay.slot_off()) + (size_t)par * PW_MAXR * PW_AR_VALS;
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            double s = 0.0;
-            for (int q = 0; q < a.world; ++q) s += *((volatile const double*)&mine[q * PW_AR_VALS + k]);
-            s_res[k] = s;
+        if (tid < a.world && tid != a.me) {
+            const unsigned long long* f =
+                reinterpret_cast<const unsigned long long*>(a.peers.base[a.me] + a.lay.arflag_off()) + par * PW_MAXR + tid;
+            if (!ps_spin([&] { return ld_acquire_sys(f) >= seq; }, a)) s_ok = 0;
         }
+        __syncthreads();
+        if (tid == 0 && s_ok) {
+            const double* mine =
+                reinterpret_cast<const double*>(a.peers.base[a.me] + a.lay.slot_off()) + (size_t)par * PW_MAXR * PW_AR_VALS;
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                double s = 0.0;
+                for (int q = 0; q < a.world; ++q)
+                    s += (q == a.me) ? s_res[k] : *((volatile const double*)&mine[q * PW_AR_VALS + k]);
+                s_res[k] = s;
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
 #pragma unroll
     for (int k = 0; k < NV; ++k) v[k] = s_res[k];
     const bool ok = s_ok != 0;
@@ -323,6 +336,7 @@ __global__ void __launch_bounds__(PS_THREADS, BK_CTAS_PER_SM) k_pcg_persist(Pers
         if (a.atol * a.atol > tol2) tol2 = a.atol * a.atol;
     }
 
+    unsigned long long t_mark = ps_now();
     if (status == 0 && rr > tol2 && bb > 0.0) {
         while (it < a.maxit) {
             const double beta = (it == 0) ? 0.0 : rz / rz_old;
@@ -345,10 +359,12 @@ __global__ void __launch_bounds__(PS_THREADS, BK_CTAS_PER_SM) k_pcg_persist(Pers
             } else {
                 for (int64_t i = gtid; i < no; i += gstride) p_new[i] = fma(beta, p_old[i], a.z[i]);
             }
+            PS_MARK(0);
             if (!ps_grid_barrier(a, sy, G) || !ps_halo_wait(a, hseq)) {
                 status = 3;
                 break;
             }
+            PS_MARK(1);
             // ---- S: q = A p, p.q
             double pq = 0.0;
             {
@@ -359,18 +375,22 @@ __global__ void __launch_bounds__(PS_THREADS, BK_CTAS_PER_SM) k_pcg_persist(Pers
                 ps_spmv<BS, BSR>(a, p_new, epi, bk_smem, &tile);
             }
             double v1[1] = {pq};
+            PS_MARK(2);
             if (!ps_reduce_bcast<1>(v1, a, sy, G)) {
                 status = 3;
                 break;
             }
+            PS_MARK(3);
             const double alpha = rz / v1[0];
             // ---- U: x, r, z, r.z, r.r
             double v2[2] = {0.0, 0.0};
             pcg_update_rows<BS>(a.x, a.r, a.z, p_new, a.q, a.minv, n_nodes, alpha, v2[0], v2[1]);
+            PS_MARK(4);
             if (!ps_reduce_bcast<2>(v2, a, sy, G)) {
                 status = 3;
                 break;
             }
+            PS_MARK(5);
             rz_old = rz;
             rz = v2[0];
             rr = v2[1];
@@ -486,6 +506,7 @@ extern "C" int32_t pgd_pcg_persist_sync(pgd_handle_t h, const int32_t* d_rowptr,
     a.seq_halo = reinterpret_cast<unsigned long long*>(h->scalars + 40);
     a.seq_ar = reinterpret_cast<unsigned long long*>(h->scalars + (multi ? 41 : 42));  // the local mailbox has its own sequence
     a.spin_ns = (unsigned long long)h->opt_spin_ms * 1000000ULL;
+    a.prof = h->opt_prof ? reinterpret_cast<unsigned long long*>(h->scalars + 48) : nullptr;  // read back with pgd_get_phase_ns
     PGD_CUDA(h, cudaMemsetAsync(a.arrive - 1, 0, 2 * sizeof(unsigned int), st));  // push_ctr, arrive
     PGD_CUDA(h, cudaMemsetAsync(a.out_fl, 0, 2 * sizeof(int), st));
     PGD_CUDA(h, cudaMemsetAsync(a.abort_word, 0, sizeof(int), st));
@@ -545,5 +566,16 @@ extern "C" int32_t pgd_pcg_persist_sync(pgd_handle_t h, const int32_t* d_rowptr,
         snprintf(h->err, sizeof(h->err), "pgd_pcg_persist_sync: NaN encountered (matrix not SPD?)");
         return -3;
     }
+    return 0;
+}
+
+/* Phase profile of the persistent kernel (pgd_set_option "prof" = 1): accumulated nanoseconds, as seen by CTA 0, in
+ * [0] direction + halo push, [1] grid barrier + halo wait, [2] SpMV, [3] reduce-broadcast of p.q, [4] vector update,
+ * [5] reduce-broadcast of r.z / r.r since the last reset.  Diagnostic only (tools/pcg_bench.py). */
+extern "C" int32_t pgd_get_phase_ns(pgd_handle_t h, int64_t* h_ns6, int32_t reset) {
+    PGD_CHECK_HANDLE(h);
+    PGD_ARG(h, h_ns6 != nullptr, "null pointer");
+    PGD_CUDA(h, cudaMemcpy(h_ns6, h->scalars + 48, 6 * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    if (reset) PGD_CUDA(h, cudaMemset(h->scalars + 48, 0, 8 * sizeof(double)));
     return 0;
 }

@@ -233,7 +233,8 @@ class Atom:
         if ent is None:
             if self.panel is None or self.n_rows == self.panel.shape[0]:
                 cap = panel_rows_hint[0] if self.panel is None else 2 * self.panel.shape[0]
-                new = torch.empty((cap, self.ds.n_dofs), dtype=torch.float64, device=self.values.device)
+                # (zeros: on a partitioned space the ghost tail of a row is never written by the SpMV below)
+                new = torch.zeros((cap, self.ds.n_dofs), dtype=torch.float64, device=self.values.device)
                 if self.panel is not None:
                     new[: self.n_rows].copy_(self.panel[: self.n_rows])
                 self.panel = new
@@ -241,8 +242,8 @@ class Atom:
             self.n_rows += 1
         else:
             row = ent[0]
-        rowptr, colidx, _, _ = self.ds.pattern
-        _lib.spmv(rowptr, colidx, self.values, fn.tensor(), self.panel[row], lpr=self.ds.lpr)
+        ds = self.ds
+        _lib.spmv(ds.rowptr_owned, ds.pattern[1], self.values, fn.tensor(), self.panel[row], lpr=ds.lpr)
         self.rows[id(fn)] = (row, fn._version, weakref.ref(fn))
         return row
 
@@ -254,6 +255,10 @@ class Atom:
 def _embed_operator(ds, op, scale, transpose):
     """Values of the user matrix (times the scalar form-tensor entry) inside the space's CSR pattern."""
     import scipy.sparse as sp
+
+    if ds.shard is not None:
+        raise NotImplementedError("MatrixOperator on an element-partitioned space (user matrices live on the replicated "
+                                  "1-D dimensions)")
 
     rowptr, colidx, _, _ = ds.pattern
     rp, ci = _lib.to_host(rowptr).astype(np.int64), _lib.to_host(colidx).astype(np.int64)
@@ -380,60 +385,79 @@ def _pool_take(dev, n):
 
 
 def _launch(leaves):
-    """Enqueue the evaluation of the given functionals: batched device launches writing into the scalar pool."""
+    """Enqueue the evaluation of the given functionals: batched device launches writing into the scalar pool.
+    Functionals on an element-partitioned space are local sums over the owned rows; they take the first slots of
+    the batch and are completed by ONE all-reduce of that slice ("one batched scalar allreduce")."""
     dev = _device()
     plan = []  # (leaf, slot)
     n_slots = 0
-    panel_jobs = {}  # (id(atom), id(x)) -> [atom, x, base_slot]
     direct = []  # (slot, kind, args)
+    all_jobs = []
+    shards = {}
     for leaf in leaves:
-        p = leaf.args[0]
-        if p.f1 is not None and p.f1._version != p.v1 or p.f2 is not None and p.f2._version != p.v2:
-            raise RuntimeError("a Function was modified between assemble(<functional>) and its evaluation")
-        if p.kind == "lin":
-            vec = get_load(p.space, p.T, p.weights, p.measure)
-            direct.append((n_slots, "dot", (vec, p.f1.tensor())))
-            plan.append((leaf, n_slots))
-            n_slots += 1
-            continue
-        if p.measure.kind != "dx":
-            raise NotImplementedError("bilinear functionals over '%s'" % p.measure.kind)
-        atom = get_atom(p.space, p.T, p.weights, p.measure, p.op)
-        x = stable = None
-        at = atom
-        if p.f2.stable or atom.has_fresh(p.f2):
-            stable, x = p.f2, p.f1
-        elif p.f1.stable:
-            stable, x = p.f1, p.f2
-            at = atom if atom.symmetric else get_atom(p.space, p.T, p.weights, p.measure, p.op, transpose=True)
-        if stable is None or stable is x:
-            direct.append((n_slots, "bil", (atom, p.f1.tensor(), p.f2.tensor())))
-            plan.append((leaf, n_slots))
-            n_slots += 1
-            continue
-        row = at.product(stable)
-        job = panel_jobs.get((id(at), id(x)))
-        if job is None:
-            job = [at, x, None, []]
-            panel_jobs[(id(at), id(x))] = job
-        job[3].append((leaf, row))
-    for job in panel_jobs.values():
-        at = job[0]
-        job[2] = n_slots
-        for leaf, row in job[3]:
-            plan.append((leaf, n_slots + row))
-        n_slots += at.n_rows
+        sh = device_space(leaf.args[0].space).shard
+        shards.setdefault(sh.space_id if sh is not None else None, (sh, []))[1].append(leaf)  # creation order: same on all ranks
+    n_sharded = 0
+    reducers = []  # (shard, first slot, end slot)
+    for key in sorted(shards, key=lambda k: (k is None, -1 if k is None else k)):  # partitioned spaces first
+        sh, group = shards[key]
+        first = n_slots
+        panel_jobs = {}  # (id(atom), id(x)) -> [atom, x, base_slot, [(leaf, row)]]
+        for leaf in group:
+            p = leaf.args[0]
+            if p.f1 is not None and p.f1._version != p.v1 or p.f2 is not None and p.f2._version != p.v2:
+                raise RuntimeError("a Function was modified between assemble(<functional>) and its evaluation")
+            if p.kind == "lin":
+                vec = get_load(p.space, p.T, p.weights, p.measure)
+                direct.append((n_slots, "dot", (vec, p.f1.tensor(), device_space(p.space).n_owned)))
+                plan.append((leaf, n_slots))
+                n_slots += 1
+                continue
+            if p.measure.kind != "dx":
+                raise NotImplementedError("bilinear functionals over '%s'" % p.measure.kind)
+            atom = get_atom(p.space, p.T, p.weights, p.measure, p.op)
+            x = stable = None
+            at = atom
+            if p.f2.stable or atom.has_fresh(p.f2):
+                stable, x = p.f2, p.f1
+            elif p.f1.stable:
+                stable, x = p.f1, p.f2
+                at = atom if atom.symmetric else get_atom(p.space, p.T, p.weights, p.measure, p.op, transpose=True)
+            if stable is None or stable is x:
+                direct.append((n_slots, "bil", (atom, p.f1.tensor(), p.f2.tensor())))
+                plan.append((leaf, n_slots))
+                n_slots += 1
+                continue
+            row = at.product(stable)
+            job = panel_jobs.get((id(at), id(x)))
+            if job is None:
+                job = [at, x, None, []]
+                panel_jobs[(id(at), id(x))] = job
+            job[3].append((leaf, row))
+        for job in panel_jobs.values():
+            at = job[0]
+            job[2] = n_slots
+            for leaf, row in job[3]:
+                plan.append((leaf, n_slots + row))
+            n_slots += at.n_rows
+            all_jobs.append(job)
+        if sh is not None:
+            reducers.append((sh, first, n_slots))
     pool, base0 = _pool_take(dev, max(n_slots, 1))
     res = pool[base0:base0 + max(n_slots, 1)]
     for slot, kind, args in direct:
         if kind == "dot":
-            _lib.dot(args[0], args[1], out=res[slot:slot + 1])
+            no = args[2]
+            _lib.dot(args[0][:no], args[1][:no], out=res[slot:slot + 1])
         else:
             atom = args[0]
-            rowptr, colidx, _, _ = atom.ds.pattern
-            _lib.bilinear(rowptr, colidx, atom.values, args[1], args[2], out=res[slot:slot + 1], lpr=atom.ds.lpr)
-    for at, x, base, _ in panel_jobs.values():
-        _lib.panel_dots(at.panel, at.n_rows, x.tensor(), out=res[base:base + at.n_rows])
+            ds = atom.ds
+            _lib.bilinear(ds.rowptr_owned, ds.pattern[1], atom.values, args[1], args[2], out=res[slot:slot + 1], lpr=ds.lpr)
+    for at, x, base, _ in all_jobs:
+        _lib.panel_dots(at.panel, at.n_rows, x.tensor()[: at.ds.n_owned], out=res[base:base + at.n_rows])
+    for sh, lo, hi in reducers:
+        if hi > lo:
+            sh.allreduce(res[lo:hi])
     for leaf, slot in plan:
         leaf._dev = base0 + slot
 
@@ -577,7 +601,7 @@ def assemble(form):
             total = term if total is None else total + term
         return total
     if rank == 1:
-        return DeviceVector(assemble_vector(groups))
+        return DeviceVector(assemble_vector(groups), device_space(groups[0].space).shard)
     return assemble_matrix(groups)
 
 
@@ -676,8 +700,9 @@ def assemble_vector(groups, out=None):
                 row = atom.product(f)
                 vecs.append(atom.panel[row])
             else:
-                rowptr, colidx, _, _ = atom.ds.pattern
-                vecs.append(_lib.spmv(rowptr, colidx, atom.values, f.tensor(), lpr=atom.ds.lpr))
+                ds = atom.ds
+                y = torch.zeros(ds.n_dofs, dtype=torch.float64, device=atom.values.device) if ds.shard is not None else None
+                vecs.append(_lib.spmv(ds.rowptr_owned, ds.pattern[1], atom.values, f.tensor(), y=y, lpr=ds.lpr))
         else:
             raise NotImplementedError("linear form with two Function operands in one term")
     coefs = _coefficients(groups)
@@ -717,8 +742,9 @@ def assemble_matrix(groups, out=None):
 def norm(f, norm_type="L2", mesh=None):
     """dolfin.norm(Function): sqrt(int f.f dx)  (fused SpMV-reduction with the mass atom)."""
     if isinstance(f, _DofOwner) and not isinstance(f, Function):
-        t = f.tensor()
-        return math.sqrt(float(_lib.dot(t, t).item()))
+        from .functions import _owned_dot
+
+        return math.sqrt(_owned_dot(f, f))
     if norm_type.lower() != "l2":
         raise NotImplementedError("norm type '%s'" % norm_type)
     return mass_product(f, f).sqrt()

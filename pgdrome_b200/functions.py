@@ -13,7 +13,7 @@ import re
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, sharding
 from .fem import FunctionSpace, tabulate_lagrange
 from . import lazy as _lazy
 from .lazy import LazyScalar
@@ -299,15 +299,14 @@ class Vector:
         return self._o.n_dofs
 
     def norm(self, kind="l2"):
-        t = self._o.tensor()
         if kind == "l2":
-            return math.sqrt(float(_lib.dot(t, t).item()))
+            return math.sqrt(_owned_dot(self._o, self._o))
         if kind == "linf":
             return float(np.abs(self._o.values_host()).max())
         raise NotImplementedError("vector norm '%s'" % kind)
 
     def inner(self, other):
-        return float(_lib.dot(self._o.tensor(), other._o.tensor()).item())
+        return _owned_dot(self._o, other._o)
 
     def max(self):
         return float(self._o.values_host().max())
@@ -357,7 +356,12 @@ class Vector:
         return self
 
     def axpy(self, a, other):
-        o = other._o.tensor() if isinstance(other, Vector) else _lib.to_device(np.asarray(other, dtype=np.float64))
+        if isinstance(other, Vector):
+            o = other._o.tensor()
+        elif self._o._shard is not None:
+            o = self._o._shard.scatter(other, self._o.tensor().device)
+        else:
+            o = _lib.to_device(np.asarray(other, dtype=np.float64))
         t = self._o.tensor()
         self._o.before_write()
         _lib.lincomb([t, o], [1.0, float(a)], out=t)
@@ -369,7 +373,7 @@ class Vector:
         self._o.touch()
 
     def copy(self):
-        return DeviceVector(self._o.tensor().clone())
+        return DeviceVector(self._o.tensor().clone(), self._o._shard)
 
     def vec(self):
         return self
@@ -390,19 +394,36 @@ class Vector:
         return self.get_local()
 
 
-class _DofOwner:
-    """Shared storage logic of Function and DeviceVector."""
+def _owned_dot(a, b):
+    """x . y over the global dofs of two dof owners (sharded spaces: local owned part + all-reduce)"""
+    sh = a._shard
+    if sh is None:
+        return float(_lib.dot(a.tensor(), b.tensor()).item())
+    no = sh.n_owned
+    return float(sh.allreduce(_lib.dot(a.tensor()[:no], b.tensor()[:no])).item())
 
-    def _init_store(self, n_dofs, tensor=None):
+
+class _DofOwner:
+    """Shared storage logic of Function and DeviceVector.  ``n_dofs`` is always the GLOBAL number of dofs; on an
+    element-partitioned space (sharding.SpaceShard) the device tensor holds this rank's ``[owned | ghost]`` entries
+    and the host-side accessors gather / scatter (collective calls: every rank executes the same script)."""
+
+    def _init_store(self, n_dofs, tensor=None, shard=None):
         self.n_dofs = int(n_dofs)
+        self._shard = shard
         self._t = tensor
         self._version = 0
         self._host = None
         self._host_version = -1
 
+    @property
+    def n_vec(self):
+        """length of the device tensor"""
+        return self._shard.n_local if self._shard is not None else self.n_dofs
+
     def tensor(self):
         if self._t is None:
-            self._t = torch.zeros(self.n_dofs, dtype=torch.float64, device=_device())
+            self._t = torch.zeros(self.n_vec, dtype=torch.float64, device=_device())
         return self._t
 
     def before_write(self):
@@ -415,7 +436,8 @@ class _DofOwner:
 
     def values_host(self):
         if self._host_version != self._version or self._host is None:
-            self._host = _lib.to_host(self.tensor())
+            t = self.tensor()
+            self._host = self._shard.gather_host(t) if self._shard is not None else _lib.to_host(t)
             self._host_version = self._version
         return self._host
 
@@ -424,7 +446,8 @@ class _DofOwner:
         if a.size != self.n_dofs:
             raise ValueError("size mismatch: %d values for %d dofs" % (a.size, self.n_dofs))
         self.before_write()
-        self.tensor().copy_(_lib.to_device(a))
+        t = self.tensor()
+        t.copy_(self._shard.scatter(a, t.device) if self._shard is not None else _lib.to_device(a))
         self.touch()
 
     def set_tensor(self, t):
@@ -442,8 +465,8 @@ class _DofOwner:
 class DeviceVector(_DofOwner):
     """Result of assembling a rank-1 form: supports ``ll[:]``, ``bc.apply(ll)``, ``ll.get_local()``."""
 
-    def __init__(self, tensor):
-        self._init_store(tensor.numel(), tensor)
+    def __init__(self, tensor, shard=None):
+        self._init_store(shard.n_global if shard is not None else tensor.numel(), tensor, shard)
 
     def vector(self):
         return Vector(self)
@@ -472,9 +495,11 @@ class Function(Leaf, _DofOwner):
         self.V = V
         self._name = name or "f"
         self.stable = False  # set for stored modes / interpolated data: K*f products are cached in panels
-        self._init_store(V.n_dofs, None)
+        self._init_store(V.n_dofs, None, sharding.shard_of(V))
         if values is not None:
             if isinstance(values, torch.Tensor):
+                if values.numel() != self.n_vec:
+                    raise ValueError("Function: tensor of %d entries for a vector of %d" % (values.numel(), self.n_vec))
                 self._t = values
             else:
                 self.set_values(values)
@@ -765,9 +790,11 @@ class DirichletBC:
         return not np.any(self.vals)
 
     def device(self):
+        """(dofs, values) on the device; on an element-partitioned space the dofs this rank holds (owned or ghost),
+        in its local numbering."""
         if self._dev is None:
-            dev = _device()
-            self._dev = (_lib.to_device(self.dofs), _lib.to_device(self.vals))
+            dofs, vals = local_bc(self.V, self.dofs, self.vals)
+            self._dev = (_lib.to_device(dofs), _lib.to_device(vals))
         return self._dev
 
     def apply(self, *objs):
@@ -778,9 +805,21 @@ class DirichletBC:
                 raise NotImplementedError("DirichletBC.apply on %r (use the variational solver for matrices)" % type(o))
             if len(self.dofs):
                 d, v = self.device()
+                if d.numel() == 0:
+                    continue
                 owner.before_write()
                 _lib.set_entries(owner.tensor(), d, None if self.homogeneous() else v)
                 owner.touch()
+
+
+def local_bc(V, dofs, vals):
+    """Dirichlet dofs / values restricted to what this rank holds of V (identity on replicated spaces)."""
+    sh = sharding.shard_of(V)
+    if sh is None:
+        return np.asarray(dofs, dtype=np.int32), np.asarray(vals, dtype=np.float64)
+    loc = sh.g2l_dofs(dofs)
+    keep = loc >= 0
+    return loc[keep].astype(np.int32), np.asarray(vals, dtype=np.float64)[keep]
 
 
 def bc_list(bc):

@@ -228,7 +228,7 @@ def sharded_pcg(A, b, rtol=1e-13, atol=0.0, maxit=10000, check_every=50, block=N
 
         if dist.is_initialized() and dist.get_world_size(group) > 1:
             _lib.comm_init(group)
-            if use_p2p and _lib.peer_window(A.n_local, group) is not None:
+            if use_p2p and _lib.peer_window(2 * A.n_local + 16, group) is not None:
                 A.halo.ensure_peer_layout()
             else:
                 A.halo.peer_ghost_base = None
@@ -277,6 +277,49 @@ def sharded_pcg(A, b, rtol=1e-13, atol=0.0, maxit=10000, check_every=50, block=N
     relres = float(np.sqrt(float(sc[3]) / float(sc[4]))) if float(sc[4]) > 0 else 0.0
     if int(fl[2]):
         raise RuntimeError("sharded_pcg: NaN encountered (matrix not SPD?)")
+    return x, iters, relres
+
+
+ops_factory = [None]  # tests: callable(A, block) -> kernel stand-in (see module docstring); None = the CUDA kernels
+
+
+def sharded_solve(A, b, x0=None, rtol=1e-13, atol=0.0, maxit=10000, check_every=50, block=None, bsr=None):
+    """Solve A x = b on an element-partitioned space.  b, x0: local vectors [n_local] (only the owned part of b is
+    read; x0 with valid ghosts is a warm start).  Returns (x [n_local] with up-to-date ghosts, iterations, relative
+    residual), identical iteration count on every rank.
+
+    CUDA: ONE persistent cooperative kernel per rank (pgd_pcg_persist_sync) -- neighbour values of the direction
+    vector are stored into the peers' ghost slots over the NVLink peer window, the dot products go through per-rank
+    mailboxes, no host round trip and no NCCL call inside the solve.  When the peers cannot be mapped the multi-launch
+    loop over NCCL (pgd_spcg_solve_sync) is used instead."""
+    import torch.distributed as dist
+
+    block = A.block if block is None else block
+    group = A.halo.group
+    no = A.n_owned
+    multi = dist.is_initialized() and dist.get_world_size(group) > 1
+    if ops_factory[0] is None and b.is_cuda:
+        from . import _lib
+
+        if multi:
+            _lib.comm_init(group)
+            if _lib.peer_window(2 * A.n_local + 16, group) is not None:
+                A.halo.ensure_peer_layout()
+                return _lib.pcg_persist(A.rowptr, A.colidx, A.values, b, n_owned=no, block=block, rtol=rtol, atol=atol,
+                                        maxit=maxit, x0=x0, halo=A.halo, bsr=bsr)
+            A.halo.peer_ghost_base = None
+            x_owned, iters, relres = _lib.spcg_solve(A, b[:no].contiguous(), rtol=rtol, atol=atol, maxit=maxit,
+                                                     check_every=check_every, block=block)
+        else:
+            return _lib.pcg_persist(A.rowptr, A.colidx, A.values, b, n_owned=no, block=block, rtol=rtol, atol=atol,
+                                    maxit=maxit, x0=x0, halo=None, bsr=bsr)
+    else:
+        ops = ops_factory[0](A, block) if ops_factory[0] is not None else None
+        x_owned, iters, relres = sharded_pcg(A, b[:no].contiguous(), rtol=rtol, atol=atol, maxit=maxit, check_every=check_every,
+                                             block=block, ops=ops)
+    x = torch.zeros(A.n_local, dtype=b.dtype, device=b.device)
+    x[:no] = x_owned
+    A.halo.exchange(x)
     return x, iters, relres
 
 

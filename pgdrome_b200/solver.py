@@ -27,7 +27,7 @@ import torch
 
 from . import _lib, forms, lazy
 from .assembly import device_space
-from .functions import Function, MatrixOperator, bc_list, merged_bc_dofs
+from .functions import Function, MatrixOperator, bc_list, local_bc, merged_bc_dofs
 from .lazy import LazyScalar
 from .ufl import Form, TestFunction, TrialFunction, derivative
 from .ufl import dx as forms_dx
@@ -178,8 +178,9 @@ class PGDProblem:
                 self._bcd[dim] = None
             else:
                 dofs, vals = merged_bc_dofs(bcs, self.V[dim])
-                dev = forms._device()
-                self._bcd[dim] = (_lib.to_device(dofs), _lib.to_device(vals) if np.any(vals) else None)
+                nonzero = bool(np.any(vals))  # decided on the GLOBAL set: every rank takes the same code path
+                dofs, vals = local_bc(self.V[dim], dofs, vals)  # partitioned space: the dofs this rank holds, local numbers
+                self._bcd[dim] = (_lib.to_device(dofs), _lib.to_device(vals) if nonzero else None)
         return self._bcd[dim]
 
     def _mm(self, dim):
@@ -223,7 +224,8 @@ class PGDProblem:
             tdim = V[dim].mesh().topology().dim()
             if V[dim].bs > 1 and tdim not in (1, 2, 3):
                 raise ValueError("ERROR DIMENSION NOT defined!!!!!!!!!!!")
-            f = Function(V[dim], torch.ones(V[dim].n_dofs, dtype=F64, device=dev))
+            f = Function(V[dim])
+            f.tensor().fill_(1.0)
             for b in bc_list(bc[dim]):
                 b.apply(f.vector())
             if self.fp_init.lower() == "randomized":
@@ -302,6 +304,7 @@ class PGDProblem:
         # residual of the initial guess (solver.py:347-395)
         res_dev = torch.zeros(D, dtype=F64, device=forms._device())
         for dim in range(D):
+            sh = None
             if solve_modes is None or solve_modes[dim] == self.solve_mode["FEM"]:
                 var_F = TestFunction(self.V[dim])
                 l = self.rhs_fct(Fs_init, var_F, Fs_init, self.meshes, self.dom, self.param, self.load, self.PGD_func,
@@ -310,11 +313,17 @@ class PGDProblem:
                 bcd = self._bc_dev(dim)
                 if bcd is not None:
                     _lib.set_entries(ll, bcd[0], bcd[1])
+                ds = device_space(self.V[dim])
+                sh = ds.shard
+                if sh is not None:
+                    ll = ll[: ds.n_owned]  # partitioned space: this rank's rows; summed over the ranks below
             else:
                 v = self.rhs_fct(Fs_init, Fs_init, Fs_init, self.meshes, self.dom, self.param, self.load, self.PGD_func,
                                  self.prob[dim], n_enr, dim)
                 ll = _lib.to_device(np.atleast_1d(np.asarray(v, dtype=np.float64)).ravel())
             _lib.dot(ll, ll, out=res_dev[dim:dim + 1])
+            if sh is not None:
+                sh.allreduce(res_dev[dim:dim + 1])
         res = _lib.to_host(res_dev)
         res_error = np.sqrt(np.sum(res))
         self.simulation_info += f"-- residuum norm: {res_error} --\n"
@@ -411,6 +420,12 @@ class PGDProblem:
                 norms[dim] = self._norm(fct_F, dim, solve_modes)
             if stop == "delta":
                 for dim in range(D):
+                    if Fs[dim]._shard is not None:  # partitioned space: the (rarely used) max-norm test on gathered copies
+                        a_new, a_old = Fs[dim].values_host(), Fs_init[dim].values_host()
+                        dt = np.abs(a_new - a_old)
+                        mi = int(np.argmax(dt))
+                        delta[dim] = dt[mi] if abs(a_new[mi]) < 1e-8 else dt[mi] / abs(a_new[mi])
+                        continue
                     d = (Fs[dim].tensor() - Fs_init[dim].tensor()).abs()
                     mx, mi = torch.max(d, dim=0)
                     at = abs(float(Fs[dim].tensor()[mi].item()))
@@ -511,7 +526,7 @@ class PGDProblem:
                 raise ValueError("right-hand side is not a linear form")
             b = forms.assemble_vector(gl)
         else:
-            b = torch.zeros(V.n_dofs, dtype=F64, device=A.values.device)
+            b = torch.zeros(ds.n_dofs, dtype=F64, device=A.values.device)
         rowptr, colidx, _, _ = ds.pattern
         bcd = self._bc_dev(dim)
         if bcd is not None:
@@ -539,11 +554,11 @@ class PGDProblem:
         maxit = int(settings.get("maximum_iterations", max(10000, 4 * V.n_dofs // max(1, V.bs))))
         prec = str(settings.get("preconditioner", "default")).lower()
         block = V.bs if (V.bs <= 3 and prec not in ("jacobi", "none_block")) else 1
-        if self._use_sharded(V, settings):
-            return self._sharded_solve(ds, values, b, block, rtol, atol, maxit, settings)
         x0 = getattr(self, "_x0", None)
         if x0 is not None and x0.numel() != b.numel():
             x0 = None
+        if ds.shard is not None:
+            return self._sharded_solve(ds, values, b, block, rtol, atol, maxit, settings, x0)
         self._collect_solve()
         if settings.get("async_solve", True):
             # SM-resident systems (known to fit from an earlier solve): enqueue and go on recording the next
@@ -552,6 +567,12 @@ class PGDProblem:
             if x is not None:
                 self._pending_solve = (rtol, maxit)
                 return x
+        if block > 1 and V.n_dofs >= 32768 and settings.get("node_block_walk", True) and ds.bsr is not None:
+            # vector operator in the HBM-bound regime: persistent kernel walking the CSR arrays by node blocks
+            x, iters, relres = _lib.pcg_persist(rowptr, colidx, values, b, block=block, rtol=rtol, atol=atol, maxit=maxit,
+                                                x0=x0, bsr=ds.bsr)
+            self._account_solve(iters, relres, rtol, maxit)
+            return x
         x, iters, relres = _lib.pcg(rowptr, colidx, values, b, rtol=rtol, atol=atol, maxit=maxit,
                                     check_every=int(settings.get("check_every", 50)), block=block, lpr=ds.lpr, x0=x0)
         self._account_solve(iters, relres, rtol, maxit)
@@ -571,39 +592,31 @@ class PGDProblem:
             if iters >= 0:
                 self._account_solve(iters, relres, *pend)
 
-    # ---- multi-GPU: the spatial solve sharded by rows over the ranks of torch.distributed
-    @staticmethod
-    def _use_sharded(V, settings):
-        """settings["sharded"]: True / False / "auto" (default: more than one rank and >= 200 000 dofs)."""
-        import torch.distributed as dist
-
-        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
-            return False
-        mode = settings.get("sharded", "auto")
-        return bool(mode) if mode != "auto" else V.n_dofs >= 200000
-
-    def _sharded_solve(self, ds, values, b, block, rtol, atol, maxit, settings):
-        """Every rank holds the (replicated) operator and right-hand side of the sub-problem, keeps its
-        slab of rows, takes part in the sharded PCG (halo exchange + dot-product all-reduces over NCCL)
-        and receives the full solution back; 1-D dimensions and mode integrals stay replicated."""
-        import torch.distributed as dist
-
+    # ---- multi-GPU: the spatial dimension is element-partitioned (sharding.py); this rank holds its rows only
+    def _sharded_solve(self, ds, values, b, block, rtol, atol, maxit, settings, x0=None):
+        """Sharded PCG on the owned rows of an element-partitioned space: halo exchange of the direction vector and
+        dot-product all-reduces per iteration (persistent kernel over the NVLink peer window, NCCL otherwise); returns
+        the local vector [owned | ghost] with up-to-date ghosts.  Nothing is replicated or gathered here."""
         from . import partition as pt
 
-        rank, world = dist.get_rank(), dist.get_world_size()
-        if getattr(ds, "shard", None) is None:
-            rowptr, colidx, _, _ = ds.pattern
-            part = pt.RowPartition(ds.n_dofs, world, block)
-            ds.shard = (part, pt.shard_csr(rowptr, colidx, None, part, rank))
-        part, S = ds.shard
-        S.values = S.take_values(values)
-        r0, r1 = part.range(rank)
-        x_owned, iters, relres = pt.sharded_pcg(S, b[r0:r1].contiguous(), rtol=rtol, atol=atol, maxit=maxit,
-                                                check_every=int(settings.get("check_every", 50)), block=block)
+        sh = ds.shard
+        no = ds.n_owned
+        S = getattr(ds, "_shard_matrix", None)
+        if S is None:
+            halo = sh.halo(b.device)
+            S = pt.ShardedMatrix(ds.rowptr_owned, ds.pattern[1][: ds.nnz_owned], None, halo, int(sh.part.bounds[sh.rank]),
+                                 int(sh.part.bounds[sh.rank + 1]), block)
+            ds._shard_matrix = S
+        S.values = values[: ds.nnz_owned]
+        x, iters, relres = pt.sharded_solve(S, b, x0=x0, rtol=rtol, atol=atol, maxit=maxit,
+                                            check_every=int(settings.get("check_every", 50)), block=block,
+                                            bsr=ds.bsr if settings.get("node_block_walk", True) else None)
         self.solver_stats["pcg_solves"] += 1
         self.solver_stats["pcg_iterations"] += iters
         self.solver_stats["sharded_solves"] = self.solver_stats.get("sharded_solves", 0) + 1
-        return pt.gather_owned(x_owned, part)
+        if relres > max(rtol, 1e-15) * 10 and iters >= maxit:
+            self.logger.warning("sharded PCG stopped at relative residual %.3e after %d iterations", relres, iters)
+        return x
 
     def direct_solve(self, a, b, dim):
         """scalar problem: every dof = b / a (solver.py:909-925)."""

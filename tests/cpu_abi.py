@@ -107,7 +107,7 @@ def p1_rowplan_build(rowptr, colidx, cell_dofs, vptr, vidx, n_nodes):
     return cell_dofs  # the stand-in below only needs the cell -> dof table
 
 
-def assemble_p1_rows(coords, cell_verts, gdim, c_mass, c_stiff, c_adv, rowptr, vptr, vent, n_nodes, out=None, coords_soa=None):
+def assemble_p1_rows(coords, cell_verts, gdim, c_mass, c_stiff, c_adv, rowptr, vptr, vent, n_nodes, out=None, coords_soa=None, nnz=None):
     """closed-form P1 simplex matrices (mass, stiffness, advection) summed into CSR order."""
     import scipy.sparse as sp
 
@@ -148,9 +148,12 @@ def lincomb(xs, coefs, out=None, accumulate=False):
     return acc
 
 
-def _csr(rowptr, colidx, values):
+def _csr(rowptr, colidx, values, ncols=None):
+    """rows = len(rowptr) - 1 (an element-partitioned space passes the owned rows of a wider local pattern)"""
     n = rowptr.numel() - 1
-    return sp.csr_matrix((_n(values), _n(colidx), _n(rowptr)), shape=(n, n))
+    rp = _n(rowptr)
+    nnz = int(rp[-1])
+    return sp.csr_matrix((_n(values)[:nnz], _n(colidx)[:nnz], rp), shape=(n, n if ncols is None else ncols))
 
 
 def apply_dirichlet(rowptr, colidx, values, b, bc_dofs, bc_vals=None):
@@ -182,9 +185,9 @@ def set_entries(x, idx, vals=None):
 
 
 def spmv(rowptr, colidx, values, x, y=None, lpr=0):
-    r = _t(_csr(rowptr, colidx, values) @ _n(x))
+    r = _t(_csr(rowptr, colidx, values, x.numel()) @ _n(x))
     if y is not None:
-        y.copy_(r)
+        y[: r.numel()].copy_(r)
         return y
     return r
 
@@ -199,7 +202,8 @@ def spmv_dot(rowptr, colidx, values, x, w, y=None, out=None, lpr=0):
 
 
 def bilinear(rowptr, colidx, values, x, y, out=None, lpr=0):
-    d = _t(np.array([_n(x) @ (_csr(rowptr, colidx, values) @ _n(y))]))
+    M = _csr(rowptr, colidx, values, y.numel())
+    d = _t(np.array([_n(x)[: M.shape[0]] @ (M @ _n(y))]))
     if out is not None:
         out.copy_(d)
         return out

@@ -88,7 +88,7 @@ def run(mesh_n=68, bs=3, iters=200, profile=False, hbm_peak=6451.2):
     k = 3 if profile else iters
     plan = _lib.bsr_plan(rowptr, colidx, bs) if bs > 1 else None
     out["bsr_plan"] = None if plan is None else {"blocks": int(plan[0].numel()), "max_blocks_per_row": plan[1]}
-    variants = [("pcg_3launch", dict(persist=0), None), ("pcg_persist_csr", dict(persist=1, bsr=0), None)]
+    variants = [("pcg_3launch", dict(persist=1), None), ("pcg_persist_csr", dict(persist=2, bsr=0), None)]
     if plan is not None:
         variants.append(("pcg_persist_bsr", dict(persist=1, bsr=1), plan))
     sols = {}
@@ -102,11 +102,17 @@ def run(mesh_n=68, bs=3, iters=200, profile=False, hbm_peak=6451.2):
             return _lib.pcg(rowptr, colidx, vals, b, rtol=rtol, maxit=maxit, check_every=maxit, block=bs, work=work)
 
         solve(1e-30, 10)
+        _lib.set_option("prof", 1)
+        _lib.phase_ns(reset=True)
+        solve(1e-30, k)
+        ph = _lib.phase_ns(reset=True)
+        _lib.set_option("prof", 0)
         _lib.stats(reset=True)
         solve(1e-30, k)
         s = _lib.stats()
         bytes_moved = it_bytes if pl is None else (8 * nnz + 4 * (nnz // (bs * bs)) + 4 * (n + 1) + 56 * n)
         entry(name, s["pcg_ms"] / max(s["pcg_iters"], 1), it_bytes, iters=s["pcg_iters"], launches=s["launches"],
+              phase_us_per_iteration={kk: v / 1e3 / k for kk, v in ph.items()} if (opts.get("persist") == 2 or pl is not None) else None,
               bytes_of_format=bytes_moved, frac_hbm_of_format=bytes_moved / (s["pcg_ms"] / max(s["pcg_iters"], 1) * 1e-3) / 1e9 / hbm_peak)
         if not profile:
             _lib.stats(reset=True)
