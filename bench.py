@@ -2,17 +2,20 @@
 """bench.py -- PGD enrichment throughput on B200 (BASELINE.json metric).
 
   python bench.py --gpus N --steps K --warmup W            this repo's B200 path
-  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU path (oracle port)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU path (oracle port, all host threads)
 
-A *step* is one enrichment step of the progressive PGD (pgdrome/solver.py:325-504: initial modes,
-residual check, alternating fixed-point solve to convergence, normalisation) on BASELINE
-configs[1]: 2-D transient heat, P1 on a 256x256 unit square (66 049 dofs) x 200 time nodes x 50
-conductivity nodes.  W warm-up steps (they also build the sparsity pattern and the separated-form
-atoms), then exactly K timed steps between barrier + synchronize, CUDA events, max over ranks.
-With N > 1 every rank enriches its own replica of the problem (configs[1] is the reference's
-single-GPU case: "replicas only") and `value` is the job total.
+Workload: BASELINE configs[2] -- 3-D linear elasticity u(x, E, F), vector P1 tetrahedra on a 68^3 unit cube
+(985 527 spatial dofs, 43.3 M nonzeros: the CSR arrays are 520 MB, far beyond the 126 MB L2) x 50 Young's-modulus
+nodes x 3 load-amplitude nodes, 30 modes.  It is the largest config that BASELINE names for one GPU.
+A *step* is one enrichment step of the progressive PGD (pgdrome/solver.py:325-504: initial modes, residual check,
+alternating fixed-point solve to convergence, normalisation).  W warm-up steps (they also build mesh, pattern and
+the separated-form atoms), then exactly K timed steps between barrier + synchronize, CUDA events, max over ranks.
 
-Prints ONE JSON line (see DESIGN.md "Measurement" for every key).
+--gpus N > 1 (launched with torchrun, one rank per GPU): ONE problem for the whole job; its spatial mesh is
+element-partitioned over the N ranks (pgdrome_b200/sharding.py), every spatial solve is the sharded persistent PCG
+over the NVLink peer window, mode integrals are all-reduced, the 1-D dimensions are replicated: STRONG scaling.
+
+Prints ONE JSON line (DESIGN.md "Measurement" explains every key).
 """
 import argparse
 import json
@@ -28,16 +31,21 @@ if ROOT not in sys.path:
 
 METRIC = "PGD enrichment iters/sec at N dofs"
 UNIT = "enrichment_steps/s"
-WORKLOAD = dict(n=256, nt=199, nk=49)
+NMAX = 30  # mode budget of configs[2]
+SETTINGS = {"linear_solver": "cg", "preconditioner": "default", "relative_tolerance": 1e-13}
+COUNTS = os.path.join(ROOT, "profiles", "r02_config2_solve_counts.json")
 
 
-def _config(args, extra=None):
+def _config(args, world, extra=None):
     n = args.n
-    c = {"workload": "configs[1]: heat2d_tk P1 %dx%d unit square (%d dofs) x %d time nodes (FD) x %d k nodes" % (
-        n, n, (n + 1) ** 2, args.nt + 1, args.nk + 1), "spatial_dofs": (n + 1) ** 2, "tol_fp_it": 1e-5, "max_fp_it": 50,
-        "stop_fp": "norm", "norm_modes": "stiff", "linear_solver": "Jacobi-PCG rtol 1e-13 (space) + banded LU (t, k)",
-        "l2": "flushed between steps (256 MiB write); per-solve working set 8 MB is L2-resident by construction of the config",
-        "parallelism": "replicas" if args.gpus > 1 else "single"}
+    dofs = 3 * (n + 1) ** 3
+    c = {"workload": "configs[2]: elasticity3d vector P1 tetrahedra %d^3 unit cube (%d dofs) x %d E nodes x %d F nodes, %d modes"
+                     % (n, dofs, args.nE + 1, args.nF + 1, NMAX),
+         "spatial_dofs": dofs, "tol_fp_it": 1e-5, "max_fp_it": 50, "stop_fp": "norm", "norm_modes": "stiff",
+         "linear_solver": "node-block-Jacobi PCG rtol 1e-13 (space: persistent kernel, node-block walk) + banded LU (E, F)",
+         "l2": "flushed between steps (256 MiB write); the spatial operator (520 MB CSR) exceeds L2 by itself",
+         "parallelism": ("spatial mesh element-partitioned over %d ranks (strong scaling, one problem)" % world) if world > 1
+                        else "single"}
     if extra:
         c.update(extra)
     return c
@@ -86,52 +94,92 @@ class ClockSampler:
             except Exception:
                 pass
         sm.sort()
-        # under load = upper half of the samples (the sampler also sees the idle gaps of host-side work)
-        med = sm[(3 * len(sm)) // 4] if sm else None
+        med = sm[len(sm) // 2] if sm else None  # the GPU is busy for ~90 % of the timed region: plain median
         return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------- oracle (CPU) legs
-def _oracle_problem(args, nmax):
+# ------------------------------------------------------------------------------- CPU legs (oracle)
+def _solve_counts(n):
+    """PCG iterations of every spatial solve of every enrichment step of the full workload, recorded by a complete
+    30-mode run on the B200 (tools/run_config.py --counts): the bounded CPU sample is scaled with them."""
+    try:
+        tab = json.load(open(COUNTS))
+        if tab.get("n") == n:
+            return tab["steps"], "profiles/r02_config2_solve_counts.json (full 30-mode B200 run)"
+    except Exception:
+        pass
+    return None, "default 7 sweeps x 1650 iterations per step (no recorded table for this size)"
+
+
+def _cpu_sample(args, step_ids, sample_iters=40):
+    """Bounded sample of the CPU port on the same workload (oracle/: C restatement of assembly + node-block-Jacobi PCG
+    with OpenMP, SciPy for the 1-D dimensions).  A full CPU step takes minutes (~1 650 CG iterations x ~7 sweeps at
+    ~15 ms), so per step ONE fixed-point sweep is executed for real -- operator and right-hand-side assembly of every
+    dimension, Dirichlet elimination, the two 1-D solves -- with the spatial CG capped at `sample_iters` iterations;
+    the step time is  sweeps x (assembly + 1-D solves) + sum(iterations) x seconds-per-iteration  with the sweep and
+    iteration counts of the full run.  Returns (seconds per step list, info)."""
+    import numpy as np
+
+    from oracle import cfem, fem
+    from oracle import pgd as opgd
     from oracle import problems as oprob
 
-    o, info = oprob.heat2d_tk(n=args.n, nt=args.nt, nk=args.nk, PGD_nmax=nmax, PGD_tol=0.0)
-    return o
-
-
-def _oracle_steps(args, n_warm, n_steps):
-    """Wall-clock seconds of enrichment steps n_warm .. n_warm+n_steps-1 of the oracle port
-    (NumPy/SciPy: COO->CSR assembly done before, SuperLU solves = the reference's default LU)."""
-    from oracle import pgd as opgd
-
-    o = _oracle_problem(args, n_warm + n_steps)
-    marks = [time.perf_counter()]
-    opgd.solve_pgd(o, step_hook=lambda n: marks.append(time.perf_counter()))
-    done = len(marks) - 1
-    if done <= n_warm:
-        return 0.0, 0
-    return marks[done] - marks[n_warm], done - n_warm
+    t0 = time.perf_counter()
+    o, _ = oprob.elasticity3d(n=args.n, nE=args.nE, nF=args.nF, PGD_nmax=NMAX, PGD_tol=0.0)
+    build_s = time.perf_counter() - t0
+    counts, src = _solve_counts(args.n)
+    rng = np.random.default_rng(0)
+    secs, t_iter_all = [], []
+    for s in step_ids:
+        # stored modes of the steps before (random stand-ins of the right size: the cost does not depend on the values)
+        o.PGD_func = [[rng.standard_normal(o.n_dofs[d]) for _ in range(s)] for d in range(o.D)]
+        Fs = opgd.get_Fsinit(o)
+        t_other = 0.0
+        t_iter = None
+        for d in (o.seq_fp or range(o.D)):
+            t1 = time.perf_counter()
+            A = opgd.lhs_matrix(o, Fs, d)
+            b = opgd.rhs_vector(o, Fs, d, s)
+            A, b = fem.apply_dirichlet_sym(A, b, o.bc_dofs[d])
+            if d == 0:
+                t_other += time.perf_counter() - t1
+                t2 = time.perf_counter()
+                x, it, _ = cfem.pcg(A, b, block=3, rtol=1e-13, max_iters=sample_iters)
+                t_iter = (time.perf_counter() - t2) / max(it, 1)
+            else:
+                x = opgd._solve(o, A, b, d)
+                t_other += time.perf_counter() - t1
+            Fs[d] = x
+        sweeps = counts[s]["pcg_iterations"] if counts and s < len(counts) else [1650] * 7
+        secs.append(len(sweeps) * t_other + sum(sweeps) * t_iter)
+        t_iter_all.append(t_iter)
+    info = {"threads": cfem.threads(), "build_s": build_s, "counts_source": src,
+            "cg_ms_per_iteration": 1e3 * float(np.mean(t_iter_all)) if t_iter_all else None}
+    return secs, info
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import scipy
-
-    nmax = 20  # the workload's mode budget (BASELINE configs[1]); a longer request is timed on this bounded sample
-    w = min(args.warmup, nmax - 1)
-    t, k = _oracle_steps(args, w, min(args.steps, nmax - w))
-    val = k / t if t > 0 else 0.0
-    cores = 1
-    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": k,
-           "warmup": args.warmup, "ms_per_step": 1e3 * t / max(k, 1), "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": _config(args),
-           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                            "sample": "enrichment steps %d..%d of the same workload, oracle port (SciPy %s SuperLU), 1 thread"
-                                      % (w, w + k - 1, scipy.__version__)},
+    W = min(args.warmup, NMAX - 1)
+    K = args.steps
+    ids = [(W + i) % NMAX for i in range(K)]
+    secs, info = _cpu_sample(args, ids)
+    t = sum(secs)
+    val = K / t if t > 0 else 0.0
+    sample = ("steps %s of the same workload; per step one fixed-point sweep executed for real (assembly of every dimension, "
+              "Dirichlet elimination, 1-D solves) with the spatial CG capped at 40 iterations, scaled to the sweep / iteration "
+              "counts of the full run [%s]; oracle port: C + OpenMP (%d threads) assembly / node-block-Jacobi PCG, SciPy 1-D"
+              % ("%d..%d" % (W, W + K - 1), info["counts_source"], info["threads"]))
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+           "warmup": args.warmup, "ms_per_step": 1e3 * t / max(K, 1), "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": _config(args, max(args.gpus, 1)),
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": info["threads"], "kind": "port", "sample": sample,
+                            "cg_ms_per_iteration": info["cg_ms_per_iteration"], "problem_build_s": info["build_s"]},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "note": "the real reference (FEniCS 2019.1 + PETSc/MUMPS) cannot be installed in this image; this is its CPU port"}
+           "note": "the real reference (FEniCS 2019.1 + PETSc) cannot be installed in this image; this is its CPU port with "
+                   "settings={'linear_solver': 'cg', 'preconditioner': 'jacobi'}-class solves (solver.py:634-635)"}
     print(json.dumps(out))
 
 
@@ -156,32 +204,32 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    from pgdrome_b200 import _lib, configs, lazy
+    from pgdrome_b200 import _lib, configs, lazy, sharding
+    from pgdrome_b200.assembly import device_space
 
+    sharding.configure(mode="auto", min_dofs=args.shard_min_dofs)
     W, K = args.warmup, args.steps
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def make(nmax):
-        p = configs.heat2d_tk(n=args.n, nt=args.nt, nk=args.nk, PGD_nmax=nmax, PGD_tol=0.0)
-        return p
+        return configs.elasticity3d(n=args.n, nE=args.nE, nF=args.nF, PGD_nmax=nmax, PGD_tol=0.0)
 
-    # ---------------- device-resident arm: W warm-up + K timed enrichment steps
-    # The workload enriches up to NMAX = 20 modes (BASELINE configs[1]).  Runs with W + K > NMAX continue on a fresh
-    # problem instance (its W warm-up steps untimed again), so that every timed step is a real enrichment step and
-    # never the cheap "residual below 1e-10, stop" exit of an exhausted enrichment.
-    NMAX = 20
     W = min(W, NMAX - 1)
 
     def fresh():
         q = make(NMAX)
-        s_ = q.begin_PGD(_problem="linear")
+        s_ = q.begin_PGD(_problem="linear", settings=dict(SETTINGS))
         for _ in range(W):
             q.step_PGD(s_)
         return q, s_
 
+    t_setup = time.perf_counter()
     p, st = fresh()
-    ds0 = p.V[0]._dev["device_space"]
-    n, nnz = ds0.n_dofs, ds0.nnz
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t_setup
+    ds0 = device_space(p.V[0])
+    n_loc, nnz_loc = ds0.n_owned, ds0.nnz_owned
+    n_glob = p.V[0].n_dofs
     barrier()
     _lib.stats(reset=True)
     flushes0 = lazy.stats["flushes"]
@@ -191,7 +239,7 @@ def run_b200(args):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K)]
     barrier()
     t0 = time.perf_counter()
-    step_ms, fp_its = [], []
+    fp_its, per_step = [], []
     done_steps, in_problem, warm_stats = 0, W, None
     while done_steps < K:
         if in_problem >= NMAX or st["done"]:
@@ -202,11 +250,15 @@ def run_b200(args):
             in_problem = W
         i = done_steps
         flush_buf.fill_(i & 0xFF)  # L2 flush between timed steps (untimed)
+        s0 = _lib.stats()
         ev[2 * i].record()
         p.step_PGD(st)
         ev[2 * i + 1].record()
         if st["done"] and len(p.num_fp_it) < in_problem + 1:
             continue  # the step only detected an exhausted residual: not an enrichment step, not counted
+        s1 = _lib.stats()
+        per_step.append({"step": in_problem, "pcg_solves": s1["pcg_solves"] - s0["pcg_solves"],
+                         "pcg_iters": s1["pcg_iters"] - s0["pcg_iters"], "pcg_ms": s1["pcg_ms"] - s0["pcg_ms"]})
         fp_its.append(p.num_fp_it[-1])
         done_steps += 1
         in_problem += 1
@@ -222,130 +274,207 @@ def run_b200(args):
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
-    value = world * K / (total_ms * 1e-3)
+    value = K / (total_ms * 1e-3)  # ONE problem for the whole job: strong scaling
 
-    # live roofline of the dominant kernel group: one Jacobi-PCG iteration (k_pcg_spmv + k_pcg_update)
+    # ---------------- live roofline of the dominant kernel: one PCG iteration of the spatial solve on this rank's rows
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
-    it_bytes = 12 * nnz + 4 * (n + 1) + 56 * n
+    it_bytes = 12 * nnz_loc + 4 * (n_loc + 1) + 56 * n_loc          # CSR fp64 / int32 operator + 7 vector passes
+    fmt_bytes = 8 * nnz_loc + 4 * (nnz_loc // 9) + 4 * (n_loc + 1) + 56 * n_loc  # what the node-block walk streams
     it_ms = s["pcg_ms"] / max(s["pcg_iters"], 1)
     achieved = it_bytes / (it_ms * 1e-3) / 1e9 if s["pcg_iters"] else 0.0
-    resident = s.get("pcg_resident_solves", 0) >= s["pcg_solves"] > 0
     traffic = None
-    try:  # DRAM bytes of the dominant kernel from the committed ncu --set full capture (per launch = per solve)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_pcg_resident_traffic.json")))
-        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+    try:  # DRAM bytes per iteration of the persistent kernel from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_pcg_persist_traffic.json")))
+        if world == 1 and tj.get("n_dofs") == n_glob:
+            traffic = tj["dram_bytes_per_iteration"]
     except Exception:
         pass
     roofline = {"bound": "hbm",
-                "kernel": ("Jacobi-PCG iteration inside k_pcg_resident (one cooperative launch per solve, matrix slice "
-                           "resident in shared memory; figures are per ITERATION)") if resident else
-                          "Jacobi-PCG iteration (k_pcg_spmv_bulk + k_pcg_update)",
+                "kernel": "one node-block-Jacobi PCG iteration inside k_pcg_persist<3, BSR> (one cooperative launch per solve: "
+                          "direction update, TMA-pipelined node-block SpMV, vector update, grid-wide reductions); figures are per "
+                          "ITERATION" + (" of rank 0's %d owned rows" % n_loc if world > 1 else ""),
                 "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic if resident else None,
-                "traffic_note": ("ncu dram__bytes_read+write of ONE k_pcg_resident launch = one whole solve (~660 iterations): the "
-                                 "matrix is read from HBM once per solve; a streaming PCG would move bytes_per_launch per "
-                                 "iteration") if resident else None,
+                "traffic": traffic,
                 "bytes_per_launch": it_bytes, "us_per_launch": 1e3 * it_ms, "launches": s["pcg_iters"],
+                "bytes_definition": "12 nnz + 4 (n+1) + 56 n (SURVEY.md 8(d): CSR operator + vector passes)",
+                "bytes_streamed_by_this_format": fmt_bytes,
+                "frac_of_streamed_bytes": fmt_bytes / (it_ms * 1e-3) / 1e9 / peak if s["pcg_iters"] else 0.0,
                 "share_of_step": s["pcg_ms"] / total_ms if total_ms else None,
-                "note": "matrix (5.5 MB) + vectors are on-chip at this config (shared memory / L2): the iteration is bound by "
-                        "two grid barriers (~2 us each), not by HBM; `kernels` carries the HBM-bound sizes (128^3 mesh: "
-                        "SpMV 80 %, PCG iteration 63 % of the measured HBM peak)"}
+                "note": "the node-block walk reads the CSR values (8 B/nnz) plus one column per 3x3 block (4/9 B/nnz) instead of "
+                        "12 B/nnz: `frac` uses the survey's CSR byte model, `frac_of_streamed_bytes` the bytes actually moved"}
 
     # ---------------- end-to-end arm: host arrays in, modes out, everything inside the timed region
-    e2e = None
-    if rank == 0 or world > 1:
-        Ke = min(K, args.e2e_steps) if args.e2e_steps else min(K, NMAX)
-        p = st = None  # the device-resident problem is done: its memory goes back to the allocator before the next one
-        q = make(Ke)
-        for V in q.V:
-            V._dev.pop("device_space", None)
-        _lib.traffic["h2d"] = _lib.traffic["d2h"] = 0
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        tw = time.perf_counter()
-        e0.record()
-        q.solve_PGD(_problem="linear")
-        modes = [[f.vector().get_local() for f in q.PGD_func[d]] for d in range(3)]
-        e1.record()
-        barrier()
-        tw = time.perf_counter() - tw
-        ms = e0.elapsed_time(e1)
-        te = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        per_rank = [ms]
-        if dist is not None:
-            allms = [torch.zeros_like(te) for _ in range(world)]
-            dist.all_gather(allms, te)
-            per_rank = [float(t.item()) for t in allms]
-        ms = max(per_rank)
-        e2e = {"value": world * q.PGD_modes / (ms * 1e-3), "unit": UNIT, "steps": q.PGD_modes,
-               "h2d_bytes_per_step": _lib.traffic["h2d"] // max(q.PGD_modes, 1),
-               "d2h_bytes_per_step": _lib.traffic["d2h"] // max(q.PGD_modes, 1), "ms_total": ms,
-               "ms_per_rank": per_rank, "host_wall_ms_rank0": tw * 1e3,
-               "what": "fresh PGDProblem from host (NumPy) mesh/dofmap arrays -> solve_PGD(%d modes) -> all modes read back "
-                       "to host; includes mesh upload, pattern build, atom assembly" % Ke}
-        del modes
+    Ke = min(K, args.e2e_steps) if args.e2e_steps else min(K, NMAX)
+    p = st = ds0 = None  # the device-resident problem is done: its memory goes back to the allocator before the next one
+    q = make(Ke)
+    _lib.traffic["h2d"] = _lib.traffic["d2h"] = 0
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw = time.perf_counter()
+    e0.record()
+    q.solve_PGD(_problem="linear", settings=dict(SETTINGS))
+    modes = [[f.vector().get_local() for f in q.PGD_func[d]] for d in range(3)]
+    e1.record()
+    barrier()
+    tw = time.perf_counter() - tw
+    ms = e0.elapsed_time(e1)
+    te = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    per_rank = [ms]
+    if dist is not None:
+        allms = [torch.zeros_like(te) for _ in range(world)]
+        dist.all_gather(allms, te)
+        per_rank = [float(t.item()) for t in allms]
+    ms = max(per_rank)
+    e2e = {"value": q.PGD_modes / (ms * 1e-3), "unit": UNIT, "steps": q.PGD_modes,
+           "h2d_bytes_per_step": _lib.traffic["h2d"] // max(q.PGD_modes, 1),
+           "d2h_bytes_per_step": _lib.traffic["d2h"] // max(q.PGD_modes, 1), "ms_total": ms,
+           "ms_per_rank": per_rank, "host_wall_ms_rank0": tw * 1e3,
+           "what": "fresh PGDProblem from host (NumPy) mesh/dofmap arrays -> solve_PGD(%d modes) -> all modes read back "
+                   "to host; includes host mesh generation / partition, upload, pattern build, atom assembly" % Ke}
+    del modes
+    q = None
 
-    sharded = None
-    if world > 1 and not args.no_kernels:
-        # the path's real exchange step (configs[2]-[3]): a spatial Jacobi-PCG sharded by rows over all ranks,
-        # NCCL send/recv halo of p + allreduce of the dot products inside libpgdb200's loop
-        try:
-            from tools import sharded_bench
-
-            sharded = sharded_bench.run(args.kernel_mesh, iters=200, hbm_peak=peak)
-        except Exception as e:
-            sharded = {"error": repr(e)}
     if rank != 0:
         if dist is not None:
+            # the evaluate sweep below is collective-free; the other ranks still take part in the sharded evaluation
+            _evaluate_e2e(args, torch, _lib, rank, world, dist, peak)
             dist.destroy_process_group()
         return
 
-    # ---------------- CPU baseline (bounded sample of the same workload) and large-mesh kernel rooflines
+    # ---------------- CPU baseline (bounded sample of the same workload), secondary objects
     cpu = None
     if world == 1 and not args.no_cpu:
-        import scipy
-
-        tc, kc = _oracle_steps(args, 0, args.cpu_steps)
-        cpu = {"value": kc / tc if tc > 0 else 0.0, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": "first %d enrichment steps of the same workload, oracle port (SciPy %s, SuperLU direct solves)"
-                         % (kc, scipy.__version__), "seconds": tc}
-    kernels = None
+        ids = [W + i for i in range(min(args.cpu_steps, K))]
+        secs, info = _cpu_sample(args, ids)
+        tc = sum(secs)
+        cpu = {"value": len(secs) / tc if tc > 0 else 0.0, "unit": UNIT, "cores": info["threads"], "kind": "port",
+               "sample": "steps %s, one real fixed-point sweep each with the spatial CG capped at 40 iterations, scaled to the sweep "
+                         "/ iteration counts of the full run [%s]; oracle port (C + OpenMP, SciPy)" % (ids, info["counts_source"]),
+               "seconds_per_step": secs, "cg_ms_per_iteration": info["cg_ms_per_iteration"]}
+    evaluate = None
+    if not args.no_kernels:
+        try:
+            evaluate = _evaluate_e2e(args, torch, _lib, rank, world, dist, peak)
+        except Exception as e:
+            evaluate = {"error": repr(e)}
+    kernels = secondary = None
     if world == 1 and not args.no_kernels:
         try:
             from tools import kernel_bench
 
-            kernels = kernel_bench.run(args.kernel_mesh, peak)
+            kernels = kernel_bench.run(args.kernel_mesh, peak, evaluate=False)
         except Exception as e:  # the headline number must not depend on the micro-benchmarks
             kernels = {"error": repr(e)}
+        try:
+            secondary = _secondary_heat2d(torch, _lib, configs)
+        except Exception as e:
+            secondary = {"error": repr(e)}
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-           "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-           "data": "synthetic", "config": _config(args), "clocks": clocks, "e2e": e2e, "gpu_launches": s["launches"],
-           "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels, "sharded_pcg": sharded,
-           "detail": {"step_ms": step_ms, "pcg_solves": s["pcg_solves"], "pcg_iters": s["pcg_iters"], "pcg_ms": s["pcg_ms"],
-                      "fp_iterations": fp_its, "functional_flushes": lazy.stats["flushes"] - flushes0,
-                      "wall_s_timed_region": wall, "nnz": nnz}}
+           "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic", "config": _config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": s["launches"],
+           "roofline": roofline, "cpu_baseline": cpu, "evaluate_e2e": evaluate, "kernels": kernels, "configs1_heat2d": secondary,
+           "detail": {"step_ms": step_ms, "per_step": per_step, "pcg_solves": s["pcg_solves"], "pcg_iters": s["pcg_iters"],
+                      "pcg_ms": s["pcg_ms"], "fp_iterations": fp_its, "functional_flushes": lazy.stats["flushes"] - flushes0,
+                      "wall_s_timed_region": wall, "nnz_rank0": nnz_loc, "rows_rank0": n_loc, "setup_and_warmup_s": t_setup,
+                      "device_mem_gb_rank0": torch.cuda.max_memory_allocated() / 1e9}}
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
 
 
+def _evaluate_e2e(args, torch, _lib, rank, world, dist, hbm_peak):
+    """BASELINE configs[4] through the public API: a 50-mode model over (x, t, k, P, v) reconstructed by
+    PGD.evaluate_batch on 1e5 spatial points x 1e4 parameter points (host points in; weights kernel + FP64 DMMA GEMM);
+    the rows of the spatial dimension are sharded over the ranks, no communication."""
+    import numpy as np
+    from scipy.stats import qmc
+
+    from pgdrome_b200 import dolfin as df
+    from pgdrome_b200.model import PGD
+
+    R, N, C = 50, args.eval_n, args.eval_c
+    sizes = [N, 200, 50, 20, 20]
+    rng = np.random.default_rng(0)
+    meshes = [df.IntervalMesh(m - 1, 0.0, 1.0) for m in sizes]
+    Vs = [df.FunctionSpace(m, "P", 1) for m in meshes]
+    modes = [[df.Function(V, rng.standard_normal(V.n_dofs)) for _ in range(R)] for V in Vs]
+    model = PGD(name="vademecum", n_modes=R, fmeshes=meshes, pgd_modes=modes, name_coord=["X", "T", "K", "P", "V"],
+                modes_info=["U", "Node", "Scalar"], verbose=False)
+    pts = qmc.LatinHypercube(d=4, seed=3452).random(n=C)  # the reference's own sampler and seed (model.py:1709)
+    n0, n1 = (N * rank) // world, (N * (rank + 1)) // world
+    n0, n1 = n0 - n0 % 2, (n1 - n1 % 2) if rank < world - 1 else n1
+    U = torch.empty((C, n1 - n0), dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        model.evaluate_batch(0, [1, 2, 3, 4], pts, 0, out=U, rows=(n0, n1))
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    reps = 3
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        model.evaluate_batch(0, [1, 2, 3, 4], pts, 0, out=U, rows=(n0, n1))
+        peak_val = float(U.amax().item())  # the step's result read back (a device reduction of the [C, N] block)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    flops = 2.0 * N * C * R
+    fp64 = None
+    try:
+        fp64 = json.load(open(os.path.join(ROOT, "profiles", "r01_fp64_peak.json"))).get("fp64_gemm_tflops")
+    except Exception:
+        pass
+    tf = flops / (ms * 1e-3) / 1e12
+    return {"what": "PGD.evaluate_batch: host parameter points [C, 4] in -> weights kernel + FP64 DMMA GEMM -> max u read back (one more pass over the [C, N] block); "
+                    "spatial rows sharded over the ranks", "N": N, "C": C, "R": R, "free_dims": 4, "ms": ms, "tflops_total": tf,
+            "fp64_peak_tflops_per_gpu": fp64, "peak_definition": "cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01_fp64_peak.json); "
+            "MEASURED_PEAKS.json has no fp64 entry", "frac_fp64_per_gpu": (tf / world / fp64) if fp64 else None,
+            "out_write_gbs_per_gpu": 8.0 * C * (n1 - n0) / (ms * 1e-3) / 1e9, "max_u": peak_val}
+
+
+def _secondary_heat2d(torch, _lib, configs, steps=5, warm=3):
+    """BASELINE configs[1] (round-1 headline, L2-resident) for continuity: device-resident steps/s on one GPU."""
+    p = configs.heat2d_tk(n=256, nt=199, nk=49, PGD_nmax=20, PGD_tol=0.0)
+    st = p.begin_PGD(_problem="linear")
+    for _ in range(warm):
+        p.step_PGD(st)
+    torch.cuda.synchronize()
+    _lib.stats(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        p.step_PGD(st)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    s = _lib.stats()
+    return {"workload": "configs[1]: heat2d_tk 256x256 (66 049 dofs) x 200 t x 50 k", "steps": steps, "steps_per_s": steps / (ms * 1e-3),
+            "ms_per_step": ms / steps, "pcg_iters": s["pcg_iters"], "pcg_share": s["pcg_ms"] / ms if ms else None}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=WORKLOAD["n"])
-    ap.add_argument("--nt", type=int, default=WORKLOAD["nt"])
-    ap.add_argument("--nk", type=int, default=WORKLOAD["nk"])
-    ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--n", type=int, default=68, help="cells per edge of the spatial mesh (68: BASELINE configs[2])")
+    ap.add_argument("--nE", type=int, default=49)
+    ap.add_argument("--nF", type=int, default=2)
+    ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--e2e-steps", type=int, default=0)
+    ap.add_argument("--shard-min-dofs", type=int, default=200000)
+    ap.add_argument("--eval-n", type=int, default=100000)
+    ap.add_argument("--eval-c", type=int, default=10000)
     ap.add_argument("--kernel-mesh", type=int, default=128, help="cells per edge of the box mesh of the kernel rooflines")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-kernels", action="store_true")

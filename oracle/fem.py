@@ -192,6 +192,9 @@ def _geometry(space, dphi):
     return grad, detJ
 
 
+C_FAST_MIN_CELLS = 20000  # assemble_bilinear uses oracle/cfem.c from this many P1 cells on (None: never)
+
+
 def sparsity(cell_dofs, n_dofs):
     """CSR pattern (rowptr, colidx): union of per-cell cliques, columns ascending."""
     nd = cell_dofs.shape[1]
@@ -210,6 +213,14 @@ def assemble_bilinear(space, T, weight=None, weight_degree=None, qdeg=None, chun
     bs, g = space.bs, space.gdim
     assert T.shape == (bs, g + 1, bs, g + 1), T.shape
     wdeg = 0 if weight is None else (weight_degree if weight_degree is not None else 2)
+    if (C_FAST_MIN_CELLS is not None and space.degree == 1 and space.tdim == g and qdeg is None and wdeg == 0
+            and space.cells.shape[0] >= C_FAST_MIN_CELLS):
+        # large P1 meshes: the same integrals in closed form by the C restatement (oracle/cfem.c, validated against
+        # the quadrature path below in tests/test_oracle_c.py); a degree-0 coefficient is its value at the cell centroid
+        from . import cfem
+
+        wc = None if weight is None else np.ascontiguousarray(weight_at_quad(space, weight, 0, np.zeros((1, g)))[:, 0])
+        return cfem.assemble_bilinear_p1(space, T, wc)
     if qdeg is None:
         qdeg = 2 * space.degree + wdeg
     pts, wts = quadrature(space.tdim, qdeg)

@@ -47,8 +47,12 @@ class SeparatedProblem:
     stop_fp: str = "norm"
     fp_init: str = ""
     norm_modes: str = "stiff"
-    solver: str = "lu"  # "lu" (reference default: direct) | "cg" (settings={"linear_solver":"cg","preconditioner":"jacobi"})
+    solver: str = "lu"  # "lu" (reference default: direct) | "cg" (settings={"linear_solver":"cg","preconditioner":"jacobi"},
+    #                      SciPy) | "ccg" (the same algorithm in C + OpenMP with node-block Jacobi, oracle/cfem.c; dimensions
+    #                      below `ccg_min_dofs` keep the direct solve)
     cg_rtol: float = 1e-13
+    cg_block: list = None  # per dim: node-block size of the Jacobi preconditioner in "ccg" mode (default 1)
+    ccg_min_dofs: int = 5000
     # outputs (same names as solver.py:105-126)
     PGD_func: list = field(default_factory=list)
     alpha: list = field(default_factory=list)
@@ -57,6 +61,7 @@ class SeparatedProblem:
     err_fp_it: list = field(default_factory=list)
     res_errors: list = field(default_factory=list)
     fp_floor: list = field(default_factory=list)
+    cg_iterations: list = field(default_factory=list)
     PGD_modes: int = None
 
     @property
@@ -120,6 +125,12 @@ def rhs_vector(p, Fs, d, n_enr):
 
 def _solve(p, A, b, d):
     A, b = apply_dirichlet_sym(A, b, p.bc_dofs[d])
+    if p.solver == "ccg" and A.shape[0] >= p.ccg_min_dofs:
+        from . import cfem
+
+        x, it, rr = cfem.pcg(A, b, block=(p.cg_block[d] if p.cg_block else 1), rtol=p.cg_rtol, max_iters=20 * A.shape[0])
+        p.cg_iterations.append(it)
+        return x
     if p.solver == "cg":
         dinv = 1.0 / A.diagonal()
         x, info = spla.cg(A, b, rtol=p.cg_rtol, atol=0.0, maxiter=20 * A.shape[0],

@@ -7,12 +7,15 @@
 // and three host-visible flag round trips of pgd_spcg_solve_sync (55 us floor per iteration).  All CG scalars
 // live in registers, identical in every CTA of every rank.
 //
-// One iteration (p is kept in two buffers pa / pb that alternate, both with a ghost tail):
-//   D  boundary entries of p_new = z + beta p_old are formed FIRST and stored straight into the neighbours'
-//      ghost slots over NVLink (+ sequence flag), then the owned part of p_new is written
-//      -> grid barrier (arrival counter), halo flags of the neighbours acquired
-//   S  q = A_loc p_new through the TMA ring, local p.q            -> reduce-broadcast #1 (alpha)
-//   U  x += alpha p ; r -= alpha q ; z = M^-1 r ; local r.z, r.r  -> reduce-broadcast #2 (beta, stop test)
+// One iteration (z carries a ghost tail that lives in the peer window; p = [owned | ghost] is purely local):
+//   D  p = z + beta p on ALL local entries -- the ghost entries of p follow the same recurrence from the ghost
+//      entries of z, which the neighbours stored during the previous reduction   -> grid barrier (arrival counter)
+//   S  q = A_loc p through the TMA ring, local p.q                 -> reduce-broadcast #1 (alpha)
+//   U  x += alpha p ; r -= alpha q ; z = M^-1 r ; local r.z, r.r   -> reduce-broadcast #2 (beta, stop test); inside it,
+//      as soon as this rank's CTAs have all arrived, a few CTAs store the boundary entries of the new z straight
+//      into the neighbours' ghost slots over NVLink (+ sequence flag): the halo travels while the dot products
+//      cross the switch, and the next D finds it in place.  (First version: halo of p pushed in D, every CTA fencing
+//      at system scope -- 9.6 us for D and 6.7 us of barrier + halo wait per iteration at 2 GPUs.)
 // reduce-broadcast: every CTA deposits its partials and arrives; CTA 0 sums them in a fixed order and stores
 // the rank's sum into the mailbox of every rank (its own included) with a release flag; every CTA of every
 // rank acquires the `world` flags and adds the mailboxes in RANK ORDER => bitwise identical scalars
@@ -42,8 +45,9 @@ struct PersistArgs {
     int64_t n_owned, n_local;
     double rtol, atol;
     int maxit, warm;
-    double *r, *z, *q, *minv;  // [n_owned] (minv: n_owned * BS)
-    double *pa, *pb;           // [n_local] each; inside the peer window when world > 1
+    double *r, *q, *minv;      // [n_owned] (minv: n_owned * BS)
+    double* z;                 // [n_local]; inside the peer window when world > 1 (neighbours write its ghost tail)
+    double* p;                 // [n_local], local
     double* part;              // [2][4][G] partial sums, double-buffered by sync parity
     unsigned int* arrive;      // monotonic arrival counter, 0 at launch
     unsigned int* push_ctr;    // "last pushing CTA" ticket, 0 at launch and whenever idle
@@ -58,7 +62,7 @@ struct PersistArgs {
     PwHalo hp;
     const int64_t* send_idx;
     int64_t n_send;
-    int64_t pb_off;            // offset (doubles) of pb inside a window (pa sits at 0)
+    unsigned int n_push;       // CTAs that take part in a halo push (the LAST n_push of the grid)
     unsigned long long spin_ns;
     BsrPlan bsr;               // node-block walk of the CSR arrays (BSR template only)
     unsigned long long* prof;  // optional [8]: ns spent (as seen by CTA 0) in D, barrier, S, reduce 1, U, reduce 2
@@ -131,8 +135,15 @@ __device__ __forceinline__ bool ps_grid_barrier(const PersistArgs& a, PsSync& sy
 // stores the rank's sum into the other ranks' mailboxes with a release flag, and every CTA acquires the `world - 1`
 // foreign flags in its LOCAL window and adds the rank sums in RANK ORDER (its own from the partials).
 // false = aborted.
-template <int NV>
-__device__ __forceinline__ bool ps_reduce_bcast(double (&v)[NV], const PersistArgs& a, PsSync& sy, unsigned int G) {
+struct PsNoHook {
+    __device__ __forceinline__ void operator()() const {}
+};
+
+// after_arrival(): executed by every CTA right after all CTAs of this rank have arrived (their global writes are
+// visible) and before the cross-rank part of the reduction -- the place where the halo of the new z is pushed.
+template <int NV, class Hook = PsNoHook>
+__device__ __forceinline__ bool ps_reduce_bcast(double (&v)[NV], const PersistArgs& a, PsSync& sy, unsigned int G,
+                                                Hook&& after_arrival = PsNoHook()) {
     __shared__ double s_res[4];
     __shared__ int s_ok;
     const int tid = threadIdx.x;
@@ -153,6 +164,7 @@ __device__ __forceinline__ bool ps_reduce_bcast(double (&v)[NV], const PersistAr
         if (!ps_spin([&] { return ps_ld_acquire_gpu(a.arrive) >= tgt; }, a)) s_ok = 0;
     }
     __syncthreads();
+    after_arrival();
     if (tid < 32) {  // every CTA: the rank's sum, same order everywhere
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
@@ -199,25 +211,25 @@ __device__ __forceinline__ bool ps_reduce_bcast(double (&v)[NV], const PersistAr
     return ok;
 }
 
-// boundary entries of v (or of z + beta p_old when z != NULL) -> the neighbours' ghost slots of buffer `dst_off`
-// (doubles from the window base); the last CTA to finish publishes the halo flag on every destination.
-__device__ __forceinline__ void ps_halo_push(const PersistArgs& a, const double* __restrict__ z, const double* __restrict__ v,
-                                             double beta, int64_t dst_buf_off, unsigned long long seq, unsigned int G) {
-    if (a.n_send == 0 || a.world <= 1) return;
+// boundary entries of v -> the neighbours' ghost slots of their z buffer (window offset 0); executed by the LAST
+// n_push CTAs of the grid only (the others return at once: no system-scope fence on their path); the last of them
+// to finish publishes the halo flag on every destination.
+__device__ __forceinline__ void ps_halo_push(const PersistArgs& a, const double* v, unsigned long long seq, unsigned int G) {
+    if (a.n_push == 0 || blockIdx.x < G - a.n_push) return;
     __shared__ bool s_last;
-    const int64_t stride = (int64_t)G * blockDim.x;
-    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < a.n_send; s += stride) {
+    const int64_t first = (int64_t)(blockIdx.x - (G - a.n_push)) * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)a.n_push * blockDim.x;
+    for (int64_t s = first; s < a.n_send; s += stride) {
         int r = 0;
         while (s >= a.hp.seg_start[r + 1]) ++r;
-        const int64_t i = a.send_idx[s];
-        double* dst = reinterpret_cast<double*>(a.peers.base[r]) + dst_buf_off + a.hp.dst_off[r] + (s - a.hp.seg_start[r]);
-        *dst = z ? fma(beta, v[i], z[i]) : v[i];
+        double* dst = reinterpret_cast<double*>(a.peers.base[r]) + a.hp.dst_off[r] + (s - a.hp.seg_start[r]);
+        *dst = v[a.send_idx[s]];
     }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned int t = atomicAdd(a.push_ctr, 1u);
-        s_last = (t == G - 1);
+        s_last = (t == a.n_push - 1);
     }
     __syncthreads();
     if (s_last) {
@@ -284,13 +296,14 @@ __global__ void __launch_bounds__(PS_THREADS, BK_CTAS_PER_SM) k_pcg_persist(Pers
     int it = 0;
     double rz = 0.0, rz_old = 1.0, rr = 0.0, bb = 0.0, tol2 = 0.0;
 
-    // ---- r = b - A x0 (warm) | b ; M^-1 ; z = M^-1 r ; pa = pb = 0
+    // ---- r = b - A x0 (warm) | b ; M^-1 ; z = M^-1 r ; p = 0
     if (a.warm) {
         auto epi = [&](int64_t row, double s) { a.q[row] = s; };
         ps_spmv<BS, BSR>(a, a.x, epi, bk_smem, &tile);
         __syncthreads();
         if (!ps_grid_barrier(a, sy, G)) status = 3;
     }
+    unsigned long long hseq = sy.seq_halo;  // sequence number of the halo of the CURRENT z
     {
         double v[3] = {0.0, 0.0, 0.0};  // r.z, b.b, r.r
         if (status == 0) {
@@ -323,11 +336,9 @@ __global__ void __launch_bounds__(PS_THREADS, BK_CTAS_PER_SM) k_pcg_persist(Pers
                     v[2] += rb[i] * rb[i];
                 }
             }
-            for (int64_t i = gtid; i < a.n_local; i += gstride) {
-                a.pa[i] = 0.0;
-                a.pb[i] = 0.0;
-            }
-            if (!ps_reduce_bcast<3>(v, a, sy, G)) status = 3;
+            for (int64_t i = gtid; i < a.n_local; i += gstride) a.p[i] = 0.0;
+            hseq = ++sy.seq_halo;
+            if (!ps_reduce_bcast<3>(v, a, sy, G, [&] { ps_halo_push(a, a.z, hseq, G); })) status = 3;
         }
         rz = v[0];
         bb = v[1];
@@ -340,27 +351,25 @@ __global__ void __launch_bounds__(PS_THREADS, BK_CTAS_PER_SM) k_pcg_persist(Pers
     if (status == 0 && rr > tol2 && bb > 0.0) {
         while (it < a.maxit) {
             const double beta = (it == 0) ? 0.0 : rz / rz_old;
-            const double* __restrict__ p_old = (it & 1) ? a.pb : a.pa;
-            double* __restrict__ p_new = (it & 1) ? a.pa : a.pb;
-            const int64_t new_off = (it & 1) ? 0 : a.pb_off;
-            // ---- D: boundary entries to the neighbours first, then the owned direction
-            const unsigned long long hseq = ++sy.seq_halo;
-            ps_halo_push(a, a.z, p_old, beta, new_off, hseq, G);
-            if ((((uintptr_t)a.z | (uintptr_t)p_old | (uintptr_t)p_new) & 15) == 0) {
-                const int64_t n2 = no >> 1;
+            // ---- D: p = z + beta p on [owned | ghost] (the ghost entries of z were stored by the neighbours)
+            if (!ps_halo_wait(a, hseq)) {
+                status = 3;
+                break;
+            }
+            if ((((uintptr_t)a.z | (uintptr_t)a.p) & 15) == 0) {
+                const int64_t n2 = a.n_local >> 1;
                 const double2* z2 = reinterpret_cast<const double2*>(a.z);
-                const double2* o2 = reinterpret_cast<const double2*>(p_old);
-                double2* p2 = reinterpret_cast<double2*>(p_new);
+                double2* p2 = reinterpret_cast<double2*>(a.p);
                 for (int64_t i = gtid; i < n2; i += gstride) {
-                    const double2 zv = z2[i], ov = o2[i];
+                    const double2 zv = z2[i], ov = p2[i];
                     p2[i] = make_double2(fma(beta, ov.x, zv.x), fma(beta, ov.y, zv.y));
                 }
-                if ((no & 1) && gtid == 0) p_new[no - 1] = fma(beta, p_old[no - 1], a.z[no - 1]);
+                if ((a.n_local & 1) && gtid == 0) a.p[a.n_local - 1] = fma(beta, a.p[a.n_local - 1], a.z[a.n_local - 1]);
             } else {
-                for (int64_t i = gtid; i < no; i += gstride) p_new[i] = fma(beta, p_old[i], a.z[i]);
+                for (int64_t i = gtid; i < a.n_local; i += gstride) a.p[i] = fma(beta, a.p[i], a.z[i]);
             }
             PS_MARK(0);
-            if (!ps_grid_barrier(a, sy, G) || !ps_halo_wait(a, hseq)) {
+            if (!ps_grid_barrier(a, sy, G)) {
                 status = 3;
                 break;
             }
@@ -370,9 +379,9 @@ __global__ void __launch_bounds__(PS_THREADS, BK_CTAS_PER_SM) k_pcg_persist(Pers
             {
                 auto epi = [&](int64_t row, double s) {
                     a.q[row] = s;
-                    pq = fma(p_new[row], s, pq);
+                    pq = fma(a.p[row], s, pq);
                 };
-                ps_spmv<BS, BSR>(a, p_new, epi, bk_smem, &tile);
+                ps_spmv<BS, BSR>(a, a.p, epi, bk_smem, &tile);
             }
             double v1[1] = {pq};
             PS_MARK(2);
@@ -382,11 +391,12 @@ __global__ void __launch_bounds__(PS_THREADS, BK_CTAS_PER_SM) k_pcg_persist(Pers
             }
             PS_MARK(3);
             const double alpha = rz / v1[0];
-            // ---- U: x, r, z, r.z, r.r
+            // ---- U: x, r, z, r.z, r.r; the halo of the new z leaves inside the reduction
             double v2[2] = {0.0, 0.0};
-            pcg_update_rows<BS>(a.x, a.r, a.z, p_new, a.q, a.minv, n_nodes, alpha, v2[0], v2[1]);
+            pcg_update_rows<BS>(a.x, a.r, a.z, a.p, a.q, a.minv, n_nodes, alpha, v2[0], v2[1]);
             PS_MARK(4);
-            if (!ps_reduce_bcast<2>(v2, a, sy, G)) {
+            hseq = ++sy.seq_halo;
+            if (!ps_reduce_bcast<2>(v2, a, sy, G, [&] { ps_halo_push(a, a.z, hseq, G); })) {
                 status = 3;
                 break;
             }
@@ -402,24 +412,31 @@ __global__ void __launch_bounds__(PS_THREADS, BK_CTAS_PER_SM) k_pcg_persist(Pers
             if (!(rr > tol2)) break;
         }
     }
-    // ---- ghosts of the solution: the boundary entries of x travel through the pa buffer of the window
+    // ---- ghosts of the solution: the boundary entries of x travel through the ghost tail of z in the window
     if (a.world > 1 && status != 3) {
-        const unsigned long long hseq = ++sy.seq_halo;
-        if (bb > 0.0) {
-            ps_halo_push(a, nullptr, a.x, 0.0, 0, hseq, G);
-        } else {
-            ps_halo_push(a, nullptr, a.pa, 0.0, 0, hseq, G);  // b = 0: x = 0 (pa is still all zero)
-        }
+        // every rank has consumed (or will never read) the last z halo: drain it first so that the pushes of x below
+        // cannot be overtaken by it, then push x behind one more cross-rank reduction
         if (!ps_halo_wait(a, hseq)) status = 3;
-        else
-            for (int64_t i = no + gtid; i < a.n_local; i += gstride) a.x[i] = a.pa[i];
-        // nobody may start the next solve's pushes into pa before every rank has copied its ghosts: one more
-        // reduce-broadcast acts as the closing barrier across ranks
         double v0[1] = {0.0};
         if (status != 3 && !ps_reduce_bcast<1>(v0, a, sy, G)) status = 3;
+        if (status != 3) {
+            if (!(bb > 0.0))
+                for (int64_t i = gtid; i < no; i += gstride) a.x[i] = 0.0;  // b = 0: the solution is 0 whatever x0 was
+            __syncthreads();
+            if (!ps_grid_barrier(a, sy, G)) status = 3;
+        }
+        if (status != 3) {
+            const unsigned long long xseq = ++sy.seq_halo;
+            ps_halo_push(a, a.x, xseq, G);
+            if (!ps_halo_wait(a, xseq)) status = 3;
+            else
+                for (int64_t i = no + gtid; i < a.n_local; i += gstride) a.x[i] = a.z[i];
+            // nobody may start the next solve's pushes into the z tail before every rank has copied its ghosts
+            if (status != 3 && !ps_reduce_bcast<1>(v0, a, sy, G)) status = 3;
+        }
+    } else if (!(bb > 0.0) && status == 0) {
+        for (int64_t i = gtid; i < no; i += gstride) a.x[i] = 0.0;
     }
-    if (!(bb > 0.0) && status == 0)
-        for (int64_t i = gtid; i < no; i += gstride) a.x[i] = 0.0;  // b = 0: the solution is 0 whatever x0 was
     if (blockIdx.x == 0 && tid == 0) {
         a.out_sc[0] = rr;
         a.out_sc[1] = bb;
@@ -430,8 +447,8 @@ __global__ void __launch_bounds__(PS_THREADS, BK_CTAS_PER_SM) k_pcg_persist(Pers
     }
 }
 
-/* d_work: r z q (stride ns = n_owned rounded up to even) | M^-1 (even(n_owned*block)) | pa pb (even(n_local) each, used
- * only without a peer window) => 3*ns + even(n_owned*block) + 2*even(n_local) + 8 doubles. */
+/* d_work: r q (stride ns = n_owned rounded up to even) | M^-1 (even(n_owned*block)) | p, z (even(n_local) each; with a
+ * peer window z lives there instead) => 2*ns + even(n_owned*block) + 2*even(n_local) + 8 doubles. */
 extern "C" int32_t pgd_pcg_persist_sync(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
                                         const double* d_b, double* d_x, int64_t n_owned, int64_t n_local, int32_t block,
                                         double rtol, double atol, int32_t maxit, int32_t warm, double* d_work,
@@ -466,19 +483,16 @@ extern "C" int32_t pgd_pcg_persist_sync(pgd_handle_t h, const int32_t* d_rowptr,
     const int64_t ns = (n_owned + 1) & ~(int64_t)1;
     const int64_t nl2 = (n_local + 1) & ~(int64_t)1;
     a.r = d_work;
-    a.z = a.r + ns;
-    a.q = a.z + ns;
+    a.q = a.r + ns;
     a.minv = a.q + ns;
-    double* ploc = a.minv + ((n_owned * block + 1) & ~(int64_t)1);
+    a.p = a.minv + ((n_owned * block + 1) & ~(int64_t)1);
+    a.z = a.p + nl2;
     a.world = world;
     a.me = multi ? h->win_rank : 0;
     a.lay = PwLayout{multi ? h->win_pcap : 0};
     if (multi) {
-        const int64_t half = (h->win_pcap / 2) & ~(int64_t)1;
-        PGD_ARG(h, n_local <= half, "peer window too small for two direction buffers");
-        a.pb_off = half;
-        a.pa = reinterpret_cast<double*>(h->win_local);
-        a.pb = a.pa + half;
+        PGD_ARG(h, n_local <= h->win_pcap, "peer window too small");
+        a.z = reinterpret_cast<double*>(h->win_local);
         int64_t n_send = 0;
         a.hp.seg_start[0] = 0;
         for (int r = 0; r < PW_MAXR; ++r) {
@@ -492,9 +506,6 @@ extern "C" int32_t pgd_pcg_persist_sync(pgd_handle_t h, const int32_t* d_rowptr,
         a.send_idx = d_send_idx;
         a.n_send = n_send;
     } else {
-        a.pa = ploc;
-        a.pb = ploc + nl2;
-        a.pb_off = nl2;
         a.peers.base[0] = reinterpret_cast<unsigned char*>(h->mailbox);
     }
     a.part = h->partials;
@@ -540,6 +551,8 @@ extern "C" int32_t pgd_pcg_persist_sync(pgd_handle_t h, const int32_t* d_rowptr,
     if (per_sm > BK_CTAS_PER_SM) per_sm = BK_CTAS_PER_SM;
     const int G = per_sm * h->sm_count;
     if ((size_t)G * 8 > PGD_MAX_PARTIALS) return -4;
+    a.n_push = multi ? (unsigned int)((a.n_send + PS_THREADS - 1) / PS_THREADS) : 0u;
+    if (a.n_push > (unsigned int)G) a.n_push = (unsigned int)G;
     void* kargs[] = {&a};
     PGD_CUDA(h, cudaEventRecord(h->ev0, st));
     PGD_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3(G), dim3(PS_THREADS), kargs, smem, st));

@@ -133,6 +133,10 @@ class PGDProblem:
         self.stop_fp = "norm"
         self.fp_init = ""
         self.norm_modes = "stiff"
+        # optional: number of fixed-point sweeps per enrichment step (overrides the stopping test of that step; steps
+        # beyond the list use the test).  Lets two runs be compared at identical sweep counts when the "norm" test
+        # sits on its round-off floor (DESIGN.md "Parity status").
+        self.fp_schedule = None
         self.simulation_info = (
             "PGD solver option: PGD_nmax %s / PGD tolerance %s and max FP iterations %s and FP tolerance %s; \n"
             % (self.PGD_nmax, self.PGD_tol, self.max_fp_it, self.tol_fp_it))
@@ -410,6 +414,7 @@ class PGDProblem:
         stop = self.stop_fp.lower()
         if stop not in ("norm", "delta"):
             raise ValueError('stopping criterion not defined %s (self.stop_fp = "delta" or "norm")')
+        forced = self.fp_schedule[n_enr] if (self.fp_schedule is not None and n_enr < len(self.fp_schedule)) else None
         for fpi in range(self.max_fp_it):
             for dim in self.seq_fp:
                 # warm start of the iterative spatial solves: the previous sweep's mode of this dimension
@@ -432,6 +437,8 @@ class PGDProblem:
                     mx = float(mx.item())
                     delta[dim] = mx if at < 1e-8 else mx / at
                 notconv = len(np.where(delta > self.tol_fp_it)[0]) > 0
+                if forced is not None:
+                    notconv = fpi + 1 < forced
                 if notconv and fpi < self.max_fp_it - 1:
                     Fs_init = list(Fs)
                     continue
@@ -460,7 +467,7 @@ class PGDProblem:
                 newold *= _f(no)
                 oldold *= _f(oo)
             max_error = np.sqrt(np.absolute(newnew + oldold - 2 * newold))
-            if max_error < self.tol_fp_it:
+            if (max_error < self.tol_fp_it) if forced is None else (fpi + 1 >= forced):
                 self.logger.info(f"fix point iteration converged !!! in number of steps: {fpi + 1} (error {max_error:8.6e})")
                 self.simulation_info += f"enrichment step {n_enr} fixed point iteration converged in {fpi + 1} / error: {max_error:8.6e} \n"
                 self.num_fp_it.append(fpi + 1)

@@ -172,3 +172,67 @@ def test_config2_heat2d_tk_full_size_against_time_stepping():
         worst = max(worst, err)
     print("heat2d_tk full size: worst relative space-time error vs time stepping", worst)
     assert worst < 2e-3  # measured 6.5e-4 with 20 modes
+
+
+# ------------------------------------------------------------------------------ parity at the sizes that are benchmarked
+def _compare_pinned(make, solve_kw, o, tol=MODE_RTOL, n_modes=None):
+    """Product run against the oracle run o at identical sweep counts (a run whose counts differ -- the "norm" test on
+    its round-off floor -- is repeated with the oracle's schedule pinned; the tolerance stays)."""
+    p = make()
+    p.solve_PGD(**solve_kw)
+    n_modes = min(p.PGD_modes, o.PGD_modes) if n_modes is None else n_modes
+    if list(p.num_fp_it[:n_modes]) != list(o.num_fp_it[:n_modes]):
+        first = list(p.num_fp_it)
+        p = make()
+        p.fp_schedule = list(o.num_fp_it)
+        p.solve_PGD(**solve_kw)
+        assert list(p.num_fp_it[:n_modes]) == list(o.num_fp_it[:n_modes]), (first, p.num_fp_it, o.num_fp_it)
+    worst = 0.0
+    for d in range(len(p.V)):
+        for k in range(n_modes):
+            worst = max(worst, _mode_err(p.PGD_func[d][k].vector()[:], o.PGD_func[d][k]))
+    assert worst < tol, worst
+    assert np.allclose(p.amplitude[:n_modes], o.amplitude[:n_modes], rtol=1e-7, atol=0)
+    return p, worst
+
+
+def test_config2_heat2d_tk_full_size_20_modes_against_oracle():
+    """BASELINE configs[1] at FULL size (66 049 dofs x 200 x 50) and full mode count (20) against oracle.solve_pgd
+    (SuperLU = the reference's direct-LU class): every mode to 1e-8, identical fixed-point sweep counts."""
+    from pgdrome_b200 import configs
+
+    make = lambda: configs.heat2d_tk(n=256, nt=199, nk=49, PGD_nmax=20)
+    o, _ = oprob.heat2d_tk(n=256, nt=199, nk=49, PGD_nmax=20, spaces=_ospaces(make()))
+    opgd.solve_pgd(o)
+    p, worst = _compare_pinned(make, dict(_problem="linear"), o, tol=1e-8)
+    assert p.PGD_modes == o.PGD_modes == 20
+
+
+def test_config3_elasticity3d_persistent_kernel_against_oracle():
+    """configs[2] at n = 22 (36 501 dofs: the smallest size that takes the HBM-regime code path -- persistent
+    cooperative PCG with the node-block walk) against the oracle in CG mode (C node-block-Jacobi PCG), 3 modes."""
+    from pgdrome_b200 import _lib, configs
+
+    kw = dict(n=22, nE=12, nF=2, PGD_nmax=3)
+    make = lambda: configs.elasticity3d(**kw)
+    o, _ = oprob.elasticity3d(spaces=_ospaces(make()), solver="ccg", cg_block=[3, 1, 1], **kw)
+    opgd.solve_pgd(o)
+    s0 = _lib.stats()
+    p, worst = _compare_pinned(make, dict(_problem="linear", settings={"linear_solver": "cg"}), o, tol=1e-8)
+    s1 = _lib.stats()
+    assert p.PGD_modes == 3
+    assert s1["pcg_solves"] > s0["pcg_solves"] and s1["pcg_resident_solves"] == s0["pcg_resident_solves"]  # not the SM-resident solver
+    # node-block-Jacobi PCG on both sides: iteration counts of the spatial solves agree closely
+    assert abs(p.solver_stats["pcg_iterations"] - sum(o.cg_iterations)) <= 0.02 * sum(o.cg_iterations) + 5
+
+
+def test_config4_thermal3d_streaming_kernels_against_oracle():
+    """configs[3] at n = 32 (35 937 dofs: three-launch streaming PCG with the TMA SpMV) against the oracle in CG mode."""
+    from pgdrome_b200 import configs
+
+    kw = dict(n=32, nt=40, nP=5, nv=5, n_src=3, PGD_nmax=2)
+    make = lambda: configs.thermal3d(**kw)
+    o, _ = oprob.thermal3d(spaces=_ospaces(make()), solver="ccg", **kw)
+    opgd.solve_pgd(o)
+    p, worst = _compare_pinned(make, dict(_problem="linear", solve_modes=None, settings={"linear_solver": "cg"}), o, tol=1e-8)
+    assert p.PGD_modes == 2

@@ -39,17 +39,25 @@ def _mode_err(a, b):
     return min(np.linalg.norm(a - b), np.linalg.norm(a + b)) / np.linalg.norm(b)
 
 
-def _compare(p, o, n_modes=None, tol=MODE_RTOL, floor_ok=False):
+def _compare(p, o, n_modes=None, tol=MODE_RTOL, floor_ok=False, rerun=None):
+    """Modes / amplitudes of the product run p against the oracle run o at IDENTICAL sweep counts.  The counts must
+    agree by themselves, except (floor_ok) where the "norm" test sits on its round-off floor: there the
+    product is run again with the oracle's sweep schedule pinned (``rerun(schedule) -> p``) and compared at the same
+    tolerance -- the tolerance is never widened."""
     n_modes = min(p.PGD_modes, o.PGD_modes) if n_modes is None else n_modes
     for n in range(n_modes):
         same = p.num_fp_it[n] == o.num_fp_it[n]
         at_floor = floor_ok and min(float(np.max(p.err_fp_it[n])), float(np.max(o.err_fp_it[n]))) < 4 * o.fp_floor[n]
         assert same or at_floor, (n, p.num_fp_it, o.num_fp_it)
+    if list(p.num_fp_it[:n_modes]) != list(o.num_fp_it[:n_modes]):
+        assert rerun is not None, (p.num_fp_it, o.num_fp_it)
+        p = rerun(list(o.num_fp_it))
+        assert list(p.num_fp_it[:n_modes]) == list(o.num_fp_it[:n_modes])
     for d in range(len(p.V)):
         for k in range(n_modes):
             assert _mode_err(p.PGD_func[d][k].vector()[:], o.PGD_func[d][k]) < tol, (d, k)
-    same_counts = list(p.num_fp_it[:n_modes]) == list(o.num_fp_it[:n_modes])
-    assert np.allclose(p.amplitude[:n_modes], o.amplitude[:n_modes], rtol=1e-7 if same_counts else 5e-6, atol=0)
+    assert np.allclose(p.amplitude[:n_modes], o.amplitude[:n_modes], rtol=1e-7, atol=0)
+    return p
 
 
 def _pgd_point(p, coord):
@@ -102,7 +110,13 @@ def case_laplace_fem():
     o, info = oprob.laplace_xyqu("FEM", spaces=_ospaces(p))
     opgd.solve_pgd(o)
     assert p.PGD_modes == 1 == o.PGD_modes
-    _compare(p, o, floor_ok=True)
+
+    def pinned(schedule):
+        q, _ = ref_cases.laplace_fem()
+        q.fp_schedule = schedule
+        return q.solve_PGD(_problem="linear")
+
+    p = _compare(p, o, floor_ok=True, rerun=pinned)
     x = p.V[0].tabulate_dof_coordinates()[:, 0]
     rng = np.random.default_rng(0)
     errs = []
@@ -123,15 +137,21 @@ def case_elasticity2d():
     o, _ = oprob.elasticity2d(spaces=_ospaces(p), **kw)
     opgd.solve_pgd(o)
     assert p.PGD_modes == o.PGD_modes == 3
-    # the first mode stops on the round-off floor of the "norm" test (floor 3e-4 > tol_fp_it 1e-4), a sweep more
-    # or less there shifts the following modes at the 1e-7 level
-    _compare(p, o, floor_ok=True, tol=1e-8 if list(p.num_fp_it) == list(o.num_fp_it) else 1e-6)
+    # the first mode stops on the round-off floor of the "norm" test (floor 3e-4 > tol_fp_it 1e-4): a sweep more or
+    # less there shifts the following modes at the 1e-7 level, so a run whose counts differ is repeated with the
+    # oracle's sweep schedule pinned and held to the same 1e-8
+
+    def pinned(schedule):
+        r = ref_cases.elasticity2d(**kw)
+        r.fp_schedule = schedule
+        return r.solve_PGD(_problem="linear")
+
+    p = _compare(p, o, floor_ok=True, rerun=pinned)
     q = ref_cases.elasticity2d(**kw)
-    q.solve_PGD()  # Newton path
-    if q.num_fp_it == p.num_fp_it:
-        assert np.allclose(p.amplitude, q.amplitude, rtol=1e-8, atol=0)
-    else:
-        assert np.allclose(p.amplitude, q.amplitude, rtol=1e-6, atol=0)
+    q.fp_schedule = list(p.num_fp_it)  # Newton path at the linear path's sweep counts (test_solver_problem.py:748-752)
+    q.solve_PGD()
+    assert q.num_fp_it == p.num_fp_it
+    assert np.allclose(p.amplitude, q.amplitude, rtol=1e-8, atol=0)
 
 
 CASES = [("truss", case_truss, ()), ("heat1d_fem_heating", case_heat1d, ("FEM", "heating")),

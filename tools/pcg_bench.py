@@ -45,6 +45,57 @@ def operator(mesh_n, bs):
     return V, ds, vals
 
 
+def run_sharded(mesh_n=68, bs=3, iters=200, hbm_peak=6451.2):
+    """torchrun: the same operator element-partitioned over the ranks; per-iteration time and phase profile of the
+    persistent sharded PCG (max over ranks)."""
+    import torch.distributed as dist
+
+    from pgdrome_b200 import _lib, partition as pt, sharding
+
+    rank, world = dist.get_rank(), dist.get_world_size()
+    sharding.configure(mode=True)
+    V, ds, vals = operator(mesh_n, bs)
+    sh = ds.shard
+    dev = vals.device
+    halo = sh.halo(dev)
+    S = pt.ShardedMatrix(ds.rowptr_owned, ds.pattern[1][: ds.nnz_owned], vals[: ds.nnz_owned], halo,
+                         int(sh.part.bounds[rank]), int(sh.part.bounds[rank + 1]), bs)
+    xg = np.random.default_rng(0).uniform(-1, 1, V.n_dofs)
+    x = sh.scatter(xg, dev)
+    b = torch.zeros(sh.n_local, dtype=torch.float64, device=dev)
+    _lib.spmv(ds.rowptr_owned, ds.pattern[1], vals, x, y=b)
+    _lib.set_option("spin_ms", 5000)
+    out = {"mesh": "BoxMesh %d^3, P1 bs=%d" % (mesh_n, bs), "world": world, "n_dofs": V.n_dofs, "rows_rank0": sh.n_owned,
+           "ghosts_rank0": sh.n_ghost, "nnz_rank0": ds.nnz_owned, "hbm_peak_gbs": hbm_peak}
+    for name, bsr in (("persist_bsr", ds.bsr), ("persist_csr", None)):
+        if name == "persist_bsr" and bsr is None:
+            continue
+        pt.sharded_solve(S, b, rtol=1e-30, maxit=10, block=bs, bsr=bsr)
+        _lib.set_option("prof", 1)
+        _lib.phase_ns(reset=True)
+        pt.sharded_solve(S, b, rtol=1e-30, maxit=iters, block=bs, bsr=bsr)
+        ph = _lib.phase_ns(reset=True)
+        _lib.set_option("prof", 0)
+        torch.cuda.synchronize()
+        dist.barrier()
+        _lib.stats(reset=True)
+        pt.sharded_solve(S, b, rtol=1e-30, maxit=iters, block=bs, bsr=bsr)
+        s = _lib.stats()
+        ms = torch.tensor([s["pcg_ms"] / max(s["pcg_iters"], 1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = float(ms.item())
+        loc = 12 * ds.nnz_owned + 4 * (sh.n_owned + 1) + 56 * sh.n_owned
+        xs, its, rr = pt.sharded_solve(S, b, rtol=1e-13, maxit=20000, block=bs, bsr=bsr)
+        err = torch.tensor([float((xs[: sh.n_owned] - x[: sh.n_owned]).pow(2).sum()), float(x[: sh.n_owned].pow(2).sum())],
+                           dtype=torch.float64, device=dev)
+        dist.all_reduce(err)
+        ghost_ok = bool(torch.allclose(xs[sh.n_owned:], x[sh.n_owned:], rtol=0, atol=1e-8))
+        out[name] = {"ms_per_iteration": ms, "local_bytes": loc, "local_gbs": loc / (ms * 1e-3) / 1e9,
+                     "frac_hbm_local": loc / (ms * 1e-3) / 1e9 / hbm_peak, "phase_us_per_iteration_rank0": {k: v / 1e3 / iters for k, v in ph.items()},
+                     "solve": {"iters": its, "relres": rr, "err": float((err[0] / err[1]).sqrt()), "ghosts_of_solution_ok": ghost_ok}}
+    return out if rank == 0 else None
+
+
 def run(mesh_n=68, bs=3, iters=200, profile=False, hbm_peak=6451.2):
     from pgdrome_b200 import _lib
 
@@ -146,4 +197,15 @@ if __name__ == "__main__":
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", peak)
     except Exception:
         pass
-    print(json.dumps(run(a.mesh, a.bs, a.iters, a.profile, peak)))
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        r = run_sharded(a.mesh, a.bs, a.iters, peak)
+        if r is not None:
+            print(json.dumps(r))
+        dist.destroy_process_group()
+    else:
+        print(json.dumps(run(a.mesh, a.bs, a.iters, a.profile, peak)))

@@ -35,6 +35,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from pgdrome_b200 import _lib, configs
 
+    _lib.set_option("spin_ms", 10000)
     peak = 6451.2
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", peak)
@@ -63,11 +64,11 @@ def main():
         if done:
             break
     ds = p.V[0]._dev["device_space"]
-    n, nnz = ds.n_dofs, ds.nnz
+    n, nnz = ds.n_owned, ds.nnz_owned  # partitioned space: this rank's rows
     s = _lib.stats()
     it_bytes = 12 * nnz + 4 * (n + 1) + 56 * n
     it_ms = s["pcg_ms"] / max(s["pcg_iters"], 1)
-    out = {"config": a.config, "world": world, "sharded_solves": p.solver_stats.get("sharded_solves", 0), "spatial_dofs": n, "nnz": nnz, "dims": [v.n_dofs for v in p.V], "modes": p.PGD_modes,
+    out = {"config": a.config, "world": world, "global_spatial_dofs": p.V[0].n_dofs, "partitioned": ds.shard is not None, "sharded_solves": p.solver_stats.get("sharded_solves", 0), "spatial_dofs": n, "nnz": nnz, "dims": [v.n_dofs for v in p.V], "modes": p.PGD_modes,
            "build_problem_s": t_build, "steps": steps, "amplitude": [float(x) for x in p.amplitude],
            "pcg": {"iterations": s["pcg_iters"], "ms_per_iteration": it_ms, "bytes_per_iteration": it_bytes,
                    "gbs": it_bytes / (it_ms * 1e-3) / 1e9 if s["pcg_iters"] else None,
