@@ -12,9 +12,8 @@
  *   - return 0 = OK, >0 = cudaError_t, <0 = argument error; pgd_last_error(h) gives the text.
  *   - asynchronous on `stream` (a cudaStream_t passed as void*) unless the name ends in _sync.
  *   - one host thread and one stream at a time per handle; one handle per GPU / rank.
- *   - reductions are deterministic (fixed-order two-stage sums, no floating-point atomics); the one exception is
- *     the right-hand-side lifting of NON-ZERO Dirichlet values in pgd_apply_dirichlet (atomicAdd per touched row;
- *     every reference example prescribes 0, for which nothing is added).
+ *   - every result is deterministic and bitwise reproducible: reductions are fixed-order two-stage sums, there are no
+ *     floating-point atomics anywhere (the lifting of non-zero Dirichlet values is one SpMV).
  */
 #ifndef PGD_B200_H
 #define PGD_B200_H
@@ -113,10 +112,12 @@ int32_t pgd_scalar_programs(pgd_handle_t h, int32_t n_prog, const int32_t* h_off
 
 /* ---- Dirichlet (DirichletBC.apply / assemble_system symmetric elimination, solver.py:186-191,
  * 364-372,704-716): zero row+col of every bc dof, diagonal 1, b lifted and set.  d_bc_vals may be
- * NULL (all reference BC values are 0).  Pattern must be structurally symmetric. d_b may be NULL. */
+ * NULL (all reference BC values are 0).  Pattern must be structurally symmetric. d_b may be NULL.
+ * Non-zero values: b -= A g is formed first as one SpMV with the un-eliminated operator (deterministic); this needs
+ * n_rows (rows of the pattern) and d_work of 2 * n_rows doubles -- both ignored when d_bc_vals is NULL. */
 int32_t pgd_apply_dirichlet(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, double* d_values,
                             double* d_b, const int32_t* d_bc_dofs, const double* d_bc_vals, int64_t n_bc,
-                            void* stream);
+                            int64_t n_rows, double* d_work, void* stream);
 int32_t pgd_set_entries(pgd_handle_t h, double* d_x, const int32_t* d_idx, const double* d_vals, int64_t n_idx,
                         void* stream);
 
@@ -195,7 +196,10 @@ int32_t pgd_spcg_solve_sync(pgd_handle_t h, const int32_t* d_rowptr, const int32
  * neighbours store their boundary values of p straight into the ghost tail over NVLink and publish a
  * sequence flag (st.release.sys); the dot products are reduced by a one-shot mailbox all-reduce summed in
  * rank order (bitwise identical on all ranks).  pgd_set_option("p2p", 0) falls back to NCCL.  Returns -6 if
- * a peer does not arrive within ~2 s (instead of hanging the GPU). */
+ * a peer does not arrive within the "spin_ms" budget (default 20 s) instead of hanging the GPU; -6 is fatal for the
+ * WINDOW (the ranks' sequence numbers may have diverged): it is disabled and later solves run over NCCL until a new
+ * window is created and opened collectively.  pgd_peer_window_create on a handle that already has a window closes
+ * the old peer mappings and frees it first (put a barrier across the ranks in front). */
 int32_t pgd_peer_window_create(pgd_handle_t h, int64_t p_capacity, void* h_ipc64);
 int32_t pgd_peer_window_open(pgd_handle_t h, int32_t rank, int32_t world, const void* h_all_ipc);
 int32_t pgd_peer_window_destroy(pgd_handle_t h);

@@ -33,7 +33,7 @@ SIGNATURES = {
     "pgd_gather_values": [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp],
     "pgd_assemble_p1": [c_vp, c_vp, c_vp, c_i64, c_i32, c_dbl, c_dbl, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp],
     "pgd_lincomb": [c_vp, c_i32, c_vp, c_vp, c_i64, c_vp, c_i32, c_vp],
-    "pgd_apply_dirichlet": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp],
+    "pgd_apply_dirichlet": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp],
     "pgd_set_entries": [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp],
     "pgd_spmv": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp],
     "pgd_spmv_dot": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp],
@@ -295,6 +295,8 @@ def peer_window(n_local, group=None):
     if key in _WINDOW and _WINDOW[key] >= need:
         return rank, world
     cap = max(need + need // 8, 1024)
+    if key in _WINDOW:
+        dist.barrier(group=group)  # growing: no rank may free its old window while a peer can still be using it
     buf = (ctypes.c_ubyte * 64)()
     _check(lib.pgd_peer_window_create(h, cap, ctypes.cast(buf, c_vp)), h, "pgd_peer_window_create")
     mine = torch.tensor(list(buf), dtype=torch.uint8, device="cuda")
@@ -499,9 +501,12 @@ def apply_dirichlet(rowptr, colidx, values, b, bc_dofs, bc_vals=None):
     if bc_dofs is None or bc_dofs.numel() == 0:
         return
     h, lib = handle(rowptr.device), load_library()
+    n = rowptr.numel() - 1
+    work = torch.empty(2 * n, dtype=F64, device=rowptr.device) if (bc_vals is not None and values is not None and b is not None) else None
     _check(lib.pgd_apply_dirichlet(h, _p(rowptr, I32), _p(colidx, I32), _p(values, F64) if values is not None else c_vp(0),
                                    _p(b, F64) if b is not None else c_vp(0), _p(bc_dofs, I32),
-                                   _p(bc_vals, F64) if bc_vals is not None else c_vp(0), bc_dofs.numel(), _stream()), h,
+                                   _p(bc_vals, F64) if bc_vals is not None else c_vp(0), bc_dofs.numel(), n,
+                                   _p(work, F64) if work is not None else c_vp(0), _stream()), h,
            "pgd_apply_dirichlet")
 
 

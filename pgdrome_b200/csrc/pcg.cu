@@ -314,6 +314,8 @@ static int32_t run_pcg(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const d
     }
     if (h_iters) *h_iters = hf[F_ITER];
     if (h_relres) *h_relres = (hs[S_BB] > 0.0) ? sqrt(hs[S_RR] / hs[S_BB]) : 0.0;
+    if (!(hs[S_BB] > 0.0) && warm)  // b = 0: the solution is 0 whatever the initial guess was (as in the SM-resident solver)
+        PGD_CUDA(h, cudaMemsetAsync(x, 0, sizeof(double) * n, st));
     if (hf[F_BAD]) {
         snprintf(h->err, sizeof(h->err), "pgd_pcg_sync: NaN encountered (matrix not SPD?)");
         return -3;

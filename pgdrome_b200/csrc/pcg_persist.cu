@@ -211,12 +211,14 @@ __device__ __forceinline__ bool ps_reduce_bcast(double (&v)[NV], const PersistAr
     return ok;
 }
 
-// boundary entries of v -> the neighbours' ghost slots of their z buffer (window offset 0); executed by the LAST
-// n_push CTAs of the grid only (the others return at once: no system-scope fence on their path); the last of them
-// to finish publishes the halo flag on every destination.
-__device__ __forceinline__ void ps_halo_push(const PersistArgs& a, const double* v, unsigned long long seq, unsigned int G) {
+// Halo push in two halves, executed by the LAST n_push CTAs of the grid only (the others return at once):
+//   issue   boundary entries of v -> the neighbours' ghost slots of their z buffer (window offset 0), plain remote stores;
+//   commit  one system-scope fence per CTA (by then the stores have long been acknowledged: the cross-rank part of the
+//           reduction sits between the two halves), ticket, and the last CTA publishes the halo flag on every destination.
+// (Fencing right behind the stores put the NVLink round trip on the critical path of the pushing CTAs: 5.4 us of
+// grid-barrier wait per iteration at 2 GPUs.)
+__device__ __forceinline__ void ps_halo_issue(const PersistArgs& a, const double* v, unsigned int G) {
     if (a.n_push == 0 || blockIdx.x < G - a.n_push) return;
-    __shared__ bool s_last;
     const int64_t first = (int64_t)(blockIdx.x - (G - a.n_push)) * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)a.n_push * blockDim.x;
     for (int64_t s = first; s < a.n_send; s += stride) {
@@ -225,9 +227,13 @@ __device__ __forceinline__ void ps_halo_push(const PersistArgs& a, const double*
         double* dst = reinterpret_cast<double*>(a.peers.base[r]) + a.hp.dst_off[r] + (s - a.hp.seg_start[r]);
         *dst = v[a.send_idx[s]];
     }
-    __threadfence_system();
-    __syncthreads();
+}
+__device__ __forceinline__ void ps_halo_commit(const PersistArgs& a, unsigned long long seq, unsigned int G) {
+    if (a.n_push == 0 || blockIdx.x < G - a.n_push) return;
+    __shared__ bool s_last;
+    __syncthreads();  // every store of this CTA is ordered before thread 0's fence (CTA barrier + cumulativity)
     if (threadIdx.x == 0) {
+        __threadfence_system();
         const unsigned int t = atomicAdd(a.push_ctr, 1u);
         s_last = (t == a.n_push - 1);
     }
@@ -239,6 +245,10 @@ __device__ __forceinline__ void ps_halo_push(const PersistArgs& a, const double*
             st_release_sys(reinterpret_cast<unsigned long long*>(a.peers.base[r] + a.lay.haloflag_off()) + a.me, seq);
         if (threadIdx.x == 0) *a.push_ctr = 0u;
     }
+}
+__device__ __forceinline__ void ps_halo_push(const PersistArgs& a, const double* v, unsigned long long seq, unsigned int G) {
+    ps_halo_issue(a, v, G);
+    ps_halo_commit(a, seq, G);
 }
 
 // all threads call; the threads r < world acquire the halo flag of rank r; false = aborted
@@ -338,7 +348,8 @@ __global__ void __launch_bounds__(PS_THREADS, BK_CTAS_PER_SM) k_pcg_persist(Pers
             }
             for (int64_t i = gtid; i < a.n_local; i += gstride) a.p[i] = 0.0;
             hseq = ++sy.seq_halo;
-            if (!ps_reduce_bcast<3>(v, a, sy, G, [&] { ps_halo_push(a, a.z, hseq, G); })) status = 3;
+            if (!ps_reduce_bcast<3>(v, a, sy, G, [&] { ps_halo_issue(a, a.z, G); })) status = 3;
+            ps_halo_commit(a, hseq, G);
         }
         rz = v[0];
         bb = v[1];
@@ -351,22 +362,26 @@ __global__ void __launch_bounds__(PS_THREADS, BK_CTAS_PER_SM) k_pcg_persist(Pers
     if (status == 0 && rr > tol2 && bb > 0.0) {
         while (it < a.maxit) {
             const double beta = (it == 0) ? 0.0 : rz / rz_old;
-            // ---- D: p = z + beta p on [owned | ghost] (the ghost entries of z were stored by the neighbours)
-            if (!ps_halo_wait(a, hseq)) {
-                status = 3;
-                break;
-            }
-            if ((((uintptr_t)a.z | (uintptr_t)a.p) & 15) == 0) {
-                const int64_t n2 = a.n_local >> 1;
-                const double2* z2 = reinterpret_cast<const double2*>(a.z);
-                double2* p2 = reinterpret_cast<double2*>(a.p);
-                for (int64_t i = gtid; i < n2; i += gstride) {
-                    const double2 zv = z2[i], ov = p2[i];
-                    p2[i] = make_double2(fma(beta, ov.x, zv.x), fma(beta, ov.y, zv.y));
+            // ---- D: p = z + beta p, owned entries first; the ghost entries of z (stored by the neighbours during the
+            // reduction above) are acquired only then, and the ghost entries of p follow the same recurrence
+            {
+                const int64_t noe = no & ~(int64_t)1;  // vector part of the owned range
+                if ((((uintptr_t)a.z | (uintptr_t)a.p) & 15) == 0) {
+                    const double2* z2 = reinterpret_cast<const double2*>(a.z);
+                    double2* p2 = reinterpret_cast<double2*>(a.p);
+                    for (int64_t i = gtid; i < (noe >> 1); i += gstride) {
+                        const double2 zv = z2[i], ov = p2[i];
+                        p2[i] = make_double2(fma(beta, ov.x, zv.x), fma(beta, ov.y, zv.y));
+                    }
+                    if (noe < no && gtid == 0) a.p[noe] = fma(beta, a.p[noe], a.z[noe]);
+                } else {
+                    for (int64_t i = gtid; i < no; i += gstride) a.p[i] = fma(beta, a.p[i], a.z[i]);
                 }
-                if ((a.n_local & 1) && gtid == 0) a.p[a.n_local - 1] = fma(beta, a.p[a.n_local - 1], a.z[a.n_local - 1]);
-            } else {
-                for (int64_t i = gtid; i < a.n_local; i += gstride) a.p[i] = fma(beta, a.p[i], a.z[i]);
+                if (!ps_halo_wait(a, hseq)) {
+                    status = 3;
+                    break;
+                }
+                for (int64_t i = no + gtid; i < a.n_local; i += gstride) a.p[i] = fma(beta, a.p[i], a.z[i]);
             }
             PS_MARK(0);
             if (!ps_grid_barrier(a, sy, G)) {
@@ -396,7 +411,9 @@ __global__ void __launch_bounds__(PS_THREADS, BK_CTAS_PER_SM) k_pcg_persist(Pers
             pcg_update_rows<BS>(a.x, a.r, a.z, a.p, a.q, a.minv, n_nodes, alpha, v2[0], v2[1]);
             PS_MARK(4);
             hseq = ++sy.seq_halo;
-            if (!ps_reduce_bcast<2>(v2, a, sy, G, [&] { ps_halo_push(a, a.z, hseq, G); })) {
+            const bool ok2 = ps_reduce_bcast<2>(v2, a, sy, G, [&] { ps_halo_issue(a, a.z, G); });
+            ps_halo_commit(a, hseq, G);
+            if (!ok2) {
                 status = 3;
                 break;
             }

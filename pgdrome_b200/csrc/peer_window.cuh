@@ -5,7 +5,6 @@
 
 #define PW_MAXR 16
 #define PW_AR_VALS 4
-#define PW_SPIN_BUDGET (4000000000LL)  // ~2 s at 1.9 GHz
 
 struct PwLayout {
     int64_t pcap;

@@ -131,6 +131,14 @@ __global__ void __launch_bounds__(256) k_halo_pack(const double* __restrict__ v,
 // ================================================================================================
 #include "peer_window.cuh"
 
+// wall-clock budget of every spin of this file (pgd_set_option "spin_ms"), refreshed at the start of each solve
+__device__ unsigned long long g_pw_budget_ns = 20000000000ULL;
+__device__ __forceinline__ unsigned long long pw_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 __global__ void __launch_bounds__(256) k_halo_push(const double* __restrict__ p, const int64_t* __restrict__ send_idx,
                                                    int64_t n_send, PwPeers peers, PwHalo hp, PwLayout lay, int me, int world,
                                                    const unsigned long long* seq_ctr, unsigned int* counter, const int* fl) {
@@ -168,9 +176,9 @@ __global__ void k_halo_wait(unsigned char* mine, PwHalo hp, PwLayout lay, int wo
     const int r = threadIdx.x;
     if (r < world && hp.recv_from[r]) {
         const unsigned long long* f = reinterpret_cast<const unsigned long long*>(mine + lay.haloflag_off()) + r;
-        const long long t0 = clock64();
+        const unsigned long long t0 = pw_now();
         while (ld_acquire_sys(f) < seq) {
-            if (clock64() - t0 > PW_SPIN_BUDGET) {
+            if (pw_now() - t0 > g_pw_budget_ns) {
                 fl[2] = 2;  // peer did not arrive: report instead of hanging
                 fl[0] = 1;
                 break;
@@ -198,9 +206,9 @@ __device__ __forceinline__ void ar_p2p_block(double* vals, int nv, const PwPeers
         st_release_sys(reinterpret_cast<unsigned long long*>(peers.base[r] + lay.arflag_off()) + par * PW_MAXR + me, seq);
         const unsigned long long* f =
             reinterpret_cast<const unsigned long long*>(peers.base[me] + lay.arflag_off()) + par * PW_MAXR + r;
-        const long long t0 = clock64();
+        const unsigned long long t0 = pw_now();
         while (ld_acquire_sys(f) < seq) {
-            if (clock64() - t0 > PW_SPIN_BUDGET) {
+            if (pw_now() - t0 > g_pw_budget_ns) {
                 s_bad = 1;
                 break;
             }
@@ -290,9 +298,9 @@ __global__ void __launch_bounds__(BK_THREADS, BK_CTAS_PER_SM) k_spcg_matvec_p2p(
     if ((int)threadIdx.x < world && hp.recv_from[threadIdx.x]) {
         const unsigned long long* f =
             reinterpret_cast<const unsigned long long*>(peers.base[me] + lay.haloflag_off()) + threadIdx.x;
-        const long long t0 = clock64();
+        const unsigned long long t0 = pw_now();
         while (ld_acquire_sys(f) < hseq) {
-            if (clock64() - t0 > PW_SPIN_BUDGET) {
+            if (pw_now() - t0 > g_pw_budget_ns) {
                 fl[F_BAD] = 2;
                 break;
             }
@@ -372,14 +380,14 @@ __global__ void __launch_bounds__(256) k_spcg_update_p2p(double* __restrict__ x,
     }
 }
 
+extern "C" int32_t pgd_peer_window_destroy(pgd_handle_t h);
+
 extern "C" int32_t pgd_peer_window_create(pgd_handle_t h, int64_t p_capacity, void* h_ipc64) {
     PGD_CHECK_HANDLE(h);
     PGD_ARG(h, p_capacity > 0 && h_ipc64, "bad arguments");
     pgd_set_device(h);
-    if (h->win_local) {
-        cudaFree(h->win_local);
-        h->win_local = nullptr;
-    }
+    if (h->win_local) pgd_peer_window_destroy(h);  // closes the peer mappings of the old window before it is freed (the
+                                                   // caller puts a barrier across the ranks in front: peers still map it)
     PwLayout lay{p_capacity};
     void* p = nullptr;
     PGD_CUDA(h, cudaMalloc(&p, lay.bytes()));
@@ -398,6 +406,13 @@ extern "C" int32_t pgd_peer_window_open(pgd_handle_t h, int32_t rank, int32_t wo
     PGD_CHECK_HANDLE(h);
     PGD_ARG(h, h->win_local && h_all_ipc && world >= 1 && world <= PW_MAXR && rank >= 0 && rank < world, "bad arguments");
     pgd_set_device(h);
+    for (int r = 0; r < h->win_world; ++r)  // re-open: drop the old mappings first
+        if (r != h->win_rank && h->win_peer[r]) cudaIpcCloseMemHandle(h->win_peer[r]);
+    h->win_world = 0;
+    {  // sequence numbers restart at 0 below: so must the flags and mailboxes of this rank's window
+        PwLayout lay0{h->win_pcap};
+        PGD_CUDA(h, cudaMemset((unsigned char*)h->win_local + lay0.slot_off(), 0, lay0.bytes() - lay0.slot_off()));
+    }
     for (int r = 0; r < world; ++r) {
         if (r == rank) {
             h->win_peer[r] = h->win_local;
@@ -414,6 +429,7 @@ extern "C" int32_t pgd_peer_window_open(pgd_handle_t h, int32_t rank, int32_t wo
     h->win_ar_seq = 0;
     h->win_halo_seq = 0;
     PGD_CUDA(h, cudaMemset(h->scalars + 40, 0, 2 * sizeof(double)));  // device-side sequence counters (halo, all-reduce)
+    PGD_CUDA(h, cudaDeviceSynchronize());
     return 0;
 }
 
@@ -425,6 +441,7 @@ extern "C" int32_t pgd_peer_window_destroy(pgd_handle_t h) {
     if (h->win_local) cudaFree(h->win_local);
     h->win_local = nullptr;
     h->win_world = 0;
+    for (int r = 0; r < PW_MAXR; ++r) h->win_peer[r] = nullptr;
     h->p_override = nullptr;
     return 0;
 }
@@ -483,6 +500,10 @@ extern "C" int32_t pgd_spcg_solve_sync(pgd_handle_t h, const int32_t* d_rowptr, 
         PGD_NCCL(h, g_nccl.AllReduce(vals, vals, (size_t)nv, ncclDouble, ncclSum, comm, st));
         return 0;
     };
+    if (p2p) {
+        const unsigned long long budget = (unsigned long long)h->opt_spin_ms * 1000000ULL;
+        PGD_CUDA(h, cudaMemcpyToSymbolAsync(g_pw_budget_ns, &budget, sizeof(budget), 0, cudaMemcpyHostToDevice, st));
+    }
     int32_t rc = pgd_spcg_init(h, d_rowptr, d_colidx, d_values, d_b, d_x, n_owned, n_local, block, d_work, sc, fl, stream);
     if (rc) return rc;
     if ((rc = allreduce(sc + 8, 3, 0, st))) return rc;
@@ -616,7 +637,11 @@ extern "C" int32_t pgd_spcg_solve_sync(pgd_handle_t h, const int32_t* d_rowptr, 
     if (h_iters) *h_iters = hf[1];
     if (h_relres) *h_relres = (hs[4] > 0.0) ? sqrt(hs[3] / hs[4]) : 0.0;
     if (hf[2] == 2) {
-        snprintf(h->err, sizeof(h->err), "pgd_spcg_solve_sync: a peer rank did not arrive at a halo / all-reduce flag in time");
+        // the ranks' sequence numbers may have diverged: the window is unusable from here on (fatal for the window, not
+        // for the solver: later solves take the NCCL path until a new window is created and opened collectively)
+        h->win_world = 0;
+        snprintf(h->err, sizeof(h->err), "pgd_spcg_solve_sync: a peer rank did not arrive at a halo / all-reduce flag within "
+                 "%d ms; the peer window has been disabled", h->opt_spin_ms);
         return -6;
     }
     if (hf[2]) {

@@ -102,10 +102,9 @@ template <int MODE>
 static int32_t launch_spmv(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const double* va, const double* x, double* y,
                            const double* w, int64_t n, double* dot, int lpr, cudaStream_t st) {
     if (h->opt_stream >= 2 && n >= PGD_BULK_MIN_ROWS && (((uintptr_t)ci | (uintptr_t)va) & 15) == 0) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        if (!(h->attr_mask & (1u << MODE))) {  // the opt-in is per device, i.e. per handle (not per process)
             PGD_CUDA(h, cudaFuncSetAttribute(k_spmv_bulk<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM_BYTES));
-            attr_set = true;
+            h->attr_mask |= (1u << MODE);
         }
         k_spmv_bulk<MODE><<<BK_CTAS_PER_SM * h->sm_count, SPMV_BULK_THREADS, BK_SMEM_BYTES, st>>>(rp, ci, va, x, y, w, n, dot, h->partials,
                                                                               h->counters);
@@ -184,15 +183,15 @@ extern "C" int32_t pgd_bilinear(pgd_handle_t h, const int32_t* d_rowptr, const i
 }
 
 // ----------------------------------------------------------------------------- Dirichlet
-// one warp per bc dof j: row j -> unit row; every (c, j) with c in pattern(row j) -> 0 (+ lifting)
+// one warp per bc dof j: row j -> unit row; every (c, j) with c in pattern(row j) -> 0.  The right-hand-side lifting of
+// non-zero values is NOT done here (it used to be an atomicAdd per touched row, i.e. order-dependent round-off): the
+// entry point below forms it beforehand as one deterministic SpMV with the un-eliminated operator.
 __global__ void __launch_bounds__(256) k_dirichlet(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
-                                                   double* __restrict__ vals, double* __restrict__ b,
-                                                   const int32_t* __restrict__ bc, const double* __restrict__ g, int64_t n_bc) {
+                                                   double* __restrict__ vals, const int32_t* __restrict__ bc, int64_t n_bc) {
     int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (wid >= n_bc) return;
     int j = bc[wid];
-    double gj = g ? g[wid] : 0.0;
     int k0 = rowptr[j], k1 = rowptr[j + 1];
     for (int k = k0 + lane; k < k1; k += 32) {
         int c = colidx[k];
@@ -206,7 +205,6 @@ __global__ void __launch_bounds__(256) k_dirichlet(const int32_t* __restrict__ r
                 int mid = (lo + hi) >> 1;
                 int cc = colidx[mid];
                 if (cc == j) {
-                    if (b && gj != 0.0) atomicAdd(&b[c], -vals[mid] * gj);
                     vals[mid] = 0.0;
                     break;
                 }
@@ -217,15 +215,34 @@ __global__ void __launch_bounds__(256) k_dirichlet(const int32_t* __restrict__ r
     }
 }
 
+__global__ void __launch_bounds__(256) k_axpy_neg(double* __restrict__ b, const double* __restrict__ y, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) b[i] -= y[i];
+}
+
 extern "C" int32_t pgd_apply_dirichlet(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, double* d_values,
                                        double* d_b, const int32_t* d_bc_dofs, const double* d_bc_vals, int64_t n_bc,
-                                       void* stream) {
+                                       int64_t n_rows, double* d_work, void* stream) {
     PGD_CHECK_HANDLE(h);
     if (n_bc <= 0) return 0;
     PGD_ARG(h, d_rowptr && d_colidx && d_bc_dofs, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
+    if (d_values && d_b && d_bc_vals) {
+        // lifting b -= A g with g = the prescribed values on the bc dofs, 0 elsewhere: one SpMV with the operator as
+        // it is BEFORE the elimination (fixed summation order per row => bitwise reproducible)
+        PGD_ARG(h, n_rows > 0 && d_work, "non-zero Dirichlet values need n_rows and 2 * n_rows doubles of work space");
+        double* g = d_work;
+        double* y = d_work + n_rows;
+        PGD_CUDA(h, cudaMemsetAsync(g, 0, sizeof(double) * n_rows, st));
+        int32_t rc = pgd_set_entries(h, g, d_bc_dofs, d_bc_vals, n_bc, stream);
+        if (rc) return rc;
+        rc = pgd_spmv_internal(h, d_rowptr, d_colidx, d_values, g, y, n_rows, 0, st);
+        if (rc) return rc;
+        k_axpy_neg<<<pgd_blocks(n_rows, 256), 256, 0, st>>>(d_b, y, n_rows);
+        PGD_LAUNCH_OK(h);
+    }
     if (d_values) {
-        k_dirichlet<<<pgd_blocks(n_bc * 32, 256), 256, 0, st>>>(d_rowptr, d_colidx, d_values, d_b, d_bc_dofs, d_bc_vals, n_bc);
+        k_dirichlet<<<pgd_blocks(n_bc * 32, 256), 256, 0, st>>>(d_rowptr, d_colidx, d_values, d_bc_dofs, n_bc);
         PGD_LAUNCH_OK(h);
     }
     if (d_b) return pgd_set_entries(h, d_b, d_bc_dofs, d_bc_vals, n_bc, stream);

@@ -634,7 +634,7 @@ class PGDProblem:
 
     def FD_solve(self, A, B, dim):
         """spsolve(A, B) of a user-assembled finite-difference system (solver.py:927-943) as a
-        banded LU on the device (dense LU through torch.linalg for bandwidth > 64)."""
+        banded LU with partial pivoting on the device (k_banded_lu, bandwidths up to 64: FD_matrices operators have 1)."""
         M = _CsrOnDevice(A)
         b = _lib.to_device(np.ascontiguousarray(np.asarray(B, dtype=np.float64).ravel()))
         if max(M.kl, M.ku) <= 64:
@@ -642,8 +642,10 @@ class PGDProblem:
             x, info = _lib.banded_solve(M.rowptr, M.colidx, M.values, b, perm, M.kl, M.ku)
             self._last_info = info
         else:
-            dense = _lib.to_device(sp.csr_matrix(A).toarray())
-            x = torch.linalg.solve(dense, b)
+            raise NotImplementedError(
+                "FD_solve: system with lower / upper bandwidth %d / %d; the device banded LU covers bandwidths up to 64 "
+                "(there is no library or CPU fallback). Reorder the unknowns along the coordinate, or solve this dimension "
+                'as "FEM".' % (M.kl, M.ku))
         self.solver_stats["banded_solves"] += 1
         return Function(self.V[dim], x)
 
