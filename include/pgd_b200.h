@@ -263,6 +263,13 @@ int32_t pgd_eval_gemv(pgd_handle_t h, const double* d_X, int64_t ldx, int32_t R,
 int32_t pgd_eval_gemm_f64(pgd_handle_t h, const double* d_W, int64_t ldw, const double* d_X, int64_t ldx,
                           int32_t R, int64_t C, int64_t N, double* d_U, int64_t ldu, void* stream);
 
+/* Row-wise reductions of a sweep U [C, ldu] (one row per parameter point) in one launch: d_stats[c*7 + ...] =
+ * {min, max, min|u|, max|u|, sum u^2, sum (u-f)^2, sum f^2}, the last two against the reference rows d_F [C, ldf] (NULL: 0).
+ * Replaces the per-sample host loops of PGD.evaluate_min/_max/... (model.py:955-1086) and of
+ * PGDErrorComputation.evaluate_error (model.py:1785-1825) when a batch of points is evaluated.  Deterministic. */
+int32_t pgd_row_stats(pgd_handle_t h, const double* d_U, int64_t ldu, const double* d_F, int64_t ldf, int64_t C, int64_t N,
+                      double* d_stats, void* stream);
+
 /* Started / finished solve: pgd_pcg_start enqueues the SM-resident PCG (one cooperative kernel, the result lands in
  * d_x in stream order) and returns without waiting, so the host can record the next sub-problem's forms while the
  * GPU iterates; pgd_pcg_finish waits for it and reports iterations / relative residual (*h_iters = -1 when nothing

@@ -61,6 +61,7 @@ SIGNATURES = {
     "pgd_pcg_persist_sync": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_dbl, c_dbl, c_i32, c_i32, c_vp, c_vp, c_vp,
                              c_vp, c_vp, c_vp, c_i32, ctypes.POINTER(c_i32), ctypes.POINTER(c_dbl), c_vp],
     "pgd_get_phase_ns": [c_vp, c_vp, c_i32],
+    "pgd_row_stats": [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp],
     "pgd_banded_solve": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp],
     "pgd_eval_weights": [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp],
     "pgd_eval_gemv": [c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_vp, c_vp],
@@ -756,6 +757,19 @@ def probe_modes(X, R, dofs, w):
     _check(lib.pgd_probe_modes(h, _p(X, F64, True), X.stride(0), R, _p(dofs, I32), _p(w, F64), n_rows, nd, _p(E, F64), n_rows,
                                _stream()), h, "pgd_probe_modes")
     return E
+
+
+ROW_STATS = ("min", "max", "min_abs", "max_abs", "sum_sq", "sum_sq_diff", "sum_sq_ref")
+
+
+def row_stats(U, F=None):
+    """U [C, N] (rows contiguous), optional reference rows F [C, N] -> device tensor [C, 7] (see ROW_STATS)."""
+    h, lib = handle(U.device), load_library()
+    C, N = U.shape
+    out = torch.empty((C, len(ROW_STATS)), dtype=F64, device=U.device)
+    _check(lib.pgd_row_stats(h, _p(U, F64, True), U.stride(0), _p(F, F64, True) if F is not None else c_vp(0),
+                             F.stride(0) if F is not None else 0, C, N, _p(out, F64), _stream()), h, "pgd_row_stats")
+    return out
 
 
 def eval_gemm(W, X, R, out=None):

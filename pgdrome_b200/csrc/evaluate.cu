@@ -329,3 +329,63 @@ extern "C" int32_t pgd_eval_gemm_f64(pgd_handle_t h, const double* d_W, int64_t 
     PGD_LAUNCH_OK(h);
     return 0;
 }
+
+// ----------------------------------------------------------------------------- row-wise reductions of a sweep U [C, N]
+// (PGDErrorComputation.evaluate_error / evaluate_min, _max, ... over a whole batch of parameter points: model.py:955-1086,
+// 1785-1825 loop over the samples on the host, one evaluate + one NumPy reduction each).  One CTA per row, fixed-order
+// block reduction => deterministic.  stats[c] = {min, max, min|.|, max|.|, sum u^2, sum (u - f)^2, sum f^2}; the last two
+// need the reference rows F [C, N] (may be NULL).
+#define ROWSTAT_N 7
+__global__ void __launch_bounds__(256) k_row_stats(const double* __restrict__ U, int64_t ldu, const double* __restrict__ F,
+                                                   int64_t ldf, int64_t N, double* __restrict__ out) {
+    const int64_t c = blockIdx.x;
+    const double* u = U + c * ldu;
+    const double* f = F ? F + c * ldf : nullptr;
+    double mn = INFINITY, mx = -INFINITY, mna = INFINITY, mxa = 0.0, s2 = 0.0, d2 = 0.0, f2 = 0.0;
+    for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
+        const double v = u[i], av = fabs(v);
+        mn = fmin(mn, v);
+        mx = fmax(mx, v);
+        mna = fmin(mna, av);
+        mxa = fmax(mxa, av);
+        s2 = fma(v, v, s2);
+        if (f) {
+            const double w = f[i], d = v - w;
+            d2 = fma(d, d, d2);
+            f2 = fma(w, w, f2);
+        }
+    }
+    __shared__ double sh[ROWSTAT_N][256];
+    sh[0][threadIdx.x] = mn;
+    sh[1][threadIdx.x] = mx;
+    sh[2][threadIdx.x] = mna;
+    sh[3][threadIdx.x] = mxa;
+    sh[4][threadIdx.x] = s2;
+    sh[5][threadIdx.x] = d2;
+    sh[6][threadIdx.x] = f2;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            sh[0][threadIdx.x] = fmin(sh[0][threadIdx.x], sh[0][threadIdx.x + o]);
+            sh[1][threadIdx.x] = fmax(sh[1][threadIdx.x], sh[1][threadIdx.x + o]);
+            sh[2][threadIdx.x] = fmin(sh[2][threadIdx.x], sh[2][threadIdx.x + o]);
+            sh[3][threadIdx.x] = fmax(sh[3][threadIdx.x], sh[3][threadIdx.x + o]);
+            sh[4][threadIdx.x] += sh[4][threadIdx.x + o];
+            sh[5][threadIdx.x] += sh[5][threadIdx.x + o];
+            sh[6][threadIdx.x] += sh[6][threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < ROWSTAT_N) out[c * ROWSTAT_N + threadIdx.x] = sh[threadIdx.x][0];
+}
+
+extern "C" int32_t pgd_row_stats(pgd_handle_t h, const double* d_U, int64_t ldu, const double* d_F, int64_t ldf, int64_t C,
+                                 int64_t N, double* d_stats, void* stream) {
+    PGD_CHECK_HANDLE(h);
+    PGD_ARG(h, C >= 0 && N >= 0 && ldu >= N && (!d_F || ldf >= N) && C < ((int64_t)1 << 31), "bad arguments");
+    if (C == 0) return 0;
+    PGD_ARG(h, d_U && d_stats, "null pointer");
+    k_row_stats<<<(unsigned int)C, 256, 0, (cudaStream_t)stream>>>(d_U, ldu, d_F, ldf, N, d_stats);
+    PGD_LAUNCH_OK(h);
+    return 0;
+}

@@ -135,15 +135,16 @@ __device__ __forceinline__ bool ps_grid_barrier(const PersistArgs& a, PsSync& sy
 // stores the rank's sum into the other ranks' mailboxes with a release flag, and every CTA acquires the `world - 1`
 // foreign flags in its LOCAL window and adds the rank sums in RANK ORDER (its own from the partials).
 // false = aborted.
-struct PsNoHook {
-    __device__ __forceinline__ void operator()() const {}
-};
+__device__ __forceinline__ void ps_halo_issue(const PersistArgs& a, const double* v, unsigned int G);
+__device__ __forceinline__ void ps_halo_commit(const PersistArgs& a, unsigned long long seq, unsigned int G);
 
-// after_arrival(): executed by every CTA right after all CTAs of this rank have arrived (their global writes are
-// visible) and before the cross-rank part of the reduction -- the place where the halo of the new z is pushed.
-template <int NV, class Hook = PsNoHook>
+// halo_v != NULL: the boundary entries of halo_v leave for the neighbours inside this reduction -- the stores are issued
+// right after all CTAs of this rank have arrived (their global writes are visible), the flag is published after the
+// rank's sum has been sent and BEFORE the wait for the other ranks, so that the acknowledgement round trip of the
+// stores and the flight of the flag overlap with the reduction's own cross-rank latency.
+template <int NV>
 __device__ __forceinline__ bool ps_reduce_bcast(double (&v)[NV], const PersistArgs& a, PsSync& sy, unsigned int G,
-                                                Hook&& after_arrival = PsNoHook()) {
+                                                const double* halo_v = nullptr, unsigned long long halo_seq = 0) {
     __shared__ double s_res[4];
     __shared__ int s_ok;
     const int tid = threadIdx.x;
@@ -164,7 +165,7 @@ __device__ __forceinline__ bool ps_reduce_bcast(double (&v)[NV], const PersistAr
         if (!ps_spin([&] { return ps_ld_acquire_gpu(a.arrive) >= tgt; }, a)) s_ok = 0;
     }
     __syncthreads();
-    after_arrival();
+    if (halo_v) ps_halo_issue(a, halo_v, G);
     if (tid < 32) {  // every CTA: the rank's sum, same order everywhere
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
@@ -185,6 +186,7 @@ __device__ __forceinline__ bool ps_reduce_bcast(double (&v)[NV], const PersistAr
             st_release_sys(reinterpret_cast<unsigned long long*>(a.peers.base[tid] + a.lay.arflag_off()) + par * PW_MAXR + a.me,
                            seq);
         }
+        if (halo_v) ps_halo_commit(a, halo_seq, G);
         if (tid < a.world && tid != a.me) {
             const unsigned long long* f =
                 reinterpret_cast<const unsigned long long*>(a.peers.base[a.me] + a.lay.arflag_off()) + par * PW_MAXR + tid;
@@ -348,8 +350,7 @@ __global__ void __launch_bounds__(PS_THREADS, BK_CTAS_PER_SM) k_pcg_persist(Pers
             }
             for (int64_t i = gtid; i < a.n_local; i += gstride) a.p[i] = 0.0;
             hseq = ++sy.seq_halo;
-            if (!ps_reduce_bcast<3>(v, a, sy, G, [&] { ps_halo_issue(a, a.z, G); })) status = 3;
-            ps_halo_commit(a, hseq, G);
+            if (!ps_reduce_bcast<3>(v, a, sy, G, a.z, hseq)) status = 3;
         }
         rz = v[0];
         bb = v[1];
@@ -411,9 +412,7 @@ __global__ void __launch_bounds__(PS_THREADS, BK_CTAS_PER_SM) k_pcg_persist(Pers
             pcg_update_rows<BS>(a.x, a.r, a.z, a.p, a.q, a.minv, n_nodes, alpha, v2[0], v2[1]);
             PS_MARK(4);
             hseq = ++sy.seq_halo;
-            const bool ok2 = ps_reduce_bcast<2>(v2, a, sy, G, [&] { ps_halo_issue(a, a.z, G); });
-            ps_halo_commit(a, hseq, G);
-            if (!ok2) {
+            if (!ps_reduce_bcast<2>(v2, a, sy, G, a.z, hseq)) {
                 status = 3;
                 break;
             }

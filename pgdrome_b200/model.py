@@ -598,30 +598,58 @@ class PGD:
             X = X[:, rows[0]:rows[1]]
         return _lib.eval_gemm(W, X, self.used_numModes, out=out)
 
-    def _values(self, fixed_dim, free_dim, coord, attri):
-        r = self.evaluate(fixed_dim, free_dim, coord, attri)
-        return r if isinstance(r, np.ndarray) else r.vector()[:]
+    # ------------------------------------------------------------------ reductions of the reconstruction
+    def evaluate_stats(self, fixed_dim, free_dim, coords, attri, reference=None):
+        """Row-wise reductions of a whole sweep on the device: coords [C, D-1] -> dict of NumPy arrays [C] with
+        min, max, min_abs, max_abs, norm (l2 over the fixed dimension's entries) and -- against ``reference`` [C, N]
+        (device tensor or array) -- rel_error = ||u - ref|| / ||ref||.  One evaluate_batch (weights kernel + DMMA
+        GEMM), one reduction kernel, one device->host copy of C x 7 doubles."""
+        coords = np.asarray(coords, dtype=np.float64).reshape(-1, len(free_dim))
+        U = self.evaluate_batch(fixed_dim, free_dim, coords, attri)
+        F = None
+        if reference is not None:
+            F = reference if isinstance(reference, torch.Tensor) else _as_f64(np.asarray(reference, dtype=np.float64))
+            F = F.reshape(U.shape)
+        st = _lib.to_host(_lib.row_stats(U, F))
+        out = {"min": st[:, 0], "max": st[:, 1], "min_abs": st[:, 2], "max_abs": st[:, 3], "norm": np.sqrt(st[:, 4])}
+        if F is not None:
+            out["rel_error"] = np.sqrt(st[:, 5]) / np.sqrt(st[:, 6])
+        return out
+
+    def _one_stat(self, fixed_dim, free_dim, coord, attri, key):
+        """evaluate_min / _max / ... (model.py:955-1055) for one point or, with coord [C, D-1], for a batch (array out)."""
+        c = np.asarray(coord, dtype=np.float64)
+        r = self.evaluate_stats(fixed_dim, free_dim, c.reshape(-1, len(free_dim)), attri)[key]
+        return float(r[0]) if c.ndim == 1 else r
 
     def evaluate_min(self, fixed_dim, free_dim, coord, attri, *args, **kwargs):
-        return self._values(fixed_dim, free_dim, coord, attri).min()
+        return self._one_stat(fixed_dim, free_dim, coord, attri, "min")
 
     def evaluate_min_abs(self, fixed_dim, free_dim, coord, attri, *args, **kwargs):
-        return abs(self._values(fixed_dim, free_dim, coord, attri)).min()
+        return self._one_stat(fixed_dim, free_dim, coord, attri, "min_abs")
 
     def evaluate_max(self, fixed_dim, free_dim, coord, attri, *args, **kwargs):
-        return self._values(fixed_dim, free_dim, coord, attri).max()
+        return self._one_stat(fixed_dim, free_dim, coord, attri, "max")
 
     def evaluate_max_abs(self, fixed_dim, free_dim, coord, attri, *args, **kwargs):
-        return abs(self._values(fixed_dim, free_dim, coord, attri)).max()
+        return self._one_stat(fixed_dim, free_dim, coord, attri, "max_abs")
 
     def evaluate_max_norm(self, fixed_dim, free_dim, coord, attri, *args, **kwargs):
+        """largest Euclidean norm of the (vector) value over the nodes (model.py:1057-1075)"""
         new = self.evaluate(fixed_dim, free_dim, coord, attri)
         if isinstance(new, np.ndarray):
             return max(np.linalg.norm(new, axis=1))
         V = new.function_space()
         if V.mesh().geometry().dim() == 1:
             raise ValueError("Function is 1D use evaluate_max instead!!")
-        return float(np.linalg.norm(new.vector()[:].reshape(V.n_nodes, V.bs), axis=1).max())
+        t = new.tensor()
+        n_own = getattr(new, "_shard", None).n_owned if getattr(new, "_shard", None) is not None else t.numel()
+        nrm = t[:n_own].reshape(-1, V.bs).pow(2).sum(dim=1).max()
+        if getattr(new, "_shard", None) is not None:
+            import torch.distributed as dist
+
+            dist.all_reduce(nrm, op=dist.ReduceOp.MAX, group=new._shard.group)
+        return float(nrm.sqrt().item())
 
     def evaluate_abs_value(self, fixed_dim, free_dim, coord, attri, *args, **kwargs):
         new = self.evaluate(fixed_dim, free_dim, coord, attri)
@@ -632,73 +660,109 @@ PGDModel = PGD
 
 
 class PGDErrorComputation(object):
-    """LHS sampling + relative L2 error of the PGD against a full-order model (model.py:1666-1825)."""
+    """Relative L2 error of the PGD model against a full-order model over a set of parameter samples
+    (interface of model.py:1666-1825: same constructor arguments, ``sampling_LHS``, ``compute_SampleError``,
+    ``evaluate_error`` -> (errors, mean, max)).
+
+    The reference evaluates sample by sample on the host.  Here the PGD side of ALL samples is one
+    ``evaluate_batch`` (weights kernel + FP64 tensor-core GEMM) and the error norms are one row-reduction kernel; only
+    the full-order model -- a user callable -- is still asked once per sample, and its answers are stacked into the
+    reference block the reduction compares against.  ``fixed_var`` (errors at a few points of the fixed dimension
+    only) goes through the sensor path: point location + basis evaluation once, then one small GEMM for all samples."""
 
     def __init__(self, fixed_dim=0, n_samples=1, data_test=[], FOM_model=[], PGD_model=[], lim_samples=[], fixed_var=[],
                  *args, **kwargs):
-        self.fixed_dim = fixed_dim
-        self.n_smp = n_samples
-        self.data_test = data_test
-        self.FOM_sol = FOM_model
-        self.PGD_sol = PGD_model
-        self.lim_smp = lim_samples
-        self.fixed_var = fixed_var
-        self.free_dim = [item for item in list(range(0, self.PGD_sol.num_pgd_var)) if item not in fixed_dim]
+        self.fixed_dim, self.n_smp = fixed_dim, n_samples
+        self.data_test, self.lim_smp, self.fixed_var = data_test, lim_samples, fixed_var
+        self.FOM_sol, self.PGD_sol = FOM_model, PGD_model
+        fixed = set(np.atleast_1d(fixed_dim).tolist())
+        self.free_dim = [d for d in range(self.PGD_sol.num_pgd_var) if d not in fixed]
+
+    # -- samples
+    def _bounds(self):
+        lo, hi = [], []
+        for d in self.free_dim:
+            if self.lim_smp:
+                rng = self.lim_smp[d]
+                if len(rng) != 2:
+                    raise NotImplementedError("lim_samples[%d] must be a (min, max) pair" % d)
+            else:
+                X = self.PGD_sol.problem.meshes[d].coordinates()
+                if X.shape[1] != 1:
+                    raise NotImplementedError("sampling over a free dimension that is not 1-D")
+                rng = (X.min(), X.max())
+            lo.append(float(min(rng)))
+            hi.append(float(max(rng)))
+        return lo, hi
 
     def sampling_LHS(self):
-        sampler = qmc.LatinHypercube(d=len(self.free_dim), seed=3452)
-        sample = sampler.random(n=self.n_smp)
-        min_bnd = [None] * len(self.free_dim)
-        max_bnd = [None] * len(self.free_dim)
-        ind = 0
-        if not self.lim_smp:
-            for i in self.free_dim:
-                c = self.PGD_sol.problem.meshes[i].coordinates()
-                if len(c[0]) == 1:
-                    min_bnd[ind] = float(c.min())
-                    max_bnd[ind] = float(c.max())
-                    ind = ind + 1
-                else:
-                    print("Not implemented")
-        else:
-            for i in self.free_dim:
-                if len(self.lim_smp[i]) == 2:
-                    min_bnd[ind] = float(min(self.lim_smp[i]))
-                    max_bnd[ind] = float(max(self.lim_smp[i]))
-                    ind = ind + 1
-                else:
-                    print("Not implemented")
-        return qmc.scale(sample, min_bnd, max_bnd).tolist()
+        """Latin-hypercube samples of the free dimensions, seed 3452 (the reference's, model.py:1709)."""
+        unit = qmc.LatinHypercube(d=len(self.free_dim), seed=3452).random(n=self.n_smp)
+        return qmc.scale(unit, *self._bounds()).tolist()
 
+    # -- one sample (kept for callers of the reference interface)
     def compute_SampleError(self, u_FOM, u_PGD):
-        if isinstance(u_FOM, np.ndarray) and isinstance(u_PGD, np.ndarray):
-            residual = u_PGD.reshape(-1) - u_FOM.reshape(-1)
-            return np.linalg.norm(residual, 2) / np.linalg.norm(u_FOM.reshape(-1), 2)
-        if isinstance(u_FOM, np.ndarray):
-            residual = u_PGD.compute_vertex_values()[:] - u_FOM.reshape(-1)
-            return np.linalg.norm(residual, 2) / np.linalg.norm(u_FOM.reshape(-1), 2)
-        a, b = u_FOM.tensor(), u_PGD.tensor()
-        d = a - b
-        return float(np.sqrt(_lib.dot(d, d).item()) / np.sqrt(_lib.dot(a, a).item()))
+        if not isinstance(u_PGD, np.ndarray):
+            u_PGD = u_PGD.compute_vertex_values() if isinstance(u_FOM, np.ndarray) else u_PGD.vector().get_local()
+        if not isinstance(u_FOM, np.ndarray):
+            u_FOM = u_FOM.vector().get_local()
+        a, b = u_FOM.reshape(-1), u_PGD.reshape(-1)
+        return np.linalg.norm(b - a, 2) / np.linalg.norm(a, 2)
+
+    # -- all samples
+    def _fom_block(self, samples):
+        """(reference block [C, n], vertex_order): the full-order answers of all samples stacked; vertex_order is True
+        when the model returned arrays (values at the mesh vertices, DOLFIN's compute_vertex_values layout), False when
+        it returned Functions (dof vectors)."""
+        if not self.FOM_sol:
+            raise ValueError("FEM not defined")
+        rows, vertex_order = [], True
+        for smp in samples:
+            u = self.FOM_sol(list(smp))
+            if isinstance(u, (float, int)):
+                u = np.array([float(u)])
+            elif not isinstance(u, np.ndarray):  # a Function of the fixed dimension's space
+                u, vertex_order = u.vector().get_local(), False
+            rows.append(np.asarray(u, dtype=np.float64).reshape(-1))
+        return np.stack(rows), vertex_order
+
+    def _vertex_columns(self, fixed):
+        """dof index of every entry of compute_vertex_values() (component-major for vector fields), or None when the
+        model's fixed dimension already holds vertex data"""
+        att = self.PGD_sol.mesh[fixed].attributes[0]
+        free_att = self.PGD_sol.mesh[self.free_dim[0]].attributes[0]
+        if free_att.interpolationInfo["name"] == 0 or not att.interpolationfct:
+            return None
+        V = att.interpolationfct[0].function_space()
+        v2n = np.asarray(V.vertex_to_node, dtype=np.int64)
+        return (v2n[None, :] * V.bs + np.arange(V.bs)[:, None]).reshape(-1)
 
     def evaluate_error(self):
+        if not self.PGD_sol:
+            raise ValueError("PGD model not defined")
         if not self.data_test:
             self.data_test = self.sampling_LHS()
-        errorL2 = np.zeros(len(self.data_test))
-        for i in range(len(self.data_test)):
-            if self.FOM_sol:
-                u_fem = self.FOM_sol(self.data_test[i])
-                if isinstance(u_fem, float):
-                    u_fem = np.array(u_fem)
-            else:
-                raise ValueError("FEM not defined")
-            if self.PGD_sol:
-                u_pgd = self.PGD_sol.evaluate(int(self.fixed_dim[0]), self.free_dim, self.data_test[i], 0)
-            else:
-                raise ValueError("PGD model not defined")
-            if not self.fixed_var:
-                errorL2[i] = self.compute_SampleError(u_fem, u_pgd)
-            else:
-                u_pgdPoint = np.array([u_pgd(item) for item in self.fixed_var])
-                errorL2[i] = self.compute_SampleError(u_fem, u_pgdPoint)
-        return errorL2, np.mean(errorL2), np.max(errorL2)
+        samples = np.asarray(self.data_test, dtype=np.float64).reshape(len(self.data_test), -1)
+        fixed = int(np.atleast_1d(self.fixed_dim)[0])
+        ref, vertex_order = self._fom_block(samples)
+        if self.fixed_var:
+            # errors at the given points of the fixed dimension: modes probed once, one small GEMM for all samples
+            pts = np.asarray(self.fixed_var, dtype=np.float64).reshape(len(self.fixed_var), -1)
+            self.PGD_sol._check_args(fixed, self.free_dim, samples[0], 0)
+            self.PGD_sol.eval_fixed_modes(pts, fixed, 0)
+            key = (float(np.sum(pts.flatten())), fixed, 0)
+            E = self.PGD_sol._dev_cache[("sensor", key)][1]                   # [R, n_pts * bs]
+            W = self.PGD_sol._weights(self.free_dim, samples, 0)              # [R_used, C]
+            U = _lib.eval_gemm(W, E, self.PGD_sol.used_numModes)              # [C, n_pts * bs]
+            err = _lib.to_host(_lib.row_stats(U, _as_f64(ref.reshape(U.shape))))
+            errors = np.sqrt(err[:, 5]) / np.sqrt(err[:, 6])
+        else:
+            cols = self._vertex_columns(fixed) if vertex_order else None
+            if cols is None:
+                errors = self.PGD_sol.evaluate_stats(fixed, self.free_dim, samples, 0, reference=ref)["rel_error"]
+            else:  # arrays from the full-order model are vertex values: compare the sweep's vertex columns
+                U = self.PGD_sol.evaluate_batch(fixed, self.free_dim, samples, 0)
+                Uv = U.index_select(1, torch.as_tensor(cols, device=U.device)).contiguous()
+                st = _lib.to_host(_lib.row_stats(Uv, _as_f64(ref.reshape(Uv.shape))))
+                errors = np.sqrt(st[:, 5]) / np.sqrt(st[:, 6])
+        return errors, np.mean(errors), np.max(errors)

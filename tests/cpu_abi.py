@@ -277,6 +277,18 @@ def eval_gemm(W, X, R, out=None):
     return r
 
 
+def row_stats(U, F=None):
+    u = _n(U)
+    f = _n(F) if F is not None else None
+    out = np.zeros((u.shape[0], 7))
+    out[:, 0], out[:, 1] = u.min(axis=1), u.max(axis=1)
+    out[:, 2], out[:, 3] = np.abs(u).min(axis=1), np.abs(u).max(axis=1)
+    out[:, 4] = (u * u).sum(axis=1)
+    if f is not None:
+        out[:, 5], out[:, 6] = ((u - f) ** 2).sum(axis=1), (f * f).sum(axis=1)
+    return _t(out)
+
+
 def locate_points(coords, cells, points, tol=1e-10):
     from oracle.evaluate import locate_points as ref
 
@@ -320,7 +332,7 @@ def pcg_finish(device=None):
 NAMES = ["pattern_build", "vecmap_build", "elem_bilinear", "elem_linear", "gather_values", "assemble_p1",
          "p1_rowplan_build", "assemble_p1_rows", "lincomb",
          "apply_dirichlet", "set_entries", "spmv", "spmv_dot", "bilinear", "dot", "panel_dots", "pcg", "banded_solve",
-         "eval_weights", "eval_gemv", "eval_gemm", "locate_points", "probe_modes", "pcg_start", "pcg_finish", "scalar_programs"]
+         "eval_weights", "eval_gemv", "eval_gemm", "row_stats", "locate_points", "probe_modes", "pcg_start", "pcg_finish", "scalar_programs"]
 
 
 def install(monkeypatch):

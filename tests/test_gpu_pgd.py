@@ -196,16 +196,57 @@ def _compare_pinned(make, solve_kw, o, tol=MODE_RTOL, n_modes=None):
     return p, worst
 
 
+def _restarted_mode_errors(make, solve_kw, o):
+    """Per-mode parity WITHOUT compounding: enrichment step k of the product is run from the ORACLE's modes 0..k-1
+    (and the oracle's sweep count), and its new mode is compared with the oracle's mode k.  Two implementations of the
+    enrichment differ by ~4x more per mode when every run feeds on its own previous modes (oracle LU against oracle CG at
+    rtol 1e-13: 1e-15 at mode 0, 2e-7 at mode 19 of configs[1]); restarted, every step is an independent check."""
+    from pgdrome_b200.functions import Function
+
+    p = make()
+    st = p.begin_PGD(**solve_kw)
+    D = len(p.V)
+    p.fp_schedule = list(o.num_fp_it)
+    errs = []
+    for k in range(o.PGD_modes):
+        for d in range(D):
+            prev = []
+            for i in range(k):
+                f = Function(p.V[d], np.asarray(o.PGD_func[d][i]))
+                f.stable = True
+                prev.append(f)
+            p.PGD_func[d] = prev
+        p.num_fp_it, p.err_fp_it, p.alpha = p.num_fp_it[:k], p.err_fp_it[:k], p.alpha[:k]
+        st["n_enr"], st["normConv"], st["relConv"], st["done"] = k - 1, [1.0] * k, [1.0] * k, False
+        p.step_PGD(st)
+        assert len(p.PGD_func[0]) == k + 1 and p.num_fp_it[k] == o.num_fp_it[k]
+        errs.append(max(_mode_err(p.PGD_func[d][k].vector()[:], o.PGD_func[d][k]) for d in range(D)))
+    return errs
+
+
 def test_config2_heat2d_tk_full_size_20_modes_against_oracle():
     """BASELINE configs[1] at FULL size (66 049 dofs x 200 x 50) and full mode count (20) against oracle.solve_pgd
-    (SuperLU = the reference's direct-LU class): every mode to 1e-8, identical fixed-point sweep counts."""
+    (SuperLU = the reference's direct-LU class), identical fixed-point sweep counts:
+      * every one of the 20 modes to 1e-8 when each step starts from the same previous modes (restarted comparison);
+      * the free-running 20-mode solve: the leading 10 modes to 1e-8 and the RECONSTRUCTION (what evaluate returns) to
+        1e-8 at parameter points -- later modes inherit the differences of all earlier ones (see _restarted_mode_errors)."""
     from pgdrome_b200 import configs
 
     make = lambda: configs.heat2d_tk(n=256, nt=199, nk=49, PGD_nmax=20)
-    o, _ = oprob.heat2d_tk(n=256, nt=199, nk=49, PGD_nmax=20, spaces=_ospaces(make()))
+    S = _ospaces(make())
+    o, _ = oprob.heat2d_tk(n=256, nt=199, nk=49, PGD_nmax=20, spaces=S)
     opgd.solve_pgd(o)
-    p, worst = _compare_pinned(make, dict(_problem="linear"), o, tol=1e-8)
-    assert p.PGD_modes == o.PGD_modes == 20
+    assert o.PGD_modes == 20
+    errs = _restarted_mode_errors(make, dict(_problem="linear"), o)
+    assert max(errs) < 1e-8, errs
+    p, worst = _compare_pinned(make, dict(_problem="linear"), o, tol=1e-8, n_modes=10)
+    assert p.PGD_modes == 20 and list(p.num_fp_it) == list(o.num_fp_it)
+    pgd = p.return_PGD()
+    pts = np.array([[0.25, 0.7], [0.6, 1.3], [1.0, 1.9]])
+    U = pgd.evaluate_batch(0, [1, 2], pts, 0).cpu().numpy()
+    for c in range(len(pts)):
+        uo = evaluate_dofs(o.PGD_func[0], S[1:], [o.PGD_func[1], o.PGD_func[2]], pts[c])
+        assert np.linalg.norm(U[c] - uo) / np.linalg.norm(uo) < 1e-8
 
 
 def test_config3_elasticity3d_persistent_kernel_against_oracle():
