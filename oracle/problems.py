@@ -260,9 +260,11 @@ def elasticity3d(n=68, nE=49, nF=2, nu=0.3, Erange=(0.5, 1.5), Frange=(0.0, 2.0)
     return p, {"spaces": S}
 
 
-def thermal3d(n=158, nt=199, nP=19, nv=19, kappa=0.05, rho_cp=1.0, a=0.12, n_src=6, spaces=None, **kw):
+def thermal3d(n=158, nt=199, nP=19, nv=19, kappa=0.05, rho_cp=1.0, a=0.12, n_src=6, spaces=None, source_terms=None, **kw):
     """configs[3] (pgdrome_b200/configs.py:thermal3d) in matrix form: moving source pre-separated into
-    n_src terms g_m(x) h_m(t) P w_m(v); FD in time.  Parity unpinned (oracle only)."""
+    n_src terms g_m(x) h_m(t) P w_m(v); FD in time.  Parity unpinned (oracle only).
+    source_terms: the separated tables of the moving Gaussian (dict with G, H, W, x, t, v, a as produced by the
+    problem's set-up tool); None = the way-point surrogate (static Gaussians switched on in turn)."""
     from .meshes import box_mesh
 
     if spaces is None:
@@ -278,6 +280,16 @@ def thermal3d(n=158, nt=199, nP=19, nv=19, kappa=0.05, rho_cp=1.0, a=0.12, n_src
     MP, Mv = _mass(S[2]), _mass(S[3])
     lhs = [(rho_cp, [Mx, At, MP, Mv]), (kappa, [Kx, Mt, MP, Mv])]
     rhs = []
+    if source_terms is not None:
+        T = source_terms
+        X0, v_dofs = S[0].node_coords, S[3].dof_coordinates().ravel()
+        lateral = np.exp(-3.0 * ((X0[:, 1] - 0.5) ** 2 + (X0[:, 2] - 1.0) ** 2) / (T["a"] * T["a"]))
+        for m in range(len(T["G"])):
+            g = np.interp(X0[:, 0], T["x"], T["G"][m]) * lateral
+            h = np.interp(t_dofs, T["t"], T["H"][m])
+            w = np.interp(v_dofs, T["v"], T["W"][m])
+            rhs.append((1.0, [Mx @ g, Mt @ h, _load(S[2], _x, 1), Mv @ w]))
+        n_src = 0
     for m in range(n_src):
         xm = 0.2 + 0.6 * m / max(n_src - 1, 1)
         tm = 0.1 + 0.8 * m / max(n_src - 1, 1)

@@ -148,7 +148,7 @@ class PGDProblem:
         self._dom_cache = None
         self._mm_dev = {}
         self._csr_cache = {}
-        self.solver_stats = {"pcg_solves": 0, "pcg_iterations": 0, "banded_solves": 0, "flushes": 0}
+        self.solver_stats = {"pcg_solves": 0, "pcg_iterations": 0, "banded_solves": 0, "flushes": 0, "pcg_log": []}
 
     # ------------------------------------------------------------------ domains / boundary conditions
     @property
@@ -588,6 +588,7 @@ class PGDProblem:
     def _account_solve(self, iters, relres, rtol, maxit):
         self.solver_stats["pcg_solves"] += 1
         self.solver_stats["pcg_iterations"] += iters
+        self.solver_stats["pcg_log"].append(int(iters))
         if relres > max(rtol, 1e-15) * 10 and iters >= maxit:
             self.logger.warning("PCG stopped at relative residual %.3e after %d iterations", relres, iters)
 
@@ -620,6 +621,7 @@ class PGDProblem:
                                             bsr=ds.bsr if settings.get("node_block_walk", True) else None)
         self.solver_stats["pcg_solves"] += 1
         self.solver_stats["pcg_iterations"] += iters
+        self.solver_stats["pcg_log"].append(int(iters))
         self.solver_stats["sharded_solves"] = self.solver_stats.get("sharded_solves", 0) + 1
         if relres > max(rtol, 1e-15) * 10 and iters >= maxit:
             self.logger.warning("sharded PCG stopped at relative residual %.3e after %d iterations", relres, iters)

@@ -103,7 +103,7 @@ def test_config4_thermal3d_reduced():
 
     p = configs.thermal3d(n=8, nt=30, nP=4, nv=4, n_src=4, PGD_nmax=4)
     p.solve_PGD(_problem="linear")
-    o, _ = oprob.thermal3d(n=8, nt=30, nP=4, nv=4, n_src=4, PGD_nmax=4, spaces=_ospaces(p))
+    o, _ = oprob.thermal3d(n=8, nt=30, nP=4, nv=4, n_src=4, PGD_nmax=4, spaces=_ospaces(p), source_terms=p.source_terms)
     opgd.solve_pgd(o)
     _compare(p, o)
     # reconstruction: batched evaluate on the device vs the oracle loop at a few parameter points
@@ -263,8 +263,10 @@ def test_config3_elasticity3d_persistent_kernel_against_oracle():
     s1 = _lib.stats()
     assert p.PGD_modes == 3
     assert s1["pcg_solves"] > s0["pcg_solves"] and s1["pcg_resident_solves"] == s0["pcg_resident_solves"]  # not the SM-resident solver
-    # node-block-Jacobi PCG on both sides: iteration counts of the spatial solves agree closely
-    assert abs(p.solver_stats["pcg_iterations"] - sum(o.cg_iterations)) <= 0.02 * sum(o.cg_iterations) + 5
+    # node-block-Jacobi PCG on both sides; the product warm-starts every solve from the previous sweep's mode, the oracle
+    # starts from zero: never more iterations than the oracle, and the very first (cold) solve agrees within a few
+    assert p.solver_stats["pcg_iterations"] <= sum(o.cg_iterations) + 5 * len(o.cg_iterations)
+    assert abs(p.solver_stats["pcg_log"][0] - o.cg_iterations[0]) <= 0.02 * o.cg_iterations[0] + 3
 
 
 def test_config4_thermal3d_streaming_kernels_against_oracle():
@@ -273,7 +275,8 @@ def test_config4_thermal3d_streaming_kernels_against_oracle():
 
     kw = dict(n=32, nt=40, nP=5, nv=5, n_src=3, PGD_nmax=2)
     make = lambda: configs.thermal3d(**kw)
-    o, _ = oprob.thermal3d(spaces=_ospaces(make()), solver="ccg", **kw)
+    first = make()
+    o, _ = oprob.thermal3d(spaces=_ospaces(first), solver="ccg", source_terms=first.source_terms, **kw)
     opgd.solve_pgd(o)
     p, worst = _compare_pinned(make, dict(_problem="linear", solve_modes=None, settings={"linear_solver": "cg"}), o, tol=1e-8)
     assert p.PGD_modes == 2

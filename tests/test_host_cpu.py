@@ -79,14 +79,21 @@ def test_elasticity3d_matches_oracle(cpu):
 
 
 def test_thermal3d_matches_oracle(cpu):
-    """configs[3] reduced: P1 tetrahedra x FD time x P x v, 3 separated source terms."""
+    """configs[3] reduced: P1 tetrahedra x FD time x P x v; the moving source separated into 3 terms (the oracle gets
+    the same separated tables) and the way-point surrogate."""
     from pgdrome_b200 import configs
 
     p = configs.thermal3d(n=4, nt=12, nP=3, nv=3, n_src=3, PGD_nmax=3)
+    assert p.source_terms is not None and len(p.source_terms["G"]) == 3 and np.all(np.diff(p.source_terms["rel_err"]) < 0)
     p.solve_PGD(_problem="linear")
-    o, _ = oprob.thermal3d(n=4, nt=12, nP=3, nv=3, n_src=3, PGD_nmax=3, spaces=_ospaces(p))
+    o, _ = oprob.thermal3d(n=4, nt=12, nP=3, nv=3, n_src=3, PGD_nmax=3, spaces=_ospaces(p), source_terms=p.source_terms)
     opgd.solve_pgd(o)
     _compare(p, o)
+    q = configs.thermal3d(n=4, nt=12, nP=3, nv=3, n_src=3, PGD_nmax=2, source="waypoints")
+    q.solve_PGD(_problem="linear")
+    o2, _ = oprob.thermal3d(n=4, nt=12, nP=3, nv=3, n_src=3, PGD_nmax=2, spaces=_ospaces(q))
+    opgd.solve_pgd(o2)
+    _compare(q, o2)
 
 
 # ---- host logic against the reference-generated golden vectors (same bodies as tests/test_gpu_golden.py,

@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--size", "--n", dest="n", type=int, default=None, help="cells per edge of the spatial mesh")
     ap.add_argument("--modes", type=int, default=3)
     ap.add_argument("--rtol", type=float, default=1e-13)
+    ap.add_argument("--counts", default=None, help="write the per-step / per-solve PCG iteration counts to this JSON file "
+                                                   "(bench.py scales its bounded CPU sample with them)")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -51,6 +53,7 @@ def main():
     for i in range(a.modes):
         torch.cuda.synchronize()
         s0 = _lib.stats()
+        log0 = len(p.solver_stats["pcg_log"])
         t1 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -60,7 +63,8 @@ def main():
         s1 = _lib.stats()
         steps.append({"ms": e0.elapsed_time(e1), "wall_s": time.perf_counter() - t1, "fp_iterations": p.num_fp_it[-1] if p.num_fp_it else None,
                       "pcg_solves": s1["pcg_solves"] - s0["pcg_solves"], "pcg_iters": s1["pcg_iters"] - s0["pcg_iters"],
-                      "pcg_ms": s1["pcg_ms"] - s0["pcg_ms"], "launches": s1["launches"] - s0["launches"]})
+                      "pcg_ms": s1["pcg_ms"] - s0["pcg_ms"], "launches": s1["launches"] - s0["launches"],
+                      "pcg_iterations": list(p.solver_stats["pcg_log"][log0:])})
         if done:
             break
     ds = p.V[0]._dev["device_space"]
@@ -78,6 +82,12 @@ def main():
            "device_mem_gb": torch.cuda.max_memory_allocated() / 1e9}
     if rank == 0:
         print(json.dumps(out))
+        if a.counts:
+            with open(a.counts, "w") as f:
+                json.dump({"config": a.config, "n": a.n, "modes": p.PGD_modes, "world": world, "rtol": a.rtol,
+                           "amplitude": [float(x) for x in p.amplitude],
+                           "steps": [{"fp_iterations": st_["fp_iterations"], "pcg_iterations": st_["pcg_iterations"],
+                                      "ms": st_["ms"]} for st_ in steps]}, f)
     if world > 1:
         import torch.distributed as dist
 
