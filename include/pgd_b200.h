@@ -92,6 +92,16 @@ int32_t pgd_assemble_p1_rows(pgd_handle_t h, const double* d_coords, const int32
                              const int32_t* d_rowptr, const int64_t* d_vptr, const int32_t* d_vent, int64_t n_nodes,
                              double* d_values, const double* d_coords_soa, int64_t n_verts, void* stream);
 
+/* Same operator with the coordinates of a row's column nodes cached in shared memory (the ~24 cells around a node only
+ * involve the ~15 nodes of its own column list): a cell visit needs its 8-byte plan entry only -- no cell -> vertex
+ * table, no global coordinate gathers (45 instead of ~290 global loads per row).  d_node_xyz: NODE coordinates,
+ * component-major [gdim][n_nodes]; max_row: longest row of the pattern (<= 64).  Same plan, same summation order and
+ * bitwise the same values as pgd_assemble_p1_rows. */
+int32_t pgd_assemble_p1_rows_nb(pgd_handle_t h, int32_t gdim, double c_mass, double c_stiff, const double* h_c_adv,
+                                const int32_t* d_rowptr, const int32_t* d_colidx, const int64_t* d_vptr,
+                                const int32_t* d_vent, int64_t n_nodes, const double* d_node_xyz, int32_t max_row,
+                                double* d_values, void* stream);
+
 /* ---- linear combinations: A_d = sum_k c_k K_{d,k} over CSR value arrays, and
  * b_d = sum c_m g_m - sum c_ik (K_k U_i) over cached vectors (the folded scalar coefficients of
  * SURVEY.md 7.1).  h_xs: HOST array of n_terms device pointers; h_coefs: HOST array. */

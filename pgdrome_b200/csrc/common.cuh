@@ -70,6 +70,7 @@ struct pgd_ctx {
     int opt_bsr;             // pgd_set_option("bsr"): 1 (default) = node-block walk of vector operators inside that kernel
     int opt_spin_ms;         // pgd_set_option("spin_ms"): budget of every in-kernel wait (default 20 000 ms)
     int opt_prof;            // pgd_set_option("prof"): 1 = the persistent kernel accumulates per-phase times (pgd_get_phase_ns)
+    int opt_single_reduction;  // pgd_set_option("single_reduction"): 0 never, 1 sharded solves, 2 always (pcg_persist.cu)
     unsigned int attr_mask;  // which kernels already carry their dynamic shared-memory opt-in on this device
     void* mailbox;           // single-GPU stand-in for the peer window's mailboxes (PwLayout{0}: slots + flags, 2 KB)
 };

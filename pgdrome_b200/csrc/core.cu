@@ -113,6 +113,10 @@ extern "C" int32_t pgd_set_option(pgd_handle_t h, const char* name, int64_t valu
         h->opt_bsr = value ? 1 : 0;
         return 0;
     }
+    if (strcmp(name, "single_reduction") == 0) {
+        h->opt_single_reduction = value < 0 ? 0 : (value > 2 ? 2 : (int)value);
+        return 0;
+    }
     if (strcmp(name, "prof") == 0) {
         h->opt_prof = value ? 1 : 0;
         return 0;

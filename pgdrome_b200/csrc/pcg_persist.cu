@@ -47,6 +47,7 @@ struct PersistArgs {
     int maxit, warm;
     double *r, *q, *minv;      // [n_owned] (minv: n_owned * BS)
     double* z;                 // [n_local]; inside the peer window when world > 1 (neighbours write its ghost tail)
+    double* s;                 // [n_owned], single-reduction variant only (A p by recurrence)
     double* p;                 // [n_local], local
     double* part;              // [2][4][G] partial sums, double-buffered by sync parity
     unsigned int* arrive;      // monotonic arrival counter, 0 at launch
@@ -463,6 +464,200 @@ __global__ void __launch_bounds__(PS_THREADS, BK_CTAS_PER_SM) k_pcg_persist(Pers
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Single-reduction variant (Chronopoulos & Gear): the same Krylov iteration with ONE grid-wide reduction per step.
+//     u = M^-1 r ; w = A u ; gamma = r.u ; delta = w.u ; beta = gamma / gamma_old ; alpha = gamma / (delta - beta gamma / alpha_old)
+//     p = u + beta p ; s = w + beta s (= A p, by recurrence) ; x += alpha p ; r -= alpha s
+// Per iteration:  V  all vector updates in one pass (p, s, x, r, u = M^-1 r, local r.u and r.r), boundary entries of u
+//                    to the neighbours -> grid barrier (+ halo flags)
+//                 S  w = A u through the TMA ring, local w.u -> reduce-broadcast of (r.u, w.u, r.r)
+// i.e. one barrier and one reduction instead of one barrier and two reductions: on 8 GPUs the two reductions are 23 of
+// the 40 us of an iteration (profiles/r02_pcg_bench_sharded8_*).  The price: s is carried by a recurrence instead of being
+// recomputed as A p, so the iterates differ from the two-reduction form in the last bits (iteration counts within
+// +-1 %, same stopping rule on the recursive residual); selected with pgd_set_option("single_reduction").
+template <int BS, bool BSR>
+__global__ void __launch_bounds__(PS_THREADS, BK_CTAS_PER_SM) k_pcg_persist_sr(PersistArgs a) {
+    extern __shared__ __align__(128) unsigned char bk_smem[];
+    const unsigned int G = gridDim.x;
+    const int tid = threadIdx.x;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + tid;
+    const int64_t gstride = (int64_t)G * blockDim.x;
+    const int64_t no = a.n_owned, n_nodes = a.n_owned / BS;
+    PsSync sy;
+    sy.target = 0;
+    sy.seq_ar = *a.seq_ar;
+    sy.seq_halo = *a.seq_halo;
+    sy.parity = 0;
+    uint32_t tile = 0;
+    if (tid == 0) {
+        if constexpr (BSR) bb_init_barriers(bk_smem);
+        else bk_init_barriers(bk_smem);
+    }
+    __syncthreads();
+    int status = 0, it = 0;
+    double* const u = a.z;   // preconditioned residual [owned | ghost] (window when sharded)
+    double* const w = a.q;   // A u
+    double* const sv = a.s;  // A p by recurrence
+    // ---- r = b - A x0 (warm) | b ; M^-1 ; u = M^-1 r ; p = s = 0
+    if (a.warm) {
+        auto epi = [&](int64_t row, double v) { w[row] = v; };
+        ps_spmv<BS, BSR>(a, a.x, epi, bk_smem, &tile);
+        __syncthreads();
+        if (!ps_grid_barrier(a, sy, G)) status = 3;
+    }
+    double part[3] = {0.0, 0.0, 0.0};  // r.u, w.u, r.r of the CURRENT u (accumulated over V and S)
+    double bb = 0.0;
+    if (status == 0) {
+        for (int64_t nd = gtid; nd < n_nodes; nd += gstride) {
+            double B[BS][BS], I[BS][BS], rb[BS];
+#pragma unroll
+            for (int i = 0; i < BS; ++i)
+#pragma unroll
+                for (int k = 0; k < BS; ++k)
+                    B[i][k] = csr_entry(a.rowptr, a.colidx, a.vals, (int)(nd * BS + i), (int)(nd * BS + k));
+            invert_block<BS>(B, I);
+#pragma unroll
+            for (int i = 0; i < BS; ++i) {
+                rb[i] = a.b[nd * BS + i];
+                bb += rb[i] * rb[i];
+                if (a.warm) rb[i] -= w[nd * BS + i];
+#pragma unroll
+                for (int k = 0; k < BS; ++k) a.minv[(nd * BS + i) * BS + k] = I[i][k];
+            }
+#pragma unroll
+            for (int i = 0; i < BS; ++i) {
+                double zi = 0.0;
+#pragma unroll
+                for (int k = 0; k < BS; ++k) zi += I[i][k] * rb[k];
+                const int64_t d = nd * BS + i;
+                a.r[d] = rb[i];
+                u[d] = zi;
+                a.p[d] = 0.0;
+                sv[d] = 0.0;
+                if (!a.warm) a.x[d] = 0.0;
+                part[0] += rb[i] * zi;
+                part[2] += rb[i] * rb[i];
+            }
+        }
+    }
+    double gamma = 0.0, gamma_old = 1.0, alpha = 1.0, beta = 0.0, rr = 0.0, tol2 = 0.0;
+    unsigned long long t_mark = ps_now();
+    bool first = true;
+    while (status == 0) {
+        // ---- halo of the current u, grid barrier (every u entry written), halo flags
+        const unsigned long long hseq = ++sy.seq_halo;
+        PS_MARK(4);
+        if (!ps_grid_barrier(a, sy, G)) {
+            status = 3;
+            break;
+        }
+        ps_halo_push(a, u, hseq, G);
+        if (!ps_halo_wait(a, hseq)) {
+            status = 3;
+            break;
+        }
+        PS_MARK(1);
+        // ---- S: w = A u, w.u
+        {
+            double wu = 0.0;
+            auto epi = [&](int64_t row, double v) {
+                w[row] = v;
+                wu = fma(u[row], v, wu);
+            };
+            ps_spmv<BS, BSR>(a, u, epi, bk_smem, &tile);
+            part[1] = wu;
+        }
+        PS_MARK(2);
+        double v4[4] = {part[0], part[1], part[2], first ? bb : 0.0};
+        if (!ps_reduce_bcast<4>(v4, a, sy, G)) {
+            status = 3;
+            break;
+        }
+        PS_MARK(3);
+        if (first) {
+            bb = v4[3];
+            tol2 = a.rtol * a.rtol * bb;
+            if (a.atol * a.atol > tol2) tol2 = a.atol * a.atol;
+            first = false;
+        }
+        const double gamma_new = v4[0], delta = v4[1];
+        rr = v4[2];
+        if (!(rr == rr) || !(gamma_new == gamma_new)) {
+            status = 2;
+            break;
+        }
+        if (!(rr > tol2) || !(bb > 0.0) || it >= a.maxit) break;
+        beta = (it == 0) ? 0.0 : gamma_new / gamma_old;
+        alpha = (it == 0) ? gamma_new / delta : gamma_new / (delta - beta * gamma_new / alpha);
+        gamma_old = gamma_new;
+        gamma = gamma_new;
+        // ---- V: p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s ; u = M^-1 r ; local r.u, r.r
+        part[0] = part[1] = part[2] = 0.0;
+        {
+            constexpr int CH = (32 / BS) * BS;
+            const int lane = tid & 31;
+            const int l0 = (lane / BS) * BS;
+            const int64_t nwarps = gstride >> 5;
+            for (int64_t base = (gtid >> 5) * CH; base < no; base += nwarps * CH) {
+                const int64_t d = base + lane;
+                const bool act = lane < CH && d < no;
+                double rn = 0.0;
+                if (act) {
+                    const double pn = fma(beta, a.p[d], u[d]);
+                    const double sn = fma(beta, sv[d], w[d]);
+                    a.p[d] = pn;
+                    sv[d] = sn;
+                    a.x[d] = fma(alpha, pn, a.x[d]);
+                    rn = fma(-alpha, sn, a.r[d]);
+                    a.r[d] = rn;
+                }
+                double rk[BS];
+#pragma unroll
+                for (int k = 0; k < BS; ++k) rk[k] = __shfl_sync(0xffffffffu, rn, (l0 + k) & 31);
+                if (act) {
+                    double zi = 0.0;
+#pragma unroll
+                    for (int k = 0; k < BS; ++k) zi = fma(__ldg(&a.minv[d * BS + k]), rk[k], zi);
+                    u[d] = zi;
+                    part[0] = fma(rn, zi, part[0]);
+                    part[2] = fma(rn, rn, part[2]);
+                }
+            }
+        }
+        ++it;
+    }
+    (void)gamma;
+    // ---- ghosts of the solution (as in k_pcg_persist)
+    if (a.world > 1 && status != 3) {
+        double v0[1] = {0.0};
+        if (!ps_reduce_bcast<1>(v0, a, sy, G)) status = 3;
+        if (status != 3) {
+            if (!(bb > 0.0))
+                for (int64_t i = gtid; i < no; i += gstride) a.x[i] = 0.0;
+            __syncthreads();
+            if (!ps_grid_barrier(a, sy, G)) status = 3;
+        }
+        if (status != 3) {
+            const unsigned long long xseq = ++sy.seq_halo;
+            ps_halo_push(a, a.x, xseq, G);
+            if (!ps_halo_wait(a, xseq)) status = 3;
+            else
+                for (int64_t i = no + gtid; i < a.n_local; i += gstride) a.x[i] = u[i];
+            if (status != 3 && !ps_reduce_bcast<1>(v0, a, sy, G)) status = 3;
+        }
+    } else if (!(bb > 0.0) && status == 0) {
+        for (int64_t i = gtid; i < no; i += gstride) a.x[i] = 0.0;
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        a.out_sc[0] = rr;
+        a.out_sc[1] = bb;
+        a.out_fl[0] = it;
+        a.out_fl[1] = status;
+        *a.seq_ar = sy.seq_ar;
+        *a.seq_halo = sy.seq_halo;
+    }
+}
+
 /* d_work: r q (stride ns = n_owned rounded up to even) | M^-1 (even(n_owned*block)) | p, z (even(n_local) each; with a
  * peer window z lives there instead) => 2*ns + even(n_owned*block) + 2*even(n_local) + 8 doubles. */
 extern "C" int32_t pgd_pcg_persist_sync(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
@@ -503,11 +698,13 @@ extern "C" int32_t pgd_pcg_persist_sync(pgd_handle_t h, const int32_t* d_rowptr,
     a.minv = a.q + ns;
     a.p = a.minv + ((n_owned * block + 1) & ~(int64_t)1);
     a.z = a.p + nl2;
+    a.s = a.z + nl2;  // single GPU: behind z; sharded (z lives in the window): the local z slot
     a.world = world;
     a.me = multi ? h->win_rank : 0;
     a.lay = PwLayout{multi ? h->win_pcap : 0};
     if (multi) {
         PGD_ARG(h, n_local <= h->win_pcap, "peer window too small");
+        a.s = a.z;
         a.z = reinterpret_cast<double*>(h->win_local);
         int64_t n_send = 0;
         a.hp.seg_start[0] = 0;
@@ -552,8 +749,14 @@ extern "C" int32_t pgd_pcg_persist_sync(pgd_handle_t h, const int32_t* d_rowptr,
             a.bsr.lpr = lpr;
         }
     }
+    // "single_reduction": 0 = never, 1 = sharded solves (where the second reduction costs more than it saves), 2 = always
+    const bool sr = h->opt_single_reduction >= 2 || (h->opt_single_reduction == 1 && multi);
     const void* fn = nullptr;
-    if (block == 1) fn = (const void*)k_pcg_persist<1, false>;
+    if (sr) {
+        if (block == 1) fn = (const void*)k_pcg_persist_sr<1, false>;
+        else if (block == 2) fn = bsr ? (const void*)k_pcg_persist_sr<2, true> : (const void*)k_pcg_persist_sr<2, false>;
+        else fn = bsr ? (const void*)k_pcg_persist_sr<3, true> : (const void*)k_pcg_persist_sr<3, false>;
+    } else if (block == 1) fn = (const void*)k_pcg_persist<1, false>;
     else if (block == 2) fn = bsr ? (const void*)k_pcg_persist<2, true> : (const void*)k_pcg_persist<2, false>;
     else fn = bsr ? (const void*)k_pcg_persist<3, true> : (const void*)k_pcg_persist<3, false>;
     const size_t smem = bsr ? BB_SMEM_BYTES : BK_SMEM_BYTES;

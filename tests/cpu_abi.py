@@ -112,7 +112,8 @@ def assemble_p1_rows(coords, cell_verts, gdim, c_mass, c_stiff, c_adv, rowptr, v
     import scipy.sparse as sp
 
     g = gdim
-    X = _n(coords).reshape(-1, g)[_n(cell_verts).astype(np.int64)]
+    # (cell_verts None: coords are NODE coordinates and the stand-in plan `vent` = cell -> node table indexes them)
+    X = _n(coords).reshape(-1, g)[_n(cell_verts if cell_verts is not None else vent).astype(np.int64)]
     J = np.swapaxes(X[:, 1:, :] - X[:, :1, :], 1, 2)
     det = np.linalg.det(J)
     Jinv = np.linalg.inv(J)  # [e, t, g]
@@ -135,6 +136,12 @@ def assemble_p1_rows(coords, cell_verts, gdim, c_mass, c_stiff, c_adv, rowptr, v
         out.copy_(r)
         return out
     return r
+
+
+def assemble_p1_rows_nb(gdim, c_mass, c_stiff, c_adv, rowptr, colidx, vptr, vent, n_nodes, node_xyz, max_row, nnz, out=None):
+    """stand-in: vertex numbering = node numbering for the spaces the host-logic tests use with this path"""
+    coords = _t(np.ascontiguousarray(_n(node_xyz).T))
+    return assemble_p1_rows(coords, None, gdim, c_mass, c_stiff, c_adv, rowptr, vptr, vent, n_nodes, out=out)
 
 
 def lincomb(xs, coefs, out=None, accumulate=False):
@@ -330,7 +337,7 @@ def pcg_finish(device=None):
 
 
 NAMES = ["pattern_build", "vecmap_build", "elem_bilinear", "elem_linear", "gather_values", "assemble_p1",
-         "p1_rowplan_build", "assemble_p1_rows", "lincomb",
+         "p1_rowplan_build", "assemble_p1_rows", "assemble_p1_rows_nb", "lincomb",
          "apply_dirichlet", "set_entries", "spmv", "spmv_dot", "bilinear", "dot", "panel_dots", "pcg", "banded_solve",
          "eval_weights", "eval_gemv", "eval_gemm", "row_stats", "locate_points", "probe_modes", "pcg_start", "pcg_finish", "scalar_programs"]
 

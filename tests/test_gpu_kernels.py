@@ -136,6 +136,12 @@ def test_fused_p1_operator(kind):
                                coords_soa=ds.coords_soa)
     Ao0 = cm * ofem.assemble_bilinear(S, ofem.T_mass(1, g)) + ck * ofem.assemble_bilinear(S, ofem.T_stiff(1, g))
     assert _relerr(_csr(ds, v5).data, Ao0.tocsr().data) < MAT_RTOL
+    # neighbour-cached variant (column-node coordinates in shared memory): same plan, same order => bitwise the same
+    xyz, max_row = ds.node_xyz
+    v6 = _lib.assemble_p1_rows_nb(g, cm, ck, cadv, rowptr, colidx, ds.vecmap[0], ds.rowplan, ds.n_dofs, xyz, max_row, ds.nnz)
+    assert torch.equal(v2, v6)
+    v7 = _lib.assemble_p1_rows_nb(g, cm, ck, None, rowptr, colidx, ds.vecmap[0], ds.rowplan, ds.n_dofs, xyz, max_row, ds.nnz)
+    assert torch.equal(v5, v7)
     # and it is what the atom assembly of a scalar P1 space uses
     K = ds.assemble_bilinear(ofem.T_stiff(1, g))
     assert _relerr(_csr(ds, K).data, ofem.assemble_bilinear(S, ofem.T_stiff(1, g)).tocsr().data) < MAT_RTOL
@@ -158,6 +164,9 @@ def test_fused_p1_rows_large_mesh():
     Ao = 0.3 * ofem.assemble_bilinear(S, ofem.T_mass(1, 3)) + 1.7 * ofem.assemble_bilinear(S, ofem.T_stiff(1, 3))
     assert _relerr(_csr(ds, v_new).data, Ao.tocsr().data) < MAT_RTOL
     assert _relerr(v_new.cpu().numpy(), v_old.cpu().numpy()) < MAT_RTOL
+    xyz, max_row = ds.node_xyz
+    v_nb = _lib.assemble_p1_rows_nb(3, 0.3, 1.7, None, rowptr, colidx, ds.vecmap[0], ds.rowplan, ds.n_dofs, xyz, max_row, ds.nnz)
+    assert torch.equal(v_nb, v_new)
 
 
 def test_facet_load_matches_oracle():

@@ -67,9 +67,13 @@ def run_sharded(mesh_n=68, bs=3, iters=200, hbm_peak=6451.2):
     _lib.set_option("spin_ms", 5000)
     out = {"mesh": "BoxMesh %d^3, P1 bs=%d" % (mesh_n, bs), "world": world, "n_dofs": V.n_dofs, "rows_rank0": sh.n_owned,
            "ghosts_rank0": sh.n_ghost, "nnz_rank0": ds.nnz_owned, "hbm_peak_gbs": hbm_peak}
-    for name, bsr in (("persist_bsr", ds.bsr), ("persist_csr", None)):
-        if name == "persist_bsr" and bsr is None:
+    for name, bsr, sr in (("persist_bsr", ds.bsr, 0), ("persist_bsr_single_reduction", ds.bsr, 1), ("persist_csr", None, 0),
+                          ("persist_csr_single_reduction", None, 1)):
+        if name.startswith("persist_bsr") and bsr is None:
             continue
+        if name.startswith("persist_csr") and ds.bsr is not None and sr == 1:
+            continue
+        _lib.set_option("single_reduction", sr)
         pt.sharded_solve(S, b, rtol=1e-30, maxit=10, block=bs, bsr=bsr)
         _lib.set_option("prof", 1)
         _lib.phase_ns(reset=True)
@@ -90,9 +94,15 @@ def run_sharded(mesh_n=68, bs=3, iters=200, hbm_peak=6451.2):
                            dtype=torch.float64, device=dev)
         dist.all_reduce(err)
         ghost_ok = bool(torch.allclose(xs[sh.n_owned:], x[sh.n_owned:], rtol=0, atol=1e-8))
+        ax = torch.zeros(sh.n_local, dtype=torch.float64, device=dev)
+        _lib.spmv(ds.rowptr_owned, ds.pattern[1], vals, xs, y=ax)
+        tr = torch.tensor([float((b[: sh.n_owned] - ax[: sh.n_owned]).pow(2).sum()), float(b[: sh.n_owned].pow(2).sum())],
+                          dtype=torch.float64, device=dev)
+        dist.all_reduce(tr)
         out[name] = {"ms_per_iteration": ms, "local_bytes": loc, "local_gbs": loc / (ms * 1e-3) / 1e9,
                      "frac_hbm_local": loc / (ms * 1e-3) / 1e9 / hbm_peak, "phase_us_per_iteration_rank0": {k: v / 1e3 / iters for k, v in ph.items()},
-                     "solve": {"iters": its, "relres": rr, "err": float((err[0] / err[1]).sqrt()), "ghosts_of_solution_ok": ghost_ok}}
+                     "solve": {"iters": its, "relres": rr, "true_relres": float((tr[0] / tr[1]).sqrt()),
+                               "err": float((err[0] / err[1]).sqrt()), "ghosts_of_solution_ok": ghost_ok}}
     return out if rank == 0 else None
 
 
@@ -142,8 +152,12 @@ def run(mesh_n=68, bs=3, iters=200, profile=False, hbm_peak=6451.2):
     variants = [("pcg_3launch", dict(persist=1), None), ("pcg_persist_csr", dict(persist=2, bsr=0), None)]
     if plan is not None:
         variants.append(("pcg_persist_bsr", dict(persist=1, bsr=1), plan))
+        variants.append(("pcg_persist_bsr_single_reduction", dict(persist=1, bsr=1, single_reduction=2), plan))
+    else:
+        variants.append(("pcg_persist_csr_single_reduction", dict(persist=2, bsr=0, single_reduction=2), None))
     sols = {}
     for name, opts, pl in variants:
+        _lib.set_option("single_reduction", 0)
         for o, v in opts.items():
             _lib.set_option(o, v)
 
@@ -170,7 +184,9 @@ def run(mesh_n=68, bs=3, iters=200, profile=False, hbm_peak=6451.2):
             xs, its, rr = solve(1e-13, 20000)
             s = _lib.stats()
             sols[name] = xs[:n].clone()
-            out[name]["solve"] = {"iters": its, "relres": rr, "err": float((xs[:n] - x).norm() / x.norm()), "ms": s["pcg_ms"]}
+            true_res = float((b - _lib.spmv(rowptr, colidx, vals, xs[:n].contiguous())).norm() / b.norm())
+            out[name]["solve"] = {"iters": its, "relres": rr, "true_relres": true_res, "err": float((xs[:n] - x).norm() / x.norm()),
+                                  "ms": s["pcg_ms"]}
             # warm start from the converged solution: must stop at once
             if pl is not None:
                 _, its2, rr2 = _lib.pcg_persist(rowptr, colidx, vals, b, block=bs, rtol=1e-12, maxit=100, x0=xs, bsr=pl, work=work)
@@ -182,6 +198,7 @@ def run(mesh_n=68, bs=3, iters=200, profile=False, hbm_peak=6451.2):
         out["max_rel_diff_vs_3launch"] = {kk: float((v - ref).norm() / ref.norm()) for kk, v in sols.items()}
     _lib.set_option("persist", 1)
     _lib.set_option("bsr", 1)
+    _lib.set_option("single_reduction", 1)
     return out
 
 
