@@ -31,7 +31,10 @@ const char* pgd_last_error(pgd_handle_t h);
 /* options: "pcg_resident" (default 1) = solve with the single-kernel SM-resident PCG whenever the
  * matrix slice of every SM fits in its shared memory; "persist" (default 1) = larger systems (>= 32 768 rows) run in the
  * persistent streaming kernel of pgd_pcg_persist_sync (0: three launches per iteration); "bsr" (default 1) = node-block
- * walk inside that kernel when a block-column list is supplied; "spin_ms" = budget of every in-kernel wait;
+ * walk inside that kernel when a block-column list is supplied; "single_reduction" (default 1) = 0 never / 1 on sharded
+ * systems / 2 always use the Chronopoulos-Gear form of the iteration (one grid-wide reduction per step instead of two: same
+ * Krylov method, A p carried by a recurrence; wins where the reductions dominate, i.e. across GPUs); "spin_ms" = budget
+ * of every in-kernel wait; "prof" = per-phase timers of that kernel (pgd_get_phase_ns);
  * "p2p", "graph", "fused", "pcg3", "spmv_stream": variants of the older multi-launch paths. */
 int32_t pgd_set_option(pgd_handle_t h, const char* name, int64_t value);
 /* library-side counters since the last reset: h_counts[0] kernels launched, [1] PCG solves,
@@ -91,16 +94,6 @@ int32_t pgd_assemble_p1_rows(pgd_handle_t h, const double* d_coords, const int32
                              int32_t gdim, double c_mass, double c_stiff, const double* h_c_adv,
                              const int32_t* d_rowptr, const int64_t* d_vptr, const int32_t* d_vent, int64_t n_nodes,
                              double* d_values, const double* d_coords_soa, int64_t n_verts, void* stream);
-
-/* Same operator with the coordinates of a row's column nodes cached in shared memory (the ~24 cells around a node only
- * involve the ~15 nodes of its own column list): a cell visit needs its 8-byte plan entry only -- no cell -> vertex
- * table, no global coordinate gathers (45 instead of ~290 global loads per row).  d_node_xyz: NODE coordinates,
- * component-major [gdim][n_nodes]; max_row: longest row of the pattern (<= 64).  Same plan, same summation order and
- * bitwise the same values as pgd_assemble_p1_rows. */
-int32_t pgd_assemble_p1_rows_nb(pgd_handle_t h, int32_t gdim, double c_mass, double c_stiff, const double* h_c_adv,
-                                const int32_t* d_rowptr, const int32_t* d_colidx, const int64_t* d_vptr,
-                                const int32_t* d_vent, int64_t n_nodes, const double* d_node_xyz, int32_t max_row,
-                                double* d_values, void* stream);
 
 /* ---- linear combinations: A_d = sum_k c_k K_{d,k} over CSR value arrays, and
  * b_d = sum c_m g_m - sum c_ik (K_k U_i) over cached vectors (the folded scalar coefficients of

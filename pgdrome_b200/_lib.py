@@ -28,7 +28,6 @@ SIGNATURES = {
     "pgd_vecmap_build_sync": [c_vp, c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_vp],
     "pgd_p1_rowplan_build_sync": [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_i64, c_vp, c_vp],
     "pgd_assemble_p1_rows": [c_vp, c_vp, c_vp, c_i64, c_i32, c_dbl, c_dbl, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp],
-    "pgd_assemble_p1_rows_nb": [c_vp, c_i32, c_dbl, c_dbl, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i32, c_vp, c_vp],
     "pgd_elem_bilinear": [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "pgd_elem_linear": [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "pgd_gather_values": [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp],
@@ -445,20 +444,6 @@ def assemble_p1_rows(coords, cell_verts, gdim, c_mass, c_stiff, c_adv, rowptr, v
                                     _p(vptr, I64), _p(vent, I32), n_nodes, _p(out),
                                     _p(coords_soa, F64) if coords_soa is not None else c_vp(0),
                                     coords_soa.shape[1] if coords_soa is not None else 0, _stream()), h, "pgd_assemble_p1_rows")
-    return out
-
-
-def assemble_p1_rows_nb(gdim, c_mass, c_stiff, c_adv, rowptr, colidx, vptr, vent, n_nodes, node_xyz, max_row, nnz, out=None):
-    """Neighbour-cached row-owner P1 operator (pgd_assemble_p1_rows_nb); node_xyz [gdim, n_nodes] component-major."""
-    h, lib = handle(rowptr.device), load_library()
-    if out is None:
-        out = torch.empty(int(nnz), dtype=F64, device=rowptr.device)
-    adv = None
-    if c_adv is not None:
-        adv = (c_dbl * 3)(*[float(v) for v in list(c_adv) + [0.0] * (3 - len(c_adv))])
-    _check(lib.pgd_assemble_p1_rows_nb(h, gdim, float(c_mass), float(c_stiff), ctypes.cast(adv, c_vp) if adv is not None else c_vp(0),
-                                       _p(rowptr, I32), _p(colidx, I32), _p(vptr, I64), _p(vent, I32), n_nodes, _p(node_xyz, F64),
-                                       int(max_row), _p(out, F64), _stream()), h, "pgd_assemble_p1_rows_nb")
     return out
 
 

@@ -117,16 +117,6 @@ class DeviceSpace:
             self._coords_soa = self.coords.reshape(-1, self.space.mesh().gdim).t().contiguous()
         return self._coords_soa
 
-    @property
-    def node_xyz(self):
-        """node coordinates, component-major [gdim, n_nodes], and the longest pattern row (neighbour-cached assembly)"""
-        if getattr(self, "_node_xyz", None) is None:
-            s = self.space
-            self._node_xyz = _up(np.ascontiguousarray(s.node_coords.T), torch.float64)
-            rp = self.pattern[0]
-            self._max_row = int((rp[1:] - rp[:-1]).max().item())
-        return self._node_xyz, self._max_row
-
     def _p1_closed_form(self, T):
         """(c_mass, c_stiff, c_adv) if T is  c_m u v + c_k grad u.grad v + sum_m c_adv[m] (d_m u) v, else None."""
         s = self.space
@@ -218,10 +208,6 @@ class DeviceSpace:
             if cf is not None and self.rowplan is not False:
                 # constant-coefficient P1 operator: one fused kernel straight into the CSR pattern
                 rowptr = self.pattern[0]
-                xyz, max_row = self.node_xyz
-                if max_row * g * 8 * 128 <= 160 * 1024:  # the rows' column coordinates fit the shared-memory cache
-                    return _lib.assemble_p1_rows_nb(g, cf[0], cf[1], cf[2] if any(cf[2]) else None, rowptr, self.pattern[1],
-                                                    self.vecmap[0], self.rowplan, self.n_dofs, xyz, max_row, self.nnz)
                 return _lib.assemble_p1_rows(self.coords, self.cell_verts, g, cf[0], cf[1], cf[2] if any(cf[2]) else None,
                                              rowptr, self.vecmap[0], self.rowplan, self.n_dofs, coords_soa=self.coords_soa,
                                              nnz=self.nnz)

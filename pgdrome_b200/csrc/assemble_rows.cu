@@ -10,6 +10,12 @@
 // value array held in shared memory; the slice is then written out fully coalesced.  The geometry is
 // evaluated nv times per cell instead of nv*nv times, each thread has 3*nv independent coordinate
 // loads in flight per cell, and the summation order is fixed => bitwise reproducible.
+//
+// Measured and rejected (round 2, profiles/README.md): a variant that first copies the coordinates of the row's ~15
+// column nodes into shared memory so that a cell visit needs only its plan entry (45 instead of ~290 global loads per
+// row).  360 B of shared memory per thread cap the occupancy at 18.5 % warps active and the kernel got SLOWER
+// (0.869 ms against 0.746 ms on the 128^3 mesh): this kernel is issue-bound (72 % issue slots, FP64 pipe 47 %) on its
+// 24 geometry evaluations per node, not on the gathers alone.
 #include "common.cuh"
 
 #define AR_ROWS 128       // rows (threads) per CTA
@@ -270,175 +276,6 @@ extern "C" int32_t pgd_assemble_p1_rows(pgd_handle_t h, const double* d_coords, 
     else AR_DISPATCH(3);
 #undef AR_DISPATCH
 #undef AR_LAUNCH
-    PGD_LAUNCH_OK(h);
-    return 0;
-}
-
-// ------------------------------------------------------------------------------------ neighbour-cached variant
-// ncu on the kernel above (profiles/r01_assembly_v2_*): L1TEX 85 % = top unit -- every one of the ~24 cell visits of a
-// row gathers the coordinates of the cell's other vertices again (9 scattered 8-byte loads) although the 24 cells
-// around a node only involve the ~15 nodes of the row's own column list.  Here a thread first copies the coordinates
-// of its row's columns into shared memory ([position][component][thread]: conflict-free), and a visit then needs
-// nothing but its 8-byte plan entry: the packed byte positions of the cell's vertices inside the row index the cached
-// coordinates directly (no cell -> vertex table, no global coordinate loads).  Global loads per row: 45 instead of ~290.
-// node_xyz: node coordinates, component-major [G][n_nodes] (rows are nodes: dof numbering = node numbering here).
-template <int G, bool ADV>
-__global__ void __launch_bounds__(AR_ROWS) k_assemble_p1_rows_nb(const double* __restrict__ node_xyz, int64_t n_nodes,
-                                                                 const int32_t* __restrict__ rowptr,
-                                                                 const int32_t* __restrict__ colidx,
-                                                                 const int64_t* __restrict__ vptr, const int2* __restrict__ vent,
-                                                                 int max_row, ArCoef cf, double* __restrict__ values) {
-    constexpr int NV = G + 1;
-    extern __shared__ double s_dyn[];
-    double* s_val = s_dyn;              // [AR_CAP]
-    double* s_xyz = s_dyn + AR_CAP;     // [max_row][G][AR_ROWS]
-    const int tid = threadIdx.x;
-    const int64_t r0 = (int64_t)blockIdx.x * AR_ROWS;
-    const int nr = (int)min((int64_t)AR_ROWS, n_nodes - r0);
-    const int kbase = __ldg(&rowptr[r0]);
-    const int kcnt = __ldg(&rowptr[r0 + nr]) - kbase;
-    const bool in_smem = kcnt <= AR_CAP;
-    double* acc = in_smem ? s_val : (values + kbase);
-    for (int j = tid; j < kcnt; j += AR_ROWS) acc[j] = 0.0;
-    __syncthreads();
-    if (tid < nr) {
-        const int64_t row = r0 + tid;
-        const int k0 = __ldg(&rowptr[row]), k1 = __ldg(&rowptr[row + 1]);
-        double* arow = acc + (k0 - kbase);
-        for (int j = 0; j < k1 - k0; ++j) {
-            const int c = __ldg(&colidx[k0 + j]);
-#pragma unroll
-            for (int g = 0; g < G; ++g) s_xyz[(j * G + g) * AR_ROWS + tid] = __ldg(&node_xyz[(int64_t)g * n_nodes + c]);
-        }
-        const int64_t e0 = __ldg(&vptr[row]), e1 = __ldg(&vptr[row + 1]);
-        constexpr double fact = (G == 1) ? 1.0 : (G == 2 ? 2.0 : 6.0);
-        int2 en1 = (e0 < e1) ? __ldg(&vent[e0]) : make_int2(0, 0);
-        for (int64_t e = e0; e < e1; ++e) {
-            const int2 en = en1;
-            if (e + 1 < e1) en1 = __ldg(&vent[e + 1]);
-            const int a = en.x % NV;
-            const unsigned int packed = (unsigned int)en.y;
-            double X[NV][G];
-#pragma unroll
-            for (int v = 0; v < NV; ++v) {
-                const int pos = (packed >> (8 * v)) & 255u;
-#pragma unroll
-                for (int g = 0; g < G; ++g) X[v][g] = s_xyz[(pos * G + g) * AR_ROWS + tid];
-            }
-            double Jinv[G][G], det;
-            if constexpr (G == 1) {
-                const double j00 = X[1][0] - X[0][0];
-                det = j00;
-                Jinv[0][0] = 1.0 / j00;
-            } else if constexpr (G == 2) {
-                const double j00 = X[1][0] - X[0][0], j01 = X[2][0] - X[0][0];
-                const double j10 = X[1][1] - X[0][1], j11 = X[2][1] - X[0][1];
-                det = j00 * j11 - j01 * j10;
-                const double id = 1.0 / det;
-                Jinv[0][0] = j11 * id;
-                Jinv[0][1] = -j01 * id;
-                Jinv[1][0] = -j10 * id;
-                Jinv[1][1] = j00 * id;
-            } else {
-                double J[3][3];
-#pragma unroll
-                for (int g = 0; g < 3; ++g)
-#pragma unroll
-                    for (int t = 0; t < 3; ++t) J[g][t] = X[t + 1][g] - X[0][g];
-                const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
-                const double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
-                const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
-                det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
-                const double id = 1.0 / det;
-                Jinv[0][0] = c00 * id;
-                Jinv[1][0] = c01 * id;
-                Jinv[2][0] = c02 * id;
-                Jinv[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * id;
-                Jinv[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * id;
-                Jinv[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * id;
-                Jinv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * id;
-                Jinv[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * id;
-                Jinv[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id;
-            }
-            const double vol = fabs(det) / fact;
-            double grad[NV][G];
-#pragma unroll
-            for (int m = 0; m < G; ++m) {
-                double s0 = 0.0;
-#pragma unroll
-                for (int t = 0; t < G; ++t) {
-                    s0 -= Jinv[t][m];
-                    grad[t + 1][m] = Jinv[t][m];
-                }
-                grad[0][m] = s0;
-            }
-            double ga[G];
-#pragma unroll
-            for (int m = 0; m < G; ++m) {
-                double v = grad[0][m];
-#pragma unroll
-                for (int t = 1; t < NV; ++t) v = (a == t) ? grad[t][m] : v;
-                ga[m] = v;
-            }
-#pragma unroll
-            for (int b = 0; b < NV; ++b) {
-                double dotg = 0.0, adv = 0.0;
-#pragma unroll
-                for (int m = 0; m < G; ++m) {
-                    dotg += ga[m] * grad[b][m];
-                    if (ADV) adv += cf.cadv[m] * grad[b][m];
-                }
-                const double mass = vol * ((a == b) ? 2.0 : 1.0) / (double)((G + 1) * (G + 2));
-                double val = cf.cm * mass + cf.ck * vol * dotg;
-                if (ADV) val += adv * vol / (double)(G + 1);
-                arow[(packed >> (8 * b)) & 255u] += val;
-            }
-        }
-    }
-    if (in_smem) {
-        __syncthreads();
-        for (int j = tid; j < kcnt; j += AR_ROWS) values[kbase + j] = s_val[j];
-    }
-}
-
-extern "C" int32_t pgd_assemble_p1_rows_nb(pgd_handle_t h, int32_t gdim, double c_mass, double c_stiff, const double* h_c_adv,
-                                           const int32_t* d_rowptr, const int32_t* d_colidx, const int64_t* d_vptr,
-                                           const int32_t* d_vent, int64_t n_nodes, const double* d_node_xyz, int32_t max_row,
-                                           double* d_values, void* stream) {
-    PGD_CHECK_HANDLE(h);
-    PGD_ARG(h, d_rowptr && d_colidx && d_vptr && d_vent && d_node_xyz && d_values, "null pointer");
-    PGD_ARG(h, gdim >= 1 && gdim <= 3 && max_row >= 1 && max_row <= 64, "gdim must be 1..3, max_row 1..64");
-    if (n_nodes <= 0) return 0;
-    ArCoef cf;
-    cf.cm = c_mass;
-    cf.ck = c_stiff;
-    bool adv = false;
-    for (int m = 0; m < 3; ++m) {
-        cf.cadv[m] = (h_c_adv && m < gdim) ? h_c_adv[m] : 0.0;
-        adv = adv || cf.cadv[m] != 0.0;
-    }
-    cudaStream_t st = (cudaStream_t)stream;
-    const unsigned int blocks = pgd_blocks(n_nodes, AR_ROWS);
-    const int2* vent = reinterpret_cast<const int2*>(d_vent);
-    const size_t smem = sizeof(double) * ((size_t)AR_CAP + (size_t)max_row * gdim * AR_ROWS);
-    PGD_ARG(h, smem <= 200 * 1024, "rows too long for the neighbour cache");
-#define NB_LAUNCH(G, A)                                                                                              \
-    do {                                                                                                             \
-        PGD_CUDA(h, cudaFuncSetAttribute(k_assemble_p1_rows_nb<G, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_assemble_p1_rows_nb<G, A><<<blocks, AR_ROWS, smem, st>>>(d_node_xyz, n_nodes, d_rowptr, d_colidx, d_vptr, vent, max_row, \
-                                                                   cf, d_values);                                   \
-    } while (0)
-    if (gdim == 1) {
-        if (adv) NB_LAUNCH(1, true);
-        else NB_LAUNCH(1, false);
-    } else if (gdim == 2) {
-        if (adv) NB_LAUNCH(2, true);
-        else NB_LAUNCH(2, false);
-    } else {
-        if (adv) NB_LAUNCH(3, true);
-        else NB_LAUNCH(3, false);
-    }
-#undef NB_LAUNCH
     PGD_LAUNCH_OK(h);
     return 0;
 }

@@ -24,6 +24,7 @@ extern "C" int32_t pgd_create(int32_t device, pgd_handle_t* out) {
     h->opt_persist = 1;
     h->opt_bsr = 1;
     h->opt_spin_ms = 20000;
+    h->opt_single_reduction = 0;
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     if ((e = cudaMalloc(&h->partials, sizeof(double) * PGD_MAX_PARTIALS)) != cudaSuccess ||
         (e = cudaMalloc(&h->counters, sizeof(unsigned int) * PGD_MAX_COUNTERS)) != cudaSuccess ||
@@ -143,7 +144,11 @@ struct LcArgs {
 };
 
 // VEC: every pointer is 16-byte aligned -> 128-bit loads/stores, two element pairs in flight per thread
-// (torch.dot reads at 7.1 TB/s on this box, the scalar version of this kernel reached 5.2: tools/micro/bw_probe.py)
+// (torch.dot reads at 7.1 TB/s on this box, the scalar version of this kernel reached 5.2: tools/micro/bw_probe.py).
+// Every array is touched exactly once: streaming (evict-first) loads and stores.  ncu on the first version
+// (profiles/r02_kernels_128cube_ncu_summary.json): 179 us for 2 atoms of 31.8 M entries, 511 MB read but 469 MB WRITTEN
+// for a 254 MB result -- 5.5 TB/s of actual DRAM traffic (85 %), i.e. the kernel was at the memory limit with ~215 MB
+// of write-back traffic it did not need.
 template <bool VEC>
 __global__ void __launch_bounds__(256) k_lincomb(LcArgs a, int64_t n, double* __restrict__ out, int accumulate) {
     if (a.dc) {
@@ -160,11 +165,11 @@ __global__ void __launch_bounds__(256) k_lincomb(LcArgs a, int64_t n, double* __
             double2 s = accumulate ? o2[i] : make_double2(0.0, 0.0);
 #pragma unroll 4
             for (int t = 0; t < a.n_terms; ++t) {
-                const double2 v = __ldg(reinterpret_cast<const double2*>(a.x[t]) + i);
+                const double2 v = __ldcs(reinterpret_cast<const double2*>(a.x[t]) + i);
                 s.x += a.c[t] * v.x;
                 s.y += a.c[t] * v.y;
             }
-            o2[i] = s;
+            __stcs(o2 + i, s);
         }
         if ((n & 1) && gtid == 0) {
             double s = accumulate ? out[n - 1] : 0.0;

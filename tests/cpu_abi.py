@@ -138,12 +138,6 @@ def assemble_p1_rows(coords, cell_verts, gdim, c_mass, c_stiff, c_adv, rowptr, v
     return r
 
 
-def assemble_p1_rows_nb(gdim, c_mass, c_stiff, c_adv, rowptr, colidx, vptr, vent, n_nodes, node_xyz, max_row, nnz, out=None):
-    """stand-in: vertex numbering = node numbering for the spaces the host-logic tests use with this path"""
-    coords = _t(np.ascontiguousarray(_n(node_xyz).T))
-    return assemble_p1_rows(coords, None, gdim, c_mass, c_stiff, c_adv, rowptr, vptr, vent, n_nodes, out=out)
-
-
 def lincomb(xs, coefs, out=None, accumulate=False):
     n = (out if out is not None else xs[0]).numel()
     acc = out.clone() if (accumulate and out is not None) else torch.zeros(n, dtype=F64)
@@ -337,7 +331,7 @@ def pcg_finish(device=None):
 
 
 NAMES = ["pattern_build", "vecmap_build", "elem_bilinear", "elem_linear", "gather_values", "assemble_p1",
-         "p1_rowplan_build", "assemble_p1_rows", "assemble_p1_rows_nb", "lincomb",
+         "p1_rowplan_build", "assemble_p1_rows", "lincomb",
          "apply_dirichlet", "set_entries", "spmv", "spmv_dot", "bilinear", "dot", "panel_dots", "pcg", "banded_solve",
          "eval_weights", "eval_gemv", "eval_gemm", "row_stats", "locate_points", "probe_modes", "pcg_start", "pcg_finish", "scalar_programs"]
 

@@ -136,12 +136,6 @@ def test_fused_p1_operator(kind):
                                coords_soa=ds.coords_soa)
     Ao0 = cm * ofem.assemble_bilinear(S, ofem.T_mass(1, g)) + ck * ofem.assemble_bilinear(S, ofem.T_stiff(1, g))
     assert _relerr(_csr(ds, v5).data, Ao0.tocsr().data) < MAT_RTOL
-    # neighbour-cached variant (column-node coordinates in shared memory): same plan, same order => bitwise the same
-    xyz, max_row = ds.node_xyz
-    v6 = _lib.assemble_p1_rows_nb(g, cm, ck, cadv, rowptr, colidx, ds.vecmap[0], ds.rowplan, ds.n_dofs, xyz, max_row, ds.nnz)
-    assert torch.equal(v2, v6)
-    v7 = _lib.assemble_p1_rows_nb(g, cm, ck, None, rowptr, colidx, ds.vecmap[0], ds.rowplan, ds.n_dofs, xyz, max_row, ds.nnz)
-    assert torch.equal(v5, v7)
     # and it is what the atom assembly of a scalar P1 space uses
     K = ds.assemble_bilinear(ofem.T_stiff(1, g))
     assert _relerr(_csr(ds, K).data, ofem.assemble_bilinear(S, ofem.T_stiff(1, g)).tocsr().data) < MAT_RTOL
@@ -164,9 +158,6 @@ def test_fused_p1_rows_large_mesh():
     Ao = 0.3 * ofem.assemble_bilinear(S, ofem.T_mass(1, 3)) + 1.7 * ofem.assemble_bilinear(S, ofem.T_stiff(1, 3))
     assert _relerr(_csr(ds, v_new).data, Ao.tocsr().data) < MAT_RTOL
     assert _relerr(v_new.cpu().numpy(), v_old.cpu().numpy()) < MAT_RTOL
-    xyz, max_row = ds.node_xyz
-    v_nb = _lib.assemble_p1_rows_nb(3, 0.3, 1.7, None, rowptr, colidx, ds.vecmap[0], ds.rowplan, ds.n_dofs, xyz, max_row, ds.nnz)
-    assert torch.equal(v_nb, v_new)
 
 
 def test_facet_load_matches_oracle():
@@ -608,3 +599,88 @@ def test_scalar_programs_bitwise_and_lincomb_dev():
     assert torch.equal(a, b)
     acc = _lib.lincomb(xs[:3], coefs_dev[:3], out=a.clone(), accumulate=True)
     assert torch.equal(acc, _lib.lincomb(xs[:3], expect[:3], out=b.clone(), accumulate=True))
+
+
+@pytest.mark.parametrize("bs", [1, 3])
+def test_persistent_pcg_variants(bs):
+    """pgd_pcg_persist_sync on one GPU: plain CSR ring, node-block walk and the single-reduction form of the iteration
+    against a direct solve; identical iteration counts (within 1 %), warm start, zero right-hand side, row statistics."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+
+    from pgdrome_b200 import _lib, fem
+    from pgdrome_b200.assembly import device_space
+
+    m = fem.UnitCubeMesh(14, 14, 14)
+    V = fem.FunctionSpace(m, "P", 1) if bs == 1 else fem.VectorFunctionSpace(m, "P", 1)
+    ds = device_space(V)
+    g = 3
+    T = np.zeros((bs, g + 1, bs, g + 1))
+    for i in range(bs):
+        T[i, 0, i, 0] = 0.3
+        for j in range(bs):
+            T[i, 1 + i, j, 1 + j] += 1.3 if bs > 1 else 0.0
+            T[i, 1 + j, j, 1 + i] += 0.7 if bs > 1 else 0.0
+            T[i, 1 + j, i, 1 + j] += 0.7 if bs > 1 else 0.0
+    if bs == 1:
+        for k in range(1, g + 1):
+            T[0, k, 0, k] = 1.7
+    vals = ds.assemble_bilinear(T)
+    rowptr, colidx, _, _ = ds.pattern
+    n = ds.n_dofs
+    A = sp.csr_matrix((vals.cpu().numpy(), colidx.cpu().numpy(), rowptr.cpu().numpy()), shape=(n, n))
+    rng = np.random.default_rng(1)
+    xs = rng.uniform(-1, 1, n)
+    b = torch.as_tensor(A @ xs, device=vals.device)
+    ref = spla.spsolve(A.tocsc(), A @ xs)
+    plan = _lib.bsr_plan(rowptr, colidx, bs) if bs > 1 else None
+    assert (plan is not None) == (bs > 1)
+    if plan is not None:
+        assert plan[0].numel() * bs * bs == colidx.numel() and plan[1] <= 27
+    results = {}
+    try:
+        for name, sr, pl in (("csr", 0, None), ("csr_sr", 2, None), ("bsr", 0, plan), ("bsr_sr", 2, plan)):
+            if pl is None and name.startswith("bsr"):
+                continue
+            _lib.set_option("single_reduction", sr)
+            x, it, rr = _lib.pcg_persist(rowptr, colidx, vals, b, block=bs, rtol=1e-13, maxit=5000, bsr=pl)
+            assert rr <= 1e-13 and 0 < it < 5000, (name, it, rr)
+            assert np.linalg.norm(x.cpu().numpy() - ref) / np.linalg.norm(ref) < 1e-10, name
+            results[name] = it
+            # warm start from the solution: no iteration; zero right-hand side: the solution is zero whatever x0 was
+            x2, it2, _ = _lib.pcg_persist(rowptr, colidx, vals, b, block=bs, rtol=1e-12, maxit=50, x0=x, bsr=pl)
+            assert it2 == 0 and torch.equal(x2, x)
+            x3, it3, rr3 = _lib.pcg_persist(rowptr, colidx, vals, torch.zeros_like(b), block=bs, rtol=1e-12, maxit=50,
+                                            x0=x.clone(), bsr=pl)
+            assert it3 == 0 and rr3 == 0.0 and float(x3.abs().max()) == 0.0
+            # bitwise reproducible
+            x4, it4, _ = _lib.pcg_persist(rowptr, colidx, vals, b, block=bs, rtol=1e-13, maxit=5000, bsr=pl)
+            assert it4 == it and torch.equal(x4, x), name
+    finally:
+        _lib.set_option("single_reduction", 0)
+    base = results["csr"]
+    assert all(abs(v - base) <= max(2, base // 100) for v in results.values()), results
+    # the multi-launch solver on the same system: same counts
+    _lib.set_option("pcg_resident", 0)
+    try:
+        x5, it5, _ = _lib.pcg(rowptr, colidx, vals, b, rtol=1e-13, maxit=5000, check_every=10, block=bs)
+    finally:
+        _lib.set_option("pcg_resident", 1)
+    assert abs(it5 - base) <= max(2, base // 100)
+
+
+def test_row_stats_kernel():
+    from pgdrome_b200 import _lib
+
+    g = torch.Generator(device="cuda").manual_seed(3)
+    U = torch.randn((37, 1001), dtype=torch.float64, device="cuda", generator=g)
+    F = U + 1e-3 * torch.randn((37, 1001), dtype=torch.float64, device="cuda", generator=g)
+    st = _lib.row_stats(U, F).cpu().numpy()
+    u, f = U.cpu().numpy(), F.cpu().numpy()
+    assert np.array_equal(st[:, 0], u.min(axis=1)) and np.array_equal(st[:, 1], u.max(axis=1))
+    assert np.array_equal(st[:, 2], np.abs(u).min(axis=1)) and np.array_equal(st[:, 3], np.abs(u).max(axis=1))
+    assert np.allclose(st[:, 4], (u * u).sum(axis=1), rtol=1e-13)
+    assert np.allclose(st[:, 5], ((u - f) ** 2).sum(axis=1), rtol=1e-12) and np.allclose(st[:, 6], (f * f).sum(axis=1), rtol=1e-13)
+    st2 = _lib.row_stats(U[:, :999]).cpu().numpy()  # strided rows, no reference block
+    assert np.array_equal(st2[:, 1], u[:, :999].max(axis=1)) and np.all(st2[:, 5] == 0.0)
+    assert torch.equal(_lib.row_stats(U, F), _lib.row_stats(U, F))

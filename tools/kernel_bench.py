@@ -74,11 +74,6 @@ def run(mesh_n=128, hbm_peak=6451.2, evaluate=True, fp64_peak=None):
     entry("assemble_p1_rows", ms, 4 * 4 * nc + 8 * 3 * m.num_vertices() + 8 * nnz,
           note="row-owner kernel; also reads the 8 B/(cell,vertex) plan (%d MB) and re-reads cell vertices 4x through L1/L2"
                % (8 * 4 * nc // 1000000))
-    xyz, max_row = ds.node_xyz
-    ms = _time(lambda: _lib.assemble_p1_rows_nb(3, 0.3, 1.7, None, rowptr, colidx, vptr, plan, n, xyz, max_row, nnz, out=vals))
-    entry("assemble_p1_rows_nb", ms, 4 * 4 * nc + 8 * 3 * m.num_vertices() + 8 * nnz,
-          note="neighbour-cached row-owner kernel: reads the 8 B/(cell,vertex) plan (%d MB) and colidx, no cell -> vertex table, "
-               "no global coordinate gathers per cell visit" % (8 * 4 * nc // 1000000))
     # generic element kernel + gather (used once per atom at set-up)
     T = np.zeros((1, 4, 1, 4))
     for k in range(1, 4):
