@@ -95,6 +95,17 @@ int32_t pgd_assemble_p1_rows(pgd_handle_t h, const double* d_coords, const int32
                              const int32_t* d_rowptr, const int64_t* d_vptr, const int32_t* d_vent, int64_t n_nodes,
                              double* d_values, const double* d_coords_soa, int64_t n_verts, void* stream);
 
+/* Row-owner assembly of ANY constant-coefficient P1 atom (form tensor h_T [bs][gdim+1][bs][gdim+1]: mass, stiffness, first
+ * derivatives, Voigt elasticity, ...) on a scalar or node-blocked vector P1 space, optional per-cell coefficient d_w_cell
+ * [n_cells] (degree-0 Expression), straight into the CSR pattern: one thread per dof row, no element-matrix buffer and no
+ * gather pass.  The plan (d_node_vptr int64 [n_nodes+1], d_node_vent int32 pairs) is pgd_vecmap_build_sync +
+ * pgd_p1_rowplan_build_sync on the NODE-level pattern (block rows / block columns; for bs = 1 the dof-level plan);
+ * d_coords_soa [gdim][n_verts] component-major; n_rows = n_nodes * bs.  Deterministic. */
+int32_t pgd_assemble_p1_tensor(pgd_handle_t h, int32_t gdim, int32_t bs, const double* h_T, const double* d_coords_soa,
+                               int64_t n_verts, const int32_t* d_cell_verts, const int32_t* d_rowptr,
+                               const int64_t* d_node_vptr, const int32_t* d_node_vent, const double* d_w_cell, int64_t n_rows,
+                               double* d_values, void* stream);
+
 /* ---- linear combinations: A_d = sum_k c_k K_{d,k} over CSR value arrays, and
  * b_d = sum c_m g_m - sum c_ik (K_k U_i) over cached vectors (the folded scalar coefficients of
  * SURVEY.md 7.1).  h_xs: HOST array of n_terms device pointers; h_coefs: HOST array. */

@@ -228,9 +228,10 @@ def heat2d_tk(n=256, nt=199, nk=49, krange=(0.5, 2.0), rho_cp=1.0, a=0.2, xc=(0.
     return p, {"spaces": S, "src": src}
 
 
-def elasticity3d(n=68, nE=49, nF=2, nu=0.3, Erange=(0.5, 1.5), Frange=(0.0, 2.0), spaces=None, **kw):
-    """configs[2] (pgdrome_b200/configs.py:elasticity3d) in matrix form: two-material cube, clamped at
-    x=0, traction on x=1.  No reference callback set exists for it: parity unpinned (oracle only)."""
+def elasticity3d(n=68, nE=49, nF=2, nu=0.3, Erange=(0.5, 1.5), Frange=(0.0, 2.0), spaces=None, zones=3, **kw):
+    """configs[2] (pgdrome_b200/configs.py:elasticity3d) in matrix form: material zones along x with moduli 1 | E | E^2
+    (zones=3; zones=2: 1 | E), clamped at x=0, traction on x=1.  No reference callback set exists for it: parity unpinned
+    (oracle only)."""
     from .meshes import box_mesh
 
     if spaces is None:
@@ -240,11 +241,15 @@ def elasticity3d(n=68, nE=49, nF=2, nu=0.3, Erange=(0.5, 1.5), Frange=(0.0, 2.0)
         S = spaces
     lam, mu = nu / ((1 + nu) * (1 - 2 * nu)), 1.0 / (2 * (1 + nu))
     T = fem.T_voigt(fem.isotropic_C(lam, mu, 3), 3)
-    chi1 = lambda x: np.where(x[..., 0] < 0.5, 1.0, 0.0)
-    chi2 = lambda x: np.where(x[..., 0] < 0.5, 0.0, 1.0)
-    K1 = fem.assemble_bilinear(S[0], T, weight=chi1, weight_degree=0)
-    K2 = fem.assemble_bilinear(S[0], T, weight=chi2, weight_degree=0)
-    ME, MEw, MF = _mass(S[1]), _mass(S[1], _x, 1), _mass(S[2])
+    if zones == 2:
+        chis = [lambda x: np.where(x[..., 0] < 0.5, 1.0, 0.0), lambda x: np.where(x[..., 0] < 0.5, 0.0, 1.0)]
+    else:
+        a, b = 1.0 / 3.0, 2.0 / 3.0
+        chis = [lambda x: np.where(x[..., 0] < a, 1.0, 0.0), lambda x: np.where((x[..., 0] >= a) & (x[..., 0] < b), 1.0, 0.0),
+                lambda x: np.where(x[..., 0] >= b, 1.0, 0.0)]
+    Ks = [fem.assemble_bilinear(S[0], T, weight=c, weight_degree=0) for c in chis]
+    MEs = [_mass(S[1]), _mass(S[1], _x, 1), _mass(S[1], lambda x: x[..., 0] * x[..., 0], 2)]
+    MF = _mass(S[2])
     near = lambda a, b: abs(a - b) < 3e-16 * max(1.0, abs(a), abs(b)) + 3e-16
     face = fem.facet_space(S[0], lambda x: near(x[0], 1.0))
     Lt = np.zeros((3, 4))
@@ -256,7 +261,7 @@ def elasticity3d(n=68, nE=49, nF=2, nu=0.3, Erange=(0.5, 1.5), Frange=(0.0, 2.0)
     opts = dict(PGD_nmax=30, tol_fp_it=1e-5, max_fp_it=50)
     opts.update(kw)
     p = SeparatedProblem(n_dofs=[s.n_dofs for s in S], mass=[_mass(s) for s in S], bc_dofs=[bcx, none, none],
-                         lhs_terms=[(1.0, [K1, ME, MF]), (1.0, [K2, MEw, MF])], rhs_terms=rhs, seq_fp=[0, 1, 2], **opts)
+                         lhs_terms=[(1.0, [Ks[k], MEs[k], MF]) for k in range(len(chis))], rhs_terms=rhs, seq_fp=[0, 1, 2], **opts)
     return p, {"spaces": S}
 
 

@@ -43,6 +43,8 @@ def build_library(force=False, verbose=False):
         obj = os.path.join(build_dir, src.replace(".cu", ".o"))
         objs.append(obj)
         cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        if src == "pcg_persist.cu":  # tuning experiments on the persistent kernel only (CTA size / CTAs per SM / stage size)
+            cmd += [f for f in os.environ.get("PGD_NVCC_EXTRA_PERSIST", "").split() if f]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

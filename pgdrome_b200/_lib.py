@@ -28,6 +28,7 @@ SIGNATURES = {
     "pgd_vecmap_build_sync": [c_vp, c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_vp],
     "pgd_p1_rowplan_build_sync": [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_i64, c_vp, c_vp],
     "pgd_assemble_p1_rows": [c_vp, c_vp, c_vp, c_i64, c_i32, c_dbl, c_dbl, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp],
+    "pgd_assemble_p1_tensor": [c_vp, c_i32, c_i32, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp],
     "pgd_elem_bilinear": [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "pgd_elem_linear": [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "pgd_gather_values": [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp],
@@ -444,6 +445,19 @@ def assemble_p1_rows(coords, cell_verts, gdim, c_mass, c_stiff, c_adv, rowptr, v
                                     _p(vptr, I64), _p(vent, I32), n_nodes, _p(out),
                                     _p(coords_soa, F64) if coords_soa is not None else c_vp(0),
                                     coords_soa.shape[1] if coords_soa is not None else 0, _stream()), h, "pgd_assemble_p1_rows")
+    return out
+
+
+def assemble_p1_tensor(gdim, bs, T, coords_soa, cell_verts, rowptr, node_vptr, node_vent, n_rows, nnz, w_cell=None, out=None):
+    """Fused row-owner assembly of a constant-coefficient P1 atom with form tensor T (pgd_assemble_p1_tensor)."""
+    h, lib = handle(rowptr.device), load_library()
+    if out is None:
+        out = torch.empty(int(nnz), dtype=F64, device=rowptr.device)
+    Th = np.ascontiguousarray(np.asarray(T, dtype=np.float64).reshape(bs, gdim + 1, bs, gdim + 1))
+    _check(lib.pgd_assemble_p1_tensor(h, gdim, bs, Th.ctypes.data_as(c_vp), _p(coords_soa, F64), coords_soa.shape[1],
+                                      _p(cell_verts, I32), _p(rowptr, I32), _p(node_vptr, I64), _p(node_vent, I32),
+                                      _p(w_cell, F64) if w_cell is not None else c_vp(0), int(n_rows), _p(out, F64), _stream()),
+           h, "pgd_assemble_p1_tensor")
     return out
 
 

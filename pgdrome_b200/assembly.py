@@ -117,6 +117,49 @@ class DeviceSpace:
             self._coords_soa = self.coords.reshape(-1, self.space.mesh().gdim).t().contiguous()
         return self._coords_soa
 
+    @property
+    def node_plan(self):
+        """(node_vptr, node_vent) of the row-owner plan on the NODE-level pattern (block rows / block columns) for the
+        general-tensor fused P1 kernel, or False (not an affine P1 space, or a node row longer than 255 blocks)."""
+        if getattr(self, "_node_plan", None) is None:
+            s = self.space
+            self._node_plan = False
+            if s.degree == 1 and s.mesh().tdim == s.mesh().gdim:
+                try:
+                    if s.bs == 1:
+                        if self.rowplan is not False:
+                            self._node_plan = (self.vecmap[0], self.rowplan)
+                    else:
+                        rowptr, colidx, _, _ = self.pattern
+                        blk = _lib.bsr_plan(rowptr, colidx, s.bs)
+                        if blk is not None:
+                            brp = torch.div(rowptr[:: s.bs], s.bs * s.bs, rounding_mode="floor").to(torch.int32).contiguous()
+                            cn = _up(np.ascontiguousarray(s.cell_nodes, dtype=np.int32), torch.int32)
+                            vptr, vidx = _lib.vecmap_build(cn, s.n_nodes)
+                            vent = _lib.p1_rowplan_build(brp, blk[0], cn, vptr, vidx, s.n_nodes)
+                            self._node_plan = (vptr, vent)
+                except _lib.PGDB200Error:
+                    self._node_plan = False
+        return self._node_plan
+
+    def _cell_weight(self, weights, weight, wdeg):
+        """per-cell coefficient (device, [n_cells]) when every weight is a degree-0 Expression / callable; None if there
+        is no weight; False if some weight varies inside the cells"""
+        specs = list(weights or [])
+        if weight is not None:
+            specs.append(("callable", weight, None, wdeg, None))
+        if not specs:
+            return None
+        w = None
+        zero = np.zeros((1, self.space.mesh().tdim))
+        for kind, obj, comp, d, _ in specs:
+            if kind == "fn" or d != 0:
+                return False
+            fn = obj if kind == "callable" else (lambda X, o=obj, c=comp: o.eval_np(X, c))
+            v = self.sample_weight(fn, 0, zero)[:, 0]
+            w = v if w is None else w * v
+        return _up(np.ascontiguousarray(w), torch.float64)
+
     def _p1_closed_form(self, T):
         """(c_mass, c_stiff, c_adv) if T is  c_m u v + c_k grad u.grad v + sum_m c_adv[m] (d_m u) v, else None."""
         s = self.space
@@ -211,6 +254,13 @@ class DeviceSpace:
                 return _lib.assemble_p1_rows(self.coords, self.cell_verts, g, cf[0], cf[1], cf[2] if any(cf[2]) else None,
                                              rowptr, self.vecmap[0], self.rowplan, self.n_dofs, coords_soa=self.coords_soa,
                                              nnz=self.nnz)
+        if s.degree == 1 and m.tdim == g:
+            # any other constant-coefficient P1 atom (vector spaces, Voigt elasticity, mixed derivative terms, material
+            # zones): the general-tensor row-owner kernel, still straight into the CSR pattern
+            wc = self._cell_weight(weights, weight, wdeg)
+            if wc is not False and self.node_plan is not False:
+                return _lib.assemble_p1_tensor(g, s.bs, T, self.coords_soa, self.cell_verts, self.pattern[0], self.node_plan[0],
+                                               self.node_plan[1], self.n_dofs, self.nnz, w_cell=wc)
         # polynomial degree of the integrand on an affine simplex
         dv = s.degree if np.any(T[:, 0, :, :] != 0) else s.degree - 1
         du = s.degree if np.any(T[:, :, :, 0] != 0) else s.degree - 1

@@ -191,11 +191,14 @@ def _separated_problem(name, name_coord, Vs, ops, coefs, loads, bc_fct, probs, P
     return p
 
 
-def elasticity3d(n=68, nE=49, nF=2, nu=0.3, Erange=(0.5, 1.5), Frange=(0.0, 2.0), PGD_nmax=30, **attrs):
+def elasticity3d(n=68, nE=49, nF=2, nu=0.3, Erange=(0.5, 1.5), Frange=(0.0, 2.0), PGD_nmax=30, zones=3, **attrs):
     """configs[2]: 3-D linear elasticity u(x, E, F) on a unit cube of vector P1 tetrahedra (n=68:
-    985 527 dofs), clamped at x=0, traction F*(0,0,-1) on the face x=1.  The stiff half x < 1/2 keeps
-    Young's modulus 1, the half x >= 1/2 has the parametric modulus E, which makes the solution
-    non-separable in (x, E); the load amplitude F enters linearly."""
+    985 527 dofs), clamped at x=0, traction F*(0,0,-1) on the face x=1.  Three material zones along x (zones=3,
+    default): x < 1/3 keeps Young's modulus 1, 1/3 <= x < 2/3 has the parametric modulus E, x >= 2/3 has E^2 -- the
+    operator is  K_1 + E K_2 + E^2 K_3, the solution is rational in E and the enrichment uses the full budget of 30
+    modes (amplitudes down to 5e-9).  zones=2 is the round-1 variant (x < 1/2: 1, x >= 1/2: E), whose separated rank is
+    only 9: its residual falls below the reference's absolute 1e-10 stop (solver.py:381-395) after 9 modes.  The load
+    amplitude F enters linearly."""
     mx = df.UnitCubeMesh(n, n, n)
     mE, mF = df.IntervalMesh(nE, Erange[0], Erange[1]), df.IntervalMesh(nF, Frange[0], Frange[1])
     Vs = [df.VectorFunctionSpace(mx, "P", 1), df.FunctionSpace(mE, "P", 1), df.FunctionSpace(mF, "P", 1)]
@@ -205,9 +208,16 @@ def elasticity3d(n=68, nE=49, nF=2, nu=0.3, Erange=(0.5, 1.5), Frange=(0.0, 2.0)
     C[np.arange(3), np.arange(3)] += 2 * mu
     C[np.arange(3, 6), np.arange(3, 6)] = mu
     Cm = df.as_matrix(C)
-    chi1 = df.Expression("x[0] < 0.5 ? 1.0 : 0.0", degree=0)
-    chi2 = df.Expression("x[0] < 0.5 ? 0.0 : 1.0", degree=0)
+    if zones == 2:
+        chis = [df.Expression("x[0] < 0.5 ? 1.0 : 0.0", degree=0), df.Expression("x[0] < 0.5 ? 0.0 : 1.0", degree=0)]
+    elif zones == 3:
+        chis = [df.Expression("x[0] < a ? 1.0 : 0.0", degree=0, a=1.0 / 3.0),
+                df.Expression("(x[0] >= a && x[0] < b) ? 1.0 : 0.0", degree=0, a=1.0 / 3.0, b=2.0 / 3.0),
+                df.Expression("x[0] >= b ? 1.0 : 0.0", degree=0, b=2.0 / 3.0)]
+    else:
+        raise ValueError("zones must be 2 or 3")
     Ew = df.Expression("x[0]", degree=1)
+    Ew2 = df.Expression("x[0]*x[0]", degree=2)
     trac = df.Constant((0.0, 0.0, -1.0))
     facets = df.MeshFunction("size_t", mx, 2, 0)
 
@@ -226,8 +236,8 @@ def elasticity3d(n=68, nE=49, nF=2, nu=0.3, Erange=(0.5, 1.5), Frange=(0.0, 2.0)
         return lambda u, v: chi * df.inner(Cm * eps(u), eps(v)) * df.dx(mx)
 
     mass = lambda mesh: (lambda u, v: u * v * df.dx(mesh))
-    ops = [[kx(chi1), mass(mE), mass(mF)],
-           [kx(chi2), lambda u, v: u * Ew * v * df.dx(mE), mass(mF)]]
+    e_ops = [mass(mE), lambda u, v: u * Ew * v * df.dx(mE), lambda u, v: u * Ew2 * v * df.dx(mE)]
+    ops = [[kx(chis[k]), e_ops[k], mass(mF)] for k in range(zones)]
     Fw = df.Expression("x[0]", degree=1)
     one = df.Expression("1.0", degree=1)
     loads = [[lambda w: df.dot(trac, w) * ds(2), lambda w: one * w * df.dx(mE), lambda w: Fw * w * df.dx(mF)]]
@@ -238,7 +248,7 @@ def elasticity3d(n=68, nE=49, nF=2, nu=0.3, Erange=(0.5, 1.5), Frange=(0.0, 2.0)
 
         return [df.DirichletBC(Vs[0], df.Constant((0.0, 0.0, 0.0)), left), 0, 0]
 
-    return _separated_problem("elasticity3d", ["X", "E", "F"], Vs, ops, [1.0, 1.0], loads, bc_fct, ["r", "s", "t"],
+    return _separated_problem("elasticity3d", ["X", "E", "F"], Vs, ops, [1.0] * zones, loads, bc_fct, ["r", "s", "t"],
                               PGD_nmax, **attrs)
 
 

@@ -111,7 +111,7 @@ extern "C" int32_t pgd_set_option(pgd_handle_t h, const char* name, int64_t valu
         return 0;
     }
     if (strcmp(name, "bsr") == 0) {
-        h->opt_bsr = value ? 1 : 0;
+        h->opt_bsr = value < 0 ? 0 : value > 2 ? 2 : (int)value;
         return 0;
     }
     if (strcmp(name, "single_reduction") == 0) {

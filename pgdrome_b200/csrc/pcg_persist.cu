@@ -32,7 +32,9 @@
 #include "spmv_bulk.cuh"
 #include "spmv_bsr.cuh"
 
+#ifndef PS_THREADS
 #define PS_THREADS 512
+#endif
 
 int32_t pgd_pcg_finish_impl(pgd_ctx* h, int32_t* h_iters, double* h_relres);
 
@@ -278,15 +280,17 @@ struct PsGather {
 };
 
 // q-type pass over the local rows: epi(row, (A v)[row]) through the CSR ring or the node-block walk
-template <int BS, bool BSR, class Epi>
+template <int BS, int BSR, class Epi>
 __device__ __forceinline__ void ps_spmv(const PersistArgs& a, const double* v, Epi&& epi, unsigned char* smem, uint32_t* tile) {
-    if constexpr (BSR)
+    if constexpr (BSR == 2)
+        bb_spmv_direct<BS, PsGather, Epi, PS_THREADS>(a.rowptr, a.vals, a.bsr, a.n_owned, PsGather{v}, epi);
+    else if constexpr (BSR == 1)
         bb_spmv_rows<BS, PsGather, Epi, PS_THREADS>(a.rowptr, a.vals, a.bsr, a.n_owned, PsGather{v}, epi, smem, tile);
     else
         bk_spmv_rows<PsGather, Epi, PS_THREADS>(a.rowptr, a.colidx, a.vals, a.n_owned, PsGather{v}, epi, smem, tile);
 }
 
-template <int BS, bool BSR>
+template <int BS, int BSR>
 __global__ void __launch_bounds__(PS_THREADS, BK_CTAS_PER_SM) k_pcg_persist(PersistArgs a) {
     extern __shared__ __align__(128) unsigned char bk_smem[];
     const unsigned int G = gridDim.x;
@@ -301,8 +305,8 @@ __global__ void __launch_bounds__(PS_THREADS, BK_CTAS_PER_SM) k_pcg_persist(Pers
     sy.parity = 0;
     uint32_t tile = 0;
     if (tid == 0) {
-        if constexpr (BSR) bb_init_barriers(bk_smem);
-        else bk_init_barriers(bk_smem);
+        if constexpr (BSR == 1) bb_init_barriers(bk_smem);
+        else if constexpr (BSR == 0) bk_init_barriers(bk_smem);
     }
     __syncthreads();
     int status = 0;
@@ -475,7 +479,7 @@ __global__ void __launch_bounds__(PS_THREADS, BK_CTAS_PER_SM) k_pcg_persist(Pers
 // the 40 us of an iteration (profiles/r02_pcg_bench_sharded8_*).  The price: s is carried by a recurrence instead of being
 // recomputed as A p, so the iterates differ from the two-reduction form in the last bits (iteration counts within
 // +-1 %, same stopping rule on the recursive residual); selected with pgd_set_option("single_reduction").
-template <int BS, bool BSR>
+template <int BS, int BSR>
 __global__ void __launch_bounds__(PS_THREADS, BK_CTAS_PER_SM) k_pcg_persist_sr(PersistArgs a) {
     extern __shared__ __align__(128) unsigned char bk_smem[];
     const unsigned int G = gridDim.x;
@@ -490,8 +494,8 @@ __global__ void __launch_bounds__(PS_THREADS, BK_CTAS_PER_SM) k_pcg_persist_sr(P
     sy.parity = 0;
     uint32_t tile = 0;
     if (tid == 0) {
-        if constexpr (BSR) bb_init_barriers(bk_smem);
-        else bk_init_barriers(bk_smem);
+        if constexpr (BSR == 1) bb_init_barriers(bk_smem);
+        else if constexpr (BSR == 0) bk_init_barriers(bk_smem);
     }
     __syncthreads();
     int status = 0, it = 0;
@@ -736,30 +740,42 @@ extern "C" int32_t pgd_pcg_persist_sync(pgd_handle_t h, const int32_t* d_rowptr,
     PGD_CUDA(h, cudaMemsetAsync(a.abort_word, 0, sizeof(int), st));
     // node-block walk: lanes per block row = the power of two covering the longest block row (<= 32), block rows per
     // tile = CTA size / lanes; the tile (nbr * block^2 * longest row entries) must fit one stage of the ring
-    bool bsr = false;
-    if (d_bcol && block > 1 && max_blocks_per_row > 0 && h->opt_bsr) {
+    // node-block walk ("bsr" option): 1 = tiles through the TMA ring (lanes per block row = the power of two covering
+    // the longest block row, block rows per tile = CTA size / lanes, the tile must fit one stage); 2 = direct walk
+    // (no shared memory; lanes per block row = the power of two covering a third of the longest row segment)
+    int bsr = 0;
+    if (d_bcol && block > 1 && max_blocks_per_row > 0 && h->opt_bsr == 1) {
         int lpr = 1;
         while (lpr < 32 && lpr < max_blocks_per_row) lpr *= 2;
         const int nbr = PS_THREADS / lpr;
         if (nbr <= BB_MAXNBR && (int64_t)nbr * block * block * max_blocks_per_row <= BK_CAP &&
             (((uintptr_t)d_bcol) & 15) == 0) {
-            bsr = true;
+            bsr = 1;
             a.bsr.bcol = d_bcol;
             a.bsr.nbr = nbr;
             a.bsr.lpr = lpr;
         }
+    } else if (d_bcol && block > 1 && max_blocks_per_row > 0 && h->opt_bsr >= 2) {
+        int lpr = 4;
+        while (lpr < 32 && 3 * lpr < block * max_blocks_per_row) lpr *= 2;
+        bsr = 2;
+        a.bsr.bcol = d_bcol;
+        a.bsr.nbr = PS_THREADS / lpr;
+        a.bsr.lpr = lpr;
     }
     // "single_reduction": 0 = never, 1 = sharded solves (where the second reduction costs more than it saves), 2 = always
     const bool sr = h->opt_single_reduction >= 2 || (h->opt_single_reduction == 1 && multi);
     const void* fn = nullptr;
+#define PS_PICK(K, B) (bsr == 2 ? (const void*)K<B, 2> : bsr == 1 ? (const void*)K<B, 1> : (const void*)K<B, 0>)
     if (sr) {
-        if (block == 1) fn = (const void*)k_pcg_persist_sr<1, false>;
-        else if (block == 2) fn = bsr ? (const void*)k_pcg_persist_sr<2, true> : (const void*)k_pcg_persist_sr<2, false>;
-        else fn = bsr ? (const void*)k_pcg_persist_sr<3, true> : (const void*)k_pcg_persist_sr<3, false>;
-    } else if (block == 1) fn = (const void*)k_pcg_persist<1, false>;
-    else if (block == 2) fn = bsr ? (const void*)k_pcg_persist<2, true> : (const void*)k_pcg_persist<2, false>;
-    else fn = bsr ? (const void*)k_pcg_persist<3, true> : (const void*)k_pcg_persist<3, false>;
-    const size_t smem = bsr ? BB_SMEM_BYTES : BK_SMEM_BYTES;
+        if (block == 1) fn = (const void*)k_pcg_persist_sr<1, 0>;
+        else if (block == 2) fn = PS_PICK(k_pcg_persist_sr, 2);
+        else fn = PS_PICK(k_pcg_persist_sr, 3);
+    } else if (block == 1) fn = (const void*)k_pcg_persist<1, 0>;
+    else if (block == 2) fn = PS_PICK(k_pcg_persist, 2);
+    else fn = PS_PICK(k_pcg_persist, 3);
+#undef PS_PICK
+    const size_t smem = bsr == 2 ? 0 : bsr == 1 ? BB_SMEM_BYTES : BK_SMEM_BYTES;
     PGD_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     PGD_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PS_THREADS, smem));

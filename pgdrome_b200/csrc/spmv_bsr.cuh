@@ -157,3 +157,77 @@ __device__ __forceinline__ void bb_spmv_rows(const int32_t* __restrict__ rowptr,
 #undef sb_bc
 #undef sb_rp
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Direct node-block walk: no shared memory, no CTA barrier.  LPR lanes own one block row; its BS row segments are
+// contiguous runs of L = BS * (blocks in the row) doubles, so lane l reads entries l, l + LPR, ... of EVERY segment
+// (fully coalesced, each sector requested once) and all BS segments share one gathered x entry per position:
+// column(idx) = BS * bcol[idx / BS] + idx % BS.  Up to 3 positions per lane are issued together (3 * BS value loads +
+// 3 gathers in flight per thread, the only dependent chain is bcol -> x); the row offsets of the next block row are
+// fetched one step ahead.  Block rows are dealt to the CTAs in contiguous chunks (DRAM page locality, and the load
+// balance is one block row per LPR lanes instead of one tile per CTA).  Row sums by the same fixed xor-shuffle tree.
+template <int BS, class Gather, class Epi, int THREADS>
+__device__ __forceinline__ void bb_spmv_direct(const int32_t* __restrict__ rowptr, const double* __restrict__ vals,
+                                               const BsrPlan& plan, int64_t n, const Gather& g, Epi&& epi) {
+    constexpr int B2 = BS * BS;
+    constexpr int M = 3;
+    const int LPR = plan.lpr;
+    const int sub = threadIdx.x / LPR, lane = threadIdx.x % LPR, nsub = THREADS / LPR;
+    const int64_t nbrows = n / BS;
+    const int64_t per = (nbrows + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = (int64_t)blockIdx.x * per;
+    const int64_t r1 = min(nbrows, r0 + per);
+    int segn[BS + 1];
+    {
+        const int64_t r = r0 + sub;
+#pragma unroll
+        for (int i = 0; i <= BS; ++i) segn[i] = (r < r1) ? __ldg(&rowptr[r * BS + i]) : 0;
+    }
+    for (int64_t base = r0; base < r1; base += nsub) {  // uniform trip count in the CTA: full-mask shuffles are safe
+        const int64_t r = base + sub;
+        int seg[BS + 1];
+#pragma unroll
+        for (int i = 0; i <= BS; ++i) seg[i] = segn[i];
+        {
+            const int64_t rn = r + nsub;
+#pragma unroll
+            for (int i = 0; i <= BS; ++i) segn[i] = (rn < r1) ? __ldg(&rowptr[rn * BS + i]) : 0;
+        }
+        double y[BS];
+#pragma unroll
+        for (int i = 0; i < BS; ++i) y[i] = 0.0;
+        if (r < r1) {
+            const int L = seg[1] - seg[0];
+            const int bbase = seg[0] / B2;
+            int cc[M];
+            double vv[M][BS];
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                const int idx = lane + m * LPR;
+                const bool ok = idx < L;
+                cc[m] = ok ? __ldg(&plan.bcol[bbase + idx / BS]) * BS + idx % BS : -1;
+#pragma unroll
+                for (int i = 0; i < BS; ++i) vv[m][i] = ok ? __ldcs(vals + seg[i] + idx) : 0.0;
+            }
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                const double xv = cc[m] >= 0 ? g(cc[m]) : 0.0;
+#pragma unroll
+                for (int i = 0; i < BS; ++i) y[i] = fma(vv[m][i], xv, y[i]);
+            }
+            for (int idx = lane + M * LPR; idx < L; idx += LPR) {  // block rows longer than 3 * LPR / BS blocks
+                const double xv = g(__ldg(&plan.bcol[bbase + idx / BS]) * BS + idx % BS);
+#pragma unroll
+                for (int i = 0; i < BS; ++i) y[i] = fma(__ldcs(vals + seg[i] + idx), xv, y[i]);
+            }
+        }
+        for (int o = LPR >> 1; o > 0; o >>= 1) {
+#pragma unroll
+            for (int i = 0; i < BS; ++i) y[i] += __shfl_xor_sync(0xffffffffu, y[i], o);
+        }
+        if (r < r1 && lane == 0) {
+#pragma unroll
+            for (int i = 0; i < BS; ++i) epi(r * BS + i, y[i]);
+        }
+    }
+}

@@ -103,6 +103,16 @@ def assemble_p1(coords, cell_verts, gdim, c_mass, c_stiff, c_adv, gptr, gidx, nn
     raise NotImplementedError("cpu_abi: fused P1 kernel is covered by the gpu tests only")
 
 
+def bsr_plan(rowptr, colidx, bs):
+    """stand-in: block columns of the first row of every node (host logic only needs the shapes)"""
+    rp, ci = _n(rowptr).astype(np.int64), _n(colidx).astype(np.int64)
+    n = len(rp) - 1
+    if bs < 2 or n % bs:
+        return None
+    cols = [ci[rp[r]:rp[r + 1]][::bs] // bs for r in range(0, n, bs)]
+    return _t(np.concatenate(cols), I32), int(max(len(c) for c in cols))
+
+
 def p1_rowplan_build(rowptr, colidx, cell_dofs, vptr, vidx, n_nodes):
     return cell_dofs  # the stand-in below only needs the cell -> dof table
 
@@ -132,6 +142,44 @@ def assemble_p1_rows(coords, cell_verts, gdim, c_mass, c_stiff, c_adv, rowptr, v
     A.sort_indices()
     assert np.array_equal(A.indptr, _n(rowptr))
     r = _t(A.data, F64)
+    if out is not None:
+        out.copy_(r)
+        return out
+    return r
+
+
+def assemble_p1_tensor(gdim, bs, T, coords_soa, cell_verts, rowptr, node_vptr, node_vent, n_rows, nnz, w_cell=None, out=None):
+    """general-tensor P1 atom: exact quadrature through the element stand-in, summed into CSR order (node_vent is the
+    stand-in plan = the cell -> node table)"""
+    from pgdrome_b200.fem import simplex_quadrature, tabulate_lagrange
+
+    g = gdim
+    pts, qw = simplex_quadrature(g, 2)
+    phi, dphi = tabulate_lagrange(g, 1, pts)
+    coords = _t(np.ascontiguousarray(_n(coords_soa).T))
+    nq = len(qw)
+    wq = None if w_cell is None else _t(np.repeat(_n(w_cell)[:, None], nq, axis=1))
+    Ae = _n(elem_bilinear(coords, cell_verts, g, g, bs, g + 1, _t(phi), _t(dphi), _t(qw), wq, _t(np.asarray(T, dtype=np.float64))))
+    cn = _n(node_vent).astype(np.int64)
+    cd = (cn[:, :, None] * bs + np.arange(bs)[None, None, :]).reshape(len(cn), -1)
+    ndl = cd.shape[1]
+    rows = np.repeat(cd[:, :, None], ndl, axis=2).ravel()
+    cols = np.repeat(cd[:, None, :], ndl, axis=1).ravel()
+    n = int(n_rows)
+    A = sp.coo_matrix((Ae.ravel(), (rows, cols)), shape=(n, n)).tocsr()
+    A.sort_indices()
+    rp, ci = _n(rowptr), None
+    # explicit zeros of the pattern are dropped by COO -> CSR: scatter into the full pattern
+    vals = np.zeros(int(nnz))
+    full_rows = np.repeat(np.arange(n), np.diff(rp))
+    import pgdrome_b200._lib as L  # pattern columns are not passed: rebuild them from the cell cliques (same union)
+    r2 = np.repeat(cd, ndl, axis=1).ravel()
+    c2 = np.tile(cd, (1, ndl)).ravel()
+    key = np.unique(r2 * n + c2)
+    assert len(key) == int(nnz)
+    pos = np.searchsorted(key, A.tocoo().row.astype(np.int64) * n + A.tocoo().col)
+    vals[pos] = A.tocoo().data
+    r = _t(vals)
     if out is not None:
         out.copy_(r)
         return out
@@ -331,7 +379,7 @@ def pcg_finish(device=None):
 
 
 NAMES = ["pattern_build", "vecmap_build", "elem_bilinear", "elem_linear", "gather_values", "assemble_p1",
-         "p1_rowplan_build", "assemble_p1_rows", "lincomb",
+         "p1_rowplan_build", "assemble_p1_rows", "assemble_p1_tensor", "bsr_plan", "lincomb",
          "apply_dirichlet", "set_entries", "spmv", "spmv_dot", "bilinear", "dot", "panel_dots", "pcg", "banded_solve",
          "eval_weights", "eval_gemv", "eval_gemm", "row_stats", "locate_points", "probe_modes", "pcg_start", "pcg_finish", "scalar_programs"]
 

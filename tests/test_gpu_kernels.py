@@ -141,6 +141,40 @@ def test_fused_p1_operator(kind):
     assert _relerr(_csr(ds, K).data, ofem.assemble_bilinear(S, ofem.T_stiff(1, g)).tocsr().data) < MAT_RTOL
 
 
+@pytest.mark.parametrize("kind,bs", [("interval", 1), ("interval", 2), ("tri", 1), ("tri", 2), ("tri_right", 3), ("tet", 1),
+                                     ("tet", 2), ("tet", 3)])
+def test_tensor_p1_kernel(kind, bs):
+    """pgd_assemble_p1_tensor: ANY constant form tensor T[iv,jv,iu,ju] on an affine P1 space (scalar or vector), with and
+    without a cell-wise coefficient, straight into the CSR pattern; it is the route assemble_bilinear takes for P1."""
+    from pgdrome_b200 import _lib
+    from pgdrome_b200.assembly import device_space
+
+    V, S = _product_space(kind, 1, bs)
+    ds = device_space(V)
+    g = S.gdim
+    assert ds.node_plan is not False
+    rng = np.random.default_rng(7 + bs)
+    T = rng.uniform(-1.0, 1.0, (bs, g + 1, bs, g + 1))
+    rowptr = ds.pattern[0]
+    vals = _lib.assemble_p1_tensor(g, bs, T, ds.coords_soa, ds.cell_verts, rowptr, ds.node_plan[0], ds.node_plan[1], ds.n_dofs, ds.nnz)
+    Ao = ofem.assemble_bilinear(S, T)
+    assert _relerr(_csr(ds, vals).data, Ao.data) < MAT_RTOL
+    again = _lib.assemble_p1_tensor(g, bs, T, ds.coords_soa, ds.cell_verts, rowptr, ds.node_plan[0], ds.node_plan[1], ds.n_dofs, ds.nnz)
+    assert torch.equal(vals, again)  # one thread owns one row, fixed cell order
+    assert torch.equal(ds.assemble_bilinear(T), vals)  # the public route uses it
+    # cell-wise (degree-0) coefficient, e.g. a material zone indicator
+    w = lambda x: 1.0 + 2.0 * (x[..., 0] > 0.45) + 0.25 * x[..., 0]  # noqa: E731
+    Aw = ds.assemble_bilinear(T, weight=w, wdeg=0)
+    Aow = ofem.assemble_bilinear(S, T, weight=w, weight_degree=0)
+    assert _relerr(_csr(ds, Aw).data, Aow.data) < MAT_RTOL
+    if bs == g:
+        C = ofem.isotropic_C(1.3, 0.7, g) if g == 3 else (np.array([[2.0, 0.6, 0.0], [0.6, 2.0, 0.0], [0.0, 0.0, 0.7]]) if g == 2 else None)
+        if C is not None:
+            Tv = ofem.T_voigt(C, g)
+            assert _relerr(_csr(ds, ds.assemble_bilinear(Tv, weight=w, wdeg=0)).data,
+                           ofem.assemble_bilinear(S, Tv, weight=w, weight_degree=0).data) < MAT_RTOL
+
+
 def test_fused_p1_rows_large_mesh():
     """Row blocks whose value slice exceeds the shared-memory buffer fall back to global accumulation;
     a 20^3 box exercises full interior rows (15 entries) over many CTAs."""
@@ -639,10 +673,12 @@ def test_persistent_pcg_variants(bs):
         assert plan[0].numel() * bs * bs == colidx.numel() and plan[1] <= 27
     results = {}
     try:
-        for name, sr, pl in (("csr", 0, None), ("csr_sr", 2, None), ("bsr", 0, plan), ("bsr_sr", 2, plan)):
+        for name, sr, pl, walk in (("csr", 0, None, 1), ("csr_sr", 2, None, 1), ("bsr", 0, plan, 1), ("bsr_sr", 2, plan, 1),
+                                   ("bsr_direct", 0, plan, 2), ("bsr_direct_sr", 2, plan, 2)):
             if pl is None and name.startswith("bsr"):
                 continue
             _lib.set_option("single_reduction", sr)
+            _lib.set_option("bsr", walk)
             x, it, rr = _lib.pcg_persist(rowptr, colidx, vals, b, block=bs, rtol=1e-13, maxit=5000, bsr=pl)
             assert rr <= 1e-13 and 0 < it < 5000, (name, it, rr)
             assert np.linalg.norm(x.cpu().numpy() - ref) / np.linalg.norm(ref) < 1e-10, name
@@ -658,6 +694,7 @@ def test_persistent_pcg_variants(bs):
             assert it4 == it and torch.equal(x4, x), name
     finally:
         _lib.set_option("single_reduction", 0)
+        _lib.set_option("bsr", 1)
     base = results["csr"]
     assert all(abs(v - base) <= max(2, base // 100) for v in results.values()), results
     # the multi-launch solver on the same system: same counts

@@ -42,6 +42,7 @@ def operator(mesh_n, bs):
                 T[i, 1 + j, j, 1 + i] += mu
                 T[i, 1 + j, i, 1 + j] += mu
     vals = ds.assemble_bilinear(T)
+    operator.T = T
     return V, ds, vals
 
 
@@ -137,6 +138,15 @@ def run(mesh_n=68, bs=3, iters=200, profile=False, hbm_peak=6451.2):
         gbs = nbytes / (ms * 1e-3) / 1e9
         out[name] = dict(ms=ms, bytes=nbytes, gbs=gbs, frac_hbm=gbs / hbm_peak, **kw)
 
+    # the atom itself: general-tensor row-owner kernel against the element-matrix + gather route it replaces for P1
+    nc, nv = V.mesh().num_cells(), V.mesh().num_vertices()
+    asm_bytes = 16 * nc + 24 * nv + 8 * nnz
+    entry("assemble_p1_tensor", timed(lambda: ds.assemble_bilinear(operator.T), reps=5, warm=2), asm_bytes,
+          kernel="k_assemble_p1_tensor<3,%d>" % bs)
+    if not profile:
+        one = lambda X: np.ones(X.shape[:-1])  # noqa: E731  (a degree-1 coefficient forces the generic route)
+        entry("assemble_elem_gather", timed(lambda: ds.assemble_bilinear(operator.T, weight=one, wdeg=1), reps=3, warm=1), asm_bytes,
+              kernel="k_elem_bilinear + k_gather_sum")
     y = torch.empty(n, dtype=torch.float64, device=dev)
     sc = torch.empty(1, dtype=torch.float64, device=dev)
     spmv_bytes = 12 * nnz + 4 * (n + 1) + 16 * n
@@ -152,6 +162,7 @@ def run(mesh_n=68, bs=3, iters=200, profile=False, hbm_peak=6451.2):
     variants = [("pcg_3launch", dict(persist=1), None), ("pcg_persist_csr", dict(persist=2, bsr=0), None)]
     if plan is not None:
         variants.append(("pcg_persist_bsr", dict(persist=1, bsr=1), plan))
+        variants.append(("pcg_persist_bsr_direct", dict(persist=1, bsr=2), plan))
         variants.append(("pcg_persist_bsr_single_reduction", dict(persist=1, bsr=1, single_reduction=2), plan))
     else:
         variants.append(("pcg_persist_csr_single_reduction", dict(persist=2, bsr=0, single_reduction=2), None))
