@@ -30,10 +30,12 @@ int32_t pgd_destroy(pgd_handle_t h);
 const char* pgd_last_error(pgd_handle_t h);
 /* options: "pcg_resident" (default 1) = solve with the single-kernel SM-resident PCG whenever the
  * matrix slice of every SM fits in its shared memory; "persist" (default 1) = larger systems (>= 32 768 rows) run in the
- * persistent streaming kernel of pgd_pcg_persist_sync (0: three launches per iteration); "bsr" (default 1) = node-block
- * walk inside that kernel when a block-column list is supplied; "single_reduction" (default 1) = 0 never / 1 on sharded
+ * persistent streaming kernel of pgd_pcg_persist_sync (0: three launches per iteration); "bsr" (default 2) = node-block
+ * walk inside that kernel when a block-column list is supplied (2: direct walk, coalesced loads of the row segments, no
+ * shared memory and no CTA barrier; 1: tiles of block rows through the TMA ring; 0: plain CSR); "single_reduction" (default 0) = 0 never / 1 on sharded
  * systems / 2 always use the Chronopoulos-Gear form of the iteration (one grid-wide reduction per step instead of two: same
- * Krylov method, A p carried by a recurrence; wins where the reductions dominate, i.e. across GPUs); "spin_ms" = budget
+ * Krylov method, A p carried by a recurrence; measured slower on this hardware at 1, 2 and 8 GPUs -- two more vector
+ * streams per iteration cost more than the reduction saves -- hence off); "spin_ms" = budget
  * of every in-kernel wait; "prof" = per-phase timers of that kernel (pgd_get_phase_ns);
  * "p2p", "graph", "fused", "pcg3", "spmv_stream": variants of the older multi-launch paths. */
 int32_t pgd_set_option(pgd_handle_t h, const char* name, int64_t value);

@@ -22,7 +22,7 @@ extern "C" int32_t pgd_create(int32_t device, pgd_handle_t* out) {
     h->opt_pcg3 = 1;
     h->opt_fused = 0;
     h->opt_persist = 1;
-    h->opt_bsr = 1;
+    h->opt_bsr = 2;
     h->opt_spin_ms = 20000;
     h->opt_single_reduction = 0;
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);

@@ -105,7 +105,18 @@ def compile_form(form):
             scalars, weights, fns = [], [], []
             for f in m.factors:
                 k = f.leaf.kind
-                if k == "constant":
+                if k == "function":
+                    fns.append(f)
+                elif k == "argument":
+                    if f.leaf.number == 0:
+                        if test is not None:
+                            raise NotImplementedError("form that is not linear in the test function")
+                        test = f
+                    else:
+                        if trial is not None:
+                            raise NotImplementedError("form that is not linear in the trial function")
+                        trial = f
+                elif k == "constant":
                     v = f.leaf.value
                     if isinstance(v, tuple):
                         coef *= v[f.comp or 0]
@@ -119,17 +130,6 @@ def compile_form(form):
                     if f.deriv is not None:
                         raise NotImplementedError("derivative of an Expression inside a form")
                     weights.append((f.leaf, f.comp))
-                elif k == "argument":
-                    if f.leaf.number == 0:
-                        if test is not None:
-                            raise NotImplementedError("form that is not linear in the test function")
-                        test = f
-                    else:
-                        if trial is not None:
-                            raise NotImplementedError("form that is not linear in the trial function")
-                        trial = f
-                elif k == "function":
-                    fns.append(f)
                 elif k == "operator":
                     if op is not None:
                         raise NotImplementedError("product of two MatrixOperators in one term")
@@ -168,19 +168,25 @@ def compile_form(form):
                     raise NotImplementedError("MatrixOperator terms must be op(u, v)*dx with two plain operands")
                 if not _same_space(op.V, space):
                     raise ValueError("MatrixOperator lives on a different space than its operands")
-            gkey = (id(space), tuple(sorted(id(s) for s in scalars)),
-                    tuple(sorted((id(w), c) for w, c in weights)), tuple(id(o.leaf) for o in operands), mkey,
+            gkey = (id(space), tuple(sorted([id(s) for s in scalars])) if scalars else (),
+                    tuple(sorted([(id(w), c) for w, c in weights])) if weights else (),
+                    tuple([id(o.leaf) for o in operands]) if operands else (), mkey,
                     test is not None, trial is not None, id(op) if op is not None else None)
             g = groups.get(gkey)
             if g is None:
                 g = Group(tuple(scalars), tuple(sorted(weights, key=lambda wc: (id(wc[0]), wc[1] or 0))),
-                          tuple(o.leaf for o in operands), meas, space, test is not None, trial is not None, op)
+                          tuple([o.leaf for o in operands]), meas, space, test is not None, trial is not None, op)
                 groups[gkey] = g
                 order.append(gkey)
             idx = ()
-            for f in ([test] if test is not None else []) + ([trial] if trial is not None else []) + operands:
-                idx += (f.comp or 0, _slot(f.deriv))
-            g.entries[idx] = g.entries.get(idx, 0.0) + coef
+            if test is not None:
+                idx += (test.comp or 0, 0 if test.deriv is None else 1 + test.deriv)
+            if trial is not None:
+                idx += (trial.comp or 0, 0 if trial.deriv is None else 1 + trial.deriv)
+            for f in operands:
+                idx += (f.comp or 0, 0 if f.deriv is None else 1 + f.deriv)
+            ent = g.entries
+            ent[idx] = ent.get(idx, 0.0) + coef
     return [groups[k] for k in order]
 
 
@@ -582,7 +588,7 @@ def assemble(form):
     if not isinstance(form, Form):
         raise TypeError("assemble expects a Form, got %r" % type(form))
     ints = form.integrals
-    if len(ints) == 1 and 1 <= len(ints[0].monos) <= 9:
+    if len(ints) == 1 and 1 <= len(ints[0].monos) <= 64:
         fast = _fast_functional(ints[0].measure, ints[0].monos)
         if fast is not None:
             return fast

@@ -27,10 +27,19 @@ class Mono:
         self.factors = tuple(factors)
 
     def times(self, other):
-        return Mono(self.coef * other.coef, self.factors + other.factors)
+        return _mono(self.coef * other.coef, self.factors + other.factors)
 
     def scaled(self, c):
-        return Mono(self.coef * c, self.factors)
+        return _mono(self.coef * c, self.factors)
+
+
+def _mono(coef, factors, _new=Mono.__new__, _cls=Mono):
+    """Mono from an already-float coefficient and an already-tuple factor list (the capture layer builds tens of
+    thousands of monomials per enrichment step: no conversions on this path)"""
+    m = _new(_cls)
+    m.coef = coef
+    m.factors = factors
+    return m
 
 
 _LAZY_SCALAR = None
@@ -116,7 +125,7 @@ class Expr:
             return NotImplemented
         if isinstance(other, Leaf) and other._n_comp == 1 and isinstance(self, Leaf) and self._n_comp == 1:
             # scalar leaf * scalar leaf (F*G, Constant*F, ...): the product monomial directly
-            return Expr((), [[Mono(1.0, (Factor(self, None, None), Factor(other, None, None)))]])
+            return Expr((), [[_mono(1.0, (Factor(self, None, None), Factor(other, None, None)))]])
         o = Expr.wrap(other)
         if o is None:
             return NotImplemented
@@ -170,7 +179,11 @@ class Expr:
         for c in self.comps:
             monos = []
             for m in c:
-                for k, f in enumerate(m.factors):
+                fs = m.factors
+                if len(fs) == 1 and fs[0].deriv is None and fs[0].leaf.kind in ("function", "argument"):
+                    monos.append(_mono(m.coef, (Factor(fs[0].leaf, fs[0].comp, j),)))  # d/dx_j of  c * leaf[comp]
+                    continue
+                for k, f in enumerate(fs):
                     kind = f.leaf.kind
                     if kind in ("constant", "lazy"):
                         continue
@@ -201,14 +214,26 @@ class Leaf(Expr):
         self._n_comp = 1 if n_comp in (None, 0, 1) else int(n_comp)
         self.ufl_shape = () if self._n_comp == 1 else (self._n_comp,)
 
+    def __getitem__(self, i):
+        if self._n_comp == 1:
+            raise IndexError("indexing a scalar expression")
+        if isinstance(i, tuple):
+            if len(i) != 1:
+                raise NotImplementedError("rank-2 indexing")
+            i = i[0]
+        i = int(i)
+        if not 0 <= i < self._n_comp:
+            raise IndexError("component %d of a %d-vector" % (i, self._n_comp))
+        return Expr((), [[_mono(1.0, (Factor(self, i, None),))]])
+
     @property
     def comps(self):
         """The leaf as a polynomial in itself -- built per use, not stored: a stored copy would make every Function /
         Constant / Expression a reference cycle (leaf -> monomial -> factor -> leaf), i.e. device vectors that only
         the cycle collector can free."""
         if self._n_comp == 1:
-            return [[Mono(1.0, (Factor(self, None, None),))]]
-        return [[Mono(1.0, (Factor(self, i, None),))] for i in range(self._n_comp)]
+            return [[_mono(1.0, (Factor(self, None, None),))]]
+        return [[_mono(1.0, (Factor(self, i, None),))] for i in range(self._n_comp)]
 
 
 class _LazyLeaf(Leaf):
@@ -248,19 +273,14 @@ class ConstantMatrix:
         self.a = np.asarray(a, dtype=np.float64)
         if self.a.ndim != 2:
             raise ValueError("as_matrix needs a 2-D array")
+        self._rows = [[(j, float(v)) for j, v in enumerate(row) if v != 0.0] for row in self.a]
 
     def __mul__(self, v):
         v = Expr.wrap(v)
         if v is None or v.is_scalar or v.ufl_shape[0] != self.a.shape[1]:
             raise NotImplementedError("matrix * non-conforming operand")
-        comps = []
-        for i in range(self.a.shape[0]):
-            monos = []
-            for j in range(self.a.shape[1]):
-                if self.a[i, j] != 0.0:
-                    monos += [m.scaled(self.a[i, j]) for m in v.comps[j]]
-            comps.append(monos)
-        return Expr((self.a.shape[0],), comps)
+        vc = v.comps
+        return Expr((self.a.shape[0],), [[m.scaled(c) for j, c in row for m in vc[j]] for row in self._rows])
 
 
 def as_matrix(rows):
@@ -286,11 +306,7 @@ def inner(a, b):
         raise ValueError("inner: shape mismatch %s vs %s" % (a.ufl_shape, b.ufl_shape))
     if a.is_scalar:
         return a * b
-    out = None
-    for i in range(a.ufl_shape[0]):
-        t = a[i] * b[i]
-        out = t if out is None else out + t
-    return out
+    return Expr((), [[x.times(y) for ca, cb in zip(a.comps, b.comps) for x in ca for y in cb]])
 
 
 dot = inner
