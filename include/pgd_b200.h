@@ -35,7 +35,9 @@ const char* pgd_last_error(pgd_handle_t h);
  * shared memory and no CTA barrier; 1: tiles of block rows through the TMA ring; 0: plain CSR); "single_reduction" (default 0) = 0 never / 1 on sharded
  * systems / 2 always use the Chronopoulos-Gear form of the iteration (one grid-wide reduction per step instead of two: same
  * Krylov method, A p carried by a recurrence; measured slower on this hardware at 1, 2 and 8 GPUs -- two more vector
- * streams per iteration cost more than the reduction saves -- hence off); "spin_ms" = budget
+ * streams per iteration cost more than the reduction saves -- hence off); "ll" (default 1) = cross-GPU
+ * sums and halo entries of that kernel travel as 8-byte words carrying 32 data bits + the 32-bit sequence number (valid on
+ * arrival: no system-scope fence, no flag; 0 = data, fence, release flag); "spin_ms" = budget
  * of every in-kernel wait; "prof" = per-phase timers of that kernel (pgd_get_phase_ns);
  * "p2p", "graph", "fused", "pcg3", "spmv_stream": variants of the older multi-launch paths. */
 int32_t pgd_set_option(pgd_handle_t h, const char* name, int64_t value);

@@ -150,15 +150,26 @@ class DeviceSpace:
             specs.append(("callable", weight, None, wdeg, None))
         if not specs:
             return None
+        if any(kind == "fn" or d != 0 for kind, _, _, d, _ in specs):
+            return False
+        # (id, component, version) keys of the Expressions: the same zone indicator is asked for by every atom that
+        # carries it; entries keep their Expression alive so that an id cannot be recycled while it is in the table
+        ckey = tuple(k for _, _, _, _, k in specs) if all(k is not None for _, _, _, _, k in specs) else None
+        cache = self.__dict__.setdefault("_cell_w", {})
+        if ckey is not None and ckey in cache:
+            return cache[ckey][0]
+        if getattr(self, "_centroids", None) is None:
+            m = self.space.mesh()
+            self._centroids = m.coordinates()[m.cells()].mean(axis=1)
         w = None
-        zero = np.zeros((1, self.space.mesh().tdim))
         for kind, obj, comp, d, _ in specs:
-            if kind == "fn" or d != 0:
-                return False
             fn = obj if kind == "callable" else (lambda X, o=obj, c=comp: o.eval_np(X, c))
-            v = self.sample_weight(fn, 0, zero)[:, 0]
+            v = np.asarray(fn(self._centroids), dtype=np.float64).reshape(-1)
             w = v if w is None else w * v
-        return _up(np.ascontiguousarray(w), torch.float64)
+        out = _up(np.ascontiguousarray(w), torch.float64)
+        if ckey is not None:
+            cache[ckey] = (out, [obj for _, obj, _, _, _ in specs])
+        return out
 
     def _p1_closed_form(self, T):
         """(c_mass, c_stiff, c_adv) if T is  c_m u v + c_k grad u.grad v + sum_m c_adv[m] (d_m u) v, else None."""

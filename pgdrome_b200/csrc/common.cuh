@@ -68,6 +68,7 @@ struct pgd_ctx {
     int opt_graph;           // pgd_set_option("graph"): 1 (default) = replay the peer-window iteration from a CUDA graph
     int opt_persist;         // pgd_set_option("persist"): 1 (default) = HBM-bound solves run in the persistent cooperative kernel
     int opt_bsr;             // pgd_set_option("bsr"): node-block walk of vector operators inside that kernel: 2 (default) = direct (no shared memory), 1 = tiles through the TMA ring, 0 = off
+    int opt_ll;              // pgd_set_option("ll"): 1 (default) = LL mailboxes / halo in the persistent sharded kernel (data + sequence per 8-byte word), 0 = data, fence, flag
     int opt_spin_ms;         // pgd_set_option("spin_ms"): budget of every in-kernel wait (default 20 000 ms)
     int opt_prof;            // pgd_set_option("prof"): 1 = the persistent kernel accumulates per-phase times (pgd_get_phase_ns)
     int opt_single_reduction;  // pgd_set_option("single_reduction"): 0 never, 1 sharded solves, 2 always (pcg_persist.cu)

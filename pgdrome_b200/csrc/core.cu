@@ -23,6 +23,7 @@ extern "C" int32_t pgd_create(int32_t device, pgd_handle_t* out) {
     h->opt_fused = 0;
     h->opt_persist = 1;
     h->opt_bsr = 2;
+    h->opt_ll = 1;
     h->opt_spin_ms = 20000;
     h->opt_single_reduction = 0;
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -108,6 +109,10 @@ extern "C" int32_t pgd_set_option(pgd_handle_t h, const char* name, int64_t valu
     }
     if (strcmp(name, "persist") == 0) {
         h->opt_persist = value < 0 ? 0 : (value > 2 ? 2 : (int)value);
+        return 0;
+    }
+    if (strcmp(name, "ll") == 0) {
+        h->opt_ll = value ? 1 : 0;
         return 0;
     }
     if (strcmp(name, "bsr") == 0) {

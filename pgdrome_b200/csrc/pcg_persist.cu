@@ -68,6 +68,7 @@ struct PersistArgs {
     unsigned int n_push;       // CTAs that take part in a halo push (the LAST n_push of the grid)
     unsigned long long spin_ns;
     BsrPlan bsr;               // node-block walk of the CSR arrays (BSR template only)
+    int ll;                    // 1: "LL" mailboxes and halo (data + sequence in one 8-byte word), 0: data, fence, flag
     unsigned long long* prof;  // optional [8]: ns spent (as seen by CTA 0) in D, barrier, S, reduce 1, U, reduce 2
 };
 
@@ -140,6 +141,7 @@ __device__ __forceinline__ bool ps_grid_barrier(const PersistArgs& a, PsSync& sy
 // false = aborted.
 __device__ __forceinline__ void ps_halo_issue(const PersistArgs& a, const double* v, unsigned int G);
 __device__ __forceinline__ void ps_halo_commit(const PersistArgs& a, unsigned long long seq, unsigned int G);
+__device__ __forceinline__ void ps_halo_issue_ll(const PersistArgs& a, const double* v, unsigned long long seq, unsigned int G);
 
 // halo_v != NULL: the boundary entries of halo_v leave for the neighbours inside this reduction -- the stores are issued
 // right after all CTAs of this rank have arrived (their global writes are visible), the flag is published after the
@@ -168,7 +170,10 @@ __device__ __forceinline__ bool ps_reduce_bcast(double (&v)[NV], const PersistAr
         if (!ps_spin([&] { return ps_ld_acquire_gpu(a.arrive) >= tgt; }, a)) s_ok = 0;
     }
     __syncthreads();
-    if (halo_v) ps_halo_issue(a, halo_v, G);
+    if (halo_v) {
+        if (a.ll) ps_halo_issue_ll(a, halo_v, halo_seq, G);
+        else ps_halo_issue(a, halo_v, G);
+    }
     if (tid < 32) {  // every CTA: the rank's sum, same order everywhere
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
@@ -179,7 +184,50 @@ __device__ __forceinline__ bool ps_reduce_bcast(double (&v)[NV], const PersistAr
         }
     }
     __syncthreads();
-    if (a.world > 1) {
+    if (a.world > 1 && a.ll) {
+        __shared__ double s_peer[PW_MAXR][PW_AR_VALS];
+        const unsigned int flag = (unsigned int)seq;  // differs from the slot's previous content (seq - 2, or 0 at start)
+        if (blockIdx.x == 0 && tid < a.world && tid != a.me) {
+            unsigned long long* ll = reinterpret_cast<unsigned long long*>(a.peers.base[tid] + a.lay.ll_off()) +
+                                     ((size_t)par * PW_MAXR + a.me) * PW_AR_VALS * 2;
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                const unsigned long long bits = (unsigned long long)__double_as_longlong(s_res[k]);
+                st_relaxed_sys(ll + 2 * k, (bits & 0xffffffffULL) | ((unsigned long long)flag << 32));
+                st_relaxed_sys(ll + 2 * k + 1, (bits >> 32) | ((unsigned long long)flag << 32));
+            }
+        }
+        if (tid < a.world && tid != a.me) {
+            const unsigned long long* ll = reinterpret_cast<const unsigned long long*>(a.peers.base[a.me] + a.lay.ll_off()) +
+                                           ((size_t)par * PW_MAXR + tid) * PW_AR_VALS * 2;
+            unsigned long long w[2 * NV];
+            const bool got = ps_spin(
+                [&] {
+                    bool all = true;
+#pragma unroll
+                    for (int j = 0; j < 2 * NV; ++j) {
+                        w[j] = ld_relaxed_sys(ll + j);
+                        all = all && ((unsigned int)(w[j] >> 32) == flag);
+                    }
+                    return all;
+                },
+                a);
+            if (!got) s_ok = 0;
+#pragma unroll
+            for (int k = 0; k < NV; ++k)
+                s_peer[tid][k] = __longlong_as_double((long long)((w[2 * k] & 0xffffffffULL) | (w[2 * k + 1] << 32)));
+        }
+        __syncthreads();
+        if (tid == 0 && s_ok) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                double s = 0.0;
+                for (int q = 0; q < a.world; ++q) s += (q == a.me) ? s_res[k] : s_peer[q][k];
+                s_res[k] = s;
+            }
+        }
+        __syncthreads();
+    } else if (a.world > 1) {
         if (blockIdx.x == 0 && tid < a.world && tid != a.me) {
             double* slot = reinterpret_cast<double*>(a.peers.base[tid] + a.lay.slot_off()) +
                            ((size_t)par * PW_MAXR + a.me) * PW_AR_VALS;
@@ -254,6 +302,44 @@ __device__ __forceinline__ void ps_halo_commit(const PersistArgs& a, unsigned lo
 __device__ __forceinline__ void ps_halo_push(const PersistArgs& a, const double* v, unsigned long long seq, unsigned int G) {
     ps_halo_issue(a, v, G);
     ps_halo_commit(a, seq, G);
+}
+
+// "LL" halo (option "ll", default): every boundary double travels as two 8-byte words {32 data bits | 32-bit sequence
+// number} into the destination's LL region (window offset llh_base, two parities), indexed by the destination's local
+// ghost index.  8-byte stores are single-copy atomic, so an entry is valid as soon as both words carry the expected
+// sequence: no system-scope fence, no ticket and no flag -- one one-way NVLink flight between the sender's store and the
+// receiver's use.  The slot's previous content carries seq - 2 (or 0 after a window (re-)open), never seq.
+__device__ __forceinline__ void ps_halo_issue_ll(const PersistArgs& a, const double* v, unsigned long long seq, unsigned int G) {
+    if (a.n_push == 0 || blockIdx.x < G - a.n_push) return;
+    const unsigned long long flag = (unsigned long long)(unsigned int)seq << 32;
+    const size_t pbase = (size_t)(seq & 1ULL) * a.lay.llh_cap();
+    const int64_t first = (int64_t)(blockIdx.x - (G - a.n_push)) * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)a.n_push * blockDim.x;
+    for (int64_t s = first; s < a.n_send; s += stride) {
+        int r = 0;
+        while (s >= a.hp.seg_start[r + 1]) ++r;
+        const size_t j = (size_t)(a.hp.dst_off[r] + (s - a.hp.seg_start[r]));
+        unsigned long long* w = reinterpret_cast<unsigned long long*>(a.peers.base[r]) + a.lay.llh_base() + (pbase + j) * 2;
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(v[a.send_idx[s]]);
+        st_relaxed_sys(w, (bits & 0xffffffffULL) | flag);
+        st_relaxed_sys(w + 1, (bits >> 32) | flag);
+    }
+}
+// ghost entry j (local index) of halo `seq`; false = aborted
+__device__ __forceinline__ bool ps_ll_read(const PersistArgs& a, unsigned long long seq, int64_t j, double& out) {
+    const unsigned long long* w = reinterpret_cast<const unsigned long long*>(a.peers.base[a.me]) + a.lay.llh_base() +
+                                  ((size_t)(seq & 1ULL) * a.lay.llh_cap() + (size_t)j) * 2;
+    const unsigned int flag = (unsigned int)seq;
+    unsigned long long w0 = 0, w1 = 0;
+    const bool ok = ps_spin(
+        [&] {
+            w0 = ld_relaxed_sys(w);
+            w1 = ld_relaxed_sys(w + 1);
+            return (unsigned int)(w0 >> 32) == flag && (unsigned int)(w1 >> 32) == flag;
+        },
+        a);
+    out = __longlong_as_double((long long)((w0 & 0xffffffffULL) | (w1 << 32)));
+    return ok;
 }
 
 // all threads call; the threads r < world acquire the halo flag of rank r; false = aborted
@@ -383,11 +469,24 @@ __global__ void __launch_bounds__(PS_THREADS, BK_CTAS_PER_SM) k_pcg_persist(Pers
                 } else {
                     for (int64_t i = gtid; i < no; i += gstride) a.p[i] = fma(beta, a.p[i], a.z[i]);
                 }
-                if (!ps_halo_wait(a, hseq)) {
-                    status = 3;
-                    break;
+                if (a.ll) {
+                    bool okl = true;
+                    for (int64_t i = no + gtid; i < a.n_local; i += gstride) {
+                        double zv;
+                        okl = ps_ll_read(a, hseq, i, zv) && okl;
+                        a.p[i] = fma(beta, a.p[i], zv);
+                    }
+                    if (__syncthreads_or(!okl)) {
+                        status = 3;
+                        break;
+                    }
+                } else {
+                    if (!ps_halo_wait(a, hseq)) {
+                        status = 3;
+                        break;
+                    }
+                    for (int64_t i = no + gtid; i < a.n_local; i += gstride) a.p[i] = fma(beta, a.p[i], a.z[i]);
                 }
-                for (int64_t i = no + gtid; i < a.n_local; i += gstride) a.p[i] = fma(beta, a.p[i], a.z[i]);
             }
             PS_MARK(0);
             if (!ps_grid_barrier(a, sy, G)) {
@@ -437,7 +536,7 @@ __global__ void __launch_bounds__(PS_THREADS, BK_CTAS_PER_SM) k_pcg_persist(Pers
     if (a.world > 1 && status != 3) {
         // every rank has consumed (or will never read) the last z halo: drain it first so that the pushes of x below
         // cannot be overtaken by it, then push x behind one more cross-rank reduction
-        if (!ps_halo_wait(a, hseq)) status = 3;
+        if (!a.ll && !ps_halo_wait(a, hseq)) status = 3;  // (LL: the x halo below uses the other parity / another sequence)
         double v0[1] = {0.0};
         if (status != 3 && !ps_reduce_bcast<1>(v0, a, sy, G)) status = 3;
         if (status != 3) {
@@ -448,10 +547,21 @@ __global__ void __launch_bounds__(PS_THREADS, BK_CTAS_PER_SM) k_pcg_persist(Pers
         }
         if (status != 3) {
             const unsigned long long xseq = ++sy.seq_halo;
-            ps_halo_push(a, a.x, xseq, G);
-            if (!ps_halo_wait(a, xseq)) status = 3;
-            else
-                for (int64_t i = no + gtid; i < a.n_local; i += gstride) a.x[i] = a.z[i];
+            if (a.ll) {
+                ps_halo_issue_ll(a, a.x, xseq, G);
+                bool okl = true;
+                for (int64_t i = no + gtid; i < a.n_local; i += gstride) {
+                    double xv;
+                    okl = ps_ll_read(a, xseq, i, xv) && okl;
+                    a.x[i] = xv;
+                }
+                if (__syncthreads_or(!okl)) status = 3;
+            } else {
+                ps_halo_push(a, a.x, xseq, G);
+                if (!ps_halo_wait(a, xseq)) status = 3;
+                else
+                    for (int64_t i = no + gtid; i < a.n_local; i += gstride) a.x[i] = a.z[i];
+            }
             // nobody may start the next solve's pushes into the z tail before every rank has copied its ghosts
             if (status != 3 && !ps_reduce_bcast<1>(v0, a, sy, G)) status = 3;
         }
@@ -706,8 +816,11 @@ extern "C" int32_t pgd_pcg_persist_sync(pgd_handle_t h, const int32_t* d_rowptr,
     a.world = world;
     a.me = multi ? h->win_rank : 0;
     a.lay = PwLayout{multi ? h->win_pcap : 0};
+    a.ll = 0;
+    const bool sr_requested = h->opt_single_reduction >= 2 || (h->opt_single_reduction == 1 && multi);
     if (multi) {
         PGD_ARG(h, n_local <= h->win_pcap, "peer window too small");
+        a.ll = (h->opt_ll && !sr_requested && (size_t)n_local <= a.lay.llh_base() && (size_t)n_local <= a.lay.llh_cap()) ? 1 : 0;
         a.s = a.z;
         a.z = reinterpret_cast<double*>(h->win_local);
         int64_t n_send = 0;
@@ -764,7 +877,7 @@ extern "C" int32_t pgd_pcg_persist_sync(pgd_handle_t h, const int32_t* d_rowptr,
         a.bsr.lpr = lpr;
     }
     // "single_reduction": 0 = never, 1 = sharded solves (where the second reduction costs more than it saves), 2 = always
-    const bool sr = h->opt_single_reduction >= 2 || (h->opt_single_reduction == 1 && multi);
+    const bool sr = sr_requested;
     const void* fn = nullptr;
 #define PS_PICK(K, B) (bsr == 2 ? (const void*)K<B, 2> : bsr == 1 ? (const void*)K<B, 1> : (const void*)K<B, 0>)
     if (sr) {

@@ -409,9 +409,9 @@ extern "C" int32_t pgd_peer_window_open(pgd_handle_t h, int32_t rank, int32_t wo
     for (int r = 0; r < h->win_world; ++r)  // re-open: drop the old mappings first
         if (r != h->win_rank && h->win_peer[r]) cudaIpcCloseMemHandle(h->win_peer[r]);
     h->win_world = 0;
-    {  // sequence numbers restart at 0 below: so must the flags and mailboxes of this rank's window
+    {  // sequence numbers restart at 0 below: so must the flags, the mailboxes and the LL halo words of this rank's window
         PwLayout lay0{h->win_pcap};
-        PGD_CUDA(h, cudaMemset((unsigned char*)h->win_local + lay0.slot_off(), 0, lay0.bytes() - lay0.slot_off()));
+        PGD_CUDA(h, cudaMemset(h->win_local, 0, lay0.bytes()));
     }
     for (int r = 0; r < world; ++r) {
         if (r == rank) {

@@ -43,19 +43,33 @@ panel_rows_hint = [MAX_PANEL_ROWS]  # first allocation of a product panel (the s
 class Group:
     """Monomials of one integral that share scalar leaves, weights, operands and measure."""
 
-    __slots__ = ("scalars", "weights", "operands", "measure", "entries", "space", "has_test", "has_trial", "op")
+    __slots__ = ("scalars", "weights", "operands", "measure", "entries", "space", "has_test", "has_trial", "op", "_sign")
 
     def __init__(self, scalars, weights, operands, measure, space, has_test, has_trial, op=None):
         self.scalars, self.weights, self.operands, self.measure = scalars, weights, operands, measure
         self.space, self.has_test, self.has_trial, self.op = space, has_test, has_trial, op
         self.entries = {}  # (iv, jv, iu, ju) | (iv, jv) | () -> float
+        self._sign = None
 
     @property
     def rank(self):
         return int(self.has_test) + int(self.has_trial)
 
+    def sign(self):
+        """+-1: sign of the first non-zero tensor entry (C order).  The tensor is handed out with that sign divided out
+        and the coefficient carries it, so that K and -K (the `-Constant(c) * op(G, v)` terms of every right-hand
+        side) are ONE assembled atom with one panel of cached products instead of two."""
+        if self._sign is None:
+            sg = 1.0
+            if int(self.has_test) + int(self.has_trial) + len(self.operands) > 0:
+                nz = [k for k, v in self.entries.items() if v != 0.0]
+                if nz and self.entries[min(nz)] < 0.0:
+                    sg = -1.0
+            self._sign = sg
+        return self._sign
+
     def tensor(self):
-        """Dense form tensor: T [bs,g+1,bs,g+1] (two slots), L [bs,g+1] (one slot) or a float."""
+        """Dense form tensor: T [bs,g+1,bs,g+1] (two slots), L [bs,g+1] (one slot) or a float; sign normalised (sign())."""
         bs, g = self.space.bs, self.space.mesh().gdim
         nslots = int(self.has_test) + int(self.has_trial) + len(self.operands)
         if nslots == 2:
@@ -64,13 +78,14 @@ class Group:
             T = np.zeros((bs, g + 1))
         else:
             return float(sum(self.entries.values()))
+        sg = self.sign()
         for k, v in self.entries.items():
-            T[k] += v
+            T[k] += sg * v
         return T
 
     def coefficient(self):
-        """float constant part is folded into the tensor; this is the product of the scalar leaves."""
-        c = 1.0
+        """float constant part is folded into the tensor; this is the product of the scalar leaves (times sign())."""
+        c = self.sign()
         for s in self.scalars:
             c = c * _scalar_value(s)
         return c
@@ -556,22 +571,28 @@ def _fast_functional(meas, monos):
         if w2 != weights:
             return None
         key += (g1.comp or 0, _slot(g1.deriv), g2.comp or 0, _slot(g2.deriv), c)
-    T = _UNIT_T.get(key)
-    if T is None:
+    ent = _UNIT_T.get(key)
+    if ent is None:
         T = np.zeros((key[0], key[1] + 1, key[0], key[1] + 1))
         for i in range(2, len(key), 5):
             T[key[i], key[i + 1], key[i + 2], key[i + 3]] += key[i + 4]
-        T.setflags(write=False)
         if not T.any():
-            T = False  # the monomials cancel: let the general path produce the zero
+            ent = (False, 1.0)  # the monomials cancel: let the general path produce the zero
         else:
+            sg = -1.0 if T.ravel()[np.flatnonzero(T)[0]] < 0.0 else 1.0  # same normalisation as Group.sign()
+            if sg < 0.0:
+                T = -T
+            T.setflags(write=False)
             _TBYTES[id(T)] = T.tobytes()
-        _UNIT_T[key] = T
+            ent = (T, sg)
+        _UNIT_T[key] = ent
+    T, sg = ent
     if T is False:
         return None
     memo = functional_memo[0]
     if memo is None:
-        return LazyScalar("leaf", (_Functional("bil", space, T, weights, meas, f1.leaf, f2.leaf, op),))
+        leaf = LazyScalar("leaf", (_Functional("bil", space, T, weights, meas, f1.leaf, f2.leaf, op),))
+        return leaf if sg > 0.0 else -leaf
     # inside an enrichment step: the same integral of the same (unchanged) functions is asked for again and again
     # (every other dimension's sub-problem needs it) -- hand out the one deferred scalar.  The entry keeps its operands
     # alive, so an id cannot be recycled while it is in the table; the solver clears the table at the end of the step.
@@ -579,6 +600,8 @@ def _fast_functional(meas, monos):
     hit = memo.get(mkey)
     if hit is None:
         hit = LazyScalar("leaf", (_Functional("bil", space, T, weights, meas, f1.leaf, f2.leaf, op),))
+        if sg < 0.0:
+            hit = -hit
         memo[mkey] = hit
     return hit
 

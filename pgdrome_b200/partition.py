@@ -228,7 +228,7 @@ def sharded_pcg(A, b, rtol=1e-13, atol=0.0, maxit=10000, check_every=50, block=N
 
         if dist.is_initialized() and dist.get_world_size(group) > 1:
             _lib.comm_init(group)
-            if use_p2p and _lib.peer_window(2 * A.n_local + 16, group) is not None:
+            if use_p2p and _lib.peer_window(6 * A.n_local + 16, group) is not None:
                 A.halo.ensure_peer_layout()
             else:
                 A.halo.peer_ghost_base = None
@@ -303,7 +303,7 @@ def sharded_solve(A, b, x0=None, rtol=1e-13, atol=0.0, maxit=10000, check_every=
 
         if multi:
             _lib.comm_init(group)
-            if _lib.peer_window(2 * A.n_local + 16, group) is not None:
+            if _lib.peer_window(6 * A.n_local + 16, group) is not None:
                 A.halo.ensure_peer_layout()
                 return _lib.pcg_persist(A.rowptr, A.colidx, A.values, b, n_owned=no, block=block, rtol=rtol, atol=atol,
                                         maxit=maxit, x0=x0, halo=A.halo, bsr=bsr)

@@ -68,13 +68,15 @@ def run_sharded(mesh_n=68, bs=3, iters=200, hbm_peak=6451.2):
     _lib.set_option("spin_ms", 5000)
     out = {"mesh": "BoxMesh %d^3, P1 bs=%d" % (mesh_n, bs), "world": world, "n_dofs": V.n_dofs, "rows_rank0": sh.n_owned,
            "ghosts_rank0": sh.n_ghost, "nnz_rank0": ds.nnz_owned, "hbm_peak_gbs": hbm_peak}
-    for name, bsr, sr in (("persist_bsr", ds.bsr, 0), ("persist_bsr_single_reduction", ds.bsr, 1), ("persist_csr", None, 0),
-                          ("persist_csr_single_reduction", None, 1)):
+    for name, bsr, sr, ll in (("persist_bsr", ds.bsr, 0, 1), ("persist_bsr_flag_protocol", ds.bsr, 0, 0),
+                              ("persist_bsr_repeat", ds.bsr, 0, 1), ("persist_bsr_single_reduction", ds.bsr, 1, 0),
+                              ("persist_csr", None, 0, 1), ("persist_csr_single_reduction", None, 1, 0)):
         if name.startswith("persist_bsr") and bsr is None:
             continue
         if name.startswith("persist_csr") and ds.bsr is not None and sr == 1:
             continue
         _lib.set_option("single_reduction", sr)
+        _lib.set_option("ll", ll)
         pt.sharded_solve(S, b, rtol=1e-30, maxit=10, block=bs, bsr=bsr)
         _lib.set_option("prof", 1)
         _lib.phase_ns(reset=True)
@@ -104,6 +106,8 @@ def run_sharded(mesh_n=68, bs=3, iters=200, hbm_peak=6451.2):
                      "frac_hbm_local": loc / (ms * 1e-3) / 1e9 / hbm_peak, "phase_us_per_iteration_rank0": {k: v / 1e3 / iters for k, v in ph.items()},
                      "solve": {"iters": its, "relres": rr, "true_relres": float((tr[0] / tr[1]).sqrt()),
                                "err": float((err[0] / err[1]).sqrt()), "ghosts_of_solution_ok": ghost_ok}}
+    _lib.set_option("single_reduction", 0)
+    _lib.set_option("ll", 1)
     return out if rank == 0 else None
 
 
