@@ -297,8 +297,8 @@ def run_b200(args):
     except Exception:
         pass
     roofline = {"bound": "hbm",
-                "kernel": "one node-block-Jacobi PCG iteration inside k_pcg_persist<3, BSR> (one cooperative launch per solve: "
-                          "direction update, TMA-pipelined node-block SpMV, vector update, grid-wide reductions); figures are per "
+                "kernel": "one node-block-Jacobi PCG iteration inside k_pcg_persist<3, 2> (one cooperative launch per solve: "
+                          "direction update, direct node-block SpMV, vector update, grid-wide reductions); figures are per "
                           "ITERATION" + (" of rank 0's %d owned rows" % n_loc if world > 1 else ""),
                 "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic,

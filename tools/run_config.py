@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--size", "--n", dest="n", type=int, default=None, help="cells per edge of the spatial mesh")
     ap.add_argument("--modes", type=int, default=3)
     ap.add_argument("--rtol", type=float, default=1e-13)
+    ap.add_argument("--setup-profile", default=None, help="write a cProfile of problem construction + step 0 (rank 0) here")
     ap.add_argument("--counts", default=None, help="write the per-step / per-solve PCG iteration counts to this JSON file "
                                                    "(bench.py scales its bounded CPU sample with them)")
     a = ap.parse_args()
@@ -43,6 +44,12 @@ def main():
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", peak)
     except Exception:
         pass
+    prof = None
+    if a.setup_profile and rank == 0:  # where does the first (set-up) step go?  cProfile of build + step 0 on rank 0
+        import cProfile
+
+        prof = cProfile.Profile()
+        prof.enable()
     t0 = time.perf_counter()
     kw = {} if a.n is None else {"n": a.n}
     p = getattr(configs, a.config)(PGD_nmax=a.modes, PGD_tol=0.0, **kw)
@@ -51,6 +58,16 @@ def main():
     steps = []
     _lib.stats(reset=True)
     for i in range(a.modes):
+        if i == 1 and prof is not None:
+            import io
+            import pstats
+
+            prof.disable()
+            sio = io.StringIO()
+            pstats.Stats(prof, stream=sio).sort_stats("cumulative").print_stats(70)
+            pstats.Stats(prof, stream=sio).sort_stats("tottime").print_stats(30)
+            open(a.setup_profile, "w").write(sio.getvalue())
+            prof = None
         torch.cuda.synchronize()
         s0 = _lib.stats()
         log0 = len(p.solver_stats["pcg_log"])
