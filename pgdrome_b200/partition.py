@@ -302,11 +302,13 @@ def sharded_solve(A, b, x0=None, rtol=1e-13, atol=0.0, maxit=10000, check_every=
         from . import _lib
 
         if multi:
-            _lib.comm_init(group)
             if _lib.peer_window(6 * A.n_local + 16, group) is not None:
                 A.halo.ensure_peer_layout()
                 return _lib.pcg_persist(A.rowptr, A.colidx, A.values, b, n_owned=no, block=block, rtol=rtol, atol=atol,
                                         maxit=maxit, x0=x0, halo=A.halo, bsr=bsr)
+            # no peer mapping (the decision above is collective): the NCCL path, whose communicator inside the library
+            # is only created now -- it costs ~2 s on 8 GPUs and the persistent kernel never uses it
+            _lib.comm_init(group)
             A.halo.peer_ghost_base = None
             x_owned, iters, relres = _lib.spcg_solve(A, b[:no].contiguous(), rtol=rtol, atol=atol, maxit=maxit,
                                                      check_every=check_every, block=block)

@@ -148,9 +148,10 @@ def run(mesh_n=68, bs=3, iters=200, profile=False, hbm_peak=6451.2):
     entry("assemble_p1_tensor", timed(lambda: ds.assemble_bilinear(operator.T), reps=5, warm=2), asm_bytes,
           kernel="k_assemble_p1_tensor<3,%d>" % bs)
     if not profile:
-        one = lambda X: np.ones(X.shape[:-1])  # noqa: E731  (a degree-1 coefficient forces the generic route)
-        entry("assemble_elem_gather", timed(lambda: ds.assemble_bilinear(operator.T, weight=one, wdeg=1), reps=3, warm=1), asm_bytes,
+        plan_keep, ds._node_plan = ds.node_plan, False  # without the node plan the same atom takes the element-matrix route
+        entry("assemble_elem_gather", timed(lambda: ds.assemble_bilinear(operator.T), reps=3, warm=1), asm_bytes,
               kernel="k_elem_bilinear + k_gather_sum")
+        ds._node_plan = plan_keep
     y = torch.empty(n, dtype=torch.float64, device=dev)
     sc = torch.empty(1, dtype=torch.float64, device=dev)
     spmv_bytes = 12 * nnz + 4 * (n + 1) + 16 * n

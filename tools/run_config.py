@@ -96,7 +96,8 @@ def main():
                    "frac_hbm": it_bytes / (it_ms * 1e-3) / 1e9 / peak if s["pcg_iters"] else None,
                    "share_of_step_time": s["pcg_ms"] / max(sum(x["ms"] for x in steps), 1e-9)},
            "enrichment_steps_per_s": len(steps) / (sum(x["ms"] for x in steps) * 1e-3),
-           "device_mem_gb": torch.cuda.max_memory_allocated() / 1e9}
+           "device_mem_gb": torch.cuda.max_memory_allocated() / 1e9,  # peak, including set-up transients (facet sort, pattern sort)
+           "device_mem_resident_gb": torch.cuda.memory_allocated() / 1e9}
     if rank == 0:
         print(json.dumps(out))
         if a.counts:
