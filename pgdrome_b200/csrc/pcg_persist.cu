@@ -868,7 +868,7 @@ extern "C" int32_t pgd_pcg_persist_sync(pgd_handle_t h, const int32_t* d_rowptr,
             a.bsr.nbr = nbr;
             a.bsr.lpr = lpr;
         }
-    } else if (d_bcol && block > 1 && max_blocks_per_row > 0 && h->opt_bsr >= 2) {
+    } else if (d_bcol && max_blocks_per_row > 0 && h->opt_bsr >= 2) {  // (block == 1: bcol = colidx, the plain CSR row walk)
         int lpr = 4;
         while (lpr < 32 && 3 * lpr < block * max_blocks_per_row) lpr *= 2;
         bsr = 2;
@@ -881,10 +881,10 @@ extern "C" int32_t pgd_pcg_persist_sync(pgd_handle_t h, const int32_t* d_rowptr,
     const void* fn = nullptr;
 #define PS_PICK(K, B) (bsr == 2 ? (const void*)K<B, 2> : bsr == 1 ? (const void*)K<B, 1> : (const void*)K<B, 0>)
     if (sr) {
-        if (block == 1) fn = (const void*)k_pcg_persist_sr<1, 0>;
+        if (block == 1) fn = bsr == 2 ? (const void*)k_pcg_persist_sr<1, 2> : (const void*)k_pcg_persist_sr<1, 0>;
         else if (block == 2) fn = PS_PICK(k_pcg_persist_sr, 2);
         else fn = PS_PICK(k_pcg_persist_sr, 3);
-    } else if (block == 1) fn = (const void*)k_pcg_persist<1, 0>;
+    } else if (block == 1) fn = bsr == 2 ? (const void*)k_pcg_persist<1, 2> : (const void*)k_pcg_persist<1, 0>;
     else if (block == 2) fn = PS_PICK(k_pcg_persist, 2);
     else fn = PS_PICK(k_pcg_persist, 3);
 #undef PS_PICK

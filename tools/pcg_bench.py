@@ -170,6 +170,9 @@ def run(mesh_n=68, bs=3, iters=200, profile=False, hbm_peak=6451.2):
         variants.append(("pcg_persist_bsr_direct", dict(persist=1, bsr=2), plan))
         variants.append(("pcg_persist_bsr_single_reduction", dict(persist=1, bsr=1, single_reduction=2), plan))
     else:
+        # scalar operator: the direct walk with bcol = colidx (lanes per row from the longest row)
+        direct = (colidx, int((rowptr[1:] - rowptr[:-1]).max().item()))
+        variants.append(("pcg_persist_csr_direct", dict(persist=2, bsr=2), direct))
         variants.append(("pcg_persist_csr_single_reduction", dict(persist=2, bsr=0, single_reduction=2), None))
     sols = {}
     for name, opts, pl in variants:
@@ -191,7 +194,7 @@ def run(mesh_n=68, bs=3, iters=200, profile=False, hbm_peak=6451.2):
         _lib.stats(reset=True)
         solve(1e-30, k)
         s = _lib.stats()
-        bytes_moved = it_bytes if pl is None else (8 * nnz + 4 * (nnz // (bs * bs)) + 4 * (n + 1) + 56 * n)
+        bytes_moved = it_bytes if (pl is None or bs == 1) else (8 * nnz + 4 * (nnz // (bs * bs)) + 4 * (n + 1) + 56 * n)
         entry(name, s["pcg_ms"] / max(s["pcg_iters"], 1), it_bytes, iters=s["pcg_iters"], launches=s["launches"],
               phase_us_per_iteration={kk: v / 1e3 / k for kk, v in ph.items()} if (opts.get("persist") == 2 or pl is not None) else None,
               bytes_of_format=bytes_moved, frac_hbm_of_format=bytes_moved / (s["pcg_ms"] / max(s["pcg_iters"], 1) * 1e-3) / 1e9 / hbm_peak)
