@@ -581,7 +581,7 @@ def _fast_functional(meas, monos):
         else:
             sg = -1.0 if T.ravel()[np.flatnonzero(T)[0]] < 0.0 else 1.0  # same normalisation as Group.sign()
             if sg < 0.0:
-                T = -T
+                T = 0.0 - T  # (not -T: the zeros must stay +0.0, the tensor's bytes are the atom's cache key)
             T.setflags(write=False)
             _TBYTES[id(T)] = T.tobytes()
             ent = (T, sg)

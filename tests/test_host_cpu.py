@@ -286,3 +286,51 @@ def test_scalar_pool_wraps_around(cpu, monkeypatch):
     for d in range(3):
         for k in range(3):
             assert np.array_equal(small.PGD_func[d][k].vector().get_local(), ref.PGD_func[d][k].vector().get_local())
+
+
+def test_negated_operator_shares_the_atom_and_long_forms_take_the_fast_path(cpu):
+    """`-Constant(c) * op(G, v)` (every old-mode term of a right-hand side) must reuse the assembled atom of `op`:
+    the sign goes into the coefficient, not into a second operator -K.  Functionals of long forms (a Voigt elasticity
+    integrand expands to 33 monomials) take the memoised fast path and agree with the general path."""
+    import pgdrome_b200.dolfin as df
+    from pgdrome_b200 import forms, lazy
+    from pgdrome_b200.assembly import device_space
+
+    m = df.UnitCubeMesh(3, 3, 3)
+    V = df.VectorFunctionSpace(m, "P", 1)
+    rng = np.random.default_rng(5)
+    f, g = df.Function(V), df.Function(V)
+    f.vector()[:] = rng.uniform(-1, 1, V.n_dofs)
+    g.vector()[:] = rng.uniform(-1, 1, V.n_dofs)
+    v = df.TestFunction(V)
+    C = np.zeros((6, 6))
+    C[:3, :3] = 0.6
+    C[np.arange(3), np.arange(3)] += 0.8
+    C[np.arange(3, 6), np.arange(3, 6)] = 0.4
+    Cm = df.as_matrix(C)
+    chi = df.Expression("x[0] < 0.5 ? 1.0 : 0.25", degree=0)
+
+    def eps(w):
+        return df.as_vector([w[0].dx(0), w[1].dx(1), w[2].dx(2), w[1].dx(2) + w[2].dx(1), w[0].dx(2) + w[2].dx(0),
+                             w[0].dx(1) + w[1].dx(0)])
+
+    k = lambda a, b: chi * df.inner(Cm * eps(a), eps(b)) * df.dx(m)  # noqa: E731
+    ds = device_space(V)
+    plus = df.assemble(k(f, v)).tensor().clone()
+    n_atoms = len(ds.atoms)
+    minus = df.assemble(-k(f, v)).tensor().clone()
+    assert len(ds.atoms) == n_atoms, "the negated form assembled a second atom"
+    assert np.array_equal(minus.numpy(), -plus.numpy())
+    # rank 0: fast path (one integral, <= 64 monomials) against the general path (two integrals of the same form)
+    fast = float(df.assemble(k(f, g)))
+    fast_neg = float(df.assemble(-1.0 * k(f, g)))
+    general = float(df.assemble(k(f, g) + k(g, f)))
+    assert len(ds.atoms) == n_atoms
+    assert fast_neg == -fast
+    assert abs(general - 2.0 * fast) <= 1e-12 * abs(general)
+    A = ofem.assemble_bilinear(ofem.Space(m.coordinates(), m.cells(), 1, 3), ofem.T_voigt(C, 3),
+                               weight=lambda x: np.where(x[..., 0] < 0.5, 1.0, 0.25), weight_degree=0)
+    ref = float(g.vector()[:] @ (A @ f.vector()[:]))
+    assert abs(fast - ref) <= 1e-11 * abs(ref)
+    lazy._pending.clear()
+    forms.functional_memo[0] = None
