@@ -25,7 +25,7 @@ import numpy as np
 import scipy.sparse as sp
 import torch
 
-from . import _lib, forms, lazy
+from . import _lib, forms, lazy, ufl
 from .assembly import device_space
 from .functions import Function, MatrixOperator, bc_list, local_bc, merged_bc_dofs
 from .lazy import LazyScalar
@@ -288,11 +288,15 @@ class PGDProblem:
             if outer is None and settings.get("memo_functionals", True):
                 forms.functional_memo[0] = {}
             forms.device_coefficients[0] = bool(settings.get("device_coefficients", True))
+            outer_cc = ufl.capture_cache[0]
+            if outer_cc is None and settings.get("memo_functionals", True):
+                ufl.capture_cache[0] = {}
             try:
                 return self._enrichment_step(n_enr, normConv, relConv, _problem, solve_modes, settings)
             finally:
                 forms.functional_memo[0] = outer
                 forms.device_coefficients[0] = outer_dc
+                ufl.capture_cache[0] = outer_cc
                 self._collect_solve()
                 lazy.fetch()  # functionals that were only consumed on the device: bring their values home, release them
 

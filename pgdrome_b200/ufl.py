@@ -44,6 +44,13 @@ def _mono(coef, factors, _new=Mono.__new__, _cls=Mono):
 
 _LAZY_SCALAR = None
 
+# While an enrichment step runs, the solver sets capture_cache[0] to a dict: `leaf[i]` of a vector leaf is then handed out
+# as ONE shared expression object per (leaf, i), and that object remembers its derivatives -- the `eps(v)` / `grad(v)`
+# algebra of the user's callbacks is evaluated hundreds of times per sweep on the same few Functions.  Expressions are
+# immutable, and the table (which keeps its leaves alive) is dropped at the end of the step, so no reference cycle
+# leaf -> cache -> expression -> leaf outlives it.
+capture_cache = [None]
+
 
 def _lazy_scalar_type():
     """LazyScalar, resolved once (a function-level import here costs ~1.5 us on every operator call)"""
@@ -64,6 +71,8 @@ class Expr:
 
     __array_ufunc__ = None  # numpy scalars defer to our reflected operators
     __array_priority__ = 1000
+
+    _dx = None  # {j: d/dx_j of this expression}, filled on demand for the shared component expressions (capture_cache)
 
     def __init__(self, shape, comps):
         self.ufl_shape = tuple(shape)
@@ -175,6 +184,11 @@ class Expr:
         if len(idx) != 1:
             raise NotImplementedError("higher derivatives .dx(i, j)")
         j = int(idx[0])
+        memo = self._dx
+        if memo is not None:
+            hit = memo.get(j)
+            if hit is not None:
+                return hit
         out = []
         for c in self.comps:
             monos = []
@@ -196,7 +210,10 @@ class Expr:
                     nf = m.factors[:k] + (Factor(f.leaf, f.comp, j),) + m.factors[k + 1:]
                     monos.append(Mono(m.coef, nf))
             out.append(monos)
-        return Expr(self.ufl_shape, out)
+        res = Expr(self.ufl_shape, out)
+        if memo is not None:
+            memo[j] = res
+        return res
 
     def __eq__(self, other):  # noqa: keep identity semantics for leaves used as dict keys
         return self is other
@@ -224,7 +241,15 @@ class Leaf(Expr):
         i = int(i)
         if not 0 <= i < self._n_comp:
             raise IndexError("component %d of a %d-vector" % (i, self._n_comp))
-        return Expr((), [[_mono(1.0, (Factor(self, i, None),))]])
+        cache = capture_cache[0]
+        if cache is None:
+            return Expr((), [[_mono(1.0, (Factor(self, i, None),))]])
+        ent = cache.get((id(self), i))
+        if ent is None or ent[0] is not self:
+            e = Expr((), [[_mono(1.0, (Factor(self, i, None),))]])
+            e._dx = {}
+            ent = cache[(id(self), i)] = (self, e)
+        return ent[1]
 
     @property
     def comps(self):

@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--modes", type=int, default=3)
     ap.add_argument("--rtol", type=float, default=1e-13)
     ap.add_argument("--setup-profile", default=None, help="write a cProfile of problem construction + step 0 (rank 0) here")
+    ap.add_argument("--step-profile", default=None, help="write a cProfile of the steps --step-profile-range (rank 0) here")
+    ap.add_argument("--step-profile-range", default="20:22")
     ap.add_argument("--counts", default=None, help="write the per-step / per-solve PCG iteration counts to this JSON file "
                                                    "(bench.py scales its bounded CPU sample with them)")
     a = ap.parse_args()
@@ -57,7 +59,25 @@ def main():
     st = p.begin_PGD(_problem="linear", settings={"linear_solver": "cg", "relative_tolerance": a.rtol})
     steps = []
     _lib.stats(reset=True)
+    sprof = None
     for i in range(a.modes):
+        if a.step_profile and rank == 0:  # cProfile of the enrichment steps [first, last] on rank 0 (host share of a warm step)
+            first, last = (int(v) for v in a.step_profile_range.split(":"))
+            if i == first:
+                import cProfile
+
+                sprof = cProfile.Profile()
+                sprof.enable()
+            if i == last + 1 and sprof is not None:
+                import io
+                import pstats
+
+                sprof.disable()
+                sio = io.StringIO()
+                pstats.Stats(sprof, stream=sio).sort_stats("cumulative").print_stats(80)
+                pstats.Stats(sprof, stream=sio).sort_stats("tottime").print_stats(40)
+                open(a.step_profile, "w").write(sio.getvalue())
+                sprof = None
         if i == 1 and prof is not None:
             import io
             import pstats
