@@ -114,8 +114,8 @@ def _solve_counts(n):
 
 def _cpu_sample(args, step_ids, sample_iters=40):
     """Bounded sample of the CPU port on the same workload (oracle/: C restatement of assembly + node-block-Jacobi PCG
-    with OpenMP, SciPy for the 1-D dimensions).  A full CPU step takes minutes (~1 650 CG iterations x ~7 sweeps at
-    ~15 ms), so per step ONE fixed-point sweep is executed for real -- operator and right-hand-side assembly of every
+    with OpenMP, SciPy for the 1-D dimensions).  A full CPU step takes most of a minute (~1 800 CG iterations per sweep, 2-4
+    sweeps per step, ~5 ms per iteration on 16 threads), so per step ONE fixed-point sweep is executed for real -- operator and right-hand-side assembly of every
     dimension, Dirichlet elimination, the two 1-D solves -- with the spatial CG capped at `sample_iters` iterations;
     the step time is  sweeps x (assembly + 1-D solves) + sum(iterations) x seconds-per-iteration  with the sweep and
     iteration counts of the full run.  Returns (seconds per step list, info)."""
