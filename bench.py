@@ -182,7 +182,7 @@ def run_reference(args):
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "note": "the real reference (FEniCS 2019.1 + PETSc) cannot be installed in this image; this is its CPU port with "
                    "settings={'linear_solver': 'cg', 'preconditioner': 'jacobi'}-class solves (solver.py:634-635)"}
-    print(json.dumps(out))
+    _emit(out)
 
 
 # ------------------------------------------------------------------------------- B200 arm
@@ -385,7 +385,7 @@ def run_b200(args):
                       "pcg_ms": s["pcg_ms"], "fp_iterations": fp_its, "functional_flushes": lazy.stats["flushes"] - flushes0,
                       "wall_s_timed_region": wall, "nnz_rank0": nnz_loc, "rows_rank0": n_loc, "setup_and_warmup_s": t_setup,
                       "device_mem_gb_rank0": torch.cuda.max_memory_allocated() / 1e9}}
-    print(json.dumps(out))
+    _emit(out)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -463,7 +463,27 @@ def _secondary_heat2d(torch, _lib, configs, steps=5, warm=3):
             "ms_per_step": ms / steps, "pcg_iters": s["pcg_iters"], "pcg_share": s["pcg_ms"] / ms if ms else None}
 
 
+_JSON_OUT = [None]
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to stdout when
+    NCCL_DEBUG is set on the box), so file descriptor 1 is pointed at stderr for the duration of the run and the line goes
+    to a private duplicate of the original stdout."""
+    if _JSON_OUT[0] is None:
+        sys.stdout.flush()
+        _JSON_OUT[0] = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(obj):
+    f = _JSON_OUT[0] or sys.stdout
+    f.write(json.dumps(obj) + "\n")
+    f.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
