@@ -2,25 +2,28 @@
 // GPU or on every GPU of a row-sharded system (the multi-GPU form of pcg_resident.cu).
 //
 // The matrix does not fit on chip here (configs[2]: 520 MB, configs[3]: 720 MB, 1/N of that per rank), so every
-// iteration streams the local CSR rows through the TMA ring of spmv_bulk.cuh; what the persistent form removes
-// is everything BETWEEN the streams: kernel launches, host polling, and -- sharded -- the 8 dependent launches
-// and three host-visible flag round trips of pgd_spcg_solve_sync (55 us floor per iteration).  All CG scalars
-// live in registers, identical in every CTA of every rank.
+// iteration streams the local rows -- vector operators by the direct node-block walk of spmv_bsr.cuh (template value
+// BSR = 2), scalar ones through the TMA ring of spmv_bulk.cuh (BSR = 0; BSR = 1 is the ring with node-block tiles);
+// what the persistent form removes is everything BETWEEN the streams: kernel launches, host polling, and -- sharded --
+// the 8 dependent launches and three host-visible flag round trips of pgd_spcg_solve_sync (55 us floor per
+// iteration).  All CG scalars live in registers, identical in every CTA of every rank.
 //
-// One iteration (z carries a ghost tail that lives in the peer window; p = [owned | ghost] is purely local):
+// One iteration (p = [owned | ghost] is purely local; the ghost values of z arrive through the peer window):
 //   D  p = z + beta p on ALL local entries -- the ghost entries of p follow the same recurrence from the ghost
-//      entries of z, which the neighbours stored during the previous reduction   -> grid barrier (arrival counter)
-//   S  q = A_loc p through the TMA ring, local p.q                 -> reduce-broadcast #1 (alpha)
+//      entries of z, which the neighbours sent during the previous reduction   -> grid barrier (arrival counter)
+//   S  q = A_loc p, local p.q                                      -> reduce-broadcast #1 (alpha)
 //   U  x += alpha p ; r -= alpha q ; z = M^-1 r ; local r.z, r.r   -> reduce-broadcast #2 (beta, stop test); inside it,
 //      as soon as this rank's CTAs have all arrived, a few CTAs store the boundary entries of the new z straight
-//      into the neighbours' ghost slots over NVLink (+ sequence flag): the halo travels while the dot products
-//      cross the switch, and the next D finds it in place.  (First version: halo of p pushed in D, every CTA fencing
-//      at system scope -- 9.6 us for D and 6.7 us of barrier + halo wait per iteration at 2 GPUs.)
-// reduce-broadcast: every CTA deposits its partials and arrives; CTA 0 sums them in a fixed order and stores
-// the rank's sum into the mailbox of every rank (its own included) with a release flag; every CTA of every
-// rank acquires the `world` flags and adds the mailboxes in RANK ORDER => bitwise identical scalars
-// everywhere, deterministic run to run, one uniform stop decision and no host round trip.  On a single GPU the
-// mailbox is a block of the handle's own memory and the scheme degenerates to a grid barrier.
+//      into the neighbours' windows over NVLink: the halo travels while the dot products cross the switch, and the
+//      next D finds it in place.  (First version: halo of p pushed in D, every CTA fencing at system scope -- 9.6 us
+//      for D and 6.7 us of barrier + halo wait per iteration at 2 GPUs.)
+// reduce-broadcast: every CTA deposits its partials, arrives and adds the G partials itself in a fixed order; CTA 0
+// sends the rank's sum to every other rank; every CTA of every rank collects the `world - 1` foreign sums from its
+// LOCAL window and adds them in RANK ORDER => bitwise identical scalars everywhere, deterministic run to run, one
+// uniform stop decision and no host round trip.  On a single GPU the scheme degenerates to a grid barrier.
+// Cross-GPU transport ("ll" option, default): sums and halo entries travel as 8-byte words {32 data bits | 32-bit
+// sequence number}; a value is complete when both of its words carry the expected sequence, so neither a system-scope
+// fence nor a flag sits on the critical path (41 -> 29 us per iteration at 8 GPUs).  "ll" = 0: data, fence, release flag.
 // Every spin carries a wall-clock budget (globaltimer) and watches a local abort word, so a missing peer ends
 // the solve with -6 instead of hanging the GPU; the window is then marked unusable (sequence numbers may have
 // diverged) and later solves use the NCCL path.
@@ -851,8 +854,6 @@ extern "C" int32_t pgd_pcg_persist_sync(pgd_handle_t h, const int32_t* d_rowptr,
     PGD_CUDA(h, cudaMemsetAsync(a.arrive - 1, 0, 2 * sizeof(unsigned int), st));  // push_ctr, arrive
     PGD_CUDA(h, cudaMemsetAsync(a.out_fl, 0, 2 * sizeof(int), st));
     PGD_CUDA(h, cudaMemsetAsync(a.abort_word, 0, sizeof(int), st));
-    // node-block walk: lanes per block row = the power of two covering the longest block row (<= 32), block rows per
-    // tile = CTA size / lanes; the tile (nbr * block^2 * longest row entries) must fit one stage of the ring
     // node-block walk ("bsr" option): 1 = tiles through the TMA ring (lanes per block row = the power of two covering
     // the longest block row, block rows per tile = CTA size / lanes, the tile must fit one stage); 2 = direct walk
     // (no shared memory; lanes per block row = the power of two covering a third of the longest row segment)
@@ -868,7 +869,9 @@ extern "C" int32_t pgd_pcg_persist_sync(pgd_handle_t h, const int32_t* d_rowptr,
             a.bsr.nbr = nbr;
             a.bsr.lpr = lpr;
         }
-    } else if (d_bcol && max_blocks_per_row > 0 && h->opt_bsr >= 2) {  // (block == 1: bcol = colidx, the plain CSR row walk)
+    } else if (d_bcol && max_blocks_per_row > 0 && h->opt_bsr >= 2) {
+        // (block == 1 with bcol = colidx is the plain CSR row walk; measured SLOWER than the ring on 15-entry rows --
+        // 0.361 vs 0.216 ms at configs[3] -- so the host side only passes a block-column list for vector operators)
         int lpr = 4;
         while (lpr < 32 && 3 * lpr < block * max_blocks_per_row) lpr *= 2;
         bsr = 2;
@@ -876,8 +879,7 @@ extern "C" int32_t pgd_pcg_persist_sync(pgd_handle_t h, const int32_t* d_rowptr,
         a.bsr.nbr = PS_THREADS / lpr;
         a.bsr.lpr = lpr;
     }
-    // "single_reduction": 0 = never, 1 = sharded solves (where the second reduction costs more than it saves), 2 = always
-    const bool sr = sr_requested;
+    const bool sr = sr_requested;  // "single_reduction": 0 = never (default), 1 = sharded solves, 2 = always
     const void* fn = nullptr;
 #define PS_PICK(K, B) (bsr == 2 ? (const void*)K<B, 2> : bsr == 1 ? (const void*)K<B, 1> : (const void*)K<B, 0>)
     if (sr) {
