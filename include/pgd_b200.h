@@ -237,10 +237,12 @@ int32_t pgd_pcg_x0_sync(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* 
  * d_x [n_local] in [owned | ghost] numbering (single GPU: n_local = n_owned, the four halo arguments NULL).
  *   warm != 0: d_x holds the initial guess INCLUDING valid ghost entries; on return d_x holds the solution and, sharded,
  *   its ghost entries are up to date as well (exchanged through the peer window inside the kernel).
- *   Sharded: needs an opened peer window (pgd_peer_window_create with p_capacity >= 2 * max n_local + 8) and the halo
- *   description of pgd_spcg_solve_sync.  Neighbour values of the direction vector are stored straight into the peers'
- *   ghost slots over NVLink, the dot products are summed through per-rank mailboxes in rank order (bitwise identical on
- *   all ranks).  Every in-kernel wait has a wall-clock budget (pgd_set_option "spin_ms", default 20 000): a missing peer
+ *   Sharded: needs an opened peer window (pgd_peer_window_create with p_capacity >= 6 * max n_local + 16 over the ranks:
+ *   the vector z at [0, p_capacity / 3) and the LL halo region behind it; with pgd_set_option "ll" = 0,
+ *   2 * max n_local + 8 suffices) and the halo description of pgd_spcg_solve_sync.  Neighbour values of the
+ *   preconditioned residual travel straight into the peers' windows over NVLink, the dot products are summed through
+ *   per-rank mailboxes in rank order (bitwise identical on all ranks).  A window that is too small for the LL halo is an
+ *   argument error (-1), not a silent change of protocol.  Every in-kernel wait has a wall-clock budget (pgd_set_option "spin_ms", default 20 000): a missing peer
  *   ends the call with -6 instead of hanging, and the peer window is disabled afterwards (the ranks' sequence numbers
  *   may have diverged; pgd_spcg_solve_sync over NCCL keeps working).
  *   d_bcol / max_blocks_per_row (optional, block > 1): block-column list of the node-block walk -- d_bcol[j] = node of the

@@ -823,7 +823,13 @@ extern "C" int32_t pgd_pcg_persist_sync(pgd_handle_t h, const int32_t* d_rowptr,
     const bool sr_requested = h->opt_single_reduction >= 2 || (h->opt_single_reduction == 1 && multi);
     if (multi) {
         PGD_ARG(h, n_local <= h->win_pcap, "peer window too small");
-        a.ll = (h->opt_ll && !sr_requested && (size_t)n_local <= a.lay.llh_base() && (size_t)n_local <= a.lay.llh_cap()) ? 1 : 0;
+        if (h->opt_ll && !sr_requested) {
+            // the protocol must be the same on every rank: a window that is too small for THIS rank is an error, not a
+            // silent switch to the flag protocol (the capacity is uniform, n_local is not)
+            PGD_ARG(h, (size_t)n_local <= a.lay.llh_base() && (size_t)n_local <= a.lay.llh_cap(),
+                    "peer window too small for the LL halo: capacity >= 6 n_local + 16 doubles of the largest rank");
+            a.ll = 1;
+        }
         a.s = a.z;
         a.z = reinterpret_cast<double*>(h->win_local);
         int64_t n_send = 0;
