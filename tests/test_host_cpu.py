@@ -334,3 +334,29 @@ def test_negated_operator_shares_the_atom_and_long_forms_take_the_fast_path(cpu)
     assert abs(fast - ref) <= 1e-11 * abs(ref)
     lazy._pending.clear()
     forms.functional_memo[0] = None
+
+
+def test_capture_cache_is_scoped_to_the_enrichment_step(cpu):
+    """Inside an enrichment step `v[i]` of a vector Function is ONE shared expression that remembers its derivatives;
+    outside a step nothing is cached (no leaf -> expression -> leaf cycle survives the step)."""
+    import pgdrome_b200.dolfin as df
+    from pgdrome_b200 import ufl
+
+    V = df.VectorFunctionSpace(df.UnitSquareMesh(2, 2), "P", 1)
+    f = df.Function(V)
+    assert ufl.capture_cache[0] is None
+    assert f[0] is not f[0] and f[0]._dx is None
+    ufl.capture_cache[0] = {}
+    try:
+        a, b = f[0], f[0]
+        assert a is b and f[1] is not a
+        assert a.dx(1) is b.dx(1) and a.dx(0) is not a.dx(1)
+        (m,) = a.dx(1).comps[0]
+        assert m.factors == (ufl.Factor(f, 0, 1),)
+        g = df.Function(V)
+        assert g[0] is not a  # another leaf, another entry
+    finally:
+        ufl.capture_cache[0] = None
+    p = __import__("pgdrome_b200.configs", fromlist=["x"]).poisson1d_k(nx=20, nk=5, PGD_nmax=2)
+    p.solve_PGD(_problem="linear")
+    assert ufl.capture_cache[0] is None
