@@ -662,11 +662,16 @@ def pcg_persist(rowptr, colidx, values, b, x=None, n_owned=None, block=1, rtol=1
         send_idx = halo.send_idx if halo.send_idx.numel() else None
     iters, relres = c_i32(0), c_dbl(0.0)
     cast = lambda a: ctypes.cast(a, c_vp) if a is not None else c_vp(0)
-    _check(lib.pgd_pcg_persist_sync(h, _p(rowptr, I32), _p(colidx, I32), _p(values, F64), _p(b, F64), _p(x, F64), no, nl, block,
-                                    float(rtol), float(atol), int(maxit), 1 if x0 is not None else 0, _p(work, F64),
-                                    _p(send_idx, I64), cast(sc), cast(rc_), cast(gbase),
-                                    _p(bsr[0], I32) if bsr else c_vp(0), int(bsr[1]) if bsr else 0,
-                                    ctypes.byref(iters), ctypes.byref(relres), _stream()), h, "pgd_pcg_persist_sync")
+    rc = lib.pgd_pcg_persist_sync(h, _p(rowptr, I32), _p(colidx, I32), _p(values, F64), _p(b, F64), _p(x, F64), no, nl, block,
+                                  float(rtol), float(atol), int(maxit), 1 if x0 is not None else 0, _p(work, F64),
+                                  _p(send_idx, I64), cast(sc), cast(rc_), cast(gbase),
+                                  _p(bsr[0], I32) if bsr else c_vp(0), int(bsr[1]) if bsr else 0,
+                                  ctypes.byref(iters), ctypes.byref(relres), _stream())
+    if rc == -6:
+        # a peer did not arrive: the library has disabled its window (sequence numbers may have diverged); forget the
+        # cached one so that the next sharded solve creates and opens a fresh window collectively
+        _WINDOW.clear()
+    _check(rc, h, "pgd_pcg_persist_sync")
     return x, iters.value, relres.value
 
 
