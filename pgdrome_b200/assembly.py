@@ -25,6 +25,34 @@ def _up(a, dtype):
     return _lib.to_device(a, dtype)
 
 
+class _Pattern:
+    """(rowptr, colidx, gptr, gidx) of a space.  The gather lists of the generic element-matrix route (gptr[nnz + 1],
+    gidx[n_cells * ndl^2]: 1.4 GB at configs[2]) are built on first use: the P1 routes never ask for them."""
+
+    __slots__ = ("rowptr", "colidx", "_gather", "_make")
+
+    def __init__(self, rowptr, colidx, gather=None, make=None):
+        self.rowptr, self.colidx, self._gather, self._make = rowptr, colidx, gather, make
+
+    def __len__(self):
+        return 4
+
+    def __getitem__(self, i):
+        if i == 0:
+            return self.rowptr
+        if i == 1:
+            return self.colidx
+        if i in (2, 3):
+            if self._gather is None:
+                self._gather = self._make()
+                self._make = None
+            return self._gather[i - 2]
+        raise IndexError(i)
+
+    def __iter__(self):
+        return (self[i] for i in range(4))
+
+
 class DeviceSpace:
     """GPU mirror of a FunctionSpace: mesh arrays, CSR pattern, gather lists, cached atoms."""
 
@@ -54,8 +82,80 @@ class DeviceSpace:
     @property
     def pattern(self):
         if self._pattern is None:
-            self._pattern = _lib.pattern_build(self.cell_dofs, self.n_dofs)
+            if self.space.bs > 1:
+                self._pattern = self._blocked_pattern()
+            else:
+                rowptr, colidx, gptr, gidx = _lib.pattern_build(self.cell_dofs, self.n_dofs)
+                self._pattern = _Pattern(rowptr, colidx, gather=(gptr, gidx))
         return self._pattern
+
+    def _blocked_pattern(self):
+        """Pattern of a vector space from the pattern of its NODES: the dofs of a space are node-blocked (dof = node * bs +
+        component, fem.FunctionSpace._finish), so row (I, a) holds the columns (J, b) for every neighbour J of I and every
+        component b -- bs^2 times fewer keys to sort than the dof-level build (30 M instead of 271 M at configs[2]); the
+        node-level arrays are at the same time the block-column list of the node-block SpMV walk and the row-owner plan
+        of the fused P1 assembly.  Index arithmetic on device tensors only (set-up plumbing); identical to the dof-level
+        pattern bit for bit."""
+        s = self.space
+        bs, n = s.bs, self.n_dofs
+        cn = _up(np.ascontiguousarray(s.cell_nodes, dtype=np.int32), torch.int32)
+        brp, bci, bgptr, bgidx = _lib.pattern_build(cn, s.n_nodes)
+        self._node_pattern = (brp, bci, cn)
+        dev = brp.device
+        blocks = (brp[1:] - brp[:-1]).to(torch.int64)                    # node blocks per node row
+        rowlen = (blocks * bs).repeat_interleave(bs)                     # entries per dof row
+        rowptr64 = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(rowlen, 0, out=rowptr64[1:])
+        nnz = int(rowptr64[-1].item())
+        if nnz >= 2**31:
+            raise ValueError("pattern with more than 2^31 entries")
+        row_of = torch.repeat_interleave(torch.arange(n, device=dev), rowlen)
+        off = torch.arange(nnz, device=dev) - rowptr64[row_of]
+        t = brp.to(torch.int64)[torch.div(row_of, bs, rounding_mode="floor")] + torch.div(off, bs, rounding_mode="floor")
+        colidx = (bci.to(torch.int64)[t] * bs + off % bs).to(torch.int32)
+        rowptr = rowptr64.to(torch.int32)
+        del row_of, off, t
+
+        bs_, nd_, nc_ = s.bs, s.nd, int(s.cell_nodes.shape[0])  # (no reference to self in the closure: no cycle)
+
+        def make_gather():
+            return DeviceSpace._blocked_gather(bs_, nd_, nc_, brp, bgptr, bgidx, rowptr64, nnz)
+
+        return _Pattern(rowptr, colidx, make=make_gather)
+
+    @staticmethod
+    def _blocked_gather(bs, nd, n_cells, brp, bgptr, bgidx, rowptr64, nnz, chunk=1 << 22):
+        """gather lists of the generic assembler on a vector space, from the node-level lists: the contribution
+        (cell e, local nodes a, b) of node entry (I, J) is the contribution (e, a*bs+i, b*bs+j) of the dof entry
+        ((I, i), (J, j)); ascending inside every group like the node-level list.  Built in chunks of entries."""
+        ndl = nd * bs
+        dev = brp.device
+        brp64, bgptr64 = brp.to(torch.int64), bgptr.to(torch.int64)
+        gptr = torch.zeros(nnz + 1, dtype=torch.int64, device=dev)
+        total = n_cells * ndl * ndl
+        gidx = torch.empty(total, dtype=torch.int32, device=dev)
+        base = 0
+        for k0 in range(0, nnz, chunk):
+            k1 = min(nnz, k0 + chunk)
+            k = torch.arange(k0, k1, device=dev)
+            r = torch.searchsorted(rowptr64, k, right=True) - 1
+            off = k - rowptr64[r]
+            ci, cj = r % bs, off % bs
+            t = brp64[torch.div(r, bs, rounding_mode="floor")] + torch.div(off, bs, rounding_mode="floor")
+            cnt = bgptr64[t + 1] - bgptr64[t]
+            csum = torch.cumsum(cnt, 0)
+            gptr[k0 + 1:k1 + 1] = base + csum
+            m = int(csum[-1].item())
+            kk = torch.repeat_interleave(torch.arange(k1 - k0, device=dev), cnt)
+            pos = torch.arange(m, device=dev) - (csum - cnt)[kk]
+            c = bgidx[bgptr64[t[kk]] + pos].to(torch.int64)
+            e = torch.div(c, nd * nd, rounding_mode="floor")
+            ab = c % (nd * nd)
+            a_, b_ = torch.div(ab, nd, rounding_mode="floor"), ab % nd
+            gidx[base:base + m] = (e * (ndl * ndl) + (a_ * bs + ci[kk]) * ndl + (b_ * bs + cj[kk])).to(torch.int32)
+            base += m
+        assert base == total, (base, total)
+        return gptr, gidx
 
     @property
     def nnz(self):
@@ -72,7 +172,13 @@ class DeviceSpace:
         """block-column plan of the node-block walk (vector spaces; None when the pattern is not block structured)"""
         if self._bsr == 0:
             s = self.space
-            self._bsr = _lib.bsr_plan(self.rowptr_owned, self.pattern[1][: self.nnz_owned], s.bs) if 1 < s.bs <= 3 else None
+            self._bsr = None
+            if 1 < s.bs <= 3:
+                self.pattern  # noqa: B018  (builds the node pattern)
+                brp, bci, _ = self._node_pattern
+                n_on = self.n_owned // s.bs  # owned node rows come first
+                nb = brp[1:n_on + 1] - brp[:n_on]
+                self._bsr = (bci[: int(brp[n_on].item())], int(nb.max().item()))
         return self._bsr
 
     @property
@@ -102,7 +208,7 @@ class DeviceSpace:
     def rowplan(self):
         """Plan of the row-owner fused P1 kernel (scalar P1 spaces only; False if a row is too long)."""
         if self._rowplan is None:
-            rowptr, colidx, _, _ = self.pattern
+            rowptr, colidx = self.pattern[0], self.pattern[1]
             vptr, vidx = self.vecmap
             try:
                 self._rowplan = _lib.p1_rowplan_build(rowptr, colidx, self.cell_dofs, vptr, vidx, self.n_dofs)
@@ -130,14 +236,11 @@ class DeviceSpace:
                         if self.rowplan is not False:
                             self._node_plan = (self.vecmap[0], self.rowplan)
                     else:
-                        rowptr, colidx, _, _ = self.pattern
-                        blk = _lib.bsr_plan(rowptr, colidx, s.bs)
-                        if blk is not None:
-                            brp = torch.div(rowptr[:: s.bs], s.bs * s.bs, rounding_mode="floor").to(torch.int32).contiguous()
-                            cn = _up(np.ascontiguousarray(s.cell_nodes, dtype=np.int32), torch.int32)
-                            vptr, vidx = _lib.vecmap_build(cn, s.n_nodes)
-                            vent = _lib.p1_rowplan_build(brp, blk[0], cn, vptr, vidx, s.n_nodes)
-                            self._node_plan = (vptr, vent)
+                        self.pattern  # noqa: B018  (builds the node pattern)
+                        brp, bci, cn = self._node_pattern
+                        vptr, vidx = _lib.vecmap_build(cn, s.n_nodes)
+                        vent = _lib.p1_rowplan_build(brp, bci, cn, vptr, vidx, s.n_nodes)
+                        self._node_plan = (vptr, vent)
                 except _lib.PGDB200Error:
                     self._node_plan = False
         return self._node_plan

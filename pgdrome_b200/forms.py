@@ -281,7 +281,7 @@ def _embed_operator(ds, op, scale, transpose):
         raise NotImplementedError("MatrixOperator on an element-partitioned space (user matrices live on the replicated "
                                   "1-D dimensions)")
 
-    rowptr, colidx, _, _ = ds.pattern
+    rowptr, colidx = ds.pattern[0], ds.pattern[1]
     rp, ci = _lib.to_host(rowptr).astype(np.int64), _lib.to_host(colidx).astype(np.int64)
     n = ds.n_dofs
     A = (op.A.T if transpose else op.A).tocoo()
@@ -745,7 +745,7 @@ class AssembledMatrix:
     def scipy(self):
         import scipy.sparse as sp
 
-        rowptr, colidx, _, _ = self.ds.pattern
+        rowptr, colidx = self.ds.pattern[0], self.ds.pattern[1]
         n = self.ds.n_dofs
         return sp.csr_matrix((_lib.to_host(self.values), _lib.to_host(colidx), _lib.to_host(rowptr)), shape=(n, n))
 

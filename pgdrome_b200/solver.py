@@ -538,7 +538,7 @@ class PGDProblem:
             b = forms.assemble_vector(gl)
         else:
             b = torch.zeros(ds.n_dofs, dtype=F64, device=A.values.device)
-        rowptr, colidx, _, _ = ds.pattern
+        rowptr, colidx = ds.pattern[0], ds.pattern[1]
         bcd = self._bc_dev(dim)
         if bcd is not None:
             _lib.apply_dirichlet(rowptr, colidx, A.values, b, bcd[0], bcd[1])
@@ -547,7 +547,7 @@ class PGDProblem:
 
     def _linear_solve(self, ds, values, b, symmetric, settings):
         V = ds.space
-        rowptr, colidx, _, _ = ds.pattern
+        rowptr, colidx = ds.pattern[0], ds.pattern[1]
         if V.mesh().tdim == 1:
             perm, bw = V.band_permutation()
             if ds.band is None:
