@@ -302,6 +302,16 @@ int32_t pgd_pcg_start(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_
                       double* d_work, int32_t warm, void* stream);
 int32_t pgd_pcg_finish(pgd_handle_t h, int32_t* h_iters, double* h_relres);
 
+/* The same hand-over for the persistent streaming kernel on ONE GPU (systems that do not fit on chip): enqueue
+ * pgd_pcg_persist_sync's kernel and return at once; pgd_pcg_finish collects iterations / residual (-3 NaN, -6 a CTA did
+ * not arrive).  The fixed-point sweep of solver.py:531-757 solves the spatial dimension first: the host records the
+ * forms of the parameter dimensions while the GPU iterates.  Arguments as pgd_pcg_persist_sync with n_local = n_owned
+ * = n and no halo description. */
+int32_t pgd_pcg_persist_start(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
+                              const double* d_b, double* d_x, int64_t n, int32_t block, double rtol, double atol,
+                              int32_t maxit, int32_t warm, double* d_work, const int32_t* d_bcol,
+                              int32_t max_blocks_per_row, void* stream);
+
 /* ---- sensor evaluation (PGD.evaluate_sensor_response, model.py:862-953; eval_fixed_modes with
  * fenicstools.Probes, model.py:107-130).
  * pgd_locate_points: for each of n_points points [n_points, gdim] find the LOWEST-numbered simplex

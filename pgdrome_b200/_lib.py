@@ -61,6 +61,7 @@ SIGNATURES = {
                         ctypes.POINTER(c_i32), ctypes.POINTER(c_dbl), c_vp],
     "pgd_pcg_persist_sync": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_dbl, c_dbl, c_i32, c_i32, c_vp, c_vp, c_vp,
                              c_vp, c_vp, c_vp, c_i32, ctypes.POINTER(c_i32), ctypes.POINTER(c_dbl), c_vp],
+    "pgd_pcg_persist_start": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_dbl, c_dbl, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp],
     "pgd_get_phase_ns": [c_vp, c_vp, c_i32],
     "pgd_row_stats": [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp],
     "pgd_banded_solve": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp],
@@ -639,10 +640,11 @@ def _ramp(lens):
 
 
 def pcg_persist(rowptr, colidx, values, b, x=None, n_owned=None, block=1, rtol=1e-13, atol=0.0, maxit=20000, x0=None,
-                halo=None, bsr=None, work=None):
+                halo=None, bsr=None, work=None, defer=False):
     """Persistent streaming PCG (pgd_pcg_persist_sync).  rowptr: the n_owned local rows; x / x0: [n_local] (ghosts of
     x0 valid); halo: partition.HaloPlan with its peer layout (sharded solves) or None; bsr: result of ``bsr_plan``.
-    Returns (x [n_local], iterations, relative residual)."""
+    Returns (x [n_local], iterations, relative residual).  defer=True (single GPU only): pgd_pcg_persist_start -- the
+    solve is only enqueued, x is valid in stream order, iterations = -1; collect with ``pcg_finish``."""
     h, lib = handle(b.device), load_library()
     no = rowptr.numel() - 1 if n_owned is None else int(n_owned)
     nl = no if halo is None else int(halo.n_local)
@@ -662,6 +664,14 @@ def pcg_persist(rowptr, colidx, values, b, x=None, n_owned=None, block=1, rtol=1
         send_idx = halo.send_idx if halo.send_idx.numel() else None
     iters, relres = c_i32(0), c_dbl(0.0)
     cast = lambda a: ctypes.cast(a, c_vp) if a is not None else c_vp(0)
+    if defer:
+        if halo is not None:
+            raise ValueError("deferred persistent solves are single-GPU only")
+        _check(lib.pgd_pcg_persist_start(h, _p(rowptr, I32), _p(colidx, I32), _p(values, F64), _p(b, F64), _p(x, F64), no, block,
+                                         float(rtol), float(atol), int(maxit), 1 if x0 is not None else 0, _p(work, F64),
+                                         _p(bsr[0], I32) if bsr else c_vp(0), int(bsr[1]) if bsr else 0, _stream()), h,
+               "pgd_pcg_persist_start")
+        return x, -1, 0.0
     rc = lib.pgd_pcg_persist_sync(h, _p(rowptr, I32), _p(colidx, I32), _p(values, F64), _p(b, F64), _p(x, F64), no, nl, block,
                                   float(rtol), float(atol), int(maxit), 1 if x0 is not None else 0, _p(work, F64),
                                   _p(send_idx, I64), cast(sc), cast(rc_), cast(gbase),

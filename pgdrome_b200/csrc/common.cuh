@@ -31,7 +31,8 @@ struct pgd_ctx {
     double pcg_ms;
     void* pinned;            // 512 B of page-locked host memory: [0,256) staging for the small device->host reads of the *_sync
                              // calls, [256,512) results of a started (pgd_pcg_start) solve
-    int res_pending;         // a solve started with pgd_pcg_start has not been finished yet
+    int res_pending;         // a solve started with pgd_pcg_start / pgd_pcg_persist_start has not been finished yet
+    int res_kind;            // ... 1 = SM-resident kernel, 2 = persistent streaming kernel (status codes differ)
     void* res_stream;        // ... on this stream
     const void* fit_key;     // rowptr / n / block of the last system the SM-resident PCG solved (=> it fits: eligible for start)
     int64_t fit_n;

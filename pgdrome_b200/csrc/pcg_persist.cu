@@ -777,12 +777,12 @@ __global__ void __launch_bounds__(PS_THREADS, BK_CTAS_PER_SM) k_pcg_persist_sr(P
 
 /* d_work: r q (stride ns = n_owned rounded up to even) | M^-1 (even(n_owned*block)) | p, z (even(n_local) each; with a
  * peer window z lives there instead) => 2*ns + even(n_owned*block) + 2*even(n_local) + 8 doubles. */
-extern "C" int32_t pgd_pcg_persist_sync(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
-                                        const double* d_b, double* d_x, int64_t n_owned, int64_t n_local, int32_t block,
-                                        double rtol, double atol, int32_t maxit, int32_t warm, double* d_work,
-                                        const int64_t* d_send_idx, const int64_t* h_send_counts, const int64_t* h_recv_counts,
-                                        const int64_t* h_peer_ghost_base, const int32_t* d_bcol, int32_t max_blocks_per_row,
-                                        int32_t* h_iters, double* h_relres, void* stream) {
+static int32_t persist_run(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
+                           const double* d_b, double* d_x, int64_t n_owned, int64_t n_local, int32_t block, double rtol,
+                           double atol, int32_t maxit, int32_t warm, double* d_work, const int64_t* d_send_idx,
+                           const int64_t* h_send_counts, const int64_t* h_recv_counts, const int64_t* h_peer_ghost_base,
+                           const int32_t* d_bcol, int32_t max_blocks_per_row, int32_t* h_iters, double* h_relres,
+                           void* stream, int defer) {
     PGD_CHECK_HANDLE(h);
     PGD_ARG(h, d_rowptr && d_colidx && d_values && d_b && d_x && d_work, "null pointer");
     PGD_ARG(h, n_owned > 0 && n_local >= n_owned && block >= 1 && block <= 3 && n_owned % block == 0, "bad sizes");
@@ -914,6 +914,20 @@ extern "C" int32_t pgd_pcg_persist_sync(pgd_handle_t h, const int32_t* d_rowptr,
     PGD_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3(G), dim3(PS_THREADS), kargs, smem, st));
     h->n_launches += 1;
     PGD_CUDA(h, cudaEventRecord(h->ev1, st));
+    if (defer) {
+        // single GPU only (checked by the caller): results -> the handle's page-locked block, collected by pgd_pcg_finish
+        // (exactly the hand-over of the SM-resident solver, pcg_resident.cu); the host goes on recording the next
+        // sub-problem while the kernel iterates
+        char* pin = static_cast<char*>(h->pinned) + 256;
+        PGD_CUDA(h, cudaMemcpyAsync(pin, a.out_fl, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        PGD_CUDA(h, cudaMemcpyAsync(pin + 64, a.out_sc, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        PGD_CUDA(h, cudaEventRecord(h->ev_done, st));
+        h->res_pending = 1;
+        h->res_kind = 2;
+        h->res_stream = (void*)st;
+        if (h_iters) *h_iters = -1;
+        return 0;
+    }
     int hf[2] = {0, 0};
     double hs[2] = {0.0, 0.0};
     PGD_CUDA(h, pgd_fetch(h, hf, a.out_fl, sizeof(hf), hs, a.out_sc, sizeof(hs), st));
@@ -936,6 +950,27 @@ extern "C" int32_t pgd_pcg_persist_sync(pgd_handle_t h, const int32_t* d_rowptr,
         return -3;
     }
     return 0;
+}
+
+extern "C" int32_t pgd_pcg_persist_sync(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
+                                        const double* d_b, double* d_x, int64_t n_owned, int64_t n_local, int32_t block,
+                                        double rtol, double atol, int32_t maxit, int32_t warm, double* d_work,
+                                        const int64_t* d_send_idx, const int64_t* h_send_counts, const int64_t* h_recv_counts,
+                                        const int64_t* h_peer_ghost_base, const int32_t* d_bcol, int32_t max_blocks_per_row,
+                                        int32_t* h_iters, double* h_relres, void* stream) {
+    return persist_run(h, d_rowptr, d_colidx, d_values, d_b, d_x, n_owned, n_local, block, rtol, atol, maxit, warm, d_work,
+                       d_send_idx, h_send_counts, h_recv_counts, h_peer_ghost_base, d_bcol, max_blocks_per_row, h_iters,
+                       h_relres, stream, 0);
+}
+
+/* Single-GPU form that does not wait: enqueue the solve and return; iterations / residual / errors are collected by
+ * pgd_pcg_finish (one solve in flight per handle; every other solver entry point finishes a pending one first). */
+extern "C" int32_t pgd_pcg_persist_start(pgd_handle_t h, const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_values,
+                                         const double* d_b, double* d_x, int64_t n, int32_t block, double rtol, double atol,
+                                         int32_t maxit, int32_t warm, double* d_work, const int32_t* d_bcol,
+                                         int32_t max_blocks_per_row, void* stream) {
+    return persist_run(h, d_rowptr, d_colidx, d_values, d_b, d_x, n, n, block, rtol, atol, maxit, warm, d_work, nullptr, nullptr,
+                       nullptr, nullptr, d_bcol, max_blocks_per_row, nullptr, nullptr, stream, 1);
 }
 
 /* Phase profile of the persistent kernel (pgd_set_option "prof" = 1): accumulated nanoseconds, as seen by CTA 0, in

@@ -474,6 +474,7 @@ int32_t pgd_pcg_resident(pgd_ctx* h, const int32_t* rp, const int32_t* ci, const
     PGD_CUDA(h, cudaMemcpyAsync(pin + 64, a.out_sc, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     PGD_CUDA(h, cudaEventRecord(h->ev_done, st));
     h->res_pending = 1;
+    h->res_kind = 1;
     h->res_stream = (void*)st;
     if (defer) {
         if (h_iters) *h_iters = -1;
@@ -495,20 +496,26 @@ int32_t pgd_pcg_finish_impl(pgd_ctx* h, int32_t* h_iters, double* h_relres) {
         return 0;
     }
     h->res_pending = 0;
+    const int kind = h->res_kind;
+    h->res_kind = 0;
     PGD_CUDA(h, cudaEventSynchronize(h->ev_done));
     const char* pin = static_cast<const char*>(h->pinned) + 256;
     int hf[2];
     double hs[2];
     memcpy(hf, pin, sizeof(hf));
     memcpy(hs, pin + 64, sizeof(hs));
-    if (hf[1] == 1) return 1;
+    if (kind != 2 && hf[1] == 1) return 1;
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->pcg_ms += ms;
     h->pcg_solves += 1;
     h->pcg_iters += hf[0];
-    h->pcg_resident_solves += 1;
+    if (kind != 2) h->pcg_resident_solves += 1;
     if (h_iters) *h_iters = hf[0];
     if (h_relres) *h_relres = (hs[1] > 0.0) ? sqrt(hs[0] / hs[1]) : 0.0;
+    if (kind == 2 && hf[1] == 3) {  // persistent streaming kernel (pgd_pcg_persist_start, single GPU): a CTA did not arrive
+        snprintf(h->err, sizeof(h->err), "pgd_pcg_persist_start: a CTA did not arrive within %d ms", h->opt_spin_ms);
+        return -6;
+    }
     if (hf[1] == 2) {
         snprintf(h->err, sizeof(h->err), "pgd_pcg: NaN encountered (matrix not SPD?)");
         return -3;

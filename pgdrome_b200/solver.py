@@ -568,9 +568,9 @@ class PGDProblem:
         x0 = getattr(self, "_x0", None)
         if x0 is not None and x0.numel() != b.numel():
             x0 = None
+        self._collect_solve()
         if ds.shard is not None:
             return self._sharded_solve(ds, values, b, block, rtol, atol, maxit, settings, x0)
-        self._collect_solve()
         if settings.get("async_solve", True):
             # SM-resident systems (known to fit from an earlier solve): enqueue and go on recording the next
             # sub-problem's forms while the GPU iterates; iterations / residual are collected before the next solve
@@ -579,10 +579,16 @@ class PGDProblem:
                 self._pending_solve = (rtol, maxit)
                 return x
         if block > 1 and V.n_dofs >= 32768 and settings.get("node_block_walk", True) and ds.bsr is not None:
-            # vector operator in the HBM-bound regime: persistent kernel walking the CSR arrays by node blocks
+            # vector operator in the HBM-bound regime: persistent kernel walking the CSR arrays by node blocks.  It is
+            # only enqueued (async_solve): the sweep solves the spatial dimension first, so the forms of the parameter
+            # dimensions are recorded while the GPU iterates; iterations / residual are collected before the next solve
+            defer = bool(settings.get("async_solve", True))
             x, iters, relres = _lib.pcg_persist(rowptr, colidx, values, b, block=block, rtol=rtol, atol=atol, maxit=maxit,
-                                                x0=x0, bsr=ds.bsr)
-            self._account_solve(iters, relres, rtol, maxit)
+                                                x0=x0, bsr=ds.bsr, defer=defer)
+            if defer:
+                self._pending_solve = (rtol, maxit)
+            else:
+                self._account_solve(iters, relres, rtol, maxit)
             return x
         x, iters, relres = _lib.pcg(rowptr, colidx, values, b, rtol=rtol, atol=atol, maxit=maxit,
                                     check_every=int(settings.get("check_every", 50)), block=block, lpr=ds.lpr, x0=x0)
