@@ -360,3 +360,34 @@ def test_capture_cache_is_scoped_to_the_enrichment_step(cpu):
     p = __import__("pgdrome_b200.configs", fromlist=["x"]).poisson1d_k(nx=20, nk=5, PGD_nmax=2)
     p.solve_PGD(_problem="linear")
     assert ufl.capture_cache[0] is None
+
+
+def test_vector_space_pattern_from_the_node_pattern(cpu):
+    """Vector spaces build the pattern of their NODES and expand it: row pointers, columns and the (lazily built) gather
+    lists must equal the dof-level build bit for bit, the block-column list must equal the plan derived from the CSR
+    arrays -- replicated spaces and the local spaces of an element partition alike."""
+    from pgdrome_b200 import fem, sharding
+    from pgdrome_b200.assembly import ShardedDeviceSpace, device_space
+
+    cases = [(fem.UnitCubeMesh(3, 4, 2), 1, 3), (fem.UnitSquareMesh(5, 4), 2, 2), (fem.UnitSquareMesh(5, 4), 1, 2),
+             (fem.IntervalMesh(7, 0.0, 1.0), 1, 2), (fem.UnitCubeMesh(2, 2, 2), 1, 2)]
+    for mesh, degree, bs in cases:
+        V = fem.FunctionSpace(mesh, "P", degree, bs)
+        ds = device_space(V)
+        rowptr, colidx, gptr, gidx = ds.pattern
+        rp, ci = ofem.sparsity(V.cell_dofs, V.n_dofs)
+        assert np.array_equal(rowptr.numpy(), rp) and np.array_equal(colidx.numpy(), ci)
+        _, _, g2, i2 = cpu_abi.pattern_build(ds.cell_dofs, V.n_dofs)
+        assert np.array_equal(gptr.numpy(), g2.numpy()) and np.array_equal(gidx.numpy(), i2.numpy())
+        ref = cpu_abi.bsr_plan(rowptr, colidx, bs)
+        assert np.array_equal(ds.bsr[0].numpy(), ref[0].numpy()) and ds.bsr[1] == ref[1]
+    for world in (2, 3):
+        for rank in range(world):
+            V = fem.FunctionSpace(fem.UnitCubeMesh(5, 4, 3), "P", 1, 3)
+            sh = sharding.SpaceShard(V, rank, world)
+            ds = ShardedDeviceSpace(V, sh)
+            rp, ci = ofem.sparsity(sh.local.cell_dofs, sh.local.n_dofs)
+            assert np.array_equal(ds.pattern[0].numpy(), rp) and np.array_equal(ds.pattern[1].numpy(), ci)
+            ref = cpu_abi.bsr_plan(ds.rowptr_owned, ds.pattern[1][: ds.nnz_owned], 3)
+            assert np.array_equal(ds.bsr[0].numpy(), ref[0].numpy()) and ds.bsr[1] == ref[1], (world, rank)
+            assert ds.node_plan is not False
